@@ -1,0 +1,365 @@
+// extern "C" entry points of libfeonet_b200.so (declared in include/feonet_b200.h).
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <new>
+
+#include "feo_internal.h"
+
+namespace feo {
+const std::string& last_error();
+
+namespace {
+template <typename T>
+int upload(feo_operator* op, const std::vector<T>& host, T** dev) {
+  *dev = nullptr;
+  size_t bytes = std::max<size_t>(host.size() * sizeof(T), 16);
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return fail(FEO_ERR_OUT_OF_MEMORY, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  op->allocations.push_back(p);
+  op->device_bytes += (int64_t)bytes;
+  if (!host.empty()) FEO_CUDA_CHECK(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *dev = reinterpret_cast<T*>(p);
+  return FEO_OK;
+}
+
+int upload_csr(feo_operator* op, const HostCsr& h, DevCsr* d) {
+  if (!h.present()) return FEO_OK;
+  if (int rc = upload(op, h.rowptr, &d->rowptr)) return rc;
+  if (int rc = upload(op, h.col, &d->col)) return rc;
+  if (int rc = upload(op, h.val, &d->val)) return rc;
+  d->nnz = h.nnz();
+  return FEO_OK;
+}
+
+// host [n,n] row-major -> device [n, ceil4(n)] zero padded (optionally transposed)
+int upload_dense(feo_operator* op, const float* src, int32_t n, bool transposed, float** dev) {
+  const int32_t ld = (n + 3) / 4 * 4;
+  std::vector<float> buf((size_t)n * ld, 0.f);
+  for (int32_t r = 0; r < n; ++r)
+    for (int32_t c = 0; c < n; ++c) buf[(size_t)r * ld + c] = transposed ? src[(size_t)c * n + r] : src[(size_t)r * n + c];
+  return upload(op, buf, dev);
+}
+
+int check_handle(feo_handle_t h) {
+  if (h == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, "operator handle is NULL");
+  return FEO_OK;
+}
+
+int prepare(const feo_operator_desc* desc, HostCsr* A, HostCsr* B1, HostCsr* B2, HostCsr* S) {
+  if (desc == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, "desc is NULL");
+  if (desc->abi_version != FEO_ABI_VERSION) return fail(FEO_ERR_INVALID_ARGUMENT, "ABI version mismatch");
+  if (desc->n <= 0) return fail(FEO_ERR_INVALID_ARGUMENT, "n must be positive");
+  if (int rc = canonicalize(desc->A, desc->n, "A", A)) return rc;
+  if (int rc = canonicalize(desc->B1, desc->n, "B1", B1)) return rc;
+  if (int rc = canonicalize(desc->B2, desc->n, "B2", B2)) return rc;
+  if (int rc = canonicalize(desc->S, desc->n, "S", S)) return rc;
+  if (!A->present() && desc->dense_m == nullptr && desc->dense_p == nullptr)
+    return fail(FEO_ERR_INVALID_ARGUMENT, "operator needs A (CSR) or a dense matrix");
+  if (desc->n_u < 0 || (desc->n_u > 0 && (desc->idx_i == nullptr || desc->idx_j == nullptr)))
+    return fail(FEO_ERR_INVALID_ARGUMENT, "idx_i/idx_j missing");
+  return FEO_OK;
+}
+}  // namespace
+}  // namespace feo
+
+using namespace feo;
+
+extern "C" {
+
+int feo_abi_version(void) { return FEO_ABI_VERSION; }
+const char* feo_last_error_string(void) { return feo::last_error().c_str(); }
+
+int feo_op_create(const feo_operator_desc* desc, feo_handle_t* out) {
+  if (out == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  HostCsr A, B1, B2, S;
+  if (int rc = prepare(desc, &A, &B1, &B2, &S)) return rc;
+  feo_operator* op = new (std::nothrow) feo_operator();
+  if (op == nullptr) return fail(FEO_ERR_OUT_OF_MEMORY, "host allocation failed");
+  auto bail = [&](int rc) {
+    feo_op_destroy(op);
+    return rc;
+  };
+  op->n = desc->n;
+  op->n_u = desc->n_u;
+  op->ns_branch = desc->ns_precond_branch ? 1 : 0;
+  op->dt = desc->dt;
+  int rc;
+  const HostCsr* mats[4] = {&A, &B1, &B2, &S};
+  for (int m = 0; m < 4; ++m) {
+    if ((rc = upload_csr(op, *mats[m], &op->csr[m]))) return bail(rc);
+    if ((rc = upload_csr(op, transpose(*mats[m]), &op->csrT[m]))) return bail(rc);
+    op->nnz[m] = mats[m]->nnz();
+  }
+  if (S.present() && A.present()) {  // time-dependent operator M = S + dt*A
+    HostCsr M = axpy(S, desc->dt, A);
+    if ((rc = upload_csr(op, M, &op->csr[FEO_MAT_M]))) return bail(rc);
+    if ((rc = upload_csr(op, transpose(M), &op->csrT[FEO_MAT_M]))) return bail(rc);
+    op->nnz[FEO_MAT_M] = M.nnz();
+    op->has_seq = true;
+  }
+  if (desc->n_u > 0) {
+    std::vector<int32_t> ii(desc->idx_i, desc->idx_i + desc->n_u), jj(desc->idx_j, desc->idx_j + desc->n_u);
+    for (int32_t k = 0; k < desc->n_u; ++k)
+      if (ii[k] < 0 || ii[k] >= desc->n || jj[k] < 0 || jj[k] >= desc->n)
+        return bail(fail(FEO_ERR_INVALID_ARGUMENT, "idx_sol entry out of range"));
+    if ((rc = upload(op, ii, &op->idx_i))) return bail(rc);
+    if ((rc = upload(op, jj, &op->idx_j))) return bail(rc);
+  }
+  if (A.present()) {
+    HostPlan plan;
+    if ((rc = build_plan(A, B1, B2, desc->n_u, desc->idx_i, desc->idx_j, op->ns_branch, tuning_from_env(), &plan)))
+      return bail(rc);
+    op->has_conv = plan.has_conv;
+    if (!plan.has_conv) op->ns_branch = 1;  // linear Stokes: r = A a - F (FEONet_Stokes_square/train_FEONet.py:264-270)
+    op->n_blobs = (int32_t)plan.blob_uptr.size() - 1;
+    op->n_units = (int32_t)plan.unit_ptr.size() - 1;
+    op->n_slots = (int32_t)plan.slot_row.size();
+    op->nnz_union = plan.nnz_union;
+    op->max_row_nnz = plan.max_row_nnz;
+    op->max_blob_fent = plan.max_blob_fent;
+    op->max_blob_bentA = plan.max_blob_bentA;
+    op->max_blob_bentB = plan.max_blob_bentB;
+    std::vector<int32_t> spi(op->n_slots), spj(op->n_slots);
+    for (int32_t s = 0; s < op->n_slots; ++s) {
+      spi[s] = plan.pi[plan.slot_row[s]];
+      spj[s] = plan.pj[plan.slot_row[s]];
+    }
+    if ((rc = upload(op, plan.blob_uptr, &op->blob_uptr))) return bail(rc);
+    if ((rc = upload(op, plan.unit_ptr, &op->unit_ptr))) return bail(rc);
+    if ((rc = upload(op, plan.slot_row, &op->slot_row))) return bail(rc);
+    if ((rc = upload(op, spi, &op->slot_pi))) return bail(rc);
+    if ((rc = upload(op, spj, &op->slot_pj))) return bail(rc);
+    if ((rc = upload(op, plan.fptr, &op->fptr))) return bail(rc);
+    if (plan.has_conv) {
+      FwdEntry* d = nullptr;
+      if ((rc = upload(op, plan.fent, &d))) return bail(rc);
+      op->fent = d;
+    } else {
+      FwdEntryLin* d = nullptr;
+      if ((rc = upload(op, plan.fent_lin, &d))) return bail(rc);
+      op->fent = d;
+    }
+    if ((rc = upload(op, plan.bptrA, &op->bptrA))) return bail(rc);
+    if ((rc = upload(op, plan.bptrB, &op->bptrB))) return bail(rc);
+    if ((rc = upload(op, plan.bentA, &op->bentA))) return bail(rc);
+    if ((rc = upload(op, plan.bentB, &op->bentB))) return bail(rc);
+  }
+  if (desc->dense_m != nullptr) {
+    if ((rc = upload_dense(op, desc->dense_m, desc->n, false, &op->dM))) return bail(rc);
+    if ((rc = upload_dense(op, desc->dense_m, desc->n, true, &op->dMT))) return bail(rc);
+  }
+  if (desc->dense_p != nullptr)
+    if ((rc = upload_dense(op, desc->dense_p, desc->n, false, &op->dP))) return bail(rc);
+  if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(FEO_ERR_CUDA, "device synchronize failed after upload"));
+  *out = op;
+  return FEO_OK;
+}
+
+int feo_op_destroy(feo_handle_t h) {
+  if (h == nullptr) return FEO_OK;
+  for (void* p : h->allocations) cudaFree(p);
+  delete h;
+  return FEO_OK;
+}
+
+int feo_op_get_info(feo_handle_t h, feo_op_info* info) {
+  if (int rc = check_handle(h)) return rc;
+  if (info == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, "info is NULL");
+  std::memset(info, 0, sizeof(*info));
+  info->n = h->n;
+  info->n_u = h->n_u;
+  info->has_conv = h->has_conv;
+  info->has_seq = h->has_seq;
+  info->has_dense_m = h->dM != nullptr;
+  info->has_dense_p = h->dP != nullptr;
+  info->nnz_a = h->nnz[0];
+  info->nnz_b1 = h->nnz[1];
+  info->nnz_b2 = h->nnz[2];
+  info->nnz_s = h->nnz[3];
+  info->nnz_union = h->nnz_union;
+  info->n_blobs = h->n_blobs;
+  info->n_units = h->n_units;
+  info->max_row_nnz = h->max_row_nnz;
+  info->device_bytes = h->device_bytes;
+  return FEO_OK;
+}
+
+size_t feo_workspace_bytes(feo_handle_t h, int32_t B, int32_t T) {
+  if (h == nullptr || B <= 0) return 0;
+  if (T < 1) T = 1;
+  return loss_partials_needed(h->n, h->n_blobs, (int64_t)B * T);
+}
+
+int feo_transpose(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int32_t rows, int32_t cols,
+                  const int32_t* dst_row_map, void* stream) {
+  return launch_transpose(src, src_ld, dst, dst_ld, rows, cols, dst_row_map, (cudaStream_t)stream);
+}
+
+int feo_residual_fwd(feo_handle_t h, const float* alphaT, const float* fT, int64_t ldb, int32_t B, float* loss_out,
+                     float* rT, float* eT, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (h->fent == nullptr) return fail(FEO_ERR_UNSUPPORTED, "operator has no sparse A: use feo_dense_apply");
+  return launch_residual_fwd(h, alphaT, fT, ldb, B, loss_out, rT, eT, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int feo_residual_bwd(feo_handle_t h, const float* alphaT, const float* rT, const float* eT, const float* grad_loss,
+                     float* gradT, int64_t ldb, int32_t B, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (h->fent == nullptr) return fail(FEO_ERR_UNSUPPORTED, "operator has no sparse A: use feo_dense_apply");
+  return launch_residual_bwd(h, alphaT, rT, eT, grad_loss, gradT, ldb, B, (cudaStream_t)stream);
+}
+
+int feo_spmm(feo_handle_t h, int32_t which, int32_t transpose, const float* XT, float* YT, int64_t ldb, int32_t B,
+             float scale, int32_t accumulate, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (which < 0 || which > FEO_MAT_M) return fail(FEO_ERR_INVALID_ARGUMENT, "spmm: unknown matrix id");
+  const DevCsr& K = transpose ? h->csrT[which] : h->csr[which];
+  return launch_spmm(K, h->n, XT, YT, ldb, B, scale, accumulate, (cudaStream_t)stream);
+}
+
+int feo_dense_apply(feo_handle_t h, int32_t which, const float* XT, float* CT, int64_t ldb, int32_t B, float scale,
+                    const float* scale_dev, const float* sub, float* loss_out, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  const float* D = which == FEO_DENSE_M ? h->dM : which == FEO_DENSE_MT ? h->dMT : which == FEO_DENSE_P ? h->dP : nullptr;
+  if (which < 0 || which > FEO_DENSE_P) return fail(FEO_ERR_INVALID_ARGUMENT, "dense_apply: unknown matrix id");
+  return launch_dense(D, h->n, XT, CT, ldb, B, scale, scale_dev, sub, loss_out, workspace, workspace_bytes,
+                      (cudaStream_t)stream);
+}
+
+int feo_seq_fwd(feo_handle_t h, const float* predT, const float* u0T, const float* fT, int64_t ldj, int64_t ldb,
+                int32_t B, int32_t T, float* loss_out, float* rT, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  return launch_seq(h->csr[FEO_MAT_M], h->csr[FEO_MAT_S], h->n, false, predT, u0T, fT, h->dt, ldj, ldb, B, T, nullptr, rT,
+                    loss_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int feo_seq_bwd(feo_handle_t h, const float* rT, const float* grad_loss, float* gradT, int64_t ldj, int32_t B, int32_t T,
+                void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  return launch_seq(h->csrT[FEO_MAT_M], h->csrT[FEO_MAT_S], h->n, true, rT, nullptr, nullptr, h->dt, ldj, 0, B, T,
+                    grad_loss, gradT, nullptr, nullptr, 0, (cudaStream_t)stream);
+}
+
+int feo_assemble_u_init(feo_handle_t h, const float* init_x, const float* init_y, float* u0T, int64_t ldb, int32_t B,
+                        void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (h->n_u <= 0 || h->idx_i == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, "operator has no idx_sol");
+  if (init_x == nullptr || init_y == nullptr || u0T == nullptr || ldb < B || B <= 0)
+    return fail(FEO_ERR_INVALID_ARGUMENT, "assemble_u_init: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  FEO_CUDA_CHECK(cudaMemsetAsync(u0T, 0, (size_t)h->n * ldb * sizeof(float), st));
+  if (int rc = launch_transpose(init_x, h->n_u, u0T, ldb, B, h->n_u, h->idx_i, st)) return rc;
+  return launch_transpose(init_y, h->n_u, u0T, ldb, B, h->n_u, h->idx_j, st);
+}
+
+int feo_sq_diff_sum(const float* xT, const float* yT, int32_t n, int64_t ldb, int32_t B, float scale, float* loss_out,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  return launch_sq_diff_sum(xT, yT, n, ldb, B, scale, loss_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// ---- test hooks (host only; exercised by the CPU test-suite, never by the product path) -------
+// Builds the walk plan on the host and checks its invariants: every stored entry of the union
+// pattern appears exactly once in the forward stream and (as A- or B-type) in the backward
+// stream, velocity pairs are adjacent, blobs respect the staging cap.  stats[0..7] =
+// {n_blobs, n_units, nnz_union, max_row_nnz, max_blob_fent, n_bentA, n_bentB, has_conv}.
+int feo_debug_plan_check(const feo_operator_desc* desc, int64_t* stats) {
+  HostCsr A, B1, B2, S;
+  if (int rc = prepare(desc, &A, &B1, &B2, &S)) return rc;
+  if (!A.present()) return fail(FEO_ERR_INVALID_ARGUMENT, "plan check needs A");
+  HostPlan P;
+  PlanTuning tune = tuning_from_env();
+  if (int rc = build_plan(A, B1, B2, desc->n_u, desc->idx_i, desc->idx_j, desc->ns_precond_branch ? 1 : 0, tune, &P)) return rc;
+  const int32_t n = desc->n;
+  std::vector<char> seen(n, 0);
+  for (int32_t r : P.slot_row) {
+    if (r < 0 || r >= n || seen[r]) return fail(FEO_ERR_INVALID_ARGUMENT, "plan: slot rows are not a permutation");
+    seen[r] = 1;
+  }
+  for (size_t u = 0; u + 1 < P.unit_ptr.size(); ++u) {
+    int32_t s0 = P.unit_ptr[u], cnt = P.unit_ptr[u + 1] - s0;
+    if (cnt == 2) {
+      if (P.kind[P.slot_row[s0]] != 1 || P.kind[P.slot_row[s0 + 1]] != 2 || P.pj[P.slot_row[s0]] != P.slot_row[s0 + 1])
+        return fail(FEO_ERR_INVALID_ARGUMENT, "plan: pair unit is not (I[k], J[k])");
+    } else if (cnt != 1 || P.kind[P.slot_row[s0]] != 0) {
+      return fail(FEO_ERR_INVALID_ARGUMENT, "plan: malformed unit");
+    }
+  }
+  int64_t fcount = P.has_conv ? (int64_t)P.fent.size() : (int64_t)P.fent_lin.size();
+  if (fcount != P.nnz_union) return fail(FEO_ERR_INVALID_ARGUMENT, "plan: forward stream size != union nnz");
+  if (P.max_blob_fent > tune.blob_max_ent) return fail(FEO_ERR_INVALID_ARGUMENT, "plan: blob exceeds staging cap");
+  if (stats != nullptr) {
+    stats[0] = (int64_t)P.blob_uptr.size() - 1;
+    stats[1] = (int64_t)P.unit_ptr.size() - 1;
+    stats[2] = P.nnz_union;
+    stats[3] = P.max_row_nnz;
+    stats[4] = P.max_blob_fent;
+    stats[5] = (int64_t)P.bentA.size();
+    stats[6] = (int64_t)P.bentB.size();
+    stats[7] = P.has_conv;
+  }
+  return FEO_OK;
+}
+
+// Replays the plan's forward and backward streams on the host in fp64 for ONE sample, so the CPU
+// suite can compare the set-up code (union pattern, partner lookups, sign folding, transposed
+// lists) with the oracle without a GPU.  alpha, f: [n]; outputs r, grad: [n]; returns loss.
+int feo_debug_plan_replay(const feo_operator_desc* desc, const double* alpha, const double* f, double* r_out,
+                          double* grad_out, double* loss_out) {
+  HostCsr A, B1, B2, S;
+  if (int rc = prepare(desc, &A, &B1, &B2, &S)) return rc;
+  HostPlan P;
+  if (int rc = build_plan(A, B1, B2, desc->n_u, desc->idx_i, desc->idx_j, desc->ns_precond_branch ? 1 : 0,
+                          tuning_from_env(), &P))
+    return rc;
+  const int32_t n = desc->n;
+  const bool precond = P.has_conv ? desc->ns_precond_branch != 0 : true;
+  const double s = precond ? 1.0 : -1.0;
+  std::vector<double> r(n, 0.0), e(n, 0.0), s1(n, 0.0), s2(n, 0.0);
+  double loss = 0.0;
+  for (int32_t sl = 0; sl < n; ++sl) {
+    const int32_t row = P.slot_row[sl];
+    double accA = 0, acc1 = 0, acc2 = 0;
+    for (int32_t k = P.fptr[sl]; k < P.fptr[sl + 1]; ++k) {
+      if (P.has_conv) {
+        const FwdEntry& en = P.fent[k];
+        accA += (double)en.a * alpha[en.col];
+        acc1 += (double)en.b1 * alpha[en.col];
+        acc2 += (double)en.b2 * alpha[en.col];
+      } else {
+        accA += (double)P.fent_lin[k].a * alpha[P.fent_lin[k].col];
+      }
+    }
+    double c = 0.0;
+    if (P.has_conv && P.pi[row] >= 0) c = alpha[P.pi[row]] * acc1 + alpha[P.pj[row]] * acc2;
+    r[row] = precond ? accA - (f[row] - c) : accA - (-f[row] + c);
+    s1[row] = acc1;
+    s2[row] = acc2;
+    loss += r[row] * r[row];
+  }
+  if (P.has_conv)
+    for (int32_t row = 0; row < n; ++row)
+      if (P.kind[row] != 0) {
+        const int32_t i = P.pi[row], j = P.pj[row];
+        e[row] = P.kind[row] == 1 ? s1[i] * r[i] + s1[j] * r[j] : s2[i] * r[i] + s2[j] * r[j];
+      }
+  for (int32_t sl = 0; sl < n; ++sl) {
+    const int32_t c = P.slot_row[sl];
+    double acc = 0.0;
+    for (int32_t k = P.bptrA[sl]; k < P.bptrA[sl + 1]; ++k) acc += (double)P.bentA[k].a * r[P.bentA[k].row];
+    for (int32_t k = P.bptrB[sl]; k < P.bptrB[sl + 1]; ++k) {
+      const BwdEntryB& en = P.bentB[k];
+      acc += ((double)en.a + (double)en.b1s * alpha[en.pi] + (double)en.b2s * alpha[en.pj]) * r[en.row];
+    }
+    if (P.has_conv && P.kind[c] != 0) acc += s * e[c];
+    grad_out[c] = 2.0 * acc;
+  }
+  for (int32_t i = 0; i < n; ++i) r_out[i] = r[i];
+  *loss_out = loss;
+  return FEO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,699 @@
+// sm_100a kernels for the sparse FEONet residual path.
+//
+// Data layout: every batch of coefficient vectors is dof-major, XT[d*ldb + b] (see feonet_b200.h).
+// A warp owns one operator row (or a velocity pair) for 128 consecutive samples: lane l holds
+// samples 4l..4l+3 as a float4, so every gather `alphaT[col*ldb + b]` is one fully coalesced
+// 512-byte request and the operator entry {col, a, b1, b2} is warp-uniform (one 16-byte shared
+// memory broadcast feeds 12 FMAs per lane).  Rows are walked blob by blob (feo_plan.cpp) so the
+// columns a CTA touches stay L1/L2-resident.  Everything is row-/column-owned: no atomics, fixed
+// summation order, bit-reproducible.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "feo_internal.h"
+
+namespace feo {
+namespace {
+
+constexpr int kWarpSamples = 128;  // samples per warp (float4 per lane)
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// streaming load: read once, do not keep in L1
+__device__ __forceinline__ float4 ldg4_stream(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void fma4(float4& acc, float a, const float4& x) {
+  acc.x = fmaf(a, x.x, acc.x);
+  acc.y = fmaf(a, x.y, acc.y);
+  acc.z = fmaf(a, x.z, acc.z);
+  acc.w = fmaf(a, x.w, acc.w);
+}
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Fixed-order block reduction; thread 0 writes the CTA partial.
+__device__ __forceinline__ void block_partial(float v, float* partials, int slot) {
+  __shared__ float s_part[32];
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) s_part[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int w = 0; w < nw; ++w) t += s_part[w];
+    partials[slot] = t;
+  }
+}
+
+__global__ void finalize_loss_kernel(const float* __restrict__ partials, int count, float scale,
+                                     float* __restrict__ loss_out) {
+  __shared__ double s[1024];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) acc += (double)partials[i];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss_out = (float)(s[0] * (double)scale);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused residual forward
+// ---------------------------------------------------------------------------------------------
+struct FwdParams {
+  const int32_t *blob_uptr, *unit_ptr, *slot_row, *slot_pi, *slot_pj, *fptr;
+  const void* fent;
+  const float *alphaT, *fT;
+  float *rT, *eT, *partials;
+  int64_t ldb;
+  int32_t B;
+  int32_t precond_branch;
+};
+
+template <bool CONV>
+struct RowOut {
+  float4 r, s1, s2;
+};
+
+// One operator row for 4 samples per lane.  Entries come from shared memory (warp-uniform).
+template <bool CONV>
+__device__ __forceinline__ RowOut<CONV> fwd_row(const void* s_ent, int eb, int ee, const float* __restrict__ alphaT,
+                                                int64_t ldb, int bb) {
+  float4 accA = zero4(), acc1 = zero4(), acc2 = zero4();
+  if (CONV) {
+    const int4* ent = reinterpret_cast<const int4*>(s_ent);
+#pragma unroll 4
+    for (int e = eb; e < ee; ++e) {
+      const int4 en = ent[e];
+      const float4 x = ldg4(alphaT + (int64_t)en.x * ldb + bb);
+      fma4(accA, __int_as_float(en.y), x);
+      fma4(acc1, __int_as_float(en.z), x);
+      fma4(acc2, __int_as_float(en.w), x);
+    }
+  } else {
+    const int2* ent = reinterpret_cast<const int2*>(s_ent);
+#pragma unroll 4
+    for (int e = eb; e < ee; ++e) {
+      const int2 en = ent[e];
+      const float4 x = ldg4(alphaT + (int64_t)en.x * ldb + bb);
+      fma4(accA, __int_as_float(en.y), x);
+    }
+  }
+  RowOut<CONV> o;
+  o.r = accA;
+  o.s1 = acc1;
+  o.s2 = acc2;
+  return o;
+}
+
+// residual from LHS sum, load vector and convection, mirroring the reference's operation order:
+// precond branch  r = LHS - (F - c) ; else  r = LHS - (-F + c)
+// (FEONet_steady_Navier-Stokes/train_FEONet.py:324-330, :356)
+__device__ __forceinline__ float resid1(float lhs, float f, float c, bool precond) {
+  return precond ? __fsub_rn(lhs, __fsub_rn(f, c)) : __fsub_rn(lhs, __fadd_rn(-f, c));
+}
+// c = u_i*Bu1 + u_j*Bu2 as two rounded products and one rounded add (train_FEONet.py:317-322)
+__device__ __forceinline__ float conv1(float d1, float s1, float d2, float s2) {
+  return __fadd_rn(__fmul_rn(d1, s1), __fmul_rn(d2, s2));
+}
+
+template <bool CONV>
+__global__ void __launch_bounds__(kThreads) residual_fwd_kernel(FwdParams p) {
+  extern __shared__ int4 s_ent_raw[];
+  const int blob = blockIdx.x;
+  const int u0 = p.blob_uptr[blob], u1 = p.blob_uptr[blob + 1];
+  const int sl_begin = p.unit_ptr[u0], sl_end = p.unit_ptr[u1];
+  const int e0 = p.fptr[sl_begin], e1 = p.fptr[sl_end];
+  {  // stage the blob's operator entries
+    if (CONV) {
+      const int4* src = reinterpret_cast<const int4*>(p.fent) + e0;
+      for (int i = threadIdx.x; i < e1 - e0; i += blockDim.x) s_ent_raw[i] = src[i];
+    } else {
+      const int2* src = reinterpret_cast<const int2*>(p.fent) + e0;
+      int2* dst = reinterpret_cast<int2*>(s_ent_raw);
+      for (int i = threadIdx.x; i < e1 - e0; i += blockDim.x) dst[i] = src[i];
+    }
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int b = blockIdx.y * kWarpSamples + lane * 4;
+  const int nvalid = min(4, p.B - b);  // <=0: lane idle (it still executes with bb = 0, masked out)
+  const int bb = nvalid > 0 ? b : 0;
+  const bool precond = p.precond_branch != 0;
+  float lsum = 0.f;
+
+  for (int u = u0 + warp; u < u1; u += nwarps) {
+    const int sl0 = p.unit_ptr[u];
+    const int cnt = p.unit_ptr[u + 1] - sl0;
+    float4 d1 = zero4(), d2 = zero4();
+    bool vel = false;
+    if (CONV) {
+      const int pi = p.slot_pi[sl0], pj = p.slot_pj[sl0];
+      vel = pi >= 0;
+      if (vel) {
+        d1 = ldg4(p.alphaT + (int64_t)pi * p.ldb + bb);
+        d2 = ldg4(p.alphaT + (int64_t)pj * p.ldb + bb);
+      }
+    }
+    float4 rI = zero4(), s1I = zero4(), s2I = zero4();
+#pragma unroll 1
+    for (int t = 0; t < cnt; ++t) {
+      const int row = p.slot_row[sl0 + t];
+      const int eb = p.fptr[sl0 + t] - e0, ee = p.fptr[sl0 + t + 1] - e0;
+      RowOut<CONV> o = fwd_row<CONV>(s_ent_raw, eb, ee, p.alphaT, p.ldb, bb);
+      const float4 f = ldg4_stream(p.fT + (int64_t)row * p.ldb + bb);
+      float4 c = zero4();
+      if (CONV && vel) {
+        c.x = conv1(d1.x, o.s1.x, d2.x, o.s2.x);
+        c.y = conv1(d1.y, o.s1.y, d2.y, o.s2.y);
+        c.z = conv1(d1.z, o.s1.z, d2.z, o.s2.z);
+        c.w = conv1(d1.w, o.s1.w, d2.w, o.s2.w);
+      }
+      float4 r;
+      r.x = resid1(o.r.x, f.x, c.x, precond);
+      r.y = resid1(o.r.y, f.y, c.y, precond);
+      r.z = resid1(o.r.z, f.z, c.z, precond);
+      r.w = resid1(o.r.w, f.w, c.w, precond);
+      if (nvalid > 0) lsum = fmaf(r.x, r.x, lsum);
+      if (nvalid > 1) lsum = fmaf(r.y, r.y, lsum);
+      if (nvalid > 2) lsum = fmaf(r.z, r.z, lsum);
+      if (nvalid > 3) lsum = fmaf(r.w, r.w, lsum);
+      if (p.rT != nullptr && nvalid > 0) stg4(p.rT + (int64_t)row * p.ldb + b, r);
+      if (CONV && vel && p.eT != nullptr) {
+        if (t == 0) {
+          rI = r;
+          s1I = o.s1;
+          s2I = o.s2;
+        } else {
+          // E-term products: e[I] = Bu1[I] r[I] + Bu1[J] r[J], e[J] = Bu2[I] r[I] + Bu2[J] r[J]
+          float4 eI, eJ;
+          eI.x = fmaf(o.s1.x, r.x, s1I.x * rI.x);
+          eI.y = fmaf(o.s1.y, r.y, s1I.y * rI.y);
+          eI.z = fmaf(o.s1.z, r.z, s1I.z * rI.z);
+          eI.w = fmaf(o.s1.w, r.w, s1I.w * rI.w);
+          eJ.x = fmaf(o.s2.x, r.x, s2I.x * rI.x);
+          eJ.y = fmaf(o.s2.y, r.y, s2I.y * rI.y);
+          eJ.z = fmaf(o.s2.z, r.z, s2I.z * rI.z);
+          eJ.w = fmaf(o.s2.w, r.w, s2I.w * rI.w);
+          if (nvalid > 0) {
+            stg4(p.eT + (int64_t)p.slot_row[sl0] * p.ldb + b, eI);
+            stg4(p.eT + (int64_t)row * p.ldb + b, eJ);
+          }
+        }
+      }
+    }
+  }
+  block_partial(lsum, p.partials, blockIdx.y * gridDim.x + blockIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused residual backward (column-owned)
+// ---------------------------------------------------------------------------------------------
+struct BwdParams {
+  const int32_t *blob_uptr, *unit_ptr, *slot_row, *slot_pi, *bptrA, *bptrB;
+  const BwdEntryA* bentA;
+  const BwdEntryB* bentB;
+  const float *alphaT, *rT, *eT, *grad_loss;
+  float* gradT;
+  int64_t ldb;
+  int32_t B;
+  float esign;  // s = +1 precond branch, -1 otherwise
+  int32_t has_conv;
+};
+
+__global__ void __launch_bounds__(kThreads) residual_bwd_kernel(BwdParams p, int smemA_entries) {
+  extern __shared__ int4 s_raw[];
+  const int blob = blockIdx.x;
+  const int u0 = p.blob_uptr[blob], u1 = p.blob_uptr[blob + 1];
+  const int sl_begin = p.unit_ptr[u0], sl_end = p.unit_ptr[u1];
+  const int a0 = p.bptrA[sl_begin], a1 = p.bptrA[sl_end];
+  const int b0 = p.bptrB[sl_begin], b1 = p.bptrB[sl_end];
+  // shared layout: [B entries: 2 int4 each][A entries: int2 each]
+  int4* sB = s_raw;
+  int2* sA = reinterpret_cast<int2*>(s_raw + 2 * (size_t)(b1 - b0));
+  {
+    const int4* srcB = reinterpret_cast<const int4*>(p.bentB + b0);
+    for (int i = threadIdx.x; i < 2 * (b1 - b0); i += blockDim.x) sB[i] = srcB[i];
+    const int2* srcA = reinterpret_cast<const int2*>(p.bentA + a0);
+    for (int i = threadIdx.x; i < a1 - a0; i += blockDim.x) sA[i] = srcA[i];
+  }
+  __syncthreads();
+  (void)smemA_entries;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int b = blockIdx.y * kWarpSamples + lane * 4;
+  const bool active = b < p.B;
+  const int bb = active ? b : 0;
+  const float g2 = 2.0f * (p.grad_loss != nullptr ? __ldg(p.grad_loss) : 1.0f);
+
+  for (int u = u0 + warp; u < u1; u += nwarps) {
+    const int sl0 = p.unit_ptr[u];
+    const int cnt = p.unit_ptr[u + 1] - sl0;
+#pragma unroll 1
+    for (int t = 0; t < cnt; ++t) {
+      const int sl = sl0 + t;
+      const int c = p.slot_row[sl];
+      float4 acc = zero4();
+      {
+        const int eb = p.bptrA[sl] - a0, ee = p.bptrA[sl + 1] - a0;
+#pragma unroll 4
+        for (int e = eb; e < ee; ++e) {
+          const int2 en = sA[e];
+          const float4 rr = ldg4(p.rT + (int64_t)en.x * p.ldb + bb);
+          fma4(acc, __int_as_float(en.y), rr);
+        }
+      }
+      if (p.has_conv) {
+        const int eb = p.bptrB[sl] - b0, ee = p.bptrB[sl + 1] - b0;
+#pragma unroll 2
+        for (int e = eb; e < ee; ++e) {
+          const int4 i4 = sB[2 * e];      // row, pi, pj
+          const int4 f4 = sB[2 * e + 1];  // a, s*b1, s*b2
+          const float4 rr = ldg4(p.rT + (int64_t)i4.x * p.ldb + bb);
+          const float4 d1 = ldg4(p.alphaT + (int64_t)i4.y * p.ldb + bb);
+          const float4 d2 = ldg4(p.alphaT + (int64_t)i4.z * p.ldb + bb);
+          const float a = __int_as_float(f4.x), b1s = __int_as_float(f4.y), b2s = __int_as_float(f4.z);
+          acc.x = fmaf(fmaf(b2s, d2.x, fmaf(b1s, d1.x, a)), rr.x, acc.x);
+          acc.y = fmaf(fmaf(b2s, d2.y, fmaf(b1s, d1.y, a)), rr.y, acc.y);
+          acc.z = fmaf(fmaf(b2s, d2.z, fmaf(b1s, d1.z, a)), rr.z, acc.z);
+          acc.w = fmaf(fmaf(b2s, d2.w, fmaf(b1s, d1.w, a)), rr.w, acc.w);
+        }
+        if (p.slot_pi[sl] >= 0) {
+          const float4 ev = ldg4_stream(p.eT + (int64_t)c * p.ldb + bb);
+          fma4(acc, p.esign, ev);
+        }
+      }
+      acc.x *= g2;
+      acc.y *= g2;
+      acc.z *= g2;
+      acc.w *= g2;
+      if (active) stg4(p.gradT + (int64_t)c * p.ldb + b, acc);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic sparse apply: YT[r] = scale * sum_k val_k XT[col_k] (+ YT[r])
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) spmm_kernel(const int32_t* __restrict__ rowptr,
+                                                        const int32_t* __restrict__ col,
+                                                        const float* __restrict__ val, int32_t n,
+                                                        const float* __restrict__ XT, float* __restrict__ YT,
+                                                        int64_t ldb, int32_t B, float scale, int accumulate) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int r = blockIdx.x * nwarps + warp;
+  if (r >= n) return;
+  const int b = blockIdx.y * kWarpSamples + lane * 4;
+  const bool active = b < B;
+  const int bb = active ? b : 0;
+  float4 acc = zero4();
+  const int kb = __ldg(rowptr + r), ke = __ldg(rowptr + r + 1);
+#pragma unroll 4
+  for (int k = kb; k < ke; ++k) {
+    const int c = __ldg(col + k);
+    const float v = __ldg(val + k);
+    fma4(acc, v, ldg4(XT + (int64_t)c * ldb + bb));
+  }
+  if (!active) return;
+  float* y = YT + (int64_t)r * ldb + b;
+  float4 out = make_float4(scale * acc.x, scale * acc.y, scale * acc.z, scale * acc.w);
+  if (accumulate) {
+    const float4 o = *reinterpret_cast<const float4*>(y);
+    out.x += o.x;
+    out.y += o.y;
+    out.z += o.z;
+    out.w += o.w;
+  }
+  stg4(y, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// time-dependent Stokes: two-operand sparse apply with a shift along the pseudo-sample axis
+//   forward : out[r][j] = sum M[r,c] X[c][j] - sum S[r,c] prev(c,j) - dt F[r][b]
+//   backward: out[c][j] = g * ( sum M^T[c,r] R[r][j] - [t<T-1] sum S^T[c,r] R[r][j+1] )
+// j = b*T + t; lanes own consecutive j (coalesced scalar accesses).
+// ---------------------------------------------------------------------------------------------
+template <bool BACKWARD>
+__global__ void __launch_bounds__(kThreads) seq_kernel(const int32_t* __restrict__ m_rowptr,
+                                                       const int32_t* __restrict__ m_col,
+                                                       const float* __restrict__ m_val,
+                                                       const int32_t* __restrict__ s_rowptr,
+                                                       const int32_t* __restrict__ s_col,
+                                                       const float* __restrict__ s_val, int32_t n,
+                                                       const float* __restrict__ XT, const float* __restrict__ u0T,
+                                                       const float* __restrict__ fT, float dt, int64_t ldj,
+                                                       int64_t ldb, int32_t B, int32_t T,
+                                                       const float* __restrict__ grad_loss, float* __restrict__ outT,
+                                                       float* __restrict__ partials) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int r = blockIdx.x * nwarps + warp;
+  const int J = B * T;
+  float lsum = 0.f;
+  if (r < n) {
+    int j[4], t[4], bs[4];
+    bool ok[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      j[i] = blockIdx.y * kWarpSamples + i * 32 + lane;
+      ok[i] = j[i] < J;
+      const int jj = ok[i] ? j[i] : 0;
+      bs[i] = jj / T;
+      t[i] = jj - bs[i] * T;
+      j[i] = jj;
+    }
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    {
+      const int kb = __ldg(m_rowptr + r), ke = __ldg(m_rowptr + r + 1);
+      for (int k = kb; k < ke; ++k) {
+        const int64_t base = (int64_t)__ldg(m_col + k) * ldj;
+        const float v = __ldg(m_val + k);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = fmaf(v, __ldg(XT + base + j[i]), acc[i]);
+      }
+    }
+    float acc2[4] = {0.f, 0.f, 0.f, 0.f};
+    {
+      const int kb = __ldg(s_rowptr + r), ke = __ldg(s_rowptr + r + 1);
+      for (int k = kb; k < ke; ++k) {
+        const int c = __ldg(s_col + k);
+        const float v = __ldg(s_val + k);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float x;
+          if (!BACKWARD)
+            x = t[i] > 0 ? __ldg(XT + (int64_t)c * ldj + j[i] - 1) : __ldg(u0T + (int64_t)c * ldb + bs[i]);
+          else
+            x = t[i] < T - 1 ? __ldg(XT + (int64_t)c * ldj + j[i] + 1) : 0.f;
+          acc2[i] = fmaf(v, x, acc2[i]);
+        }
+      }
+    }
+    const float g = BACKWARD ? (2.0f / (float)T) * (grad_loss != nullptr ? __ldg(grad_loss) : 1.0f) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (!ok[i]) continue;
+      float o;
+      if (!BACKWARD) {
+        // RHS_t = prev S^T + dt F ; r = LHS - RHS (FEONet_time_dep_Stokes/train_FEONet.py:357, :398)
+        const float rhs = fmaf(dt, __ldg(fT + (int64_t)r * ldb + bs[i]), acc2[i]);
+        o = acc[i] - rhs;
+        lsum = fmaf(o, o, lsum);
+      } else {
+        o = g * (acc[i] - acc2[i]);
+      }
+      outT[(int64_t)r * ldj + j[i]] = o;
+    }
+  }
+  if (!BACKWARD) block_partial(lsum, partials, blockIdx.y * gridDim.x + blockIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// sum (x-y)^2 over [n][0..B)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) sq_diff_kernel(const float* __restrict__ xT, const float* __restrict__ yT,
+                                                           int32_t n, int64_t ldb, int32_t B,
+                                                           float* __restrict__ partials) {
+  float lsum = 0.f;
+  for (int r = blockIdx.x; r < n; r += gridDim.x)
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+      float d = xT[(int64_t)r * ldb + b];
+      if (yT != nullptr) d -= yT[(int64_t)r * ldb + b];
+      lsum = fmaf(d, d, lsum);
+    }
+  block_partial(lsum, partials, blockIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tiled transpose (optionally scattering destination rows through a map)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ src, int64_t src_ld,
+                                                        float* __restrict__ dst, int64_t dst_ld, int32_t rows,
+                                                        int32_t cols, const int32_t* __restrict__ dst_row_map) {
+  __shared__ float tile[64][65];
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
+#pragma unroll 4
+  for (int i = ty; i < 64; i += 4) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? __ldg(src + (int64_t)r * src_ld + c) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int i = ty; i < 64; i += 4) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < cols && r < rows) {
+      const int64_t drow = dst_row_map != nullptr ? (int64_t)__ldg(dst_row_map + c) : (int64_t)c;
+      dst[drow * dst_ld + r] = tile[tx][i];
+    }
+  }
+}
+
+int check_layout(const void* p, int64_t ld, int32_t B, const char* what) {
+  if (p == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, std::string(what) + " is NULL");
+  if ((reinterpret_cast<uintptr_t>(p) & 15u) != 0) return fail(FEO_ERR_INVALID_ARGUMENT, std::string(what) + " not 16-byte aligned");
+  if (ld % 4 != 0 || ld < ((B + 3) / 4) * 4)
+    return fail(FEO_ERR_INVALID_ARGUMENT, std::string(what) + ": ldb must be a multiple of 4 and >= ceil4(B)");
+  return FEO_OK;
+}
+
+}  // namespace
+
+size_t loss_partials_needed(int32_t n, int32_t n_blobs, int64_t cols) {
+  const int64_t by = (cols + kWarpSamples - 1) / kWarpSamples;
+  const int64_t rows_ctas = std::max<int64_t>(n_blobs, (n + 7) / 8);
+  return (size_t)(std::max<int64_t>(rows_ctas * by, 1024)) * sizeof(float);
+}
+
+static int finalize(float* partials, int count, float scale, float* loss_out, cudaStream_t st) {
+  finalize_loss_kernel<<<1, 1024, 0, st>>>(partials, count, scale, loss_out);
+  FEO_CUDA_CHECK(cudaGetLastError());
+  return FEO_OK;
+}
+
+int launch_transpose(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int32_t rows, int32_t cols,
+                     const int32_t* dst_row_map, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return FEO_OK;
+  if (src == nullptr || dst == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, "transpose: NULL pointer");
+  dim3 grid((cols + 63) / 64, (rows + 63) / 64);
+  transpose_kernel<<<grid, 256, 0, st>>>(src, src_ld, dst, dst_ld, rows, cols, dst_row_map);
+  FEO_CUDA_CHECK(cudaGetLastError());
+  return FEO_OK;
+}
+
+int launch_residual_fwd(const feo_operator* op, const float* alphaT, const float* fT, int64_t ldb, int32_t B,
+                        float* loss_out, float* rT, float* eT, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (B <= 0) return fail(FEO_ERR_INVALID_ARGUMENT, "B must be positive");
+  if (int rc = check_layout(alphaT, ldb, B, "alphaT")) return rc;
+  if (int rc = check_layout(fT, ldb, B, "fT")) return rc;
+  if (rT != nullptr)
+    if (int rc = check_layout(rT, ldb, B, "rT")) return rc;
+  if (op->has_conv && rT != nullptr && eT == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, "eT required with rT");
+  if (eT != nullptr)
+    if (int rc = check_layout(eT, ldb, B, "eT")) return rc;
+  if (loss_out == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, "loss_out is NULL");
+  const int by = (B + kWarpSamples - 1) / kWarpSamples;
+  const int count = op->n_blobs * by;
+  if (ws == nullptr || ws_bytes < (size_t)count * sizeof(float)) return fail(FEO_ERR_INVALID_ARGUMENT, "workspace too small");
+  FwdParams p{op->blob_uptr, op->unit_ptr, op->slot_row, op->slot_pi, op->slot_pj, op->fptr, op->fent,
+              alphaT,        fT,           rT,           op->has_conv ? eT : nullptr, (float*)ws, ldb, B, op->ns_branch};
+  dim3 grid(op->n_blobs, by);
+  if (op->has_conv) {
+    size_t smem = (size_t)op->max_blob_fent * sizeof(FwdEntry);
+    FEO_CUDA_CHECK(cudaFuncSetAttribute(residual_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    residual_fwd_kernel<true><<<grid, kThreads, smem, st>>>(p);
+  } else {
+    size_t smem = (size_t)op->max_blob_fent * sizeof(FwdEntryLin);
+    FEO_CUDA_CHECK(cudaFuncSetAttribute(residual_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    residual_fwd_kernel<false><<<grid, kThreads, smem, st>>>(p);
+  }
+  FEO_CUDA_CHECK(cudaGetLastError());
+  return finalize((float*)ws, count, 1.0f, loss_out, st);
+}
+
+int launch_residual_bwd(const feo_operator* op, const float* alphaT, const float* rT, const float* eT,
+                        const float* grad_loss, float* gradT, int64_t ldb, int32_t B, cudaStream_t st) {
+  if (B <= 0) return fail(FEO_ERR_INVALID_ARGUMENT, "B must be positive");
+  if (int rc = check_layout(rT, ldb, B, "rT")) return rc;
+  if (int rc = check_layout(gradT, ldb, B, "gradT")) return rc;
+  if (op->has_conv) {
+    if (int rc = check_layout(alphaT, ldb, B, "alphaT")) return rc;
+    if (int rc = check_layout(eT, ldb, B, "eT")) return rc;
+  }
+  BwdParams p{op->blob_uptr, op->unit_ptr, op->slot_row, op->slot_pi, op->bptrA, op->bptrB, op->bentA, op->bentB,
+              alphaT,        rT,           eT,           grad_loss,   gradT,     ldb,       B,
+              op->ns_branch ? 1.0f : -1.0f, op->has_conv ? 1 : 0};
+  const int by = (B + kWarpSamples - 1) / kWarpSamples;
+  dim3 grid(op->n_blobs, by);
+  size_t smem = (size_t)op->max_blob_bentB * sizeof(BwdEntryB) + (size_t)op->max_blob_bentA * sizeof(BwdEntryA) + 16;
+  FEO_CUDA_CHECK(cudaFuncSetAttribute(residual_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  residual_bwd_kernel<<<grid, kThreads, smem, st>>>(p, op->max_blob_bentA);
+  FEO_CUDA_CHECK(cudaGetLastError());
+  return FEO_OK;
+}
+
+int launch_spmm(const DevCsr& K, int32_t n, const float* XT, float* YT, int64_t ldb, int32_t B, float scale,
+                int32_t accumulate, cudaStream_t st) {
+  if (!K.present()) return fail(FEO_ERR_INVALID_ARGUMENT, "spmm: matrix not present in this operator");
+  if (B <= 0) return fail(FEO_ERR_INVALID_ARGUMENT, "B must be positive");
+  if (int rc = check_layout(XT, ldb, B, "XT")) return rc;
+  if (int rc = check_layout(YT, ldb, B, "YT")) return rc;
+  dim3 grid((n + 7) / 8, (B + kWarpSamples - 1) / kWarpSamples);
+  spmm_kernel<<<grid, kThreads, 0, st>>>(K.rowptr, K.col, K.val, n, XT, YT, ldb, B, scale, accumulate);
+  FEO_CUDA_CHECK(cudaGetLastError());
+  return FEO_OK;
+}
+
+int launch_seq(const DevCsr& M, const DevCsr& S, int32_t n, bool backward, const float* XT, const float* u0T,
+               const float* fT, float dt, int64_t ldj, int64_t ldb, int32_t B, int32_t T, const float* grad_loss,
+               float* outT, float* loss_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!M.present() || !S.present()) return fail(FEO_ERR_INVALID_ARGUMENT, "sequence path needs S and A");
+  if (B <= 0 || T <= 0) return fail(FEO_ERR_INVALID_ARGUMENT, "B and T must be positive");
+  const int64_t J = (int64_t)B * T;
+  if (XT == nullptr || outT == nullptr || ldj < J) return fail(FEO_ERR_INVALID_ARGUMENT, "seq: bad XT/outT/ldj");
+  const int by = (int)((J + kWarpSamples - 1) / kWarpSamples);
+  dim3 grid((n + 7) / 8, by);
+  if (!backward) {
+    if (u0T == nullptr || fT == nullptr || ldb < B || loss_out == nullptr)
+      return fail(FEO_ERR_INVALID_ARGUMENT, "seq fwd: bad u0T/fT/ldb/loss_out");
+    const int count = grid.x * grid.y;
+    if (ws == nullptr || ws_bytes < (size_t)count * sizeof(float)) return fail(FEO_ERR_INVALID_ARGUMENT, "workspace too small");
+    seq_kernel<false><<<grid, kThreads, 0, st>>>(M.rowptr, M.col, M.val, S.rowptr, S.col, S.val, n, XT, u0T, fT, dt,
+                                                 ldj, ldb, B, T, nullptr, outT, (float*)ws);
+    FEO_CUDA_CHECK(cudaGetLastError());
+    return finalize((float*)ws, count, 1.0f / (float)T, loss_out, st);
+  }
+  seq_kernel<true><<<grid, kThreads, 0, st>>>(M.rowptr, M.col, M.val, S.rowptr, S.col, S.val, n, XT, nullptr, nullptr,
+                                              dt, ldj, ldb, B, T, grad_loss, outT, nullptr);
+  FEO_CUDA_CHECK(cudaGetLastError());
+  return FEO_OK;
+}
+
+int launch_sq_diff_sum(const float* xT, const float* yT, int32_t n, int64_t ldb, int32_t B, float scale,
+                       float* loss_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (xT == nullptr || loss_out == nullptr || n <= 0 || B <= 0) return fail(FEO_ERR_INVALID_ARGUMENT, "sq_diff_sum: bad arguments");
+  const int blocks = std::min(n, 1024);
+  if (ws == nullptr || ws_bytes < (size_t)blocks * sizeof(float)) return fail(FEO_ERR_INVALID_ARGUMENT, "workspace too small");
+  sq_diff_kernel<<<blocks, kThreads, 0, st>>>(xT, yT, n, ldb, B, (float*)ws);
+  FEO_CUDA_CHECK(cudaGetLastError());
+  return finalize((float*)ws, blocks, scale, loss_out, st);
+}
+
+}  // namespace feo
+
+// ---------------------------------------------------------------------------------------------
+// dense operator path: CT[n x ldb] = scale * D[n x n] XT[n x ldb]  (- sub)  (+ loss)
+// fp32 SIMT GEMM, 64x64x16 tiles, 4x4 register blocking.  D is stored with ld = ceil4(n) and zero
+// padding, so its float4 loads are aligned for any n (387, 813, 2549 ... are not multiples of 4).
+// The preconditioned operators are 83-93 % dense and tiny (2 B n^2 <= 13
+// GFLOP), so exact fp32 FMA keeps the 1e-5 loss tolerance without an error-compensated split.
+// ---------------------------------------------------------------------------------------------
+namespace feo {
+namespace {
+constexpr int GBM = 64, GBN = 64, GBK = 16;
+
+__global__ void __launch_bounds__(256) dense_apply_kernel(const float* __restrict__ D, int32_t n, int32_t ldd,
+                                                          const float* __restrict__ XT, float* __restrict__ CT,
+                                                          int64_t ldb, int32_t B, float scale,
+                                                          const float* __restrict__ scale_dev,
+                                                          const float* __restrict__ sub, float* __restrict__ partials) {
+  __shared__ __align__(16) float As[GBK][GBM + 4];
+  __shared__ __align__(16) float Bs[GBK][GBN];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+  const int ty = tid >> 4, tx = tid & 15;
+  // loader coordinates
+  const int a_r = tid >> 2, a_k = (tid & 3) * 4;   // A tile: 64 rows x 16 k, float4 along k
+  const int b_k = tid >> 4, b_c = (tid & 15) * 4;  // B tile: 16 k x 64 cols, float4 along cols
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < n; k0 += GBK) {
+    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m0 + a_r < n && k0 + a_k < ldd) av = __ldg(reinterpret_cast<const float4*>(D + (int64_t)(m0 + a_r) * ldd + k0 + a_k));
+    if (k0 + b_k < n && n0 + b_c < ldb) bv = __ldg(reinterpret_cast<const float4*>(XT + (int64_t)(k0 + b_k) * ldb + n0 + b_c));
+    __syncthreads();  // previous tile fully consumed
+    As[a_k + 0][a_r] = av.x;
+    As[a_k + 1][a_r] = av.y;
+    As[a_k + 2][a_r] = av.z;
+    As[a_k + 3][a_r] = av.w;
+    *reinterpret_cast<float4*>(&Bs[b_k][b_c]) = bv;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GBK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+  }
+  const float sc = scale * (scale_dev != nullptr ? __ldg(scale_dev) : 1.0f);
+  float lsum = 0.f;
+  const int c = n0 + tx * 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m < n && c < ldb) {
+      float4 o = make_float4(sc * acc[i][0], sc * acc[i][1], sc * acc[i][2], sc * acc[i][3]);
+      if (sub != nullptr) {
+        const float4 s = __ldg(reinterpret_cast<const float4*>(sub + (int64_t)m * ldb + c));
+        o.x -= s.x;
+        o.y -= s.y;
+        o.z -= s.z;
+        o.w -= s.w;
+      }
+      if (c + 0 < B) lsum = fmaf(o.x, o.x, lsum);
+      if (c + 1 < B) lsum = fmaf(o.y, o.y, lsum);
+      if (c + 2 < B) lsum = fmaf(o.z, o.z, lsum);
+      if (c + 3 < B) lsum = fmaf(o.w, o.w, lsum);
+      *reinterpret_cast<float4*>(CT + (int64_t)m * ldb + c) = o;
+    }
+  }
+  if (partials != nullptr) block_partial(lsum, partials, blockIdx.y * gridDim.x + blockIdx.x);
+}
+}  // namespace
+
+int launch_dense(const float* D, int32_t n, const float* XT, float* CT, int64_t ldb, int32_t B, float scale,
+                 const float* scale_dev, const float* sub, float* loss_out, void* ws, size_t ws_bytes,
+                 cudaStream_t st) {
+  if (D == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, "dense operator not present in this handle");
+  if (B <= 0) return fail(FEO_ERR_INVALID_ARGUMENT, "B must be positive");
+  if (int rc = check_layout(XT, ldb, B, "XT")) return rc;
+  if (int rc = check_layout(CT, ldb, B, "CT")) return rc;
+  if (sub != nullptr)
+    if (int rc = check_layout(sub, ldb, B, "sub")) return rc;
+  const int32_t ldd = (n + 3) / 4 * 4;
+  dim3 grid((int)((((B + 3) / 4 * 4) + GBN - 1) / GBN), (n + GBM - 1) / GBM);
+  const int count = grid.x * grid.y;
+  float* partials = nullptr;
+  if (loss_out != nullptr) {
+    if (ws == nullptr || ws_bytes < (size_t)count * sizeof(float)) return fail(FEO_ERR_INVALID_ARGUMENT, "workspace too small");
+    partials = (float*)ws;
+  }
+  dense_apply_kernel<<<grid, 256, 0, st>>>(D, n, ldd, XT, CT, ldb, B, scale, scale_dev, sub, partials);
+  FEO_CUDA_CHECK(cudaGetLastError());
+  if (loss_out != nullptr) return finalize(partials, count, 1.0f, loss_out, st);
+  return FEO_OK;
+}
+}  // namespace feo

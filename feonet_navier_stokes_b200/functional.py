@@ -1,0 +1,188 @@
+"""torch.autograd glue over the C ABI.
+
+Tensors cross this layer as ordinary `[B, N]` torch tensors.  The device-native layout is
+dof-major (`strides == (1, ldb)`, see include/feonet_b200.h); a tensor that already has it is
+used in place (zero copy), anything else goes through `feo_transpose`.  Gradients come back in
+the layout the input arrived in.  `dof_major_empty/zeros` create native tensors; `LinearT`
+(network.py) makes a network emit them.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+from .operator import FEOperator, ceil4
+
+
+def dof_major_empty(B: int, N: int, device, ldb: Optional[int] = None) -> torch.Tensor:
+    """A [B,N] fp32 tensor whose memory is dof-major ([N, ldb] storage)."""
+    ldb = ceil4(B) if ldb is None else ldb
+    return torch.empty((N, ldb), dtype=torch.float32, device=device)[:, :B].t()
+
+
+def dof_major_zeros(B: int, N: int, device, ldb: Optional[int] = None) -> torch.Tensor:
+    ldb = ceil4(B) if ldb is None else ldb
+    return torch.zeros((N, ldb), dtype=torch.float32, device=device)[:, :B].t()
+
+
+def to_dof_major_tensor(x: torch.Tensor) -> torch.Tensor:
+    """Copy a [B,N] tensor into dof-major memory (pure torch; for data set-up, e.g. load vectors)."""
+    out = dof_major_empty(x.shape[0], x.shape[1], x.device)
+    out.copy_(x)
+    return out
+
+
+def is_dof_major(x: torch.Tensor) -> bool:
+    return x.dim() == 2 and (x.stride(0) == 1 or x.shape[0] == 1) and x.stride(1) % 4 == 0 \
+        and x.stride(1) >= ceil4(x.shape[0]) and x.data_ptr() % 16 == 0
+
+
+def _prep(op: FEOperator, x: torch.Tensor, ldb: Optional[int] = None) -> torch.Tensor:
+    if x.dtype != torch.float32:
+        x = x.float()
+    return op.to_dof_major(x, ldb)
+
+
+class _TransposeCache:
+    """Load vectors are data: the same tensor comes back every epoch (full-batch training is the
+    reference default, train_FEONet.py:109-112).  Cache its dof-major copy keyed on identity."""
+
+    def __init__(self):
+        self.key = None
+        self.val = None
+
+    def get(self, op: FEOperator, f: torch.Tensor, ldb: int) -> torch.Tensor:
+        key = (f.data_ptr(), f._version, tuple(f.shape), tuple(f.stride()), ldb)
+        if self.key != key:
+            self.val = _prep(op, f, ldb)
+            self.key = key
+        return self.val
+
+
+class ResidualLossFn(torch.autograd.Function):
+    """loss = sum (A a -/+ (F - c))^2, fused sparse forward/backward (feo_residual_fwd/bwd).
+
+    Reference: weak_form + loss loop of closure, FEONet_steady_Navier-Stokes/train_FEONet.py:301-360,
+    FEONet_Stokes_square/train_FEONet.py:261-296 (un-preconditioned)."""
+
+    @staticmethod
+    def forward(ctx, alpha: torch.Tensor, F: torch.Tensor, op: FEOperator, fcache: Optional[_TransposeCache]):
+        B, N = alpha.shape
+        native = is_dof_major(alpha)
+        aT = _prep(op, alpha.detach())
+        ldb = aT.shape[1]
+        fT = fcache.get(op, F.detach(), ldb) if fcache is not None else _prep(op, F.detach(), ldb)
+        need = bool(ctx.needs_input_grad[0])
+        loss, rT, eT = op.residual_fwd(aT, fT, B, save=need)
+        ctx.op, ctx.B, ctx.native = op, B, native
+        if need:
+            ctx.save_for_backward(aT, rT, eT)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        aT, rT, eT = ctx.saved_tensors
+        op: FEOperator = ctx.op
+        g = grad_out.detach().to(torch.float32).contiguous()
+        gT = op.residual_bwd(aT, rT, eT, ctx.B, grad_loss=g)
+        return op.from_dof_major(gT, ctx.B, contiguous=not ctx.native), None, None, None
+
+
+class DenseResidualLossFn(torch.autograd.Function):
+    """loss = sum (M a - F)^2 with a dense operator M = A @ P (preconditioned linear Stokes,
+    FEONet_Stokes_square/train_FEONet.py:264, :290-296)."""
+
+    @staticmethod
+    def forward(ctx, alpha, F, op: FEOperator, fcache):
+        B, N = alpha.shape
+        native = is_dof_major(alpha)
+        aT = _prep(op, alpha.detach())
+        ldb = aT.shape[1]
+        fT = fcache.get(op, F.detach(), ldb) if fcache is not None else _prep(op, F.detach(), ldb)
+        rT, loss = op.dense_apply(L.FEO_DENSE_M, aT, B, sub=fT, want_loss=True)
+        ctx.op, ctx.B, ctx.native = op, B, native
+        ctx.save_for_backward(rT)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (rT,) = ctx.saved_tensors
+        op: FEOperator = ctx.op
+        g = grad_out.detach().to(torch.float32).contiguous()
+        gT = op.dense_apply(L.FEO_DENSE_MT, rT, ctx.B, scale=2.0, scale_dev=g)
+        return op.from_dof_major(gT, ctx.B, contiguous=not ctx.native), None, None, None
+
+
+class SpmmFn(torch.autograd.Function):
+    """Y = X @ K^T for a stored sparse matrix K (the reference's `u_batch @ K.T`,
+    FEONet_steady_Navier-Stokes/train_FEONet.py:308-309, :329); VJP = G @ K."""
+
+    @staticmethod
+    def forward(ctx, x, op: FEOperator, which: int):
+        B = x.shape[0]
+        native = is_dof_major(x)
+        yT = op.spmm(which, False, _prep(op, x.detach()), B)
+        ctx.op, ctx.which, ctx.B, ctx.native = op, which, B, native
+        return op.from_dof_major(yT, B, contiguous=not native)
+
+    @staticmethod
+    def backward(ctx, g):
+        op: FEOperator = ctx.op
+        gT = op.spmm(ctx.which, True, _prep(op, g), ctx.B)
+        return op.from_dof_major(gT, ctx.B, contiguous=not ctx.native), None, None
+
+
+class DenseFn(torch.autograd.Function):
+    """Y = X @ M^T for the stored dense LHS operator (VJP through the stored M^T)."""
+
+    @staticmethod
+    def forward(ctx, x, op: FEOperator):
+        B = x.shape[0]
+        native = is_dof_major(x)
+        yT = op.dense_apply(L.FEO_DENSE_M, _prep(op, x.detach()), B)
+        ctx.op, ctx.B, ctx.native = op, B, native
+        return op.from_dof_major(yT, B, contiguous=not native)
+
+    @staticmethod
+    def backward(ctx, g):
+        op: FEOperator = ctx.op
+        gT = op.dense_apply(L.FEO_DENSE_MT, _prep(op, g), ctx.B)
+        return op.from_dof_major(gT, ctx.B, contiguous=not ctx.native), None
+
+
+class SeqResidualLossFn(torch.autograd.Function):
+    """loss = (1/T) sum_t |(S+dt A) x_t - S prev_t - dt F|^2, un-preconditioned sparse form of
+    FEONet_time_dep_Stokes/train_FEONet.py:343-362, :398-400. pred_seq [B,T,N], u_init/F [B,N]."""
+
+    @staticmethod
+    def forward(ctx, pred_seq, u_init, F, op: FEOperator):
+        B, T, N = pred_seq.shape
+        p2 = pred_seq.detach().reshape(B * T, N)
+        pT = _prep(op, p2)
+        u0T = _prep(op, u_init.detach())
+        fT = _prep(op, F.detach(), u0T.shape[1])
+        loss, rT = op.seq_fwd(pT, u0T, fT, B, T)
+        ctx.op, ctx.B, ctx.T = op, B, T
+        ctx.save_for_backward(rT)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (rT,) = ctx.saved_tensors
+        op: FEOperator = ctx.op
+        g = grad_out.detach().to(torch.float32).contiguous()
+        gT = op.seq_bwd(rT, ctx.B, ctx.T, grad_loss=g)
+        grad = op.from_dof_major(gT, ctx.B * ctx.T, contiguous=True).reshape(ctx.B, ctx.T, -1)
+        return grad, None, None, None
+
+
+def precond_output(op: FEOperator, pred: torch.Tensor) -> torch.Tensor:
+    """u = (P @ pred^T)^T, the second output of `closure`.  Only ever used detached in the reference
+    (FEONet_Stokes_square/train_FEONet.py:401, steady NS :478 -- quirk 9), so no graph is kept."""
+    shape = pred.shape
+    x = pred.detach().reshape(-1, shape[-1])
+    B = x.shape[0]
+    uT = op.dense_apply(L.FEO_DENSE_P, _prep(op, x), B)
+    return op.from_dof_major(uT, B, contiguous=True).reshape(shape)

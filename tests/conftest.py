@@ -21,3 +21,14 @@ def golden_dir():
 
 def golden_cases(prefix=""):
     return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f.startswith(prefix))
+
+
+def pytest_sessionstart(session):
+    # keep the in-tree library in sync with its sources during development (mtime based)
+    try:
+        from feonet_navier_stokes_b200 import build as _b
+
+        if _b.needs_build():
+            _b.build_library()
+    except Exception as exc:  # pragma: no cover
+        print(f"[conftest] could not (re)build libfeonet_b200.so: {exc}")

@@ -1,0 +1,293 @@
+"""GPU parity tests: the CUDA path (through the C ABI) vs the reference's own outputs
+(tests/golden) and vs the oracle on seeded inputs.
+
+Tolerances are the ones BASELINE.json's north_star states: fp32 loss within 1e-5 relative,
+gradients within 1e-4 relative; integer/index work (layout transposes, assemble_u_init) bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR, golden_cases
+from oracle import feonet_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-5
+GRAD_RTOL = 1e-4
+
+
+def _load(name):
+    return np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+
+
+def _rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def _relmax(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def _idx_sol(g):
+    out = np.empty(3, dtype=object)
+    out[0], out[1], out[2] = g["idx_u1"].tolist(), g["idx_u2"].tolist(), g["idx_p"].tolist()
+    return out
+
+
+@pytest.fixture(scope="module")
+def feo():
+    import feonet_navier_stokes_b200 as f
+
+    assert torch.cuda.is_available()
+    f.load_library(build_if_missing=False)  # the prebuilt in-tree .so must be the thing that runs
+    return f
+
+
+class Leaf(torch.nn.Module):
+    def __init__(self, alpha):
+        super().__init__()
+        self.alpha = torch.nn.Parameter(alpha.clone())
+
+    def forward(self, *a, **k):
+        return self.alpha
+
+
+# ------------------------------------------------------------------------------------------------
+# golden vectors = outputs of the unmodified reference functions
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_cases("ns_"))
+def test_golden_steady_ns(feo, name):
+    g = _load(name)
+    dev = torch.device("cuda")
+    t = lambda a: torch.tensor(a, device=dev)  # noqa: E731
+    A, B1, B2, P = t(g["A"]), t(g["B1"]), t(g["B2"]), t(g["P"])
+    idx_sol = _idx_sol(g)
+    ns = feo.SteadyNavierStokes(A, B1, B2, idx_sol, do_precond=bool(g["do_precond"]), precond=P, model_name="FCNN", device=dev)
+    model = Leaf(t(g["alpha"]))
+    loss, u_pred = ns.closure(model, torch.zeros(g["alpha"].shape[0], 6, device=dev), None, t(g["F"]), A, B1, B2, 8)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= LOSS_RTOL * abs(float(g["loss"]))
+    assert _rel(model.alpha.grad.cpu().numpy(), g["grad"]) < GRAD_RTOL
+    assert _relmax(model.alpha.grad.cpu().numpy(), g["grad"]) < GRAD_RTOL
+    assert _rel(u_pred.detach().cpu().numpy().reshape(g["u_pred"].shape), g["u_pred"]) < 1e-5
+    # materialised weak_form, with autograd through it
+    a2 = t(g["alpha"]).requires_grad_(True)
+    LHS, RHS = ns.weak_form(a2.unsqueeze(1), t(g["F"]), A, B1, B2, idx_sol)
+    assert _rel(LHS.detach().cpu().numpy(), g["LHS"]) < 1e-5 and _rel(RHS.detach().cpu().numpy(), g["RHS"]) < 1e-5
+    torch.sum((LHS - RHS) ** 2).backward()
+    assert _rel(a2.grad.cpu().numpy(), g["grad"]) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("name", golden_cases("stokes_") + golden_cases("hole_"))
+def test_golden_linear_stokes(feo, name):
+    g = _load(name)
+    dev = torch.device("cuda")
+    t = lambda a: torch.tensor(a, device=dev)  # noqa: E731
+    A, P = t(g["A"]), t(g["P"])
+    hole = name.startswith("hole_")
+    st = feo.LinearStokes(A, P, do_precond=bool(g["do_precond"]), model_name="FCNN", hole_signature=hole, device=dev)
+    model = Leaf(t(g["alpha"]))
+    coeff = torch.zeros(g["alpha"].shape[0], 6, device=dev)
+    args = (None, t(g["F"]), A, P, 8) if hole else (t(g["F"]), A, P, 8)
+    loss, u_pred = st.closure(model, coeff, *args)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= LOSS_RTOL * abs(float(g["loss"]))
+    assert _rel(model.alpha.grad.cpu().numpy(), g["grad"]) < GRAD_RTOL
+    assert _relmax(model.alpha.grad.cpu().numpy(), g["grad"]) < GRAD_RTOL
+    assert _rel(u_pred.detach().cpu().numpy().reshape(g["u_pred"].shape), g["u_pred"]) < 1e-5
+    LHS, RHS = st.weak_form(t(g["alpha"]).unsqueeze(1), t(g["F"]), A, P)
+    assert _rel(LHS.cpu().numpy(), g["LHS"]) < 1e-5 and np.array_equal(RHS.cpu().numpy(), g["RHS"])
+
+
+@pytest.mark.parametrize("name", golden_cases("timedep_"))
+def test_golden_time_dep(feo, name):
+    g = _load(name)
+    dev = torch.device("cuda")
+    t = lambda a: torch.tensor(a, device=dev)  # noqa: E731
+    S, A, P, dt = t(g["S"]), t(g["A"]), t(g["P"]), float(g["dt"])
+    td = feo.TimeDependentStokes(S, A, _idx_sol(g), dt=dt, do_precond=bool(g["do_precond"]), precond=P, model_name="RNN", device=dev)
+
+    class SeqLeaf(Leaf):
+        def forward(self, u_init, seq_len=None):
+            return self.alpha
+
+    model = SeqLeaf(t(g["pred"]))
+    ix, iy = t(g["init_x"]).unsqueeze(1), t(g["init_y"]).unsqueeze(1)
+    u0 = td.assemble_u_init(ix, iy)
+    assert np.array_equal(u0.cpu().numpy(), g["u_init"])  # index scatter: bit-exact
+    T = g["pred"].shape[1]
+    loss, out = td.closure(model, None, ix, iy, t(g["F"]), S, A, None, P, dt, T)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= LOSS_RTOL * abs(float(g["loss"]))
+    assert _rel(model.alpha.grad.cpu().numpy(), g["grad"]) < GRAD_RTOL
+    assert _rel(out.detach().cpu().numpy(), g["u_pred"]) < 1e-5
+    LHS, RHS = td.weak_form_sequence(t(g["pred"]), t(g["F"]), S, A, P, dt, u0, bool(g["do_precond"]))
+    assert _rel(LHS.cpu().numpy(), g["LHS"]) < 1e-5 and _rel(RHS.cpu().numpy(), g["RHS"]) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# oracle on seeded inputs at the reference's config sizes (cfg3 N=2178, cfg4 N=1003, cfg1 N=387)
+# ------------------------------------------------------------------------------------------------
+def _ns_case(feo, n, B, branch, ordering, native, seed=0):
+    from feonet_navier_stokes_b200.fixtures import config_operators
+
+    fx = config_operators("steady_ns", n, ordering=ordering)
+    rng = np.random.default_rng(seed)
+    alpha = (0.3 * rng.standard_normal((B, fx.N))).astype(np.float32)
+    F = rng.standard_normal((B, fx.N)).astype(np.float32)
+    dev = torch.device("cuda")
+    ns = feo.SteadyNavierStokes(fx.A, fx.B1, fx.B2, fx.idx_sol, do_precond=bool(branch), precond=None, device=dev)
+    a = torch.tensor(alpha, device=dev)
+    if native:
+        a = feo.to_dof_major_tensor(a)
+    a.requires_grad_(True)
+    loss = ns.residual_loss(a, torch.tensor(F, device=dev), fx.A, fx.B1, fx.B2, fx.idx_sol)
+    (grad,) = torch.autograd.grad(loss, a)
+    lo, go, _ = orc.ns_loss_and_grad(alpha, F, fx.A, fx.B1, fx.B2, fx.idx_u1, fx.idx_u2, bool(branch), dtype=np.float64)
+    return loss.item(), grad, lo, go, ns
+
+
+@pytest.mark.parametrize("n,B,branch,ordering,native", [
+    (15, 64, 1, "blocked", False),      # cfg3 operator, precond (identity) branch
+    (15, 64, 0, "interleaved", True),   # non-precond branch, dof-major native input
+    (15, 37, 1, "interleaved", False),  # ragged batch (B % 4 != 0, B % 128 != 0)
+    (6, 1, 0, "blocked", False),        # single sample
+    (6, 130, 1, "blocked", True),       # crosses one 128-sample block
+    (24, 256, 0, "interleaved", True),
+])
+def test_ns_vs_oracle(feo, n, B, branch, ordering, native):
+    loss, grad, lo, go, _ = _ns_case(feo, n, B, branch, ordering, native)
+    assert abs(loss - lo) <= LOSS_RTOL * abs(lo)
+    assert grad.shape == go.shape
+    assert _rel(grad.cpu().numpy(), go) < GRAD_RTOL and _relmax(grad.cpu().numpy(), go) < GRAD_RTOL
+    if native:
+        assert feo.is_dof_major(grad)
+
+
+def test_ns_is_deterministic_and_blob_size_independent(feo, monkeypatch):
+    l1, g1, _, _, _ = _ns_case(feo, 10, 96, 1, "interleaved", True)
+    l2, g2, _, _, _ = _ns_case(feo, 10, 96, 1, "interleaved", True)
+    assert l1 == l2 and torch.equal(g1, g2)  # bit-reproducible: no atomics anywhere
+    monkeypatch.setenv("FEO_BLOB_ROWS", "9")
+    l3, g3, lo, go, _ = _ns_case(feo, 10, 96, 1, "interleaved", True)
+    assert torch.equal(g1, g3)  # per-row arithmetic does not depend on the walk order
+    assert abs(l3 - lo) <= LOSS_RTOL * abs(lo)
+
+
+def test_linear_properties_at_scale(feo):
+    """Size-independent properties on a larger operator (n=64, N=37 442): linearity of the residual
+    in (alpha, F) and gradient = 2 A^T r checked against the generic sparse apply."""
+    from feonet_navier_stokes_b200 import _lib as L
+    from feonet_navier_stokes_b200.fixtures import config_operators
+
+    fx = config_operators("stokes_square", 64)
+    dev = torch.device("cuda")
+    st = feo.LinearStokes(fx.A, None, do_precond=False, device=dev)
+    op = st.operator
+    B = 256
+    gen = torch.Generator(device=dev).manual_seed(1)
+    a1 = torch.randn(B, fx.N, device=dev, generator=gen)
+    a2 = torch.randn(B, fx.N, device=dev, generator=gen)
+    zero = torch.zeros(B, fx.N, device=dev)
+    Y1, _ = st.weak_form(a1, zero, fx.A, None)
+    Y2, _ = st.weak_form(a2, zero, fx.A, None)
+    Y12, _ = st.weak_form(a1 + 2 * a2, zero, fx.A, None)
+    assert _rel((Y1 + 2 * Y2).cpu().numpy(), Y12.cpu().numpy()) < 1e-6
+    F = torch.randn(B, fx.N, device=dev, generator=gen)
+    a = a1.clone().requires_grad_(True)
+    loss = st.residual_loss(a, F, fx.A, None)
+    (g,) = torch.autograd.grad(loss, a)
+    r = Y1 - F
+    assert abs(loss.item() - float((r.double() ** 2).sum())) <= LOSS_RTOL * loss.item()
+    rT = op.to_dof_major(r)
+    gref = op.from_dof_major(op.spmm(L.FEO_MAT_A, True, rT, B, scale=2.0), B)
+    assert _rel(g.cpu().numpy(), gref.cpu().numpy()) < 1e-6
+
+
+def test_grad_scaling_and_loss_only(feo):
+    """Upstream gradient scaling (loss * k).backward and the no-grad (validation) path."""
+    from feonet_navier_stokes_b200.fixtures import config_operators
+
+    fx = config_operators("steady_ns", 8)
+    dev = torch.device("cuda")
+    ns = feo.SteadyNavierStokes(fx.A, fx.B1, fx.B2, fx.idx_sol, do_precond=True, device=dev)
+    a = (0.2 * torch.randn(50, fx.N, device=dev)).requires_grad_(True)
+    F = torch.randn(50, fx.N, device=dev)
+    l1 = ns.residual_loss(a, F, fx.A, fx.B1, fx.B2, fx.idx_sol)
+    (g1,) = torch.autograd.grad(l1, a)
+    l2 = ns.residual_loss(a, F, fx.A, fx.B1, fx.B2, fx.idx_sol)
+    (g2,) = torch.autograd.grad(l2 * 0.25, a)
+    assert torch.allclose(g2, 0.25 * g1, rtol=1e-6, atol=0)
+    with torch.no_grad():
+        l3 = ns.residual_loss(a, F, fx.A, fx.B1, fx.B2, fx.idx_sol)
+    assert l3.item() == l1.item()
+
+
+def test_layout_roundtrip_bit_exact(feo):
+    from feonet_navier_stokes_b200.fixtures import config_operators
+
+    fx = config_operators("stokes_square", 3)
+    op = feo.FEOperator(fx.N, A=fx.A)
+    for B in (1, 5, 64, 131):
+        x = torch.randn(B, fx.N, device="cuda")
+        xT = op.to_dof_major(x)
+        assert xT.shape == (fx.N, (B + 3) // 4 * 4)
+        assert torch.equal(xT[:, :B].t(), x)
+        assert torch.equal(op.from_dof_major(xT, B, contiguous=True), x)
+        assert op.to_dof_major(xT[:, :B].t()).data_ptr() == xT.data_ptr()  # native input: zero copy
+
+
+def test_dense_precond_cfg1_vs_oracle(feo):
+    """cfg1: N=387 operator with the shipped preconditioner blob (from the golden file), B=1000."""
+    g = _load("stokes_precond72_n6")
+    dev = torch.device("cuda")
+    A, P = torch.tensor(g["A"], device=dev), torch.tensor(g["P"], device=dev)
+    rng = np.random.default_rng(3)
+    alpha = (0.3 * rng.standard_normal((1000, 387))).astype(np.float32)
+    F = rng.standard_normal((1000, 387)).astype(np.float32)
+    st = feo.LinearStokes(A, P, do_precond=True, device=dev)
+    a = torch.tensor(alpha, device=dev, requires_grad=True)
+    loss = st.residual_loss(a, torch.tensor(F, device=dev), A, P)
+    (grad,) = torch.autograd.grad(loss, a)
+    lo, go, _ = orc.stokes_loss_and_grad(alpha, F, g["A"], g["P"], True, dtype=np.float64)
+    assert abs(loss.item() - lo) <= LOSS_RTOL * abs(lo)
+    assert _rel(grad.cpu().numpy(), go) < GRAD_RTOL and _relmax(grad.cpu().numpy(), go) < GRAD_RTOL
+
+
+def test_time_dep_cfg4_vs_oracle(feo):
+    from feonet_navier_stokes_b200.fixtures import config_operators
+
+    fx = config_operators("time_dep", 10)  # N = 1003
+    dev = torch.device("cuda")
+    B, T, dt = 33, 10, 0.1
+    rng = np.random.default_rng(4)
+    pred = (0.3 * rng.standard_normal((B, T, fx.N))).astype(np.float32)
+    u0 = rng.standard_normal((B, fx.N)).astype(np.float32)
+    F = np.repeat(rng.standard_normal((1, fx.N)).astype(np.float32), B, axis=0)
+    td = feo.TimeDependentStokes(fx.S, fx.A, fx.idx_sol, dt=dt, do_precond=False, device=dev)
+    p = torch.tensor(pred, device=dev, requires_grad=True)
+    loss = td.residual_loss(p, torch.tensor(F, device=dev), fx.S, fx.A, None, dt, torch.tensor(u0, device=dev))
+    (grad,) = torch.autograd.grad(loss, p)
+    lo, go, _ = orc.seq_loss_and_grad(pred, F, fx.S, fx.A, None, dt, u0, False, dtype=np.float64)
+    assert abs(loss.item() - lo) <= LOSS_RTOL * abs(lo)
+    assert _rel(grad.cpu().numpy(), go) < GRAD_RTOL
+
+
+def test_errors_are_loud(feo):
+    from feonet_navier_stokes_b200 import _lib as L
+    from feonet_navier_stokes_b200.fixtures import config_operators
+
+    fx = config_operators("stokes_square", 2)
+    op = feo.FEOperator(fx.N, A=fx.A)
+    x = torch.zeros(fx.N, 8, device="cuda")
+    with pytest.raises(L.FeoError):
+        op.spmm(L.FEO_MAT_B1, False, x, 8)  # matrix not present
+    with pytest.raises(L.FeoError):
+        op.dense_apply(L.FEO_DENSE_M, x, 8)  # no dense operator
