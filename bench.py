@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- FEM residual fwd+bwd samples/s (BASELINE.json's metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # CPU arm (oracle port on the host cores)
+
+Workload (config.workload): BASELINE.json configs[4] -- synthetic structured P2-P1 channel
+mesh, n=333 cells/side => N = 1 001 334 dofs, steady Navier-Stokes residual (A, B1, B2 as CSR,
+no preconditioner), batch 1024 per GPU (weak scaling: samples are independent, the operator is
+replicated, no data-path collective).  A "step" = residual loss forward + backward to
+d loss / d alpha for one batch, through the public autograd API.
+
+One JSON line on stdout (rank 0); everything else goes to stderr.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "fem_residual_fwd_bwd_samples_per_s"
+UNIT = "samples/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--n", type=int, default=333, help="mesh cells per side (333 -> N=1 001 334)")
+    ap.add_argument("--batch", type=int, default=1024, help="samples per GPU")
+    ap.add_argument("--ordering", default="interleaved", choices=["interleaved", "blocked"])
+    ap.add_argument("--layout", default="dof_major", choices=["dof_major", "row_major"],
+                    help="memory layout of alpha/F/grad for the headline value")
+    ap.add_argument("--cpu-samples", type=int, default=8, help="samples per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    return ap.parse_args()
+
+
+def workload_name(args, N):
+    return (f"cfg5: synthetic structured P2-P1 channel mesh n={args.n} ({N} dofs, {args.ordering} dof order), "
+            f"steady Navier-Stokes residual (A,B1,B2 CSR, no preconditioner), batch {args.batch}/GPU")
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception as exc:  # pragma: no cover
+            log(f"[bench] nvidia-smi unavailable: {exc}")
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # pragma: no cover
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+                pw.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+def build_fixture(args):
+    from feonet_navier_stokes_b200.fixtures import config_operators
+
+    t0 = time.time()
+    fx = config_operators("steady_ns", args.n, ordering=args.ordering)
+    log(f"[bench] fixture n={args.n}: N={fx.N} nnz(A,B1,B2)=({fx.A.nnz},{fx.B1.nnz},{fx.B2.nnz}) in {time.time() - t0:.1f}s")
+    return fx
+
+
+def cpu_port_rate(fx, args, steps, warmup, seed=0):
+    """samples/s of the oracle's multi-threaded CPU port on a bounded sample of the workload."""
+    from oracle.feonet_oracle import TorchCpuSteadyNS
+
+    port = TorchCpuSteadyNS(fx.A, fx.B1, fx.B2, fx.idx_u1, fx.idx_u2, do_precond=True, threads=os.cpu_count())
+    rng = np.random.default_rng(seed)
+    bs = args.cpu_samples
+    alpha = (0.1 * rng.standard_normal((bs, fx.N))).astype(np.float32)
+    F = rng.standard_normal((bs, fx.N)).astype(np.float32)
+    for _ in range(max(1, warmup)):
+        port.loss_and_grad(alpha, F)
+    times = []
+    for _ in range(max(1, steps)):
+        t0 = time.perf_counter()
+        port.loss_and_grad(alpha, F)
+        times.append(time.perf_counter() - t0)
+    dt = sum(times)
+    return bs * len(times) / dt, port.threads, 1e3 * dt / len(times)
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on the host cores.  The reference is pure
+    Python/PyTorch (nothing to compile into oracle/_ref) and stores its operators dense, which is
+    infeasible at this workload (4 TB per matrix), so this arm runs the oracle's sparse CPU port of the
+    same formula -- a generous stand-in for the reference's dense-GEMM CPU path."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    fx = build_fixture(args)
+    steps = min(args.steps, 10)
+    rate, threads, ms = cpu_port_rate(fx, args, steps, min(args.warmup, 2))
+    sample = f"{args.cpu_samples} of the {args.batch} samples per step, full N={fx.N} operator, fp32, torch CPU sparse-CSR"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args, fx.N), "device": "host CPU"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import feonet_navier_stokes_b200 as feo
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs CUDA devices (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    feo.load_library(build_if_missing=False)
+
+    fx = build_fixture(args)
+    N, B = fx.N, args.batch
+    t0 = time.time()
+    ns = feo.SteadyNavierStokes(fx.A, fx.B1, fx.B2, fx.idx_sol, do_precond=True, precond=None, model_name="FCNN", device=dev)
+    op = ns.operator
+    log(f"[bench] rank {rank}: operator on device in {time.time() - t0:.1f}s: blobs={op.info.n_blobs} "
+        f"nnz_union={op.info.nnz_union} device_MB={op.info.device_bytes / 2**20:.0f}")
+
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    native = args.layout == "dof_major"
+
+    def make(scale):
+        if native:
+            t = feo.dof_major_empty(B, N, dev)
+            t.normal_(0.0, scale, generator=gen)
+            return t
+        return torch.empty(B, N, device=dev).normal_(0.0, scale, generator=gen)
+
+    alpha = make(0.1).requires_grad_(True)  # alpha ~ N(0, 0.1^2), F ~ N(0,1)  
+    F = make(1.0)
+    loss_buf = torch.zeros((), device=dev)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    def step(e_mid=None):
+        alpha.grad = None
+        loss = ns.residual_loss(alpha, F, fx.A, fx.B1, fx.B2, fx.idx_sol)
+        if e_mid is not None:
+            e_mid.record()
+        loss.backward()
+        if world > 1:  # DP bookkeeping: summed loss over ranks (the only collective; parameters are not part of this path)
+            dist.all_reduce(loss.detach(), op=dist.ReduceOp.SUM)
+        return loss
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    K = args.steps
+    marks = [(ev(), ev(), ev()) for _ in range(K)]
+    launches0 = op.launches
+    t_wall = time.perf_counter()
+    for k in range(K):
+        marks[k][0].record()
+        loss = step(marks[k][1])
+        marks[k][2].record()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = op.launches - launches0
+
+    total_ms = marks[0][0].elapsed_time(marks[-1][2])
+    fwd_ms = sum(m[0].elapsed_time(m[1]) for m in marks) / K
+    bwd_ms = sum(m[1].elapsed_time(m[2]) for m in marks) / K
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = world * B * K / (total_ms * 1e-3)
+    loss_val = float(loss.item())
+
+    # same path with the reference's row-major [B,N] tensors (includes the layout transposes)
+    alt_value = None
+    if rank == 0 and native and world == 1:
+        a2 = torch.empty(B, N, device=dev).normal_(0.0, 0.1, generator=gen).requires_grad_(True)
+        F2 = torch.empty(B, N, device=dev).normal_(0.0, 1.0, generator=gen)
+
+        def step2():
+            a2.grad = None
+            ns.residual_loss(a2, F2, fx.A, fx.B1, fx.B2, fx.idx_sol).backward()
+
+        for _ in range(3):
+            step2()
+        e0, e1 = ev(), ev()
+        k2 = max(3, K // 2)
+        e0.record()
+        for _ in range(k2):
+            step2()
+        e1.record()
+        torch.cuda.synchronize()
+        alt_value = B * k2 / (e0.elapsed_time(e1) * 1e-3)
+        del a2, F2
+
+    # end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        try:
+            e2e = run_e2e(args, torch, feo, ns, fx, dev, world, rank)
+        except Exception as exc:  # pragma: no cover
+            log(f"[bench] e2e leg failed: {exc!r}")
+            e2e = None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak_gbs()
+    alg_fwd = 12.0 * N * B  # read alpha, F; write r
+    alg_bwd = 12.0 * N * B  # read r, alpha; write grad
+    dom = "residual_bwd_kernel" if bwd_ms >= fwd_ms else "residual_fwd_kernel"
+    dom_ms, dom_alg = (bwd_ms, alg_bwd) if bwd_ms >= fwd_ms else (fwd_ms, alg_fwd)
+    achieved = dom_alg / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom)
+        except Exception:
+            traffic = None
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": workload_name(args, N), "N": N, "batch_per_gpu": B, "layout": args.layout,
+            "l2": "alpha and F are 4.1 GB each per GPU: every step streams far more than the 126 MB L2",
+            "parallelism": f"dp{world} (batch sharded, operator replicated, loss all-reduce only)",
+        },
+        "clocks": clocks,
+        "gpu_launches": launches,
+        "roofline": {
+            "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": dom_alg, "ms_per_launch": dom_ms,
+            "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
+            "step_algorithmic_GBs": 24.0 * N * B / (total_ms / K * 1e-3) / 1e9,
+        },
+        "loss": loss_val,
+        "wall_ms_per_step": 1e3 * t_wall / K,
+    }
+    if alt_value is not None:
+        out["value_row_major_layout"] = alt_value
+    if e2e is not None:
+        out["e2e"] = e2e
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            rate, threads, ms = cpu_port_rate(fx, args, 3, 1)
+            out["cpu_baseline"] = {
+                "value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": f"{args.cpu_samples} of the {B} samples, full N={N} operator, fp32, oracle torch-CPU sparse-CSR port, 3 repeats",
+            }
+        except Exception as exc:  # pragma: no cover
+            log(f"[bench] cpu_baseline failed: {exc!r}")
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, torch, feo, ns, fx, dev, world, rank):
+    """Public-API call with host inputs: alpha and F start in pinned host memory in the reference's
+    row-major [B,N] layout, are copied to the device, go through residual_loss + backward, and the
+    loss is read back to the host -- every step."""
+    import torch.distributed as dist
+
+    N, B = fx.N, args.batch
+    a_dev = torch.empty(B, N, device=dev).normal_(0.0, 0.1)
+    f_dev = torch.empty(B, N, device=dev).normal_(0.0, 1.0)
+    a_host = torch.empty(B, N, pin_memory=True)
+    f_host = torch.empty(B, N, pin_memory=True)
+    a_host.copy_(a_dev)
+    f_host.copy_(f_dev)
+
+    def step():
+        a_dev.copy_(a_host, non_blocking=True)
+        f_dev.copy_(f_host, non_blocking=True)
+        a = a_dev.detach().requires_grad_(True)
+        loss = ns.residual_loss(a, f_dev, fx.A, fx.B1, fx.B2, fx.idx_sol)
+        loss.backward()
+        return float(loss.item()), a.grad
+
+    step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    k = max(1, args.e2e_steps)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(k):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"value": world * B * k / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * 4 * N * B,
+            "d2h_bytes_per_step": 4, "steps": k, "ms_per_step": ms / k,
+            "note": "host pinned row-major alpha,F -> H2D -> layout transposes -> fused fwd+bwd -> loss D2H"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -218,3 +218,59 @@ def sincos_forcing_grid(coeff_f: Array, resol_in: int, dtype=np.float32) -> Arra
     f1 = c[:, [0]] * np.sin(c[:, [2]] * x + c[:, [3]] * y)
     f2 = c[:, [1]] * np.cos(c[:, [4]] * x + c[:, [5]] * y)
     return np.stack([f1, f2], axis=1).reshape(-1, 2, resol_in, resol_in).astype(dtype)
+
+
+# ----------------------------------------------------------------------------------------------
+# Multi-threaded CPU port used ONLY as bench.py's cpu_baseline / --impl reference leg
+# ----------------------------------------------------------------------------------------------
+class TorchCpuSteadyNS:
+    """The A.2 formula (ns_loss_and_grad above, i.e. FEONet_steady_Navier-Stokes/train_FEONet.py:301-360
+    and its autograd) on the host cores with torch CPU sparse-CSR matrices, fp32.
+
+    The reference itself stores A, B1, B2 as dense N x N tensors (:293-295), which is infeasible at
+    ~1M dofs (4 TB per matrix); this is the same arithmetic with the zeros skipped, so it is a
+    generous CPU baseline ("port"), not the reference's dense timing."""
+
+    def __init__(self, A, B1, B2, I, J, do_precond: bool, threads: Optional[int] = None):
+        import torch
+
+        if threads:
+            torch.set_num_threads(int(threads))
+        self.torch = torch
+        self.threads = torch.get_num_threads()
+
+        def csr(K):
+            K = sp.csr_matrix(K).astype(np.float32)
+            return torch.sparse_csr_tensor(torch.from_numpy(K.indptr.astype(np.int64)),
+                                           torch.from_numpy(K.indices.astype(np.int64)),
+                                           torch.from_numpy(K.data), size=K.shape)
+
+        self.A, self.B1, self.B2 = csr(A), csr(B1), csr(B2)
+        self.AT, self.B1T, self.B2T = csr(sp.csr_matrix(A).T), csr(sp.csr_matrix(B1).T), csr(sp.csr_matrix(B2).T)
+        self.I = torch.as_tensor(np.asarray(I, dtype=np.int64))
+        self.J = torch.as_tensor(np.asarray(J, dtype=np.int64))
+        self.do_precond = bool(do_precond)
+
+    def loss_and_grad(self, alpha, F):
+        """alpha, F: [B,N] float32 (numpy or torch). Returns (loss float, grad [B,N] torch)."""
+        torch = self.torch
+        X = torch.as_tensor(alpha).t().contiguous()  # [N,B]
+        Ft = torch.as_tensor(F).t()
+        I, J = self.I, self.J
+        Bu1, Bu2, LHS = self.B1 @ X, self.B2 @ X, self.A @ X
+        conv = torch.zeros_like(X)
+        conv[I] = X[I] * Bu1[I] + X[J] * Bu2[I]
+        conv[J] = X[I] * Bu1[J] + X[J] * Bu2[J]
+        if self.do_precond:
+            r, s = LHS - (Ft - conv), 1.0
+        else:
+            r, s = LHS - (-Ft + conv), -1.0
+        loss = float((r * r).sum())
+        G = 2.0 * r
+        d1, d2 = torch.zeros_like(X), torch.zeros_like(X)
+        d1[I], d1[J], d2[I], d2[J] = X[I], X[I], X[J], X[J]
+        grad = self.AT @ G + s * (self.B1T @ (d1 * G) + self.B2T @ (d2 * G))
+        w1, w2 = Bu1 * G, Bu2 * G
+        grad[I] += s * (w1[I] + w1[J])
+        grad[J] += s * (w2[I] + w2[J])
+        return loss, grad.t()
