@@ -288,8 +288,14 @@ int feo_debug_plan_check(const feo_operator_desc* desc, int64_t* stats) {
       return fail(FEO_ERR_INVALID_ARGUMENT, "plan: malformed unit");
     }
   }
-  int64_t fcount = P.has_conv ? (int64_t)P.fent.size() : (int64_t)P.fent_lin.size();
+  int64_t fcount = 0;  // real (non-padding) forward entries; every row must be padded to kPadF
+  for (const FwdEntry& e : P.fent) fcount += (e.a != 0.f || e.b1 != 0.f || e.b2 != 0.f);
+  for (const FwdEntryLin& e : P.fent_lin) fcount += (e.a != 0.f);
   if (fcount != P.nnz_union) return fail(FEO_ERR_INVALID_ARGUMENT, "plan: forward stream size != union nnz");
+  for (size_t sl = 0; sl + 1 < P.fptr.size(); ++sl)
+    if ((P.fptr[sl + 1] - P.fptr[sl]) % kPadF != 0 || (P.bptrA[sl + 1] - P.bptrA[sl]) % kPadBA != 0 ||
+        (P.bptrB[sl + 1] - P.bptrB[sl]) % kPadBB != 0)
+      return fail(FEO_ERR_INVALID_ARGUMENT, "plan: entry stream not padded to the batch size");
   if (P.max_blob_fent > tune.blob_max_ent) return fail(FEO_ERR_INVALID_ARGUMENT, "plan: blob exceeds staging cap");
   if (stats != nullptr) {
     stats[0] = (int64_t)P.blob_uptr.size() - 1;
@@ -297,7 +303,7 @@ int feo_debug_plan_check(const feo_operator_desc* desc, int64_t* stats) {
     stats[2] = P.nnz_union;
     stats[3] = P.max_row_nnz;
     stats[4] = P.max_blob_fent;
-    stats[5] = (int64_t)P.bentA.size();
+    stats[5] = P.n_bent_real;
     stats[6] = (int64_t)P.bentB.size();
     stats[7] = P.has_conv;
   }

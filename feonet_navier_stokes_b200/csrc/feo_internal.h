@@ -66,9 +66,13 @@ struct HostPlan {
   std::vector<BwdEntryA> bentA;
   std::vector<BwdEntryB> bentB;
   int64_t nnz_union = 0;
+  int64_t n_bent_real = 0;  // backward entries before batch padding
   int32_t max_row_nnz = 0;
   int32_t max_blob_fent = 0, max_blob_bentA = 0, max_blob_bentB = 0;
 };
+
+// entry streams are padded per row/column to these multiples (= the kernels' load-batch sizes)
+constexpr int kPadF = 4, kPadBA = 4, kPadBB = 2;
 
 struct PlanTuning {
   int32_t blob_rows = 64;      // target rows per blob
@@ -81,6 +85,35 @@ HostCsr transpose(const HostCsr& a);
 HostCsr axpy(const HostCsr& s, float dt, const HostCsr& a);  // S + dt*A
 int build_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int32_t n_u, const int32_t* idx_i,
                const int32_t* idx_j, int32_t ns_branch, const PlanTuning& tune, HostPlan* plan);
+
+// ---- tile plan for the shared-memory-staged kernels (feo_tiles.cpp / feo_tiled.cu) -----------------
+constexpr int kTileSamples = 64;                           // samples per CTA = floats per staged dof line
+constexpr int kTileBatchF = 4, kTileBatchB = 2, kTileBatchA = 4;  // steps per load batch
+struct TilePlan {
+  bool backward = false, has_conv = false;
+  int32_t n_tiles = 0, max_lines = 0, max_pairs = 0;
+  std::vector<int32_t> tile_line_ptr, tile_pair_ptr;   // [n_tiles+1]
+  std::vector<int32_t> line_dof, line_src;             // staged line -> dof id, source (fwd: alpha; bwd: 0 = r, 1 = alpha)
+  std::vector<int32_t> pair_a, pair_b;                 // dofs owned by the two half-warps (-1: idle half)
+  std::vector<int32_t> pair_li, pair_lj, pair_vel;     // fwd: local lines of alpha[pi], alpha[pj]; velocity flag
+  std::vector<int32_t> pair_step_ptr, pair_stepA_ptr;  // [n_pairs+1] step offsets (bwd: convective / plain lists)
+  std::vector<FwdEntry> steps_f;                       // 2 per step (half A, half B); col = local line
+  std::vector<BwdEntryB> steps_b;
+  std::vector<BwdEntryA> steps_a;
+};
+int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int32_t n_u, const int32_t* idx_i,
+                    const int32_t* idx_j, int32_t ns_branch, bool backward, int32_t max_lines, int32_t max_pairs,
+                    TilePlan* out);
+
+struct DevTilePlan {
+  int32_t n_tiles = 0, max_lines = 0, max_pairs = 0;
+  int32_t *tile_line_ptr = nullptr, *tile_pair_ptr = nullptr, *line_dof = nullptr, *line_src = nullptr,
+          *pair_a = nullptr, *pair_b = nullptr, *pair_li = nullptr, *pair_lj = nullptr, *pair_vel = nullptr,
+          *pair_step_ptr = nullptr, *pair_stepA_ptr = nullptr;
+  FwdEntry* steps_f = nullptr;
+  BwdEntryB* steps_b = nullptr;
+  BwdEntryA* steps_a = nullptr;
+};
 
 // ---- device-side operator ---------------------------------------------------------------------
 struct DevCsr {
@@ -110,6 +143,9 @@ struct feo_operator {
   feo::BwdEntryA* bentA = nullptr;
   feo::BwdEntryB* bentB = nullptr;
   int32_t max_blob_fent = 0, max_blob_bentA = 0, max_blob_bentB = 0;
+  // shared-memory-staged walk (default path)
+  feo::DevTilePlan tiles_f, tiles_b;
+  bool use_tiled = true;
   // dense
   float *dM = nullptr, *dMT = nullptr, *dP = nullptr;
   // bookkeeping
@@ -139,4 +175,8 @@ int launch_dense(const float* D, int32_t n, const float* XT, float* CT, int64_t 
                  const float* scale_dev, const float* sub, float* loss_out, void* ws, size_t ws_bytes,
                  cudaStream_t st);
 size_t loss_partials_needed(int32_t n, int32_t n_blobs, int64_t cols);
+int launch_residual_fwd_tiled(const feo_operator* op, const float* alphaT, const float* fT, int64_t ldb, int32_t B,
+                              float* loss_out, float* rT, float* eT, void* ws, size_t ws_bytes, cudaStream_t st);
+int launch_residual_bwd_tiled(const feo_operator* op, const float* alphaT, const float* rT, const float* eT,
+                              const float* grad_loss, float* gradT, int64_t ldb, int32_t B, cudaStream_t st);
 }  // namespace feo

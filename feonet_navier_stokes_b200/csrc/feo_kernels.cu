@@ -82,6 +82,7 @@ struct FwdParams {
   int64_t ldb;
   int32_t B;
   int32_t precond_branch;
+  int32_t nby;  // sample blocks per blob
 };
 
 template <bool CONV>
@@ -89,28 +90,56 @@ struct RowOut {
   float4 r, s1, s2;
 };
 
-// One operator row for 4 samples per lane.  Entries come from shared memory (warp-uniform).
-template <bool CONV>
+// Address of (dof `col`, sample `bb`) in a dof-major array.  32-bit element index whenever the
+// array has < 2^32 elements (1M dofs x 1024 samples = 1.03e9): one IMAD + one IMAD.WIDE instead of
+// a 6-instruction 64-bit chain per gather.
+template <bool IDX64>
+__device__ __forceinline__ const float* at(const float* __restrict__ base, int col, int64_t ldb, int bb) {
+  if (IDX64) return base + ((int64_t)col * ldb + bb);
+  return base + (uint32_t)((uint32_t)col * (uint32_t)ldb + (uint32_t)bb);
+}
+
+constexpr int kFwdBatch = 4;   // entries per batch (rows are padded to a multiple of this by feo_plan.cpp)
+constexpr int kBwdBatchA = 4;
+constexpr int kBwdBatchB = 2;
+static_assert(kFwdBatch == kPadF && kBwdBatchA == kPadBA && kBwdBatchB == kPadBB, "plan padding must match the load batches");
+
+// One operator row for 4 samples per lane.  Entries come from shared memory (warp-uniform broadcast).
+// Gathers are issued kFwdBatch at a time BEFORE any FMA consumes them, so every warp keeps
+// kFwdBatch 512-byte requests in flight (ptxas otherwise serialises load -> use -> load).
+template <bool CONV, bool IDX64>
 __device__ __forceinline__ RowOut<CONV> fwd_row(const void* s_ent, int eb, int ee, const float* __restrict__ alphaT,
                                                 int64_t ldb, int bb) {
   float4 accA = zero4(), acc1 = zero4(), acc2 = zero4();
   if (CONV) {
     const int4* ent = reinterpret_cast<const int4*>(s_ent);
-#pragma unroll 4
-    for (int e = eb; e < ee; ++e) {
-      const int4 en = ent[e];
-      const float4 x = ldg4(alphaT + (int64_t)en.x * ldb + bb);
-      fma4(accA, __int_as_float(en.y), x);
-      fma4(acc1, __int_as_float(en.z), x);
-      fma4(acc2, __int_as_float(en.w), x);
+#pragma unroll 1
+    for (int e = eb; e < ee; e += kFwdBatch) {
+      int4 en[kFwdBatch];
+      float4 x[kFwdBatch];
+#pragma unroll
+      for (int u = 0; u < kFwdBatch; ++u) en[u] = ent[e + u];
+#pragma unroll
+      for (int u = 0; u < kFwdBatch; ++u) x[u] = ldg4(at<IDX64>(alphaT, en[u].x, ldb, bb));
+#pragma unroll
+      for (int u = 0; u < kFwdBatch; ++u) {
+        fma4(accA, __int_as_float(en[u].y), x[u]);
+        fma4(acc1, __int_as_float(en[u].z), x[u]);
+        fma4(acc2, __int_as_float(en[u].w), x[u]);
+      }
     }
   } else {
     const int2* ent = reinterpret_cast<const int2*>(s_ent);
-#pragma unroll 4
-    for (int e = eb; e < ee; ++e) {
-      const int2 en = ent[e];
-      const float4 x = ldg4(alphaT + (int64_t)en.x * ldb + bb);
-      fma4(accA, __int_as_float(en.y), x);
+#pragma unroll 1
+    for (int e = eb; e < ee; e += kFwdBatch) {
+      int2 en[kFwdBatch];
+      float4 x[kFwdBatch];
+#pragma unroll
+      for (int u = 0; u < kFwdBatch; ++u) en[u] = ent[e + u];
+#pragma unroll
+      for (int u = 0; u < kFwdBatch; ++u) x[u] = ldg4(at<IDX64>(alphaT, en[u].x, ldb, bb));
+#pragma unroll
+      for (int u = 0; u < kFwdBatch; ++u) fma4(accA, __int_as_float(en[u].y), x[u]);
     }
   }
   RowOut<CONV> o;
@@ -131,10 +160,12 @@ __device__ __forceinline__ float conv1(float d1, float s1, float d2, float s2) {
   return __fadd_rn(__fmul_rn(d1, s1), __fmul_rn(d2, s2));
 }
 
-template <bool CONV>
-__global__ void __launch_bounds__(kThreads) residual_fwd_kernel(FwdParams p) {
+template <bool CONV, bool IDX64>
+__global__ void __launch_bounds__(kThreads, 3) residual_fwd_kernel(FwdParams p) {
   extern __shared__ int4 s_ent_raw[];
-  const int blob = blockIdx.x;
+  // 1-D grid, sample block fastest: CTAs that run together cover neighbouring 512-byte slices of the
+  // SAME dof rows (whole DRAM pages get consumed) and re-use the blob's operator entries from L2.
+  const int blob = blockIdx.x / p.nby, by = blockIdx.x - blob * p.nby;
   const int u0 = p.blob_uptr[blob], u1 = p.blob_uptr[blob + 1];
   const int sl_begin = p.unit_ptr[u0], sl_end = p.unit_ptr[u1];
   const int e0 = p.fptr[sl_begin], e1 = p.fptr[sl_end];
@@ -151,7 +182,7 @@ __global__ void __launch_bounds__(kThreads) residual_fwd_kernel(FwdParams p) {
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int b = blockIdx.y * kWarpSamples + lane * 4;
+  const int b = by * kWarpSamples + lane * 4;
   const int nvalid = min(4, p.B - b);  // <=0: lane idle (it still executes with bb = 0, masked out)
   const int bb = nvalid > 0 ? b : 0;
   const bool precond = p.precond_branch != 0;
@@ -166,8 +197,8 @@ __global__ void __launch_bounds__(kThreads) residual_fwd_kernel(FwdParams p) {
       const int pi = p.slot_pi[sl0], pj = p.slot_pj[sl0];
       vel = pi >= 0;
       if (vel) {
-        d1 = ldg4(p.alphaT + (int64_t)pi * p.ldb + bb);
-        d2 = ldg4(p.alphaT + (int64_t)pj * p.ldb + bb);
+        d1 = ldg4(at<IDX64>(p.alphaT, pi, p.ldb, bb));
+        d2 = ldg4(at<IDX64>(p.alphaT, pj, p.ldb, bb));
       }
     }
     float4 rI = zero4(), s1I = zero4(), s2I = zero4();
@@ -175,7 +206,7 @@ __global__ void __launch_bounds__(kThreads) residual_fwd_kernel(FwdParams p) {
     for (int t = 0; t < cnt; ++t) {
       const int row = p.slot_row[sl0 + t];
       const int eb = p.fptr[sl0 + t] - e0, ee = p.fptr[sl0 + t + 1] - e0;
-      RowOut<CONV> o = fwd_row<CONV>(s_ent_raw, eb, ee, p.alphaT, p.ldb, bb);
+      RowOut<CONV> o = fwd_row<CONV, IDX64>(s_ent_raw, eb, ee, p.alphaT, p.ldb, bb);
       const float4 f = ldg4_stream(p.fT + (int64_t)row * p.ldb + bb);
       float4 c = zero4();
       if (CONV && vel) {
@@ -218,7 +249,7 @@ __global__ void __launch_bounds__(kThreads) residual_fwd_kernel(FwdParams p) {
       }
     }
   }
-  block_partial(lsum, p.partials, blockIdx.y * gridDim.x + blockIdx.x);
+  block_partial(lsum, p.partials, blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -234,11 +265,13 @@ struct BwdParams {
   int32_t B;
   float esign;  // s = +1 precond branch, -1 otherwise
   int32_t has_conv;
+  int32_t nby;
 };
 
-__global__ void __launch_bounds__(kThreads) residual_bwd_kernel(BwdParams p, int smemA_entries) {
+template <bool IDX64>
+__global__ void __launch_bounds__(kThreads, 4) residual_bwd_kernel(BwdParams p, int smemA_entries) {
   extern __shared__ int4 s_raw[];
-  const int blob = blockIdx.x;
+  const int blob = blockIdx.x / p.nby, by = blockIdx.x - blob * p.nby;
   const int u0 = p.blob_uptr[blob], u1 = p.blob_uptr[blob + 1];
   const int sl_begin = p.unit_ptr[u0], sl_end = p.unit_ptr[u1];
   const int a0 = p.bptrA[sl_begin], a1 = p.bptrA[sl_end];
@@ -256,7 +289,7 @@ __global__ void __launch_bounds__(kThreads) residual_bwd_kernel(BwdParams p, int
   (void)smemA_entries;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int b = blockIdx.y * kWarpSamples + lane * 4;
+  const int b = by * kWarpSamples + lane * 4;
   const bool active = b < p.B;
   const int bb = active ? b : 0;
   const float g2 = 2.0f * (p.grad_loss != nullptr ? __ldg(p.grad_loss) : 1.0f);
@@ -271,30 +304,46 @@ __global__ void __launch_bounds__(kThreads) residual_bwd_kernel(BwdParams p, int
       float4 acc = zero4();
       {
         const int eb = p.bptrA[sl] - a0, ee = p.bptrA[sl + 1] - a0;
-#pragma unroll 4
-        for (int e = eb; e < ee; ++e) {
-          const int2 en = sA[e];
-          const float4 rr = ldg4(p.rT + (int64_t)en.x * p.ldb + bb);
-          fma4(acc, __int_as_float(en.y), rr);
+#pragma unroll 1
+        for (int e = eb; e < ee; e += kBwdBatchA) {
+          int2 en[kBwdBatchA];
+          float4 rr[kBwdBatchA];
+#pragma unroll
+          for (int u = 0; u < kBwdBatchA; ++u) en[u] = sA[e + u];
+#pragma unroll
+          for (int u = 0; u < kBwdBatchA; ++u) rr[u] = ldg4(at<IDX64>(p.rT, en[u].x, p.ldb, bb));
+#pragma unroll
+          for (int u = 0; u < kBwdBatchA; ++u) fma4(acc, __int_as_float(en[u].y), rr[u]);
         }
       }
       if (p.has_conv) {
         const int eb = p.bptrB[sl] - b0, ee = p.bptrB[sl + 1] - b0;
-#pragma unroll 2
-        for (int e = eb; e < ee; ++e) {
-          const int4 i4 = sB[2 * e];      // row, pi, pj
-          const int4 f4 = sB[2 * e + 1];  // a, s*b1, s*b2
-          const float4 rr = ldg4(p.rT + (int64_t)i4.x * p.ldb + bb);
-          const float4 d1 = ldg4(p.alphaT + (int64_t)i4.y * p.ldb + bb);
-          const float4 d2 = ldg4(p.alphaT + (int64_t)i4.z * p.ldb + bb);
-          const float a = __int_as_float(f4.x), b1s = __int_as_float(f4.y), b2s = __int_as_float(f4.z);
-          acc.x = fmaf(fmaf(b2s, d2.x, fmaf(b1s, d1.x, a)), rr.x, acc.x);
-          acc.y = fmaf(fmaf(b2s, d2.y, fmaf(b1s, d1.y, a)), rr.y, acc.y);
-          acc.z = fmaf(fmaf(b2s, d2.z, fmaf(b1s, d1.z, a)), rr.z, acc.z);
-          acc.w = fmaf(fmaf(b2s, d2.w, fmaf(b1s, d1.w, a)), rr.w, acc.w);
+#pragma unroll 1
+        for (int e = eb; e < ee; e += kBwdBatchB) {
+          int4 i4[kBwdBatchB], f4[kBwdBatchB];
+          float4 rr[kBwdBatchB], d1[kBwdBatchB], d2[kBwdBatchB];
+#pragma unroll
+          for (int u = 0; u < kBwdBatchB; ++u) {
+            i4[u] = sB[2 * (e + u)];      // row, pi, pj
+            f4[u] = sB[2 * (e + u) + 1];  // a, s*b1, s*b2
+          }
+#pragma unroll
+          for (int u = 0; u < kBwdBatchB; ++u) {
+            rr[u] = ldg4(at<IDX64>(p.rT, i4[u].x, p.ldb, bb));
+            d1[u] = ldg4(at<IDX64>(p.alphaT, i4[u].y, p.ldb, bb));
+            d2[u] = ldg4(at<IDX64>(p.alphaT, i4[u].z, p.ldb, bb));
+          }
+#pragma unroll
+          for (int u = 0; u < kBwdBatchB; ++u) {
+            const float a = __int_as_float(f4[u].x), b1s = __int_as_float(f4[u].y), b2s = __int_as_float(f4[u].z);
+            acc.x = fmaf(fmaf(b2s, d2[u].x, fmaf(b1s, d1[u].x, a)), rr[u].x, acc.x);
+            acc.y = fmaf(fmaf(b2s, d2[u].y, fmaf(b1s, d1[u].y, a)), rr[u].y, acc.y);
+            acc.z = fmaf(fmaf(b2s, d2[u].z, fmaf(b1s, d1[u].z, a)), rr[u].z, acc.z);
+            acc.w = fmaf(fmaf(b2s, d2[u].w, fmaf(b1s, d1[u].w, a)), rr[u].w, acc.w);
+          }
         }
         if (p.slot_pi[sl] >= 0) {
-          const float4 ev = ldg4_stream(p.eT + (int64_t)c * p.ldb + bb);
+          const float4 ev = ldg4_stream(at<IDX64>(p.eT, c, p.ldb, bb));
           fma4(acc, p.esign, ev);
         }
       }
@@ -510,17 +559,22 @@ int launch_residual_fwd(const feo_operator* op, const float* alphaT, const float
   const int count = op->n_blobs * by;
   if (ws == nullptr || ws_bytes < (size_t)count * sizeof(float)) return fail(FEO_ERR_INVALID_ARGUMENT, "workspace too small");
   FwdParams p{op->blob_uptr, op->unit_ptr, op->slot_row, op->slot_pi, op->slot_pj, op->fptr, op->fent,
-              alphaT,        fT,           rT,           op->has_conv ? eT : nullptr, (float*)ws, ldb, B, op->ns_branch};
-  dim3 grid(op->n_blobs, by);
+              alphaT,        fT,           rT,           op->has_conv ? eT : nullptr, (float*)ws, ldb, B, op->ns_branch, by};
+  dim3 grid((unsigned)((int64_t)op->n_blobs * by));
+  const bool idx64 = (int64_t)op->n * ldb >= ((int64_t)1 << 32);
+  const size_t smem = (size_t)op->max_blob_fent * (op->has_conv ? sizeof(FwdEntry) : sizeof(FwdEntryLin));
+#define FEO_LAUNCH_FWD(CONV, I64)                                                                                  \
+  do {                                                                                                             \
+    FEO_CUDA_CHECK(cudaFuncSetAttribute(residual_fwd_kernel<CONV, I64>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        (int)smem));                                                               \
+    residual_fwd_kernel<CONV, I64><<<grid, kThreads, smem, st>>>(p);                                               \
+  } while (0)
   if (op->has_conv) {
-    size_t smem = (size_t)op->max_blob_fent * sizeof(FwdEntry);
-    FEO_CUDA_CHECK(cudaFuncSetAttribute(residual_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    residual_fwd_kernel<true><<<grid, kThreads, smem, st>>>(p);
+    if (idx64) FEO_LAUNCH_FWD(true, true); else FEO_LAUNCH_FWD(true, false);
   } else {
-    size_t smem = (size_t)op->max_blob_fent * sizeof(FwdEntryLin);
-    FEO_CUDA_CHECK(cudaFuncSetAttribute(residual_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    residual_fwd_kernel<false><<<grid, kThreads, smem, st>>>(p);
+    if (idx64) FEO_LAUNCH_FWD(false, true); else FEO_LAUNCH_FWD(false, false);
   }
+#undef FEO_LAUNCH_FWD
   FEO_CUDA_CHECK(cudaGetLastError());
   return finalize((float*)ws, count, 1.0f, loss_out, st);
 }
@@ -536,12 +590,17 @@ int launch_residual_bwd(const feo_operator* op, const float* alphaT, const float
   }
   BwdParams p{op->blob_uptr, op->unit_ptr, op->slot_row, op->slot_pi, op->bptrA, op->bptrB, op->bentA, op->bentB,
               alphaT,        rT,           eT,           grad_loss,   gradT,     ldb,       B,
-              op->ns_branch ? 1.0f : -1.0f, op->has_conv ? 1 : 0};
+              op->ns_branch ? 1.0f : -1.0f, op->has_conv ? 1 : 0, (B + kWarpSamples - 1) / kWarpSamples};
   const int by = (B + kWarpSamples - 1) / kWarpSamples;
-  dim3 grid(op->n_blobs, by);
+  dim3 grid((unsigned)((int64_t)op->n_blobs * by));
   size_t smem = (size_t)op->max_blob_bentB * sizeof(BwdEntryB) + (size_t)op->max_blob_bentA * sizeof(BwdEntryA) + 16;
-  FEO_CUDA_CHECK(cudaFuncSetAttribute(residual_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  residual_bwd_kernel<<<grid, kThreads, smem, st>>>(p, op->max_blob_bentA);
+  if ((int64_t)op->n * ldb >= ((int64_t)1 << 32)) {
+    FEO_CUDA_CHECK(cudaFuncSetAttribute(residual_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    residual_bwd_kernel<true><<<grid, kThreads, smem, st>>>(p, op->max_blob_bentA);
+  } else {
+    FEO_CUDA_CHECK(cudaFuncSetAttribute(residual_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    residual_bwd_kernel<false><<<grid, kThreads, smem, st>>>(p, op->max_blob_bentA);
+  }
   FEO_CUDA_CHECK(cudaGetLastError());
   return FEO_OK;
 }

@@ -203,7 +203,7 @@ int build_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int32_t n
     }
     P.nnz_union = (int64_t)uent.size();
   }
-  if (2 * (int64_t)P.max_row_nnz > tune.blob_max_ent)
+  if (2 * (int64_t)(P.max_row_nnz + kPadF) > tune.blob_max_ent)
     return fail(FEO_ERR_UNSUPPORTED, "a row is too dense for the sparse path; use the dense operator path");
 
   // blobs: grow compact neighbourhoods by BFS over the union pattern so that the rows a CTA walks
@@ -240,7 +240,7 @@ int build_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int32_t n
       int32_t rr[2];
       int32_t nr = unit_rows(u, rr);
       int64_t ue = 0;
-      for (int32_t t = 0; t < nr; ++t) ue += uptr[rr[t] + 1] - uptr[rr[t]];
+      for (int32_t t = 0; t < nr; ++t) ue += (uptr[rr[t] + 1] - uptr[rr[t]] + kPadF - 1) / kPadF * kPadF;
       if (rows_in_blob > 0 && (rows_in_blob + nr > tune.blob_rows || ent_in_blob + ue > tune.blob_max_ent)) {
         full = true;
         break;
@@ -277,16 +277,25 @@ int build_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int32_t n
   const int32_t n_slots = (int32_t)P.slot_row.size();
   if (n_slots != n) return fail(FEO_ERR_INVALID_ARGUMENT, "internal: slot count != n");
 
-  // forward stream
+  // forward stream; every row is padded to a multiple of kPadF with zero-valued entries that repeat
+  // the last column (a harmless L1-hit gather) so the kernels run fixed-size load batches
   P.fptr.assign(1, 0);
   for (int32_t s = 0; s < n_slots; ++s) {
     int32_t r = P.slot_row[s];
-    for (int32_t k = uptr[r]; k < uptr[r + 1]; ++k) {
+    int32_t cnt = 0, last = 0;
+    for (int32_t k = uptr[r]; k < uptr[r + 1]; ++k, ++cnt) {
       const UEnt& e = uent[k];
+      last = e.col;
       if (P.has_conv)
         P.fent.push_back(FwdEntry{e.col, e.a, e.b1, e.b2});
       else
         P.fent_lin.push_back(FwdEntryLin{e.col, e.a});
+    }
+    for (; cnt % kPadF != 0; ++cnt) {
+      if (P.has_conv)
+        P.fent.push_back(FwdEntry{last, 0.f, 0.f, 0.f});
+      else
+        P.fent_lin.push_back(FwdEntryLin{last, 0.f});
     }
     P.fptr.push_back(P.has_conv ? (int32_t)P.fent.size() : (int32_t)P.fent_lin.size());
   }
@@ -310,14 +319,25 @@ int build_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int32_t n
     P.bptrB.assign(1, 0);
     for (int32_t sl = 0; sl < n_slots; ++sl) {
       int32_t c = P.slot_row[sl];
+      int32_t cntA = 0, cntB = 0;
       for (int32_t p = tptr[c]; p < tptr[c + 1]; ++p) {
         int32_t h = trow[p];
         const UEnt& e = uent[tsrc[p]];
         bool conv = P.has_conv && P.kind[h] != 0 && (e.b1 != 0.f || e.b2 != 0.f);
-        if (conv)
+        if (conv) {
           P.bentB.push_back(BwdEntryB{h, P.pi[h], P.pj[h], 0, e.a, s * e.b1, s * e.b2, 0.f});
-        else if (e.a != 0.f)
+          ++cntB;
+        } else if (e.a != 0.f) {
           P.bentA.push_back(BwdEntryA{h, e.a});
+          ++cntA;
+        }
+      }
+      P.n_bent_real += cntA + cntB;
+      for (; cntA % kPadBA != 0; ++cntA) P.bentA.push_back(BwdEntryA{P.bentA.back().row, 0.f});
+      for (; cntB % kPadBB != 0; ++cntB) {
+        BwdEntryB z = P.bentB.back();
+        z.a = z.b1s = z.b2s = 0.f;
+        P.bentB.push_back(z);
       }
       P.bptrA.push_back((int32_t)P.bentA.size());
       P.bptrB.push_back((int32_t)P.bentB.size());
