@@ -200,7 +200,7 @@ def run_ours(args):
     t0 = time.time()
     ns = feo.SteadyNavierStokes(fx.A, fx.B1, fx.B2, fx.idx_sol, do_precond=True, precond=None, model_name="FCNN", device=dev)
     op = ns.operator
-    log(f"[bench] rank {rank}: operator on device in {time.time() - t0:.1f}s: blobs={op.info.n_blobs} "
+    log(f"[bench] rank {rank}: operator on device in {time.time() - t0:.1f}s: tiles(fwd,bwd)=({op.info.n_tiles_fwd},{op.info.n_tiles_bwd}) "
         f"nnz_union={op.info.nnz_union} device_MB={op.info.device_bytes / 2**20:.0f}")
 
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -304,7 +304,7 @@ def run_ours(args):
     peak, peak_src = measured_peak_gbs()
     alg_fwd = 12.0 * N * B  # read alpha, F; write r
     alg_bwd = 12.0 * N * B  # read r, alpha; write grad
-    dom = "residual_bwd_kernel" if bwd_ms >= fwd_ms else "residual_fwd_kernel"
+    dom = "residual_bwd_tiled" if bwd_ms >= fwd_ms else "residual_fwd_tiled"
     dom_ms, dom_alg = (bwd_ms, alg_bwd) if bwd_ms >= fwd_ms else (fwd_ms, alg_fwd)
     achieved = dom_alg / (dom_ms * 1e-3) / 1e9
     traffic = None

@@ -11,7 +11,7 @@ import threading
 
 from . import build as _build
 
-FEO_ABI_VERSION = 1
+FEO_ABI_VERSION = 2
 FEO_MAT_A, FEO_MAT_B1, FEO_MAT_B2, FEO_MAT_S, FEO_MAT_M = range(5)
 FEO_DENSE_M, FEO_DENSE_MT, FEO_DENSE_P = range(3)
 
@@ -40,7 +40,7 @@ class FeoOpInfo(C.Structure):
         ("n", C.c_int32), ("n_u", C.c_int32), ("has_conv", C.c_int32), ("has_seq", C.c_int32),
         ("has_dense_m", C.c_int32), ("has_dense_p", C.c_int32),
         ("nnz_a", C.c_int64), ("nnz_b1", C.c_int64), ("nnz_b2", C.c_int64), ("nnz_s", C.c_int64),
-        ("nnz_union", C.c_int64), ("n_blobs", C.c_int32), ("n_units", C.c_int32), ("max_row_nnz", C.c_int32),
+        ("nnz_union", C.c_int64), ("n_tiles_fwd", C.c_int32), ("n_tiles_bwd", C.c_int32), ("max_row_nnz", C.c_int32),
         ("device_bytes", C.c_int64),
     ]
 
@@ -55,16 +55,15 @@ SIGNATURES = {
     "feo_op_get_info": (C.c_int, [_vp, C.POINTER(FeoOpInfo)]),
     "feo_workspace_bytes": (_sz, [_vp, _i32, _i32]),
     "feo_transpose": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp]),
-    "feo_residual_fwd": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "feo_residual_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "feo_residual_fwd": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "feo_residual_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "feo_spmm": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i64, _i32, _f32, _i32, _vp]),
     "feo_dense_apply": (C.c_int, [_vp, _i32, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "feo_seq_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "feo_seq_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "feo_assemble_u_init": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "feo_sq_diff_sum": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _f32, _vp, _vp, _sz, _vp]),
-    "feo_debug_plan_check": (C.c_int, [C.POINTER(FeoOperatorDesc), i64p]),
-    "feo_debug_plan_replay": (C.c_int, [C.POINTER(FeoOperatorDesc), f64p, f64p, f64p, f64p, f64p]),
+    "feo_debug_tile_replay": (C.c_int, [C.POINTER(FeoOperatorDesc), _i32, _i32, _i32, f64p, f64p, f64p, i64p]),
 }
 
 _lock = threading.Lock()

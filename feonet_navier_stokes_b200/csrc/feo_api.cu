@@ -7,8 +7,6 @@
 #include "feo_internal.h"
 
 namespace feo {
-const std::string& last_error();
-
 namespace {
 template <typename T>
 int upload(feo_operator* op, const std::vector<T>& host, T** dev) {
@@ -109,43 +107,29 @@ int feo_op_create(const feo_operator_desc* desc, feo_handle_t* out) {
     if ((rc = upload(op, jj, &op->idx_j))) return bail(rc);
   }
   if (A.present()) {
-    HostPlan plan;
-    if ((rc = build_plan(A, B1, B2, desc->n_u, desc->idx_i, desc->idx_j, op->ns_branch, tuning_from_env(), &plan)))
-      return bail(rc);
-    op->has_conv = plan.has_conv;
-    if (!plan.has_conv) op->ns_branch = 1;  // linear Stokes: r = A a - F (FEONet_Stokes_square/train_FEONet.py:264-270)
-    op->n_blobs = (int32_t)plan.blob_uptr.size() - 1;
-    op->n_units = (int32_t)plan.unit_ptr.size() - 1;
-    op->n_slots = (int32_t)plan.slot_row.size();
-    op->nnz_union = plan.nnz_union;
-    op->max_row_nnz = plan.max_row_nnz;
-    op->max_blob_fent = plan.max_blob_fent;
-    op->max_blob_bentA = plan.max_blob_bentA;
-    op->max_blob_bentB = plan.max_blob_bentB;
-    std::vector<int32_t> spi(op->n_slots), spj(op->n_slots);
-    for (int32_t s = 0; s < op->n_slots; ++s) {
-      spi[s] = plan.pi[plan.slot_row[s]];
-      spj[s] = plan.pj[plan.slot_row[s]];
+    // tile plans of the fused residual kernels (forward: row-owned, backward: column-pair-owned)
+    for (int bw = 0; bw < 2; ++bw) {
+      TilePlan plan;
+      if ((rc = build_tile_plan(A, B1, B2, desc->n_u, desc->idx_i, desc->idx_j, op->ns_branch, bw != 0,
+                                tile_tuning_from_env(bw != 0), &plan)))
+        return bail(rc);
+      DevTilePlan& D = bw ? op->tiles_b : op->tiles_f;
+      D.n_tiles = plan.n_tiles;
+      D.max_lines = plan.max_lines;
+      D.warps = plan.warps;
+      if ((rc = upload(op, plan.tile_box_ptr, &D.tile_box_ptr))) return bail(rc);
+      if ((rc = upload(op, plan.tile_lines, &D.tile_lines))) return bail(rc);
+      if ((rc = upload(op, plan.boxes, &D.boxes))) return bail(rc);
+      if ((rc = upload(op, plan.warp_range, &D.warp_range))) return bail(rc);
+      if ((rc = upload(op, plan.stream, &D.stream))) return bail(rc);
+      if (!bw) {
+        op->has_conv = plan.has_conv;
+        op->nnz_union = plan.real_entries;
+      }
     }
-    if ((rc = upload(op, plan.blob_uptr, &op->blob_uptr))) return bail(rc);
-    if ((rc = upload(op, plan.unit_ptr, &op->unit_ptr))) return bail(rc);
-    if ((rc = upload(op, plan.slot_row, &op->slot_row))) return bail(rc);
-    if ((rc = upload(op, spi, &op->slot_pi))) return bail(rc);
-    if ((rc = upload(op, spj, &op->slot_pj))) return bail(rc);
-    if ((rc = upload(op, plan.fptr, &op->fptr))) return bail(rc);
-    if (plan.has_conv) {
-      FwdEntry* d = nullptr;
-      if ((rc = upload(op, plan.fent, &d))) return bail(rc);
-      op->fent = d;
-    } else {
-      FwdEntryLin* d = nullptr;
-      if ((rc = upload(op, plan.fent_lin, &d))) return bail(rc);
-      op->fent = d;
-    }
-    if ((rc = upload(op, plan.bptrA, &op->bptrA))) return bail(rc);
-    if ((rc = upload(op, plan.bptrB, &op->bptrB))) return bail(rc);
-    if ((rc = upload(op, plan.bentA, &op->bentA))) return bail(rc);
-    if ((rc = upload(op, plan.bentB, &op->bentB))) return bail(rc);
+    if (!op->has_conv) op->ns_branch = 1;  // linear Stokes: r = A a - F (FEONet_Stokes_square/train_FEONet.py:264-270)
+    op->has_sparse = true;
+    for (int32_t r = 0; r < A.n; ++r) op->max_row_nnz = std::max(op->max_row_nnz, A.rowptr[r + 1] - A.rowptr[r]);
   }
   if (desc->dense_m != nullptr) {
     if ((rc = upload_dense(op, desc->dense_m, desc->n, false, &op->dM))) return bail(rc);
@@ -180,8 +164,8 @@ int feo_op_get_info(feo_handle_t h, feo_op_info* info) {
   info->nnz_b2 = h->nnz[2];
   info->nnz_s = h->nnz[3];
   info->nnz_union = h->nnz_union;
-  info->n_blobs = h->n_blobs;
-  info->n_units = h->n_units;
+  info->n_tiles_fwd = h->tiles_f.n_tiles;
+  info->n_tiles_bwd = h->tiles_b.n_tiles;
   info->max_row_nnz = h->max_row_nnz;
   info->device_bytes = h->device_bytes;
   return FEO_OK;
@@ -190,7 +174,7 @@ int feo_op_get_info(feo_handle_t h, feo_op_info* info) {
 size_t feo_workspace_bytes(feo_handle_t h, int32_t B, int32_t T) {
   if (h == nullptr || B <= 0) return 0;
   if (T < 1) T = 1;
-  return loss_partials_needed(h->n, h->n_blobs, (int64_t)B * T);
+  return loss_partials_needed(h->n, h->tiles_f.n_tiles, (int64_t)B * T);
 }
 
 int feo_transpose(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int32_t rows, int32_t cols,
@@ -199,17 +183,17 @@ int feo_transpose(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, 
 }
 
 int feo_residual_fwd(feo_handle_t h, const float* alphaT, const float* fT, int64_t ldb, int32_t B, float* loss_out,
-                     float* rT, float* eT, void* workspace, size_t workspace_bytes, void* stream) {
+                     float* rT, void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = check_handle(h)) return rc;
-  if (h->fent == nullptr) return fail(FEO_ERR_UNSUPPORTED, "operator has no sparse A: use feo_dense_apply");
-  return launch_residual_fwd(h, alphaT, fT, ldb, B, loss_out, rT, eT, workspace, workspace_bytes, (cudaStream_t)stream);
+  if (!h->has_sparse) return fail(FEO_ERR_UNSUPPORTED, "operator has no sparse A: use feo_dense_apply");
+  return launch_residual_fwd(h, alphaT, fT, ldb, B, loss_out, rT, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-int feo_residual_bwd(feo_handle_t h, const float* alphaT, const float* rT, const float* eT, const float* grad_loss,
-                     float* gradT, int64_t ldb, int32_t B, void* stream) {
+int feo_residual_bwd(feo_handle_t h, const float* alphaT, const float* rT, const float* grad_loss, float* gradT, int64_t ldb,
+                     int32_t B, void* stream) {
   if (int rc = check_handle(h)) return rc;
-  if (h->fent == nullptr) return fail(FEO_ERR_UNSUPPORTED, "operator has no sparse A: use feo_dense_apply");
-  return launch_residual_bwd(h, alphaT, rT, eT, grad_loss, gradT, ldb, B, (cudaStream_t)stream);
+  if (!h->has_sparse) return fail(FEO_ERR_UNSUPPORTED, "operator has no sparse A: use feo_dense_apply");
+  return launch_residual_bwd(h, alphaT, rT, grad_loss, gradT, ldb, B, (cudaStream_t)stream);
 }
 
 int feo_spmm(feo_handle_t h, int32_t which, int32_t transpose, const float* XT, float* YT, int64_t ldb, int32_t B,
@@ -261,111 +245,36 @@ int feo_sq_diff_sum(const float* xT, const float* yT, int32_t n, int64_t ldb, in
   return launch_sq_diff_sum(xT, yT, n, ldb, B, scale, loss_out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-// ---- test hooks (host only; exercised by the CPU test-suite, never by the product path) -------
-// Builds the walk plan on the host and checks its invariants: every stored entry of the union
-// pattern appears exactly once in the forward stream and (as A- or B-type) in the backward
-// stream, velocity pairs are adjacent, blobs respect the staging cap.  stats[0..7] =
-// {n_blobs, n_units, nnz_union, max_row_nnz, max_blob_fent, n_bentA, n_bentB, has_conv}.
-int feo_debug_plan_check(const feo_operator_desc* desc, int64_t* stats) {
+// ---- test hook (host only; exercised by the CPU test-suite, never by the product path) ----------
+// Builds the tile plan of the fused residual kernels on the host and replays its staging boxes and
+// per-warp streams in fp64 for ONE sample, decoding them exactly as the kernels do, so the CPU suite
+// can compare the set-up code (union pattern, partner lookups, sign folding, pair/duo streams) with
+// the oracle without a GPU.  forward: in0 = alpha, in1 = f, out = r; backward: in0 = r, in1 = alpha,
+// out = grad / (2 g).  max_lines / warps <= 0: defaults.
+// stats[0..7] = {n_tiles, max_lines, total_lines, n_boxes, n_items, real_entries, slot_entries, stream_words}.
+int feo_debug_tile_replay(const feo_operator_desc* desc, int32_t backward, int32_t max_lines, int32_t warps,
+                          const double* in0, const double* in1, double* out, int64_t* stats) {
   HostCsr A, B1, B2, S;
   if (int rc = prepare(desc, &A, &B1, &B2, &S)) return rc;
-  if (!A.present()) return fail(FEO_ERR_INVALID_ARGUMENT, "plan check needs A");
-  HostPlan P;
-  PlanTuning tune = tuning_from_env();
-  if (int rc = build_plan(A, B1, B2, desc->n_u, desc->idx_i, desc->idx_j, desc->ns_precond_branch ? 1 : 0, tune, &P)) return rc;
-  const int32_t n = desc->n;
-  std::vector<char> seen(n, 0);
-  for (int32_t r : P.slot_row) {
-    if (r < 0 || r >= n || seen[r]) return fail(FEO_ERR_INVALID_ARGUMENT, "plan: slot rows are not a permutation");
-    seen[r] = 1;
-  }
-  for (size_t u = 0; u + 1 < P.unit_ptr.size(); ++u) {
-    int32_t s0 = P.unit_ptr[u], cnt = P.unit_ptr[u + 1] - s0;
-    if (cnt == 2) {
-      if (P.kind[P.slot_row[s0]] != 1 || P.kind[P.slot_row[s0 + 1]] != 2 || P.pj[P.slot_row[s0]] != P.slot_row[s0 + 1])
-        return fail(FEO_ERR_INVALID_ARGUMENT, "plan: pair unit is not (I[k], J[k])");
-    } else if (cnt != 1 || P.kind[P.slot_row[s0]] != 0) {
-      return fail(FEO_ERR_INVALID_ARGUMENT, "plan: malformed unit");
-    }
-  }
-  int64_t fcount = 0;  // real (non-padding) forward entries; every row must be padded to kPadF
-  for (const FwdEntry& e : P.fent) fcount += (e.a != 0.f || e.b1 != 0.f || e.b2 != 0.f);
-  for (const FwdEntryLin& e : P.fent_lin) fcount += (e.a != 0.f);
-  if (fcount != P.nnz_union) return fail(FEO_ERR_INVALID_ARGUMENT, "plan: forward stream size != union nnz");
-  for (size_t sl = 0; sl + 1 < P.fptr.size(); ++sl)
-    if ((P.fptr[sl + 1] - P.fptr[sl]) % kPadF != 0 || (P.bptrA[sl + 1] - P.bptrA[sl]) % kPadBA != 0 ||
-        (P.bptrB[sl + 1] - P.bptrB[sl]) % kPadBB != 0)
-      return fail(FEO_ERR_INVALID_ARGUMENT, "plan: entry stream not padded to the batch size");
-  if (P.max_blob_fent > tune.blob_max_ent) return fail(FEO_ERR_INVALID_ARGUMENT, "plan: blob exceeds staging cap");
+  if (!A.present()) return fail(FEO_ERR_INVALID_ARGUMENT, "tile replay needs A");
+  TileTuning tune = tile_tuning_from_env(backward != 0);
+  if (max_lines > 0) tune.max_lines = max_lines;
+  if (warps > 0) tune.warps = warps;
+  TilePlan T;
+  const int32_t branch = desc->ns_precond_branch ? 1 : 0;
+  if (int rc = build_tile_plan(A, B1, B2, desc->n_u, desc->idx_i, desc->idx_j, branch, backward != 0, tune, &T)) return rc;
   if (stats != nullptr) {
-    stats[0] = (int64_t)P.blob_uptr.size() - 1;
-    stats[1] = (int64_t)P.unit_ptr.size() - 1;
-    stats[2] = P.nnz_union;
-    stats[3] = P.max_row_nnz;
-    stats[4] = P.max_blob_fent;
-    stats[5] = P.n_bent_real;
-    stats[6] = (int64_t)P.bentB.size();
-    stats[7] = P.has_conv;
+    stats[0] = T.n_tiles;
+    stats[1] = T.max_lines;
+    stats[2] = T.total_lines;
+    stats[3] = (int64_t)T.boxes.size();
+    stats[4] = T.n_items;
+    stats[5] = T.real_entries;
+    stats[6] = T.slot_entries;
+    stats[7] = (int64_t)T.stream.size();
   }
-  return FEO_OK;
-}
-
-// Replays the plan's forward and backward streams on the host in fp64 for ONE sample, so the CPU
-// suite can compare the set-up code (union pattern, partner lookups, sign folding, transposed
-// lists) with the oracle without a GPU.  alpha, f: [n]; outputs r, grad: [n]; returns loss.
-int feo_debug_plan_replay(const feo_operator_desc* desc, const double* alpha, const double* f, double* r_out,
-                          double* grad_out, double* loss_out) {
-  HostCsr A, B1, B2, S;
-  if (int rc = prepare(desc, &A, &B1, &B2, &S)) return rc;
-  HostPlan P;
-  if (int rc = build_plan(A, B1, B2, desc->n_u, desc->idx_i, desc->idx_j, desc->ns_precond_branch ? 1 : 0,
-                          tuning_from_env(), &P))
-    return rc;
-  const int32_t n = desc->n;
-  const bool precond = P.has_conv ? desc->ns_precond_branch != 0 : true;
-  const double s = precond ? 1.0 : -1.0;
-  std::vector<double> r(n, 0.0), e(n, 0.0), s1(n, 0.0), s2(n, 0.0);
-  double loss = 0.0;
-  for (int32_t sl = 0; sl < n; ++sl) {
-    const int32_t row = P.slot_row[sl];
-    double accA = 0, acc1 = 0, acc2 = 0;
-    for (int32_t k = P.fptr[sl]; k < P.fptr[sl + 1]; ++k) {
-      if (P.has_conv) {
-        const FwdEntry& en = P.fent[k];
-        accA += (double)en.a * alpha[en.col];
-        acc1 += (double)en.b1 * alpha[en.col];
-        acc2 += (double)en.b2 * alpha[en.col];
-      } else {
-        accA += (double)P.fent_lin[k].a * alpha[P.fent_lin[k].col];
-      }
-    }
-    double c = 0.0;
-    if (P.has_conv && P.pi[row] >= 0) c = alpha[P.pi[row]] * acc1 + alpha[P.pj[row]] * acc2;
-    r[row] = precond ? accA - (f[row] - c) : accA - (-f[row] + c);
-    s1[row] = acc1;
-    s2[row] = acc2;
-    loss += r[row] * r[row];
-  }
-  if (P.has_conv)
-    for (int32_t row = 0; row < n; ++row)
-      if (P.kind[row] != 0) {
-        const int32_t i = P.pi[row], j = P.pj[row];
-        e[row] = P.kind[row] == 1 ? s1[i] * r[i] + s1[j] * r[j] : s2[i] * r[i] + s2[j] * r[j];
-      }
-  for (int32_t sl = 0; sl < n; ++sl) {
-    const int32_t c = P.slot_row[sl];
-    double acc = 0.0;
-    for (int32_t k = P.bptrA[sl]; k < P.bptrA[sl + 1]; ++k) acc += (double)P.bentA[k].a * r[P.bentA[k].row];
-    for (int32_t k = P.bptrB[sl]; k < P.bptrB[sl + 1]; ++k) {
-      const BwdEntryB& en = P.bentB[k];
-      acc += ((double)en.a + (double)en.b1s * alpha[en.pi] + (double)en.b2s * alpha[en.pj]) * r[en.row];
-    }
-    if (P.has_conv && P.kind[c] != 0) acc += s * e[c];
-    grad_out[c] = 2.0 * acc;
-  }
-  for (int32_t i = 0; i < n; ++i) r_out[i] = r[i];
-  *loss_out = loss;
-  return FEO_OK;
+  if (in0 == nullptr || in1 == nullptr || out == nullptr) return FEO_OK;
+  return replay_tile_plan(T, branch, in0, in1, out);
 }
 
 }  // extern "C"

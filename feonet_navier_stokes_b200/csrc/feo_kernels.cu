@@ -1,12 +1,11 @@
-// sm_100a kernels for the sparse FEONet residual path.
+// sm_100a kernels around the fused residual path (feo_tiled.cu): generic sparse applies for the
+// materialised (LHS, RHS) API, the time-dependent sequence kernels, the dense operator GEMM, layout
+// transposes and the loss reductions.
 //
 // Data layout: every batch of coefficient vectors is dof-major, XT[d*ldb + b] (see feonet_b200.h).
-// A warp owns one operator row (or a velocity pair) for 128 consecutive samples: lane l holds
-// samples 4l..4l+3 as a float4, so every gather `alphaT[col*ldb + b]` is one fully coalesced
-// 512-byte request and the operator entry {col, a, b1, b2} is warp-uniform (one 16-byte shared
-// memory broadcast feeds 12 FMAs per lane).  Rows are walked blob by blob (feo_plan.cpp) so the
-// columns a CTA touches stay L1/L2-resident.  Everything is row-/column-owned: no atomics, fixed
-// summation order, bit-reproducible.
+// In the generic kernels a warp owns one operator row for 128 consecutive samples: lane l holds
+// samples 4l..4l+3 as a float4, so every gather `XT[col*ldb + b]` is one fully coalesced 512-byte
+// request.  Everything is row-owned: no atomics, fixed summation order, bit-reproducible.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -69,291 +68,6 @@ __global__ void finalize_loss_kernel(const float* __restrict__ partials, int cou
     __syncthreads();
   }
   if (threadIdx.x == 0) *loss_out = (float)(s[0] * (double)scale);
-}
-
-// ---------------------------------------------------------------------------------------------
-// fused residual forward
-// ---------------------------------------------------------------------------------------------
-struct FwdParams {
-  const int32_t *blob_uptr, *unit_ptr, *slot_row, *slot_pi, *slot_pj, *fptr;
-  const void* fent;
-  const float *alphaT, *fT;
-  float *rT, *eT, *partials;
-  int64_t ldb;
-  int32_t B;
-  int32_t precond_branch;
-  int32_t nby;  // sample blocks per blob
-};
-
-template <bool CONV>
-struct RowOut {
-  float4 r, s1, s2;
-};
-
-// Address of (dof `col`, sample `bb`) in a dof-major array.  32-bit element index whenever the
-// array has < 2^32 elements (1M dofs x 1024 samples = 1.03e9): one IMAD + one IMAD.WIDE instead of
-// a 6-instruction 64-bit chain per gather.
-template <bool IDX64>
-__device__ __forceinline__ const float* at(const float* __restrict__ base, int col, int64_t ldb, int bb) {
-  if (IDX64) return base + ((int64_t)col * ldb + bb);
-  return base + (uint32_t)((uint32_t)col * (uint32_t)ldb + (uint32_t)bb);
-}
-
-constexpr int kFwdBatch = 4;   // entries per batch (rows are padded to a multiple of this by feo_plan.cpp)
-constexpr int kBwdBatchA = 4;
-constexpr int kBwdBatchB = 2;
-static_assert(kFwdBatch == kPadF && kBwdBatchA == kPadBA && kBwdBatchB == kPadBB, "plan padding must match the load batches");
-
-// One operator row for 4 samples per lane.  Entries come from shared memory (warp-uniform broadcast).
-// Gathers are issued kFwdBatch at a time BEFORE any FMA consumes them, so every warp keeps
-// kFwdBatch 512-byte requests in flight (ptxas otherwise serialises load -> use -> load).
-template <bool CONV, bool IDX64>
-__device__ __forceinline__ RowOut<CONV> fwd_row(const void* s_ent, int eb, int ee, const float* __restrict__ alphaT,
-                                                int64_t ldb, int bb) {
-  float4 accA = zero4(), acc1 = zero4(), acc2 = zero4();
-  if (CONV) {
-    const int4* ent = reinterpret_cast<const int4*>(s_ent);
-#pragma unroll 1
-    for (int e = eb; e < ee; e += kFwdBatch) {
-      int4 en[kFwdBatch];
-      float4 x[kFwdBatch];
-#pragma unroll
-      for (int u = 0; u < kFwdBatch; ++u) en[u] = ent[e + u];
-#pragma unroll
-      for (int u = 0; u < kFwdBatch; ++u) x[u] = ldg4(at<IDX64>(alphaT, en[u].x, ldb, bb));
-#pragma unroll
-      for (int u = 0; u < kFwdBatch; ++u) {
-        fma4(accA, __int_as_float(en[u].y), x[u]);
-        fma4(acc1, __int_as_float(en[u].z), x[u]);
-        fma4(acc2, __int_as_float(en[u].w), x[u]);
-      }
-    }
-  } else {
-    const int2* ent = reinterpret_cast<const int2*>(s_ent);
-#pragma unroll 1
-    for (int e = eb; e < ee; e += kFwdBatch) {
-      int2 en[kFwdBatch];
-      float4 x[kFwdBatch];
-#pragma unroll
-      for (int u = 0; u < kFwdBatch; ++u) en[u] = ent[e + u];
-#pragma unroll
-      for (int u = 0; u < kFwdBatch; ++u) x[u] = ldg4(at<IDX64>(alphaT, en[u].x, ldb, bb));
-#pragma unroll
-      for (int u = 0; u < kFwdBatch; ++u) fma4(accA, __int_as_float(en[u].y), x[u]);
-    }
-  }
-  RowOut<CONV> o;
-  o.r = accA;
-  o.s1 = acc1;
-  o.s2 = acc2;
-  return o;
-}
-
-// residual from LHS sum, load vector and convection, mirroring the reference's operation order:
-// precond branch  r = LHS - (F - c) ; else  r = LHS - (-F + c)
-// (FEONet_steady_Navier-Stokes/train_FEONet.py:324-330, :356)
-__device__ __forceinline__ float resid1(float lhs, float f, float c, bool precond) {
-  return precond ? __fsub_rn(lhs, __fsub_rn(f, c)) : __fsub_rn(lhs, __fadd_rn(-f, c));
-}
-// c = u_i*Bu1 + u_j*Bu2 as two rounded products and one rounded add (train_FEONet.py:317-322)
-__device__ __forceinline__ float conv1(float d1, float s1, float d2, float s2) {
-  return __fadd_rn(__fmul_rn(d1, s1), __fmul_rn(d2, s2));
-}
-
-template <bool CONV, bool IDX64>
-__global__ void __launch_bounds__(kThreads, 3) residual_fwd_kernel(FwdParams p) {
-  extern __shared__ int4 s_ent_raw[];
-  // 1-D grid, sample block fastest: CTAs that run together cover neighbouring 512-byte slices of the
-  // SAME dof rows (whole DRAM pages get consumed) and re-use the blob's operator entries from L2.
-  const int blob = blockIdx.x / p.nby, by = blockIdx.x - blob * p.nby;
-  const int u0 = p.blob_uptr[blob], u1 = p.blob_uptr[blob + 1];
-  const int sl_begin = p.unit_ptr[u0], sl_end = p.unit_ptr[u1];
-  const int e0 = p.fptr[sl_begin], e1 = p.fptr[sl_end];
-  {  // stage the blob's operator entries
-    if (CONV) {
-      const int4* src = reinterpret_cast<const int4*>(p.fent) + e0;
-      for (int i = threadIdx.x; i < e1 - e0; i += blockDim.x) s_ent_raw[i] = src[i];
-    } else {
-      const int2* src = reinterpret_cast<const int2*>(p.fent) + e0;
-      int2* dst = reinterpret_cast<int2*>(s_ent_raw);
-      for (int i = threadIdx.x; i < e1 - e0; i += blockDim.x) dst[i] = src[i];
-    }
-  }
-  __syncthreads();
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int b = by * kWarpSamples + lane * 4;
-  const int nvalid = min(4, p.B - b);  // <=0: lane idle (it still executes with bb = 0, masked out)
-  const int bb = nvalid > 0 ? b : 0;
-  const bool precond = p.precond_branch != 0;
-  float lsum = 0.f;
-
-  for (int u = u0 + warp; u < u1; u += nwarps) {
-    const int sl0 = p.unit_ptr[u];
-    const int cnt = p.unit_ptr[u + 1] - sl0;
-    float4 d1 = zero4(), d2 = zero4();
-    bool vel = false;
-    if (CONV) {
-      const int pi = p.slot_pi[sl0], pj = p.slot_pj[sl0];
-      vel = pi >= 0;
-      if (vel) {
-        d1 = ldg4(at<IDX64>(p.alphaT, pi, p.ldb, bb));
-        d2 = ldg4(at<IDX64>(p.alphaT, pj, p.ldb, bb));
-      }
-    }
-    float4 rI = zero4(), s1I = zero4(), s2I = zero4();
-#pragma unroll 1
-    for (int t = 0; t < cnt; ++t) {
-      const int row = p.slot_row[sl0 + t];
-      const int eb = p.fptr[sl0 + t] - e0, ee = p.fptr[sl0 + t + 1] - e0;
-      RowOut<CONV> o = fwd_row<CONV, IDX64>(s_ent_raw, eb, ee, p.alphaT, p.ldb, bb);
-      const float4 f = ldg4_stream(p.fT + (int64_t)row * p.ldb + bb);
-      float4 c = zero4();
-      if (CONV && vel) {
-        c.x = conv1(d1.x, o.s1.x, d2.x, o.s2.x);
-        c.y = conv1(d1.y, o.s1.y, d2.y, o.s2.y);
-        c.z = conv1(d1.z, o.s1.z, d2.z, o.s2.z);
-        c.w = conv1(d1.w, o.s1.w, d2.w, o.s2.w);
-      }
-      float4 r;
-      r.x = resid1(o.r.x, f.x, c.x, precond);
-      r.y = resid1(o.r.y, f.y, c.y, precond);
-      r.z = resid1(o.r.z, f.z, c.z, precond);
-      r.w = resid1(o.r.w, f.w, c.w, precond);
-      if (nvalid > 0) lsum = fmaf(r.x, r.x, lsum);
-      if (nvalid > 1) lsum = fmaf(r.y, r.y, lsum);
-      if (nvalid > 2) lsum = fmaf(r.z, r.z, lsum);
-      if (nvalid > 3) lsum = fmaf(r.w, r.w, lsum);
-      if (p.rT != nullptr && nvalid > 0) stg4(p.rT + (int64_t)row * p.ldb + b, r);
-      if (CONV && vel && p.eT != nullptr) {
-        if (t == 0) {
-          rI = r;
-          s1I = o.s1;
-          s2I = o.s2;
-        } else {
-          // E-term products: e[I] = Bu1[I] r[I] + Bu1[J] r[J], e[J] = Bu2[I] r[I] + Bu2[J] r[J]
-          float4 eI, eJ;
-          eI.x = fmaf(o.s1.x, r.x, s1I.x * rI.x);
-          eI.y = fmaf(o.s1.y, r.y, s1I.y * rI.y);
-          eI.z = fmaf(o.s1.z, r.z, s1I.z * rI.z);
-          eI.w = fmaf(o.s1.w, r.w, s1I.w * rI.w);
-          eJ.x = fmaf(o.s2.x, r.x, s2I.x * rI.x);
-          eJ.y = fmaf(o.s2.y, r.y, s2I.y * rI.y);
-          eJ.z = fmaf(o.s2.z, r.z, s2I.z * rI.z);
-          eJ.w = fmaf(o.s2.w, r.w, s2I.w * rI.w);
-          if (nvalid > 0) {
-            stg4(p.eT + (int64_t)p.slot_row[sl0] * p.ldb + b, eI);
-            stg4(p.eT + (int64_t)row * p.ldb + b, eJ);
-          }
-        }
-      }
-    }
-  }
-  block_partial(lsum, p.partials, blockIdx.x);
-}
-
-// ---------------------------------------------------------------------------------------------
-// fused residual backward (column-owned)
-// ---------------------------------------------------------------------------------------------
-struct BwdParams {
-  const int32_t *blob_uptr, *unit_ptr, *slot_row, *slot_pi, *bptrA, *bptrB;
-  const BwdEntryA* bentA;
-  const BwdEntryB* bentB;
-  const float *alphaT, *rT, *eT, *grad_loss;
-  float* gradT;
-  int64_t ldb;
-  int32_t B;
-  float esign;  // s = +1 precond branch, -1 otherwise
-  int32_t has_conv;
-  int32_t nby;
-};
-
-template <bool IDX64>
-__global__ void __launch_bounds__(kThreads, 4) residual_bwd_kernel(BwdParams p, int smemA_entries) {
-  extern __shared__ int4 s_raw[];
-  const int blob = blockIdx.x / p.nby, by = blockIdx.x - blob * p.nby;
-  const int u0 = p.blob_uptr[blob], u1 = p.blob_uptr[blob + 1];
-  const int sl_begin = p.unit_ptr[u0], sl_end = p.unit_ptr[u1];
-  const int a0 = p.bptrA[sl_begin], a1 = p.bptrA[sl_end];
-  const int b0 = p.bptrB[sl_begin], b1 = p.bptrB[sl_end];
-  // shared layout: [B entries: 2 int4 each][A entries: int2 each]
-  int4* sB = s_raw;
-  int2* sA = reinterpret_cast<int2*>(s_raw + 2 * (size_t)(b1 - b0));
-  {
-    const int4* srcB = reinterpret_cast<const int4*>(p.bentB + b0);
-    for (int i = threadIdx.x; i < 2 * (b1 - b0); i += blockDim.x) sB[i] = srcB[i];
-    const int2* srcA = reinterpret_cast<const int2*>(p.bentA + a0);
-    for (int i = threadIdx.x; i < a1 - a0; i += blockDim.x) sA[i] = srcA[i];
-  }
-  __syncthreads();
-  (void)smemA_entries;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int b = by * kWarpSamples + lane * 4;
-  const bool active = b < p.B;
-  const int bb = active ? b : 0;
-  const float g2 = 2.0f * (p.grad_loss != nullptr ? __ldg(p.grad_loss) : 1.0f);
-
-  for (int u = u0 + warp; u < u1; u += nwarps) {
-    const int sl0 = p.unit_ptr[u];
-    const int cnt = p.unit_ptr[u + 1] - sl0;
-#pragma unroll 1
-    for (int t = 0; t < cnt; ++t) {
-      const int sl = sl0 + t;
-      const int c = p.slot_row[sl];
-      float4 acc = zero4();
-      {
-        const int eb = p.bptrA[sl] - a0, ee = p.bptrA[sl + 1] - a0;
-#pragma unroll 1
-        for (int e = eb; e < ee; e += kBwdBatchA) {
-          int2 en[kBwdBatchA];
-          float4 rr[kBwdBatchA];
-#pragma unroll
-          for (int u = 0; u < kBwdBatchA; ++u) en[u] = sA[e + u];
-#pragma unroll
-          for (int u = 0; u < kBwdBatchA; ++u) rr[u] = ldg4(at<IDX64>(p.rT, en[u].x, p.ldb, bb));
-#pragma unroll
-          for (int u = 0; u < kBwdBatchA; ++u) fma4(acc, __int_as_float(en[u].y), rr[u]);
-        }
-      }
-      if (p.has_conv) {
-        const int eb = p.bptrB[sl] - b0, ee = p.bptrB[sl + 1] - b0;
-#pragma unroll 1
-        for (int e = eb; e < ee; e += kBwdBatchB) {
-          int4 i4[kBwdBatchB], f4[kBwdBatchB];
-          float4 rr[kBwdBatchB], d1[kBwdBatchB], d2[kBwdBatchB];
-#pragma unroll
-          for (int u = 0; u < kBwdBatchB; ++u) {
-            i4[u] = sB[2 * (e + u)];      // row, pi, pj
-            f4[u] = sB[2 * (e + u) + 1];  // a, s*b1, s*b2
-          }
-#pragma unroll
-          for (int u = 0; u < kBwdBatchB; ++u) {
-            rr[u] = ldg4(at<IDX64>(p.rT, i4[u].x, p.ldb, bb));
-            d1[u] = ldg4(at<IDX64>(p.alphaT, i4[u].y, p.ldb, bb));
-            d2[u] = ldg4(at<IDX64>(p.alphaT, i4[u].z, p.ldb, bb));
-          }
-#pragma unroll
-          for (int u = 0; u < kBwdBatchB; ++u) {
-            const float a = __int_as_float(f4[u].x), b1s = __int_as_float(f4[u].y), b2s = __int_as_float(f4[u].z);
-            acc.x = fmaf(fmaf(b2s, d2[u].x, fmaf(b1s, d1[u].x, a)), rr[u].x, acc.x);
-            acc.y = fmaf(fmaf(b2s, d2[u].y, fmaf(b1s, d1[u].y, a)), rr[u].y, acc.y);
-            acc.z = fmaf(fmaf(b2s, d2[u].z, fmaf(b1s, d1[u].z, a)), rr[u].z, acc.z);
-            acc.w = fmaf(fmaf(b2s, d2[u].w, fmaf(b1s, d1[u].w, a)), rr[u].w, acc.w);
-          }
-        }
-        if (p.slot_pi[sl] >= 0) {
-          const float4 ev = ldg4_stream(at<IDX64>(p.eT, c, p.ldb, bb));
-          fma4(acc, p.esign, ev);
-        }
-      }
-      acc.x *= g2;
-      acc.y *= g2;
-      acc.z *= g2;
-      acc.w *= g2;
-      if (active) stg4(p.gradT + (int64_t)c * p.ldb + b, acc);
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -522,16 +236,20 @@ int check_layout(const void* p, int64_t ld, int32_t B, const char* what) {
 
 }  // namespace
 
-size_t loss_partials_needed(int32_t n, int32_t n_blobs, int64_t cols) {
-  const int64_t by = (cols + kWarpSamples - 1) / kWarpSamples;
-  const int64_t rows_ctas = std::max<int64_t>(n_blobs, (n + 7) / 8);
-  return (size_t)(std::max<int64_t>(rows_ctas * by, 1024)) * sizeof(float);
+size_t loss_partials_needed(int32_t n, int32_t n_tiles, int64_t cols) {
+  // the fused forward writes one partial per (tile, 64-sample slab), the generic kernels one per (8 rows, 128 samples)
+  const int64_t fused = (int64_t)n_tiles * ((cols + kSlab - 1) / kSlab);
+  const int64_t generic = (int64_t)((n + 7) / 8) * ((cols + kWarpSamples - 1) / kWarpSamples);
+  return (size_t)(std::max<int64_t>(std::max(fused, generic), 1024)) * sizeof(float);
 }
 
-static int finalize(float* partials, int count, float scale, float* loss_out, cudaStream_t st) {
+int finalize_loss(float* partials, int count, float scale, float* loss_out, cudaStream_t st) {
   finalize_loss_kernel<<<1, 1024, 0, st>>>(partials, count, scale, loss_out);
   FEO_CUDA_CHECK(cudaGetLastError());
   return FEO_OK;
+}
+static int finalize(float* partials, int count, float scale, float* loss_out, cudaStream_t st) {
+  return finalize_loss(partials, count, scale, loss_out, st);
 }
 
 int launch_transpose(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int32_t rows, int32_t cols,
@@ -540,67 +258,6 @@ int launch_transpose(const float* src, int64_t src_ld, float* dst, int64_t dst_l
   if (src == nullptr || dst == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, "transpose: NULL pointer");
   dim3 grid((cols + 63) / 64, (rows + 63) / 64);
   transpose_kernel<<<grid, 256, 0, st>>>(src, src_ld, dst, dst_ld, rows, cols, dst_row_map);
-  FEO_CUDA_CHECK(cudaGetLastError());
-  return FEO_OK;
-}
-
-int launch_residual_fwd(const feo_operator* op, const float* alphaT, const float* fT, int64_t ldb, int32_t B,
-                        float* loss_out, float* rT, float* eT, void* ws, size_t ws_bytes, cudaStream_t st) {
-  if (B <= 0) return fail(FEO_ERR_INVALID_ARGUMENT, "B must be positive");
-  if (int rc = check_layout(alphaT, ldb, B, "alphaT")) return rc;
-  if (int rc = check_layout(fT, ldb, B, "fT")) return rc;
-  if (rT != nullptr)
-    if (int rc = check_layout(rT, ldb, B, "rT")) return rc;
-  if (op->has_conv && rT != nullptr && eT == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, "eT required with rT");
-  if (eT != nullptr)
-    if (int rc = check_layout(eT, ldb, B, "eT")) return rc;
-  if (loss_out == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, "loss_out is NULL");
-  const int by = (B + kWarpSamples - 1) / kWarpSamples;
-  const int count = op->n_blobs * by;
-  if (ws == nullptr || ws_bytes < (size_t)count * sizeof(float)) return fail(FEO_ERR_INVALID_ARGUMENT, "workspace too small");
-  FwdParams p{op->blob_uptr, op->unit_ptr, op->slot_row, op->slot_pi, op->slot_pj, op->fptr, op->fent,
-              alphaT,        fT,           rT,           op->has_conv ? eT : nullptr, (float*)ws, ldb, B, op->ns_branch, by};
-  dim3 grid((unsigned)((int64_t)op->n_blobs * by));
-  const bool idx64 = (int64_t)op->n * ldb >= ((int64_t)1 << 32);
-  const size_t smem = (size_t)op->max_blob_fent * (op->has_conv ? sizeof(FwdEntry) : sizeof(FwdEntryLin));
-#define FEO_LAUNCH_FWD(CONV, I64)                                                                                  \
-  do {                                                                                                             \
-    FEO_CUDA_CHECK(cudaFuncSetAttribute(residual_fwd_kernel<CONV, I64>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        (int)smem));                                                               \
-    residual_fwd_kernel<CONV, I64><<<grid, kThreads, smem, st>>>(p);                                               \
-  } while (0)
-  if (op->has_conv) {
-    if (idx64) FEO_LAUNCH_FWD(true, true); else FEO_LAUNCH_FWD(true, false);
-  } else {
-    if (idx64) FEO_LAUNCH_FWD(false, true); else FEO_LAUNCH_FWD(false, false);
-  }
-#undef FEO_LAUNCH_FWD
-  FEO_CUDA_CHECK(cudaGetLastError());
-  return finalize((float*)ws, count, 1.0f, loss_out, st);
-}
-
-int launch_residual_bwd(const feo_operator* op, const float* alphaT, const float* rT, const float* eT,
-                        const float* grad_loss, float* gradT, int64_t ldb, int32_t B, cudaStream_t st) {
-  if (B <= 0) return fail(FEO_ERR_INVALID_ARGUMENT, "B must be positive");
-  if (int rc = check_layout(rT, ldb, B, "rT")) return rc;
-  if (int rc = check_layout(gradT, ldb, B, "gradT")) return rc;
-  if (op->has_conv) {
-    if (int rc = check_layout(alphaT, ldb, B, "alphaT")) return rc;
-    if (int rc = check_layout(eT, ldb, B, "eT")) return rc;
-  }
-  BwdParams p{op->blob_uptr, op->unit_ptr, op->slot_row, op->slot_pi, op->bptrA, op->bptrB, op->bentA, op->bentB,
-              alphaT,        rT,           eT,           grad_loss,   gradT,     ldb,       B,
-              op->ns_branch ? 1.0f : -1.0f, op->has_conv ? 1 : 0, (B + kWarpSamples - 1) / kWarpSamples};
-  const int by = (B + kWarpSamples - 1) / kWarpSamples;
-  dim3 grid((unsigned)((int64_t)op->n_blobs * by));
-  size_t smem = (size_t)op->max_blob_bentB * sizeof(BwdEntryB) + (size_t)op->max_blob_bentA * sizeof(BwdEntryA) + 16;
-  if ((int64_t)op->n * ldb >= ((int64_t)1 << 32)) {
-    FEO_CUDA_CHECK(cudaFuncSetAttribute(residual_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    residual_bwd_kernel<true><<<grid, kThreads, smem, st>>>(p, op->max_blob_bentA);
-  } else {
-    FEO_CUDA_CHECK(cudaFuncSetAttribute(residual_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    residual_bwd_kernel<false><<<grid, kThreads, smem, st>>>(p, op->max_blob_bentA);
-  }
   FEO_CUDA_CHECK(cudaGetLastError());
   return FEO_OK;
 }

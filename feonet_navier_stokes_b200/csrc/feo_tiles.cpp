@@ -1,20 +1,37 @@
-// Host-side tile plan for the shared-memory-staged residual kernels (feo_tiled.cu).
+// Host-side tile plan of the fused residual kernels (feo_tiled.cu).  Pure host code; the CPU test
+// suite checks it through replay_tile_plan (feo_debug_tile_replay), which decodes the staging boxes
+// and the per-warp streams exactly as the kernels do.
 //
-// A tile = a compact set of operator rows (forward) / columns (backward) grown by BFS over the
-// union pattern, plus the list of dof "lines" it has to stage: in the dof-major layout one line is
-// the 64 consecutive samples of one dof (256 contiguous bytes), fetched with one bulk-async copy.
-// A warp owns a PAIR of rows -- a velocity pair (I[l], J[l]) or two single dofs -- one per
-// half-warp, and walks "steps": step k holds one entry for each half.  Entries of the two rows are
-// aligned by the unit (velocity pair / single dof) of their column so that lines needed by both
-// halves in the same step (pressure columns in the forward, alpha[I[k]], alpha[J[k]] in the
-// backward) are one shared-memory broadcast.  Pure host code; checked on CPU via the debug hooks.
+// A tile = a compact set of operator rows (forward) / columns (backward), grown by BFS over the union
+// pattern of A, B1, B2, plus the dof "lines" it has to stage in shared memory (one line = the 64
+// samples of one dof in the dof-major batch layout).  Lines are sorted by dof so that runs of
+// consecutive dofs become a handful of 2-D TMA boxes.  Nothing here assumes a mesh: I, J are opaque
+// index lists, the matrices arbitrary CSR (quirks 3, 10).
+//
+// forward : rows are sorted by length and grouped four by four into QUADS (one row per quarter-warp).
+// backward: columns are handled in PAIRS -- the velocity pair (I[k], J[k]) or two single dofs -- so
+//   that one gather of r[I[m]], r[J[m]], alpha[I[m]], alpha[J[m]] serves both columns; two pairs of
+//   similar length form a DUO (one pair per half-warp).  The backward recomputes Bu1, Bu2 of its own
+//   rows (the E-term of SURVEY.md Appendix A.2) from the alpha lines it gathers anyway, so the forward
+//   saves nothing but r.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <deque>
-#include <unordered_map>
+#include <map>
 
 #include "feo_internal.h"
 
 namespace feo {
+
+TileTuning tile_tuning_from_env(bool backward) {
+  TileTuning t;
+  if (const char* s = std::getenv(backward ? "FEO_TILE_LINES_BWD" : "FEO_TILE_LINES_FWD")) t.max_lines = atoi(s);
+  if (const char* s = std::getenv(backward ? "FEO_TILE_WARPS_BWD" : "FEO_TILE_WARPS_FWD")) t.warps = atoi(s);
+  t.max_lines = std::min(std::max(t.max_lines, 32), 800);
+  t.warps = std::min(std::max(t.warps, 1), 32);
+  return t;
+}
 
 namespace {
 
@@ -23,188 +40,366 @@ struct UEnt {
   float a, b1, b2;
 };
 
-struct Graph {
+struct Front {
   int32_t n = 0;
-  std::vector<int32_t> ptr;   // union rows
+  bool conv = false;
+  float sgn = 1.f;
+  std::vector<int32_t> pi, pj, kind, mate;   // per dof: partners, 0 none / 1 I-dof / 2 J-dof, the other dof of the pair
+  std::vector<int32_t> unit_of, unit_first;  // units: a velocity pair (I[k], J[k]) or a single dof
+  std::vector<int32_t> ptr;                  // union rows
   std::vector<UEnt> ent;
-  std::vector<int32_t> tptr;  // transposed union: for column c, source rows + index into ent
-  std::vector<int32_t> trow, tsrc;
-};
+  std::vector<int32_t> tptr, trow, tsrc;     // transposed union: per column the source rows + index into ent
+  int32_t max_row_nnz = 0;
 
-void build_graph(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, bool conv, Graph* g) {
-  const int32_t n = A.n;
-  g->n = n;
-  g->ptr.assign(n + 1, 0);
-  for (int32_t r = 0; r < n; ++r) {
-    int32_t i = A.rowptr[r], ie = A.rowptr[r + 1];
-    int32_t j = conv ? B1.rowptr[r] : 0, je = conv ? B1.rowptr[r + 1] : 0;
-    int32_t k = conv ? B2.rowptr[r] : 0, ke = conv ? B2.rowptr[r + 1] : 0;
-    while (i < ie || j < je || k < ke) {
-      int32_t ca = i < ie ? A.col[i] : INT32_MAX, c1 = j < je ? B1.col[j] : INT32_MAX,
-              c2 = k < ke ? B2.col[k] : INT32_MAX;
-      int32_t c = std::min(ca, std::min(c1, c2));
-      UEnt e{c, 0.f, 0.f, 0.f};
-      if (ca == c) e.a = A.val[i++];
-      if (c1 == c) e.b1 = B1.val[j++];
-      if (c2 == c) e.b2 = B2.val[k++];
-      g->ent.push_back(e);
-    }
-    g->ptr[r + 1] = (int32_t)g->ent.size();
-  }
-  g->tptr.assign(n + 1, 0);
-  for (const UEnt& e : g->ent) g->tptr[e.col + 1]++;
-  for (int32_t i = 0; i < n; ++i) g->tptr[i + 1] += g->tptr[i];
-  g->trow.resize(g->ent.size());
-  g->tsrc.resize(g->ent.size());
-  std::vector<int32_t> cur(g->tptr.begin(), g->tptr.end() - 1);
-  for (int32_t r = 0; r < n; ++r)
-    for (int32_t k = g->ptr[r]; k < g->ptr[r + 1]; ++k) {
-      int32_t p = cur[g->ent[k].col]++;
-      g->trow[p] = r;
-      g->tsrc[p] = k;
-    }
-}
-
-struct Units {
-  std::vector<int32_t> unit_of, first, mate;  // per dof unit id; per unit first dof; per dof partner (-1)
-  int32_t rows(int32_t u, const std::vector<int32_t>& kind, int32_t out[2]) const {
-    int32_t r = first[u];
-    out[0] = r;
+  int unit_rows(int32_t u, int32_t o[2]) const {
+    const int32_t r = unit_first[u];
+    o[0] = r;
     if (kind[r] == 1) {
-      out[1] = mate[r];
+      o[1] = mate[r];
       return 2;
     }
     return 1;
   }
+  // entry (h, c) takes part in the convective term: row h is a velocity row and B1 or B2 is stored there
+  bool is_conv(int32_t h, const UEnt& e) const { return conv && kind[h] != 0 && (e.b1 != 0.f || e.b2 != 0.f); }
 };
+
+int build_front(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int32_t n_u, const int32_t* idx_i,
+                const int32_t* idx_j, int32_t ns_branch, Front* out) {
+  Front& F = *out;
+  const int32_t n = A.n;
+  F.n = n;
+  if (B1.present() != B2.present()) return fail(FEO_ERR_INVALID_ARGUMENT, "B1 and B2 must be given together");
+  F.conv = B1.present() && B2.present() && n_u > 0;
+  if (F.conv && (idx_i == nullptr || idx_j == nullptr)) return fail(FEO_ERR_INVALID_ARGUMENT, "convection needs idx_i/idx_j");
+  F.sgn = ns_branch ? 1.0f : -1.0f;
+  F.pi.assign(n, -1);
+  F.pj.assign(n, -1);
+  F.kind.assign(n, 0);
+  F.mate.assign(n, -1);
+  if (F.conv)
+    for (int32_t k = 0; k < n_u; ++k) {
+      const int32_t i = idx_i[k], j = idx_j[k];
+      if (i < 0 || i >= n || j < 0 || j >= n) return fail(FEO_ERR_INVALID_ARGUMENT, "idx_sol entry out of range");
+      if (i == j || F.kind[i] != 0 || F.kind[j] != 0)
+        return fail(FEO_ERR_UNSUPPORTED, "idx_sol[0]/idx_sol[1] must be duplicate-free and disjoint");
+      F.kind[i] = 1;
+      F.kind[j] = 2;
+      F.pi[i] = F.pi[j] = i;
+      F.pj[i] = F.pj[j] = j;
+      F.mate[i] = j;
+      F.mate[j] = i;
+    }
+  F.unit_of.assign(n, -1);
+  for (int32_t r = 0; r < n; ++r) {
+    if (F.unit_of[r] >= 0) continue;
+    const int32_t u = (int32_t)F.unit_first.size();
+    if (F.kind[r] == 0) {
+      F.unit_first.push_back(r);
+      F.unit_of[r] = u;
+    } else {
+      F.unit_first.push_back(F.pi[r]);
+      F.unit_of[F.pi[r]] = F.unit_of[F.pj[r]] = u;
+    }
+  }
+  // union pattern (rows sorted by column) and its transpose
+  F.ptr.assign(n + 1, 0);
+  for (int32_t r = 0; r < n; ++r) {
+    int32_t i = A.rowptr[r], ie = A.rowptr[r + 1];
+    int32_t j = F.conv ? B1.rowptr[r] : 0, je = F.conv ? B1.rowptr[r + 1] : 0;
+    int32_t k = F.conv ? B2.rowptr[r] : 0, ke = F.conv ? B2.rowptr[r + 1] : 0;
+    while (i < ie || j < je || k < ke) {
+      const int32_t ca = i < ie ? A.col[i] : INT32_MAX, c1 = j < je ? B1.col[j] : INT32_MAX, c2 = k < ke ? B2.col[k] : INT32_MAX;
+      const int32_t c = std::min(ca, std::min(c1, c2));
+      UEnt e{c, 0.f, 0.f, 0.f};
+      if (ca == c) e.a = A.val[i++];
+      if (c1 == c) e.b1 = B1.val[j++];
+      if (c2 == c) e.b2 = B2.val[k++];
+      F.ent.push_back(e);
+    }
+    F.ptr[r + 1] = (int32_t)F.ent.size();
+    F.max_row_nnz = std::max(F.max_row_nnz, F.ptr[r + 1] - F.ptr[r]);
+  }
+  F.tptr.assign(n + 1, 0);
+  for (const UEnt& e : F.ent) F.tptr[e.col + 1]++;
+  for (int32_t c = 0; c < n; ++c) F.tptr[c + 1] += F.tptr[c];
+  F.trow.resize(F.ent.size());
+  F.tsrc.resize(F.ent.size());
+  std::vector<int32_t> cur(F.tptr.begin(), F.tptr.end() - 1);
+  for (int32_t r = 0; r < n; ++r)
+    for (int32_t k = F.ptr[r]; k < F.ptr[r + 1]; ++k) {
+      const int32_t p = cur[F.ent[k].col]++;
+      F.trow[p] = r;
+      F.tsrc[p] = k;
+    }
+  return FEO_OK;
+}
+
+// ---- backward pair description -------------------------------------------------------------------
+struct VStep {
+  int32_t hI, hJ;    // source rows feeding column cI / cJ (-1: none)
+  int32_t kpi, kpj;  // dofs whose alpha lines are d1, d2
+  float aI, b1I, b2I, aJ, b1J, b2J, f1I, f2I, f1J, f2J;
+};
+struct AStep {
+  int32_t hI, hJ;
+  float aI, aJ;
+};
+struct XStep {
+  int32_t x;
+  float c1I, c2I, c1J, c2J;
+};
+struct PairItem {
+  int32_t cI = -1, cJ = -1;
+  bool vel = false;
+  std::vector<VStep> v;
+  std::vector<AStep> a;
+  std::vector<XStep> x;
+  int64_t cost() const { return 22 * (int64_t)v.size() + 10 * (int64_t)a.size() + 8 * (int64_t)x.size() + 20; }
+};
+
+struct TEnt {
+  int32_t h;
+  float a, b1s, b2s;
+};
+struct FEnt {
+  int32_t x;
+  float b1, b2;
+  bool used;
+};
+
+void build_pair(const Front& F, int32_t cI, int32_t cJ, PairItem* out, int64_t* real_entries) {
+  PairItem& P = *out;
+  P.cI = cI;
+  P.cJ = cJ;
+  P.vel = F.kind[cI] != 0;
+  const int32_t cols[2] = {cI, cJ};
+  std::vector<TEnt> conv[2], plain[2];
+  std::vector<FEnt> fwd[2];
+  for (int s = 0; s < 2; ++s) {
+    const int32_t c = cols[s];
+    if (c < 0) continue;
+    for (int32_t p = F.tptr[c]; p < F.tptr[c + 1]; ++p) {
+      const UEnt& e = F.ent[F.tsrc[p]];
+      const int32_t h = F.trow[p];
+      if (F.is_conv(h, e))
+        conv[s].push_back(TEnt{h, e.a, F.sgn * e.b1, F.sgn * e.b2});
+      else if (e.a != 0.f)
+        plain[s].push_back(TEnt{h, e.a, 0.f, 0.f});
+      else
+        continue;  // B1/B2 stored on a non-velocity row: no effect on the residual
+      ++*real_entries;
+    }
+    if (F.kind[c] != 0)
+      for (int32_t k = F.ptr[c]; k < F.ptr[c + 1]; ++k)
+        if (F.is_conv(c, F.ent[k])) fwd[s].push_back(FEnt{F.ent[k].col, F.ent[k].b1, F.ent[k].b2, false});
+  }
+  // convective entries: those of cI and cJ whose source rows share (pi, pj) ride in one V-step
+  std::map<std::pair<int32_t, int32_t>, std::pair<std::vector<int32_t>, std::vector<int32_t>>> groups;
+  for (int s = 0; s < 2; ++s)
+    for (int32_t t = 0; t < (int32_t)conv[s].size(); ++t) {
+      const int32_t h = conv[s][t].h;
+      auto& g = groups[{F.pi[h], F.pj[h]}];
+      (s == 0 ? g.first : g.second).push_back(t);
+    }
+  auto take = [](std::vector<FEnt>& list, int32_t x, float* b1, float* b2) {
+    for (FEnt& f : list)
+      if (!f.used && f.x == x) {
+        *b1 = f.b1;
+        *b2 = f.b2;
+        f.used = true;
+        return;
+      }
+  };
+  for (auto& kv : groups) {
+    const size_t m = std::max(kv.second.first.size(), kv.second.second.size());
+    for (size_t t = 0; t < m; ++t) {
+      VStep s{-1, -1, kv.first.first, kv.first.second, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (t < kv.second.first.size()) {
+        const TEnt& e = conv[0][kv.second.first[t]];
+        s.hI = e.h;
+        s.aI = e.a;
+        s.b1I = e.b1s;
+        s.b2I = e.b2s;
+      }
+      if (t < kv.second.second.size()) {
+        const TEnt& e = conv[1][kv.second.second[t]];
+        s.hJ = e.h;
+        s.aJ = e.a;
+        s.b1J = e.b1s;
+        s.b2J = e.b2s;
+      }
+      if (P.vel) {
+        take(fwd[0], s.kpi, &s.f1I, &s.f2I);
+        take(fwd[1], s.kpj, &s.f1J, &s.f2J);
+      }
+      P.v.push_back(s);
+    }
+  }
+  // forward entries of the own rows that no V-step gathers: extra steps
+  if (P.vel) {
+    std::map<int32_t, XStep> extra;
+    for (int s = 0; s < 2; ++s)
+      for (const FEnt& f : fwd[s])
+        if (!f.used) {
+          XStep& x = extra.emplace(f.x, XStep{f.x, 0.f, 0.f, 0.f, 0.f}).first->second;
+          if (s == 0) {
+            x.c1I += f.b1;
+            x.c2I += f.b2;
+          } else {
+            x.c1J += f.b1;
+            x.c2J += f.b2;
+          }
+        }
+    for (auto& kv : extra) P.x.push_back(kv.second);
+  }
+  // plain entries: a source row feeding both columns is one step; the rest are zipped
+  {
+    auto by_h = [](const TEnt& x, const TEnt& y) { return x.h < y.h; };
+    std::stable_sort(plain[0].begin(), plain[0].end(), by_h);
+    std::stable_sort(plain[1].begin(), plain[1].end(), by_h);
+    std::vector<TEnt> restI, restJ;
+    size_t i = 0, j = 0;
+    while (i < plain[0].size() || j < plain[1].size()) {
+      const bool hi = i < plain[0].size(), hj = j < plain[1].size();
+      if (hi && hj && plain[0][i].h == plain[1][j].h) {
+        P.a.push_back(AStep{plain[0][i].h, plain[1][j].h, plain[0][i].a, plain[1][j].a});
+        ++i;
+        ++j;
+      } else if (hi && (!hj || plain[0][i].h < plain[1][j].h)) {
+        restI.push_back(plain[0][i++]);
+      } else {
+        restJ.push_back(plain[1][j++]);
+      }
+    }
+    const size_t m = std::max(restI.size(), restJ.size());
+    for (size_t t = 0; t < m; ++t) {
+      AStep s{-1, -1, 0.f, 0.f};
+      if (t < restI.size()) {
+        s.hI = restI[t].h;
+        s.aI = restI[t].a;
+      }
+      if (t < restJ.size()) {
+        s.hJ = restJ[t].h;
+        s.aJ = restJ[t].a;
+      }
+      P.a.push_back(s);
+    }
+  }
+}
+
+Word16 mk(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return Word16{{a, b, c, d}}; }
 
 }  // namespace
 
 int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int32_t n_u, const int32_t* idx_i,
-                    const int32_t* idx_j, int32_t ns_branch, bool backward, int32_t max_lines, int32_t max_pairs,
-                    TilePlan* out) {
-  const int32_t n = A.n;
+                    const int32_t* idx_j, int32_t ns_branch, bool backward, const TileTuning& tune, TilePlan* out) {
+  Front F;
+  if (int rc = build_front(A, B1, B2, n_u, idx_i, idx_j, ns_branch, &F)) return rc;
+  const int32_t n = F.n;
+  const int32_t W = tune.warps;
   TilePlan& T = *out;
   T = TilePlan();
   T.backward = backward;
-  const bool conv = B1.present() && B2.present() && n_u > 0;
-  T.has_conv = conv;
-  std::vector<int32_t> pi(n, -1), pj(n, -1), kind(n, 0);
-  Units U;
-  U.mate.assign(n, -1);
-  if (conv)
-    for (int32_t k = 0; k < n_u; ++k) {
-      int32_t i = idx_i[k], j = idx_j[k];
-      if (i < 0 || i >= n || j < 0 || j >= n) return fail(FEO_ERR_INVALID_ARGUMENT, "idx_sol entry out of range");
-      if (i == j || kind[i] != 0 || kind[j] != 0)
-        return fail(FEO_ERR_UNSUPPORTED, "idx_sol[0]/idx_sol[1] must be duplicate-free and disjoint");
-      kind[i] = 1;
-      kind[j] = 2;
-      pi[i] = pi[j] = i;
-      pj[i] = pj[j] = j;
-      U.mate[i] = j;
-      U.mate[j] = i;
-    }
-  U.unit_of.assign(n, -1);
-  for (int32_t r = 0; r < n; ++r) {
-    if (U.unit_of[r] >= 0) continue;
-    int32_t u = (int32_t)U.first.size();
-    if (kind[r] == 0) {
-      U.first.push_back(r);
-      U.unit_of[r] = u;
-    } else {
-      U.first.push_back(pi[r]);
-      U.unit_of[pi[r]] = U.unit_of[pj[r]] = u;
-    }
-  }
-  const int32_t n_units = (int32_t)U.first.size();
-  Graph G;
-  build_graph(A, B1, B2, conv, &G);
-  const float sgn = ns_branch ? 1.0f : -1.0f;
+  T.has_conv = F.conv;
+  T.n = n;
+  T.warps = W;
+  const int32_t n_units = (int32_t)F.unit_first.size();
 
-  // lines a dof row/column needs: forward = union columns (+ its partners); backward = source rows of
-  // the transposed pattern as r-lines (tag 0) and, for convective entries, alpha[pi], alpha[pj] (tag 1)
-  auto is_conv_entry = [&](int32_t h, const UEnt& e) { return conv && kind[h] != 0 && (e.b1 != 0.f || e.b2 != 0.f); };
+  // lines a row (forward) / column (backward) needs.  key = dof (forward) or src * n + dof (backward;
+  // src 0 = r, 1 = alpha): sorting by key sorts by (src, dof)
   auto for_each_line = [&](int32_t d, auto&& fn) {
     if (!backward) {
-      for (int32_t k = G.ptr[d]; k < G.ptr[d + 1]; ++k) fn(2 * (int64_t)G.ent[k].col);
-      if (kind[d] != 0) {
-        fn(2 * (int64_t)pi[d]);
-        fn(2 * (int64_t)pj[d]);
+      for (int32_t k = F.ptr[d]; k < F.ptr[d + 1]; ++k) fn((int64_t)F.ent[k].col);
+      if (F.kind[d] != 0) {
+        fn((int64_t)F.pi[d]);
+        fn((int64_t)F.pj[d]);
       }
     } else {
-      for (int32_t p = G.tptr[d]; p < G.tptr[d + 1]; ++p) {
-        int32_t h = G.trow[p];
-        const UEnt& e = G.ent[G.tsrc[p]];
-        bool cv = is_conv_entry(h, e);
+      for (int32_t p = F.tptr[d]; p < F.tptr[d + 1]; ++p) {
+        const int32_t h = F.trow[p];
+        const UEnt& e = F.ent[F.tsrc[p]];
+        const bool cv = F.is_conv(h, e);
         if (!cv && e.a == 0.f) continue;
-        fn(2 * (int64_t)h);
+        fn((int64_t)h);
         if (cv) {
-          fn(2 * (int64_t)pi[h] + 1);
-          fn(2 * (int64_t)pj[h] + 1);
+          fn((int64_t)n + F.pi[h]);
+          fn((int64_t)n + F.pj[h]);
         }
+      }
+      if (F.kind[d] != 0) {  // E-term: the residual lines of the own pair and the alpha lines of the row's B entries
+        fn((int64_t)F.pi[d]);
+        fn((int64_t)F.pj[d]);
+        for (int32_t k = F.ptr[d]; k < F.ptr[d + 1]; ++k)
+          if (F.is_conv(d, F.ent[k])) fn((int64_t)n + F.ent[k].col);
       }
     }
   };
 
-  // ---- grow tiles ------------------------------------------------------------------------------
+  // ---- grow tiles --------------------------------------------------------------------------------
   std::vector<char> seen(n_units, 0);
-  std::vector<int32_t> stamp(2 * (size_t)n, -1);
+  std::vector<int32_t> stamp((backward ? 2 : 1) * (size_t)n, -1);
   std::deque<int32_t> frontier, q;
   int32_t next_unseen = 0, placed = 0;
   std::vector<std::vector<int32_t>> tile_units;
+  std::vector<int64_t> fresh;
   while (placed < n_units) {
     const int32_t tid = (int32_t)tile_units.size();
     tile_units.emplace_back();
-    int32_t lines = 0, rows_in = 0;
+    int32_t lines = 0;
     q.clear();
     while (true) {
       if (q.empty()) {
         int32_t seed = -1;
-        while (!frontier.empty() && seed < 0) {
-          int32_t c = frontier.front();
-          frontier.pop_front();
-          if (!seen[c]) seed = c;
+        if (tile_units.back().empty()) {
+          while (!frontier.empty() && seed < 0) {
+            const int32_t u = frontier.front();
+            frontier.pop_front();
+            if (!seen[u]) seed = u;
+          }
         }
-        if (seed < 0) {
+        if (seed < 0 && tile_units.back().empty()) {
           while (next_unseen < n_units && seen[next_unseen]) ++next_unseen;
-          if (next_unseen >= n_units) break;
-          seed = next_unseen;
+          if (next_unseen < n_units) seed = next_unseen;
         }
+        if (seed < 0) break;
         seen[seed] = 1;
         q.push_back(seed);
       }
-      int32_t u = q.front();
+      const int32_t u = q.front();
       int32_t rr[2];
-      int32_t nr = U.rows(u, kind, rr);
-      int32_t add = 0;
+      const int32_t nr = F.unit_rows(u, rr);
+      fresh.clear();
       for (int32_t t = 0; t < nr; ++t)
         for_each_line(rr[t], [&](int64_t key) {
           if (stamp[key] != tid) {
             stamp[key] = tid;
-            ++add;
+            fresh.push_back(key);
           }
         });
-      // (stamps of a unit that does not fit are harmless: the tile is closed and the next tile has a new id)
-      if (rows_in > 0 && (lines + add > max_lines || rows_in + nr > 2 * max_pairs)) break;
-      if (add > max_lines) return fail(FEO_ERR_UNSUPPORTED, "a row needs more dof lines than a tile can stage; use the dense path");
+      const int32_t add = (int32_t)fresh.size();
+      if (!tile_units.back().empty() && lines + add > tune.max_lines) {
+        for (int64_t key : fresh) stamp[key] = -1;  // not staged after all
+        break;
+      }
+      if (add > tune.max_lines)
+        return fail(FEO_ERR_UNSUPPORTED, "a row needs more dof lines than a tile can stage; use the dense operator path");
       q.pop_front();
       tile_units.back().push_back(u);
       ++placed;
       lines += add;
-      rows_in += nr;
       for (int32_t t = 0; t < nr; ++t) {
         if (!backward) {
-          for (int32_t k = G.ptr[rr[t]]; k < G.ptr[rr[t] + 1]; ++k) {
-            int32_t v = U.unit_of[G.ent[k].col];
+          for (int32_t k = F.ptr[rr[t]]; k < F.ptr[rr[t] + 1]; ++k) {
+            const int32_t v = F.unit_of[F.ent[k].col];
             if (!seen[v]) {
               seen[v] = 1;
               q.push_back(v);
             }
           }
         } else {
-          for (int32_t p = G.tptr[rr[t]]; p < G.tptr[rr[t] + 1]; ++p) {
-            int32_t v = U.unit_of[G.trow[p]];
+          for (int32_t p = F.tptr[rr[t]]; p < F.tptr[rr[t] + 1]; ++p) {
+            const int32_t v = F.unit_of[F.trow[p]];
             if (!seen[v]) {
               seen[v] = 1;
               q.push_back(v);
@@ -213,154 +408,307 @@ int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int3
         }
       }
     }
-    for (int32_t v : q) {
-      seen[v] = 0;
-      frontier.push_back(v);
+    // whatever is still queued seeds the following tiles (keeps consecutive tiles adjacent)
+    for (int32_t u : q) {
+      seen[u] = 0;
+      frontier.push_back(u);
     }
     if (tile_units.back().empty()) tile_units.pop_back();
   }
 
-  // ---- emit tiles ------------------------------------------------------------------------------
-  T.tile_line_ptr.assign(1, 0);
-  T.tile_pair_ptr.assign(1, 0);
-  T.pair_step_ptr.assign(1, 0);
-  T.pair_stepA_ptr.assign(1, 0);
-  std::unordered_map<int64_t, int32_t> lmap;
+  // ---- emit tiles --------------------------------------------------------------------------------
+  T.tile_box_ptr.assign(1, 0);
   std::vector<int64_t> keys;
   for (const auto& units : tile_units) {
-    // 1. the tile's lines, sorted by (array, dof) so the bulk copies walk memory in address order
+    // 1. the tile's lines, sorted by (src, dof); runs of consecutive dofs become TMA boxes
     keys.clear();
-    lmap.clear();
     for (int32_t u : units) {
       int32_t rr[2];
-      int32_t nr = U.rows(u, kind, rr);
-      for (int32_t t = 0; t < nr; ++t) for_each_line(rr[t], [&](int64_t key) { if (lmap.emplace(key, 0).second) keys.push_back(key); });
+      const int32_t nr = F.unit_rows(u, rr);
+      for (int32_t t = 0; t < nr; ++t) for_each_line(rr[t], [&](int64_t key) { keys.push_back(key); });
     }
-    std::sort(keys.begin(), keys.end(), [](int64_t x, int64_t y) { return (x & 1) != (y & 1) ? (x & 1) < (y & 1) : x < y; });
-    for (size_t i = 0; i < keys.size(); ++i) {
-      lmap[keys[i]] = (int32_t)i;
-      T.line_dof.push_back((int32_t)(keys[i] >> 1));
-      T.line_src.push_back((int32_t)(keys[i] & 1));
-    }
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    if (keys.size() > 65535) return fail(FEO_ERR_UNSUPPORTED, "tile stages too many lines");
     T.max_lines = std::max<int32_t>(T.max_lines, (int32_t)keys.size());
-    T.tile_line_ptr.push_back((int32_t)T.line_dof.size());
-    auto L = [&](int32_t dof, int32_t tag) { return lmap.at(2 * (int64_t)dof + tag); };
-
-    // 2. pairs: velocity pairs as they are, single dofs two by two
-    std::vector<std::pair<int32_t, int32_t>> pairs;
-    int32_t pending = -1;
-    for (int32_t u : units) {
-      int32_t rr[2];
-      if (U.rows(u, kind, rr) == 2) {
-        pairs.emplace_back(rr[0], rr[1]);
-      } else if (pending < 0) {
-        pending = rr[0];
-      } else {
-        pairs.emplace_back(pending, rr[0]);
-        pending = -1;
-      }
-    }
-    if (pending >= 0) pairs.emplace_back(pending, -1);
-
-    // 3. steps
-    struct Item {
-      int32_t unit, dof;  // unit + dof of the "other side" (column in fwd, source row in bwd)
-      UEnt e;
-    };
-    for (auto [da, db] : pairs) {
-      T.pair_a.push_back(da);
-      T.pair_b.push_back(db);
-      const bool vel = kind[da] != 0;
-      T.pair_li.push_back(vel && !backward ? L(pi[da], 0) : -1);
-      T.pair_lj.push_back(vel && !backward ? L(pj[da], 0) : -1);
-      T.pair_vel.push_back(vel ? 1 : 0);
-      std::vector<Item> it[2];
-      const int32_t dofs[2] = {da, db};
-      for (int h = 0; h < 2; ++h) {
-        int32_t d = dofs[h];
-        if (d < 0) continue;
-        if (!backward) {
-          for (int32_t k = G.ptr[d]; k < G.ptr[d + 1]; ++k) it[h].push_back(Item{U.unit_of[G.ent[k].col], G.ent[k].col, G.ent[k]});
-        } else {
-          for (int32_t p = G.tptr[d]; p < G.tptr[d + 1]; ++p) {
-            const UEnt& e = G.ent[G.tsrc[p]];
-            int32_t hrow = G.trow[p];
-            if (!is_conv_entry(hrow, e) && e.a == 0.f) continue;
-            it[h].push_back(Item{U.unit_of[hrow], hrow, e});
-          }
+    T.tile_lines.push_back((int32_t)keys.size());
+    T.total_lines += (int64_t)keys.size();
+    for (size_t i = 0; i < keys.size();) {
+      size_t j = i + 1;
+      while (j < keys.size() && keys[j] == keys[j - 1] + 1 && (keys[j] >= n) == (keys[i] >= n)) ++j;
+      size_t len = j - i, pos = i;
+      for (int cls = 0; cls < 3; ++cls)
+        while (len >= (size_t)kBoxRows[cls]) {
+          const int64_t key = keys[pos];
+          T.boxes.push_back(StageBox{(int32_t)(key >= n ? key - n : key), (uint16_t)pos, (uint8_t)cls, (uint8_t)(key >= n ? 1 : 0)});
+          pos += kBoxRows[cls];
+          len -= kBoxRows[cls];
         }
-        std::stable_sort(it[h].begin(), it[h].end(), [](const Item& x, const Item& y) { return x.unit != y.unit ? x.unit < y.unit : x.dof < y.dof; });
+      i = j;
+    }
+    T.tile_box_ptr.push_back((int32_t)T.boxes.size());
+    auto LINE = [&](int32_t dof, int32_t src) -> uint32_t {
+      const int64_t key = (int64_t)src * n + dof;
+      return (uint32_t)(std::lower_bound(keys.begin(), keys.end(), key) - keys.begin());
+    };
+
+    // 2. work items and their streams, one list of words per item
+    std::vector<std::vector<Word16>> item_words;
+    std::vector<int64_t> item_cost;
+    if (!backward) {
+      std::vector<int32_t> rows;
+      for (int32_t u : units) {
+        int32_t rr[2];
+        const int32_t nr = F.unit_rows(u, rr);
+        for (int32_t t = 0; t < nr; ++t) rows.push_back(rr[t]);
       }
-      // merge by unit; in the backward, convective (3-gather) entries and plain entries go to separate lists
-      for (int pass = 0; pass < (backward ? 2 : 1); ++pass) {
-        size_t ia = 0, ib = 0;
-        int32_t nsteps = 0;
-        auto want = [&](const Item& x) { return !backward || (pass == 0) == is_conv_entry(x.dof, x.e); };
-        auto emit = [&](const Item* xa, const Item* xb) {
-          const Item* xs[2] = {xa, xb};
-          for (int h = 0; h < 2; ++h) {
-            const Item* x = xs[h] ? xs[h] : xs[1 - h];  // padding half re-reads the other half's line(s): a broadcast
-            const bool real = xs[h] != nullptr;
-            if (!backward) {
-              T.steps_f.push_back(FwdEntry{L(x->dof, 0), real ? x->e.a : 0.f, real ? x->e.b1 : 0.f, real ? x->e.b2 : 0.f});
-            } else if (pass == 0) {
-              T.steps_b.push_back(BwdEntryB{L(x->dof, 0), L(pi[x->dof], 1), L(pj[x->dof], 1), 0, real ? x->e.a : 0.f,
-                                            real ? sgn * x->e.b1 : 0.f, real ? sgn * x->e.b2 : 0.f, 0.f});
+      std::stable_sort(rows.begin(), rows.end(), [&](int32_t x, int32_t y) { return F.ptr[x + 1] - F.ptr[x] > F.ptr[y + 1] - F.ptr[y]; });
+      for (size_t g = 0; g < rows.size(); g += 4) {
+        int32_t r4[4], n_steps = 0;
+        for (int qd = 0; qd < 4; ++qd) {
+          r4[qd] = g + qd < rows.size() ? rows[g + qd] : -1;
+          if (r4[qd] >= 0) n_steps = std::max(n_steps, F.ptr[r4[qd] + 1] - F.ptr[r4[qd]]);
+        }
+        n_steps = (n_steps + 1) / 2 * 2;  // the kernel consumes steps two by two
+        std::vector<Word16> w;
+        for (int qd = 0; qd < 4; ++qd) {
+          const int32_t r = r4[qd];
+          const bool vel = r >= 0 && F.kind[r] != 0;
+          const uint32_t offs = vel ? (LINE(F.pi[r], 0) | (LINE(F.pj[r], 0) << 16)) : 0u;
+          w.push_back(mk((uint32_t)r, (uint32_t)n_steps, offs, vel ? 1u : 0u));
+        }
+        for (int32_t s = 0; s < n_steps; ++s)
+          for (int qd = 0; qd < 4; ++qd) {
+            const int32_t r = r4[qd];
+            if (r >= 0 && F.ptr[r] + s < F.ptr[r + 1]) {
+              const UEnt& e = F.ent[F.ptr[r] + s];
+              w.push_back(mk(LINE(e.col, 0) * kLineBytes, f2u(e.a), f2u(e.b1), f2u(e.b2)));
+              ++T.real_entries;
             } else {
-              T.steps_a.push_back(BwdEntryA{L(x->dof, 0), real ? x->e.a : 0.f});
+              w.push_back(mk(0u, 0u, 0u, 0u));  // padding: line 0 of the tile with zero coefficients
+            }
+            ++T.slot_entries;
+          }
+        item_cost.push_back(10 * (int64_t)n_steps + 12);
+        item_words.push_back(std::move(w));
+      }
+    } else {
+      std::vector<PairItem> pairs;
+      int32_t pending = -1;
+      for (int32_t u : units) {
+        int32_t rr[2];
+        if (F.unit_rows(u, rr) == 2) {
+          pairs.emplace_back();
+          build_pair(F, rr[0], rr[1], &pairs.back(), &T.real_entries);
+        } else if (pending < 0) {
+          pending = rr[0];
+        } else {
+          pairs.emplace_back();
+          build_pair(F, pending, rr[0], &pairs.back(), &T.real_entries);
+          pending = -1;
+        }
+      }
+      if (pending >= 0) {
+        pairs.emplace_back();
+        build_pair(F, pending, -1, &pairs.back(), &T.real_entries);
+      }
+      std::stable_sort(pairs.begin(), pairs.end(), [](const PairItem& x, const PairItem& y) {
+        if (x.v.size() != y.v.size()) return x.v.size() > y.v.size();
+        if (x.a.size() != y.a.size()) return x.a.size() > y.a.size();
+        return x.x.size() > y.x.size();
+      });
+      const PairItem idle;
+      for (size_t g = 0; g < pairs.size(); g += 2) {
+        const PairItem* pp[2] = {&pairs[g], g + 1 < pairs.size() ? &pairs[g + 1] : &idle};
+        const uint32_t nV = (uint32_t)std::max(pp[0]->v.size(), pp[1]->v.size());
+        const uint32_t nA = (uint32_t)std::max(pp[0]->a.size(), pp[1]->a.size());
+        const uint32_t nX = (uint32_t)std::max(pp[0]->x.size(), pp[1]->x.size());
+        std::vector<Word16> w;
+        for (int h = 0; h < 2; ++h) w.push_back(mk((uint32_t)pp[h]->cI, (uint32_t)pp[h]->cJ, nV, nA));
+        for (int h = 0; h < 2; ++h) {
+          const PairItem& P = *pp[h];
+          const uint32_t own = P.vel ? (LINE(P.cI, 0) | (LINE(P.cJ, 0) << 16)) : 0u;
+          w.push_back(mk(nX, own, P.vel ? 1u : 0u, 0u));
+        }
+        for (uint32_t s = 0; s < nV; ++s) {
+          Word16 ws[2][3];
+          for (int h = 0; h < 2; ++h) {
+            ws[h][0] = ws[h][1] = ws[h][2] = mk(0u, 0u, 0u, 0u);
+            if (s < pp[h]->v.size()) {
+              const VStep& v = pp[h]->v[s];
+              const uint32_t lrI = LINE(v.hI >= 0 ? v.hI : v.hJ, 0), lrJ = LINE(v.hJ >= 0 ? v.hJ : v.hI, 0);
+              ws[h][0] = mk(lrI | (lrJ << 16), LINE(v.kpi, 1) | (LINE(v.kpj, 1) << 16), f2u(v.aI), f2u(v.b1I));
+              ws[h][1] = mk(f2u(v.b2I), f2u(v.aJ), f2u(v.b1J), f2u(v.b2J));
+              ws[h][2] = mk(f2u(v.f1I), f2u(v.f2I), f2u(v.f1J), f2u(v.f2J));
+            }
+            T.slot_entries += 2;
+          }
+          for (int k = 0; k < 3; ++k)
+            for (int h = 0; h < 2; ++h) w.push_back(ws[h][k]);
+        }
+        for (uint32_t s = 0; s < nA; ++s)
+          for (int h = 0; h < 2; ++h) {
+            Word16 x = mk(0u, 0u, 0u, 0u);
+            if (s < pp[h]->a.size()) {
+              const AStep& a = pp[h]->a[s];
+              const uint32_t lrI = LINE(a.hI >= 0 ? a.hI : a.hJ, 0), lrJ = LINE(a.hJ >= 0 ? a.hJ : a.hI, 0);
+              x = mk(lrI | (lrJ << 16), f2u(a.aI), f2u(a.aJ), 0u);
+            }
+            T.slot_entries += 2;
+            w.push_back(x);
+          }
+        for (uint32_t s = 0; s < nX; ++s) {
+          Word16 ws[2][2];
+          for (int h = 0; h < 2; ++h) {
+            ws[h][0] = ws[h][1] = mk(0u, 0u, 0u, 0u);
+            if (s < pp[h]->x.size()) {
+              const XStep& x = pp[h]->x[s];
+              ws[h][0] = mk(LINE(x.x, 1), f2u(x.c1I), f2u(x.c2I), f2u(x.c1J));
+              ws[h][1] = mk(f2u(x.c2J), 0u, 0u, 0u);
             }
           }
-          ++nsteps;
-        };
-        while (true) {
-          while (ia < it[0].size() && !want(it[0][ia])) ++ia;
-          while (ib < it[1].size() && !want(it[1][ib])) ++ib;
-          const bool ha = ia < it[0].size(), hb = ib < it[1].size();
-          if (!ha && !hb) break;
-          if (ha && hb && it[0][ia].unit == it[1][ib].unit) {
-            emit(&it[0][ia], &it[1][ib]);
-            ++ia;
-            ++ib;
-          } else if (ha && (!hb || it[0][ia].unit < it[1][ib].unit)) {
-            emit(&it[0][ia], nullptr);
-            ++ia;
-          } else {
-            emit(nullptr, &it[1][ib]);
-            ++ib;
-          }
+          for (int k = 0; k < 2; ++k)
+            for (int h = 0; h < 2; ++h) w.push_back(ws[h][k]);
         }
-        // pad to the kernel's batch size by repeating the last step with zero coefficients
-        const int32_t batch = !backward ? kTileBatchF : (pass == 0 ? kTileBatchB : kTileBatchA);
-        for (; nsteps % batch != 0; ++nsteps) {
-          if (!backward) {
-            FwdEntry za = T.steps_f[T.steps_f.size() - 2], zb = T.steps_f[T.steps_f.size() - 1];
-            za.a = za.b1 = za.b2 = zb.a = zb.b1 = zb.b2 = 0.f;
-            T.steps_f.push_back(za);
-            T.steps_f.push_back(zb);
-          } else if (pass == 0) {
-            BwdEntryB za = T.steps_b[T.steps_b.size() - 2], zb = T.steps_b[T.steps_b.size() - 1];
-            za.a = za.b1s = za.b2s = zb.a = zb.b1s = zb.b2s = 0.f;
-            T.steps_b.push_back(za);
-            T.steps_b.push_back(zb);
-          } else {
-            BwdEntryA za = T.steps_a[T.steps_a.size() - 2], zb = T.steps_a[T.steps_a.size() - 1];
-            za.a = zb.a = 0.f;
-            T.steps_a.push_back(za);
-            T.steps_a.push_back(zb);
-          }
-        }
-        if (!backward)
-          T.pair_step_ptr.push_back((int32_t)(T.steps_f.size() / 2));
-        else if (pass == 0)
-          T.pair_step_ptr.push_back((int32_t)(T.steps_b.size() / 2));
-        else
-          T.pair_stepA_ptr.push_back((int32_t)(T.steps_a.size() / 2));
+        item_cost.push_back(22 * (int64_t)nV + 10 * (int64_t)nA + 8 * (int64_t)nX + 20);
+        item_words.push_back(std::move(w));
       }
     }
-    T.max_pairs = std::max<int32_t>(T.max_pairs, (int32_t)pairs.size());
-    T.tile_pair_ptr.push_back((int32_t)T.pair_a.size());
+    T.n_items += (int64_t)item_words.size();
+
+    // 3. longest-processing-time assignment of the items to the warps; a warp's items are contiguous in the stream
+    std::vector<int32_t> order(item_words.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return item_cost[x] > item_cost[y]; });
+    std::vector<int64_t> load(W, 0);
+    std::vector<std::vector<int32_t>> mine(W);
+    for (int32_t it : order) {
+      int32_t best = 0;
+      for (int32_t w = 1; w < W; ++w)
+        if (load[w] < load[best]) best = w;
+      load[best] += item_cost[it];
+      mine[best].push_back(it);
+    }
+    for (int32_t w = 0; w < W; ++w) {
+      WarpRange R{(int32_t)T.stream.size(), 0};
+      for (int32_t it : mine[w]) {
+        T.stream.insert(T.stream.end(), item_words[it].begin(), item_words[it].end());
+        R.n_words += (int32_t)item_words[it].size();
+      }
+      while (T.stream.size() % kChunkWords != 0) T.stream.push_back(mk(0u, 0u, 0u, 0u));
+      T.warp_range.push_back(R);
+    }
+    if (T.stream.size() >= (size_t)INT32_MAX / 2) return fail(FEO_ERR_UNSUPPORTED, "operator stream too large");
   }
-  T.n_tiles = (int32_t)T.tile_line_ptr.size() - 1;
+  T.n_tiles = (int32_t)T.tile_lines.size();
+  return FEO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp64 replay: decodes boxes and streams exactly as feo_tiled.cu does
+// ---------------------------------------------------------------------------------------------
+int replay_tile_plan(const TilePlan& T, int32_t ns_branch, const double* in0, const double* in1, double* out) {
+  const bool precond = T.has_conv ? ns_branch != 0 : true;
+  const double esign = precond ? 1.0 : -1.0;
+  const int32_t W = T.warps;
+  std::vector<double> smem;
+  std::vector<char> valid;
+  for (int32_t t = 0; t < T.n_tiles; ++t) {
+    const int32_t nl = T.tile_lines[t];
+    smem.assign(nl, 0.0);
+    valid.assign(nl, 0);
+    for (int32_t b = T.tile_box_ptr[t]; b < T.tile_box_ptr[t + 1]; ++b) {
+      const StageBox& bx = T.boxes[b];
+      for (int32_t k = 0; k < kBoxRows[bx.cls]; ++k) {
+        const int32_t l = bx.line0 + k, dof = bx.dof0 + k;
+        if (l >= nl || dof >= T.n || valid[l]) return fail(FEO_ERR_INVALID_ARGUMENT, "tile plan: staging boxes overlap or overflow");
+        valid[l] = 1;
+        smem[l] = !T.backward ? in0[dof] : (bx.src ? in1[dof] : in0[dof]);
+      }
+    }
+    for (int32_t l = 0; l < nl; ++l)
+      if (!valid[l]) return fail(FEO_ERR_INVALID_ARGUMENT, "tile plan: a staged line is not covered by a box");
+    bool bad = false;
+    auto S = [&](uint32_t line) -> double {
+      if ((int32_t)line >= nl) {
+        bad = true;
+        return 0.0;
+      }
+      return smem[line];
+    };
+    for (int32_t w = 0; w < W; ++w) {
+      const WarpRange& R = T.warp_range[(size_t)t * W + w];
+      if (R.begin % kChunkWords != 0) return fail(FEO_ERR_INVALID_ARGUMENT, "tile plan: warp stream not chunk aligned");
+      const Word16* s = T.stream.data() + R.begin;
+      const Word16* const end = s + R.n_words;
+      while (s < end) {
+        if (!T.backward) {
+          const int32_t n_steps = (int32_t)s[0].w[1];
+          for (int qd = 0; qd < 4; ++qd) {
+            const Word16& H = s[qd];
+            if ((int32_t)H.w[1] != n_steps) return fail(FEO_ERR_INVALID_ARGUMENT, "tile plan: quad step counts differ");
+            double accA = 0, acc1 = 0, acc2 = 0;
+            for (int32_t st = 0; st < n_steps; ++st) {
+              const Word16& e = s[4 + 4 * st + qd];
+              if (e.w[0] % kLineBytes != 0) bad = true;
+              const double x = S(e.w[0] / kLineBytes);
+              accA += (double)u2f(e.w[1]) * x;
+              acc1 += (double)u2f(e.w[2]) * x;
+              acc2 += (double)u2f(e.w[3]) * x;
+            }
+            const int32_t row = (int32_t)H.w[0];
+            if (row < 0) continue;
+            const double c = (H.w[3] & 1u) ? S(H.w[2] & 0xffffu) * acc1 + S(H.w[2] >> 16) * acc2 : 0.0;
+            const double f = in1[row];
+            out[row] = precond ? accA - (f - c) : accA - (-f + c);
+          }
+          s += 4 + 4 * (size_t)n_steps;
+        } else {
+          const uint32_t nV = s[0].w[2], nA = s[0].w[3], nX = s[2].w[0];
+          for (int h = 0; h < 2; ++h) {
+            const Word16 &H0 = s[h], &H1 = s[2 + h];
+            if (H0.w[2] != nV || H0.w[3] != nA || H1.w[0] != nX) return fail(FEO_ERR_INVALID_ARGUMENT, "tile plan: duo step counts differ");
+            double accI = 0, accJ = 0, bu1I = 0, bu2I = 0, bu1J = 0, bu2J = 0;
+            const Word16* p = s + 4;
+            for (uint32_t v = 0; v < nV; ++v, p += 6) {
+              const Word16 &w0 = p[h], &w1 = p[2 + h], &w2 = p[4 + h];
+              const double rI = S(w0.w[0] & 0xffffu), rJ = S(w0.w[0] >> 16), d1 = S(w0.w[1] & 0xffffu), d2 = S(w0.w[1] >> 16);
+              accI += rI * ((double)u2f(w0.w[2]) + (double)u2f(w0.w[3]) * d1 + (double)u2f(w1.w[0]) * d2);
+              accJ += rJ * ((double)u2f(w1.w[1]) + (double)u2f(w1.w[2]) * d1 + (double)u2f(w1.w[3]) * d2);
+              bu1I += (double)u2f(w2.w[0]) * d1;
+              bu2I += (double)u2f(w2.w[1]) * d1;
+              bu1J += (double)u2f(w2.w[2]) * d2;
+              bu2J += (double)u2f(w2.w[3]) * d2;
+            }
+            for (uint32_t a = 0; a < nA; ++a, p += 2) {
+              const Word16& w0 = p[h];
+              accI += (double)u2f(w0.w[1]) * S(w0.w[0] & 0xffffu);
+              accJ += (double)u2f(w0.w[2]) * S(w0.w[0] >> 16);
+            }
+            for (uint32_t x = 0; x < nX; ++x, p += 4) {
+              const Word16 &w0 = p[h], &w1 = p[2 + h];
+              const double xv = S(w0.w[0]);
+              bu1I += (double)u2f(w0.w[1]) * xv;
+              bu2I += (double)u2f(w0.w[2]) * xv;
+              bu1J += (double)u2f(w0.w[3]) * xv;
+              bu2J += (double)u2f(w1.w[0]) * xv;
+            }
+            if (H1.w[2] & 1u) {
+              const double rI = S(H1.w[1] & 0xffffu), rJ = S(H1.w[1] >> 16);
+              accI += esign * (bu1I * rI + bu1J * rJ);
+              accJ += esign * (bu2I * rI + bu2J * rJ);
+            }
+            const int32_t cI = (int32_t)H0.w[0], cJ = (int32_t)H0.w[1];
+            if (cI >= 0) out[cI] = accI;
+            if (cJ >= 0) out[cJ] = accJ;
+          }
+          s += 4 + 6 * (size_t)nV + 2 * (size_t)nA + 4 * (size_t)nX;
+        }
+      }
+      if (s != end) return fail(FEO_ERR_INVALID_ARGUMENT, "tile plan: warp stream boundaries inconsistent");
+    }
+    if (bad) return fail(FEO_ERR_INVALID_ARGUMENT, "tile plan: stream references a line outside the tile");
+  }
   return FEO_OK;
 }
 

@@ -75,18 +75,18 @@ class ResidualLossFn(torch.autograd.Function):
         ldb = aT.shape[1]
         fT = fcache.get(op, F.detach(), ldb) if fcache is not None else _prep(op, F.detach(), ldb)
         need = bool(ctx.needs_input_grad[0])
-        loss, rT, eT = op.residual_fwd(aT, fT, B, save=need)
+        loss, rT = op.residual_fwd(aT, fT, B, save=need)
         ctx.op, ctx.B, ctx.native = op, B, native
         if need:
-            ctx.save_for_backward(aT, rT, eT)
+            ctx.save_for_backward(aT, rT)
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        aT, rT, eT = ctx.saved_tensors
+        aT, rT = ctx.saved_tensors
         op: FEOperator = ctx.op
         g = grad_out.detach().to(torch.float32).contiguous()
-        gT = op.residual_bwd(aT, rT, eT, ctx.B, grad_loss=g)
+        gT = op.residual_bwd(aT, rT, ctx.B, grad_loss=g)
         return op.from_dof_major(gT, ctx.B, contiguous=not ctx.native), None, None, None
 
 

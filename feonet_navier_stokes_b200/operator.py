@@ -134,7 +134,7 @@ class FEOperator:
         self.has_seq = bool(info.has_seq)
         self.has_dense_m = bool(info.has_dense_m)
         self.has_dense_p = bool(info.has_dense_p)
-        self.has_sparse = info.n_blobs > 0
+        self.has_sparse = info.n_tiles_fwd > 0
         self.ns_precond_branch = bool(ns_precond_branch)
         self._ws = None
         self.launches = 0  # kernels launched through this handle (bench.py's gpu_launches)
@@ -206,17 +206,16 @@ class FEOperator:
         assert fT.shape[1] == ldb
         loss = torch.empty((), dtype=torch.float32, device=self.device)
         rT = self.new(ldb) if save else None
-        eT = self.new(ldb) if (save and self.has_conv) else None
         ws = self.workspace(B)
         L.check(self.lib.feo_residual_fwd(self._handle, self._p(aT), self._p(fT), ldb, B, self._p(loss), self._p(rT),
-                                          self._p(eT), self._p(ws), ws.numel() * 4, self._stream()))
+                                          self._p(ws), ws.numel() * 4, self._stream()))
         self.launches += 2
-        return loss, rT, eT
+        return loss, rT
 
-    def residual_bwd(self, aT, rT, eT, B: int, grad_loss: Optional[torch.Tensor] = None, out=None) -> torch.Tensor:
+    def residual_bwd(self, aT, rT, B: int, grad_loss: Optional[torch.Tensor] = None, out=None) -> torch.Tensor:
         ldb = rT.shape[1]
         gT = self.new(ldb) if out is None else out
-        L.check(self.lib.feo_residual_bwd(self._handle, self._p(aT), self._p(rT), self._p(eT), self._p(grad_loss),
+        L.check(self.lib.feo_residual_bwd(self._handle, self._p(aT), self._p(rT), self._p(grad_loss),
                                           self._p(gT), ldb, B, self._stream()))
         self.launches += 1
         return gT

@@ -37,7 +37,7 @@ extern "C" {
 #define FEO_ERR_UNSUPPORTED (-3)
 #define FEO_ERR_OUT_OF_MEMORY (-4)
 
-#define FEO_ABI_VERSION 1
+#define FEO_ABI_VERSION 2
 
 /* Which stored matrix a generic apply uses. */
 enum feo_matrix_id { FEO_MAT_A = 0, FEO_MAT_B1 = 1, FEO_MAT_B2 = 2, FEO_MAT_S = 3, FEO_MAT_M = 4 /* S + dt*A */ };
@@ -80,7 +80,7 @@ typedef struct feo_operator* feo_handle_t;
 typedef struct feo_op_info {
   int32_t n, n_u, has_conv, has_seq, has_dense_m, has_dense_p;
   int64_t nnz_a, nnz_b1, nnz_b2, nnz_s, nnz_union; /* stored (value != 0) entries */
-  int32_t n_blobs, n_units, max_row_nnz;
+  int32_t n_tiles_fwd, n_tiles_bwd, max_row_nnz; /* tiles of the fused forward / backward kernels */
   int64_t device_bytes; /* device memory owned by the handle */
 } feo_op_info;
 
@@ -89,7 +89,8 @@ int feo_abi_version(void);
 const char* feo_last_error_string(void);
 
 /* Builds device CSR (+ transposes), the fused union pattern {col, a, b1, b2}, partner lookups
- * from (idx_i, idx_j) and the locality blobs the kernels walk.  One-off; synchronous. */
+ * from (idx_i, idx_j) and the tile plans (staging boxes + per-warp operator streams) the fused
+ * kernels walk.  One-off; synchronous. */
 int feo_op_create(const feo_operator_desc* desc, feo_handle_t* out);
 int feo_op_destroy(feo_handle_t h);
 int feo_op_get_info(feo_handle_t h, feo_op_info* info);
@@ -113,16 +114,18 @@ int feo_transpose(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, 
  *   alphaT, fT  [N][ldb] dof-major inputs
  *   loss_out    device fp32 scalar
  *   rT          [N][ldb] residual, saved for backward (NULL: loss only)
- *   eT          [N][ldb] E-term product sums saved for backward (NULL if no convection or rT NULL)
  *   workspace   >= feo_workspace_bytes(h, B, 1) bytes
+ * Samples are processed in slabs of 64; rows of alphaT beyond B (up to ldb) may hold anything.
  */
 int feo_residual_fwd(feo_handle_t h, const float* alphaT, const float* fT, int64_t ldb, int32_t B,
-                     float* loss_out, float* rT, float* eT, void* workspace, size_t workspace_bytes, void* stream);
+                     float* loss_out, float* rT, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of the above (autograd of steady NS :463 / Stokes :396):
- *   gradT = 2 * (*grad_loss) * [A^T r + s(B1^T(d1.r) + B2^T(d2.r) + e)],  grad_loss NULL means 1. */
-int feo_residual_bwd(feo_handle_t h, const float* alphaT, const float* rT, const float* eT,
-                     const float* grad_loss, float* gradT, int64_t ldb, int32_t B, void* stream);
+ *   gradT = 2 * (*grad_loss) * [A^T r + s(B1^T(d1.r) + B2^T(d2.r) + e)],  grad_loss NULL means 1.
+ * e (the derivative through the advecting velocity) is recomputed from
+ * alphaT and rT; alphaT may be NULL when the handle has no convection. */
+int feo_residual_bwd(feo_handle_t h, const float* alphaT, const float* rT, const float* grad_loss,
+                     float* gradT, int64_t ldb, int32_t B, void* stream);
 
 /* Generic sparse apply ------------------------------------------------------------------------
  * YT = scale * op(K) XT (+ YT if accumulate), K = stored matrix `which`, op = transpose?K^T:K.
@@ -163,14 +166,14 @@ int feo_assemble_u_init(feo_handle_t h, const float* init_x, const float* init_y
 int feo_sq_diff_sum(const float* xT, const float* yT, int32_t n, int64_t ldb, int32_t B, float scale,
                     float* loss_out, void* workspace, size_t workspace_bytes, void* stream);
 
-/* Test hooks (HOST ONLY, no CUDA calls) --------------------------------------------------------
+/* Test hook (HOST ONLY, no CUDA calls) ----------------------------------------------------------
  * Exercised by the CPU test-suite to validate the set-up code without a GPU; never called by the
- * product path.  feo_debug_plan_check verifies the walk-plan invariants and returns
- * stats[0..7] = {n_blobs, n_units, nnz_union, max_row_nnz, max_blob_fent, n_bwdA, n_bwdB, has_conv}.
- * feo_debug_plan_replay replays the forward and backward entry streams in fp64 for one sample. */
-int feo_debug_plan_check(const feo_operator_desc* desc, int64_t* stats);
-int feo_debug_plan_replay(const feo_operator_desc* desc, const double* alpha, const double* f, double* r_out,
-                          double* grad_out, double* loss_out);
+ * product path.  Builds the tile plan of the fused residual kernels and replays its staging boxes and
+ * per-warp streams in fp64 for one sample, decoding them as the kernels do.  forward: in0 = alpha,
+ * in1 = f, out = r; backward: in0 = r, in1 = alpha, out = grad / (2 g).  in0 == NULL: statistics only.
+ * stats[0..7] = {n_tiles, max_lines, total_lines, n_boxes, n_items, real_entries, slot_entries, stream_words}. */
+int feo_debug_tile_replay(const feo_operator_desc* desc, int32_t backward, int32_t max_lines, int32_t warps,
+                          const double* in0, const double* in1, double* out, int64_t* stats);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,5 @@
 """CPU: the C-ABI library loads, exports every declared symbol, and its host-side set-up code
-(union pattern, partner lookups, blobs, forward/backward entry streams) agrees with the oracle.
+(union pattern, partner lookups, tiles, staging boxes, forward/backward operator streams) agrees with the oracle.
 No CUDA call is made here."""
 import ctypes as C
 import os
@@ -33,45 +33,75 @@ def test_to_host_csr_threshold_zero():
     assert val.dtype == np.float32 and val[1] == np.float32(1e-30)
 
 
-@pytest.mark.parametrize("n,ordering,branch", [(3, "blocked", 1), (3, "interleaved", 0), (5, "interleaved", 1), (6, "blocked", 0)])
-def test_plan_replay_matches_oracle_ns(n, ordering, branch):
+def _replay(lib, desc, backward, in0, in1, n, max_lines=0, warps=0):
+    out = np.full(n, np.nan)
+    stats = (C.c_int64 * 8)()
+    L.check(lib.feo_debug_tile_replay(C.byref(desc), int(backward), max_lines, warps, in0.ctypes.data_as(L.f64p),
+                                      in1.ctypes.data_as(L.f64p), out.ctypes.data_as(L.f64p), stats))
+    return out, list(stats)
+
+
+@pytest.mark.parametrize("n,ordering,branch,max_lines,warps", [
+    (3, "blocked", 1, 0, 0), (3, "interleaved", 0, 0, 0), (5, "interleaved", 1, 96, 3), (6, "blocked", 0, 96, 16),
+    (8, "interleaved", 1, 128, 5)])
+def test_tile_replay_matches_oracle_ns(n, ordering, branch, max_lines, warps):
+    """The staging boxes and the per-warp streams of the fused kernels, decoded on the host as the kernels
+    decode them, reproduce the oracle's residual and gradient (fp64, one sample)."""
     lib = L.load_library()
     op = config_operators("steady_ns", n, ordering=ordering)
     desc, keep = build_desc(op.N, op.A, op.B1, op.B2, None, op.idx_u1, op.idx_u2, bool(branch))
-    stats = (C.c_int64 * 8)()
-    L.check(lib.feo_debug_plan_check(C.byref(desc), stats))
-    U = abs(op.A.astype(np.float32)) + abs(op.B1.astype(np.float32)) + abs(op.B2.astype(np.float32))
-    assert stats[2] == U.nnz and stats[7] == 1 and stats[1] == op.mesh.n_u + op.mesh.n_p
     rng = np.random.default_rng(n)
     alpha = rng.standard_normal(op.N)
     f = rng.standard_normal(op.N)
-    r = np.zeros(op.N)
-    g = np.zeros(op.N)
-    loss = C.c_double()
-    L.check(lib.feo_debug_plan_replay(C.byref(desc), alpha.ctypes.data_as(L.f64p), f.ctypes.data_as(L.f64p),
-                                      r.ctypes.data_as(L.f64p), g.ctypes.data_as(L.f64p), C.byref(loss)))
     A32, B132, B232 = (K.astype(np.float32).astype(np.float64) for K in (op.A, op.B1, op.B2))
     lo, go, ro = orc.ns_loss_and_grad(alpha[None], f[None], A32, B132, B232, op.idx_u1, op.idx_u2, bool(branch), dtype=np.float64)
-    assert abs(loss.value - lo) < 1e-11 * abs(lo)
-    assert np.allclose(r, ro[0], rtol=1e-11, atol=1e-12) and np.allclose(g, go[0], rtol=1e-10, atol=1e-11)
+    r, st_f = _replay(lib, desc, False, alpha, f, op.N, max_lines, warps)
+    U = abs(op.A.astype(np.float32)) + abs(op.B1.astype(np.float32)) + abs(op.B2.astype(np.float32))
+    assert st_f[5] == U.nnz  # every stored entry of the union pattern appears exactly once
+    assert np.allclose(r, ro[0], rtol=1e-11, atol=1e-12)
+    assert abs(np.sum(r * r) - lo) < 1e-11 * abs(lo)
+    g, st_b = _replay(lib, desc, True, ro[0], alpha, op.N, max_lines, warps)
+    assert np.allclose(2.0 * g, go[0], rtol=1e-10, atol=1e-11)
+    if max_lines:
+        assert st_f[1] <= max_lines and st_b[1] <= max_lines and st_f[0] > 1
 
 
-def test_plan_replay_linear_and_small_blobs(monkeypatch):
+def test_tile_replay_noncolocated_pairs_and_cross_terms():
+    """I, J are opaque lists (quirk 4): shuffle the pairing, and add B1/B2 entries that couple the two
+    components and the pressure columns so that the generic V-/X-step paths are exercised."""
     lib = L.load_library()
-    monkeypatch.setenv("FEO_BLOB_ROWS", "7")
+    op = config_operators("steady_ns", 4, ordering="interleaved")
+    rng = np.random.default_rng(7)
+    idx_i = np.asarray(op.idx_u1).copy()
+    idx_j = np.asarray(op.idx_u2).copy()
+    perm = rng.permutation(len(idx_j))
+    idx_j = idx_j[perm]  # pairs are no longer the two components of one node
+    import scipy.sparse as sp
+    noise = sp.random(op.N, op.N, density=0.01, random_state=3, data_rvs=rng.standard_normal).tocsr()
+    B1 = (op.B1 + noise).tocsr()
+    B2 = (op.B2 + noise.T).tocsr()
+    desc, keep = build_desc(op.N, op.A, B1, B2, None, idx_i, idx_j, True)
+    alpha, f = rng.standard_normal(op.N), rng.standard_normal(op.N)
+    A32, B132, B232 = (K.astype(np.float32).astype(np.float64) for K in (op.A, B1, B2))
+    lo, go, ro = orc.ns_loss_and_grad(alpha[None], f[None], A32, B132, B232, idx_i, idx_j, True, dtype=np.float64)
+    r, _ = _replay(lib, desc, False, alpha, f, op.N, 96, 4)
+    assert np.allclose(r, ro[0], rtol=1e-11, atol=1e-12)
+    g, _ = _replay(lib, desc, True, ro[0], alpha, op.N, 200, 4)
+    assert np.allclose(2.0 * g, go[0], rtol=1e-10, atol=1e-11)
+
+
+def test_tile_replay_linear_and_small_tiles():
+    lib = L.load_library()
     op = config_operators("hole", 5)
     desc, keep = build_desc(op.N, op.A)
-    stats = (C.c_int64 * 8)()
-    L.check(lib.feo_debug_plan_check(C.byref(desc), stats))
-    assert stats[7] == 0 and stats[0] >= op.N // 7 and stats[1] == op.N
     rng = np.random.default_rng(0)
     alpha, f = rng.standard_normal(op.N), rng.standard_normal(op.N)
-    r, g, loss = np.zeros(op.N), np.zeros(op.N), C.c_double()
-    L.check(lib.feo_debug_plan_replay(C.byref(desc), alpha.ctypes.data_as(L.f64p), f.ctypes.data_as(L.f64p),
-                                      r.ctypes.data_as(L.f64p), g.ctypes.data_as(L.f64p), C.byref(loss)))
     A32 = op.A.astype(np.float32).astype(np.float64)
     lo, go, _ = orc.stokes_loss_and_grad(alpha[None], f[None], A32, dtype=np.float64)
-    assert abs(loss.value - lo) < 1e-11 * abs(lo) and np.allclose(g, go[0], rtol=1e-10, atol=1e-11)
+    r, st = _replay(lib, desc, False, alpha, f, op.N, 48, 2)
+    assert st[0] > 4 and np.allclose(r, A32 @ alpha - f, rtol=1e-11, atol=1e-12)
+    g, _ = _replay(lib, desc, True, r, alpha, op.N, 48, 2)
+    assert np.allclose(2.0 * g, go[0], rtol=1e-10, atol=1e-11)
 
 
 def test_bad_inputs_are_rejected():
@@ -80,7 +110,10 @@ def test_bad_inputs_are_rejected():
     bad_i = op.idx_u1.copy()
     bad_i[0] = op.idx_u2[0]  # I and J overlap
     desc, keep = build_desc(op.N, op.A, op.B1, op.B2, None, bad_i, op.idx_u2, True)
-    assert lib.feo_debug_plan_check(C.byref(desc), None) == -3
+    assert lib.feo_debug_tile_replay(C.byref(desc), 0, 0, 0, None, None, None, None) == -3
     assert b"disjoint" in lib.feo_last_error_string()
     desc, keep = build_desc(op.N, op.A, op.B1, None)
-    assert lib.feo_debug_plan_check(C.byref(desc), None) == -1
+    assert lib.feo_debug_tile_replay(C.byref(desc), 0, 0, 0, None, None, None, None) == -1
+    # a row that touches more lines than a tile can stage is refused, not mis-computed
+    desc, keep = build_desc(op.N, np.ones((op.N, op.N)))
+    assert lib.feo_debug_tile_replay(C.byref(desc), 0, 32, 0, None, None, None, None) == -3
