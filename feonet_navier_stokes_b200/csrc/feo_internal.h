@@ -44,7 +44,7 @@ HostCsr axpy(const HostCsr& s, float dt, const HostCsr& a);  // S + dt*A
 constexpr int kSlab = 64;                  // samples per CTA
 constexpr int kLineBytes = kSlab * 4;      // one staged dof line
 constexpr int kChunkWords = 32;            // stream words (16 B) per bulk copy: 512 B
-constexpr int kRingChunks = 2;             // chunks per warp ring
+constexpr int kRingChunks = 4;             // chunks per warp ring (power of two)
 constexpr int kBoxRows[3] = {16, 4, 1};    // TMA box heights (dofs) available for staging
 
 struct Word16 {
@@ -87,8 +87,8 @@ struct WarpRange {  // 8 B
 //   A-step (1)  : {line(r[hI]) | line(r[hJ]) << 16, aI, aJ, 0}
 //   X-step (2)  : w0 = {line(alpha[x]), c1I, c2I, c1J}  w1 = {c2J, 0, 0, 0}: Bu1[cI] += c1I x, Bu2[cI] += c2I x, Bu1[cJ] += c1J x, ...
 struct TileTuning {
-  int32_t max_lines = 368;  // staged lines per tile (shared-memory budget: lines * 256 B)
-  int32_t warps = 16;       // warps per CTA
+  int32_t max_lines = 376;  // staged lines per tile (shared-memory budget: lines * 256 B)
+  int32_t warps = 8;        // warps per CTA
 };
 TileTuning tile_tuning_from_env(bool backward);
 

@@ -9,7 +9,7 @@
 //   3. gathers are conflict-free LDS.128 from the staged lines, the arithmetic is packed fp32
 //      (fma.rn.f32x2: two IEEE fp32 FMAs per instruction).
 // The load-store pipe (128 B/clk of shared-memory data per SM) is what bounds these kernels, so the
-// mapping minimises its use: forward = one row per quarter-warp, 8 samples per lane (10 LSU cycles per
+// mapping minimises its use: forward = one row per quarter-warp, 2 x 4 samples per lane (10 LSU cycles per
 // 4 row entries); backward = one column PAIR per half-warp, 4 samples per lane, so that the gathers of
 // r[I], r[J], alpha[I], alpha[J] of a neighbour node serve both columns.
 // Everything is row-/column-owned with a fixed summation order: no atomics, bit-reproducible.
@@ -197,7 +197,7 @@ __device__ __forceinline__ void stage_tile(const TensorMaps& maps, const TiledPa
 // ---------------------------------------------------------------------------------------------
 // forward: r = A a -/+ (F - c), loss partial = sum r^2
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512, 2) residual_fwd_tiled(const __grid_constant__ TensorMaps maps, const TiledParams p) {
+__global__ void __launch_bounds__(256, 2) residual_fwd_tiled(const __grid_constant__ TensorMaps maps, const TiledParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ float s_part[32];
   const uint32_t sb = smem_u32(smem);
@@ -206,9 +206,11 @@ __global__ void __launch_bounds__(512, 2) residual_fwd_tiled(const __grid_consta
   Ring ring;
   stage_tile(maps, p, sb, tile, slab, warp, lane, ring);
 
-  const int q = lane >> 3;                               // this lane's row slot in the quad
-  const uint32_t lane_off = (uint32_t)(lane & 7) * 32;   // 8 samples = 32 B of every line
-  const int b0 = slab * kSlab + (lane & 7) * 8;          // first sample of this lane
+  const int q = lane >> 3;  // this lane's row slot in the quad
+  // a lane owns samples [4l, 4l+4) and [32+4l, 32+4l+4), l = lane & 7: each LDS.128 of a quarter-warp then
+  // reads 128 contiguous bytes of one line (conflict-free), the second one 128 B further
+  const uint32_t lane_off = (uint32_t)(lane & 7) * 16;
+  const int b0 = slab * kSlab + (lane & 7) * 4;
   const bool precond = p.precond != 0;
   float lsum = 0.f;
 
@@ -217,6 +219,14 @@ __global__ void __launch_bounds__(512, 2) residual_fwd_tiled(const __grid_consta
     const int4 hdr = lds_word(ring.addr(ring.pos + q));
     ring.advance(4, lane);
     const int n_steps = hdr.y;
+    const int row = hdr.x;
+    // the load vector of this row is fetched now and consumed in the epilogue (hides the DRAM latency)
+    float4 fv[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      fv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row >= 0 && b0 + 32 * k < p.ldb) fv[k] = ldg4_stream(p.fT + (int64_t)row * p.ldb + b0 + 32 * k);
+    }
     u64 accA[4], acc1[4], acc2[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) accA[i] = acc1[i] = acc2[i] = 0ull;
@@ -227,9 +237,9 @@ __global__ void __launch_bounds__(512, 2) residual_fwd_tiled(const __grid_consta
       const int4 e1 = lds_word(ring.addr(ring.pos + 4 + q));
       u64 x0[4], x1[4];
       lds_pairs(sb + (uint32_t)e0.x + lane_off, x0[0], x0[1]);
-      lds_pairs(sb + (uint32_t)e0.x + lane_off + 16, x0[2], x0[3]);
+      lds_pairs(sb + (uint32_t)e0.x + lane_off + 128, x0[2], x0[3]);
       lds_pairs(sb + (uint32_t)e1.x + lane_off, x1[0], x1[1]);
-      lds_pairs(sb + (uint32_t)e1.x + lane_off + 16, x1[2], x1[3]);
+      lds_pairs(sb + (uint32_t)e1.x + lane_off + 128, x1[2], x1[3]);
       {
         const u64 a = bc(__int_as_float(e0.y)), b1 = bc(__int_as_float(e0.z)), b2 = bc(__int_as_float(e0.w));
 #pragma unroll
@@ -251,7 +261,6 @@ __global__ void __launch_bounds__(512, 2) residual_fwd_tiled(const __grid_consta
       ring.advance(8, lane);
     }
     // epilogue: convection product, load vector, residual, loss, store
-    const int row = hdr.x;
     if (row >= 0) {
       float lhs[8], c[8];
 #pragma unroll
@@ -262,9 +271,9 @@ __global__ void __launch_bounds__(512, 2) residual_fwd_tiled(const __grid_consta
         u64 d1[4], d2[4];
         const uint32_t li = ((uint32_t)hdr.z & 0xffffu) * kLineBytes, lj = ((uint32_t)hdr.z >> 16) * kLineBytes;
         lds_pairs(sb + li + lane_off, d1[0], d1[1]);
-        lds_pairs(sb + li + lane_off + 16, d1[2], d1[3]);
+        lds_pairs(sb + li + lane_off + 128, d1[2], d1[3]);
         lds_pairs(sb + lj + lane_off, d2[0], d2[1]);
-        lds_pairs(sb + lj + lane_off + 16, d2[2], d2[3]);
+        lds_pairs(sb + lj + lane_off + 128, d2[2], d2[3]);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float u0, u1, v0, v1, s10, s11, s20, s21;
@@ -276,13 +285,12 @@ __global__ void __launch_bounds__(512, 2) residual_fwd_tiled(const __grid_consta
           c[2 * i + 1] = conv1(u1, s11, v1, s21);
         }
       }
-      const float* frow = p.fT + (int64_t)row * p.ldb + b0;
       float* rrow = p.outT != nullptr ? p.outT + (int64_t)row * p.ldb + b0 : nullptr;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        const int b = b0 + 4 * k;
+        const int b = b0 + 32 * k;
         if (b < p.ldb) {
-          const float4 f = ldg4_stream(frow + 4 * k);
+          const float4 f = fv[k];
           float4 r;
           r.x = resid1(lhs[4 * k + 0], f.x, c[4 * k + 0], precond);
           r.y = resid1(lhs[4 * k + 1], f.y, c[4 * k + 1], precond);
@@ -292,7 +300,7 @@ __global__ void __launch_bounds__(512, 2) residual_fwd_tiled(const __grid_consta
           if (b + 1 < p.B) lsum = fmaf(r.y, r.y, lsum);
           if (b + 2 < p.B) lsum = fmaf(r.z, r.z, lsum);
           if (b + 3 < p.B) lsum = fmaf(r.w, r.w, lsum);
-          if (rrow != nullptr && b < p.B) *reinterpret_cast<float4*>(rrow + 4 * k) = r;
+          if (rrow != nullptr && b < p.B) *reinterpret_cast<float4*>(rrow + 32 * k) = r;
         }
       }
     }
@@ -312,7 +320,7 @@ __global__ void __launch_bounds__(512, 2) residual_fwd_tiled(const __grid_consta
 // ---------------------------------------------------------------------------------------------
 // backward: grad = 2 g [A^T r + s (B1^T (d1 r) + B2^T (d2 r) + E-term)], column-pair owned
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512, 2) residual_bwd_tiled(const __grid_constant__ TensorMaps maps, const TiledParams p) {
+__global__ void __launch_bounds__(256, 2) residual_bwd_tiled(const __grid_constant__ TensorMaps maps, const TiledParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sb = smem_u32(smem);
   const int tile = blockIdx.x / p.n_slabs, slab = blockIdx.x - tile * p.n_slabs;
@@ -455,7 +463,9 @@ int make_maps(const float* base, int64_t ldb, int32_t n, CUtensorMap out[3]) {
   if (int rc = get_encode(&enc)) return rc;
   // the driver entry point needs the primary context current on THIS thread (autograd runs the backward
   // on its own threads, where no runtime call may have bound it yet)
-  FEO_CUDA_CHECK(cudaFree(nullptr));
+  int dev = 0;
+  FEO_CUDA_CHECK(cudaGetDevice(&dev));
+  FEO_CUDA_CHECK(cudaSetDevice(dev));
   for (int cls = 0; cls < 3; ++cls) {
     const cuuint64_t dims[2] = {(cuuint64_t)ldb, (cuuint64_t)n};
     const cuuint64_t strides[1] = {(cuuint64_t)ldb * sizeof(float)};

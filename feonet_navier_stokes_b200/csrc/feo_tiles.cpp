@@ -29,7 +29,7 @@ TileTuning tile_tuning_from_env(bool backward) {
   if (const char* s = std::getenv(backward ? "FEO_TILE_LINES_BWD" : "FEO_TILE_LINES_FWD")) t.max_lines = atoi(s);
   if (const char* s = std::getenv(backward ? "FEO_TILE_WARPS_BWD" : "FEO_TILE_WARPS_FWD")) t.warps = atoi(s);
   t.max_lines = std::min(std::max(t.max_lines, 32), 800);
-  t.warps = std::min(std::max(t.warps, 1), 32);
+  t.warps = std::min(std::max(t.warps, 1), 8);
   return t;
 }
 

@@ -247,10 +247,14 @@ class StokesOperators:
     @property
     def idx_sol(self) -> np.ndarray:
         """Object array of three python int lists, exactly what `np.load(...)['idx_sol']` yields
-        (`FEONet_steady_Navier-Stokes/assemble_fenics.py:142-143`)."""
-        out = np.empty(3, dtype=object)
-        out[0], out[1], out[2] = self.idx_u1.tolist(), self.idx_u2.tolist(), self.idx_p.tolist()
-        return out
+        (`FEONet_steady_Navier-Stokes/assemble_fenics.py:142-143`).  Built once (it is a module-level
+        global in the reference): converting ~1e6 ints to python lists costs milliseconds."""
+        cached = self.__dict__.get("_idx_sol")
+        if cached is None:
+            cached = np.empty(3, dtype=object)
+            cached[0], cached[1], cached[2] = self.idx_u1.tolist(), self.idx_u2.tolist(), self.idx_p.tolist()
+            self.__dict__["_idx_sol"] = cached
+        return cached
 
     def load_vector_sincos(self, coeff: np.ndarray) -> np.ndarray:
         """L_a = int f.v for f=(m0 sin(n0 x+n1 y), m1 cos(n2 x+n3 y)); Dirichlet rows hold the BC

@@ -57,6 +57,11 @@ __global__ void __launch_bounds__(512, 2) k_ls(const int4* __restrict__ g, int i
         int2 v;
         asm volatile("ld.global.nc.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(gb + o + u * 32));
         acc ^= v.x ^ v.y;
+      } else if (MODE == 14) {
+        int4 v;
+        if (u & 1) asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(gb + lane * 16 + (o & 0xc00) + (u >> 1) * 512));
+        else asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sb + lane * 16 + (o & 0xc00) + (u >> 1) * 512));
+        acc ^= v.x ^ v.y; acc ^= v.z ^ v.w;
       } else {
         const int4 v = ctab[((o >> 4) + u * 2 + warp * 8) & 4095];
         acc ^= v.x ^ v.y; acc ^= v.z ^ v.w;
@@ -79,7 +84,7 @@ int main() {
   const int iters = 20000;
   const char* names[] = {"LDS.128 contiguous 512B", "LDS.128 half-uniform", "LDS.128 uniform", "LDS.64 contiguous 256B", "LDS.64 uniform",
                          "LDS.32 contiguous 128B", "LDS.32 uniform", "LDG.128 uniform (L1 hit)", "LDG.128 half-uniform (L1 hit)", "LDG.32 uniform (L1 hit)",
-                         "LDG.128 contiguous 512B (L1 hit)", "LDC.128 uniform index", "LDC.128 half-uniform index", "LDG.64 uniform (L1 hit)"};
+                         "LDG.128 contiguous 512B (L1 hit)", "LDC.128 uniform index", "LDC.128 half-uniform index", "LDG.64 uniform (L1 hit)", "mix LDS.128 + LDG.128 contiguous (per instr)"};
 #define RUN(MODE)                                                                                         \
   do {                                                                                                   \
     CK(cudaFuncSetAttribute(k_ls<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 81920));             \
@@ -94,6 +99,6 @@ int main() {
     double ops_per_sm = 32.0 * iters * 8;                                                                \
     printf("%-36s %.3f ms -> %.3f cycles per warp-instr per SM (@1.95 GHz)\n", names[MODE], ms, ms * 1e-3 * 1.95e9 / ops_per_sm); \
   } while (0)
-  RUN(0); RUN(1); RUN(2); RUN(3); RUN(4); RUN(5); RUN(6); RUN(7); RUN(8); RUN(9); RUN(10); RUN(11); RUN(12); RUN(13);
+  RUN(0); RUN(10); RUN(13); RUN(14);
   return 0;
 }
