@@ -75,7 +75,7 @@ struct WarpRange {  // 8 B
 
 // Stream formats (all offsets are LINE indices within the tile; byte offset = index * 256).
 //
-// forward, per quad, quarter q reads word 4*unit + q:
+// forward, per quad, quarter q reads word 4*unit + q; [header unit][spare unit][n_steps step units], n_steps even:
 //   header unit : {row (-1: idle), n_steps, line(alpha[pi]) | line(alpha[pj]) << 16, flags (bit 0: velocity row)}
 //   step unit   : {line(col) * 256, a, b1, b2}
 // backward, per duo, half h reads word 2*k + h:

@@ -101,6 +101,23 @@ __device__ __forceinline__ u64 fma2r(u64 a, u64 b, u64 c) {
   return d;
 }
 __device__ __forceinline__ u64 bc(float a) { return pk(a, a); }
+// Accumulator pair kept as two fp32 registers: (lo, hi) += a * (b.lo, b.hi) as ONE packed FMA.  Passing the
+// accumulator as scalars (packed only inside the asm block) lets ptxas update it in place; with 64-bit
+// loop-carried accumulators it parks results in the dying gather registers and copies them back.
+struct P2 {
+  float lo, hi;
+};
+__device__ __forceinline__ void fma2s(P2& d, float a, u64 b) {
+  asm("{\n"
+      ".reg .b64 c, aa;\n"
+      "mov.b64 c, {%0,%1};\n"
+      "mov.b64 aa, {%2,%2};\n"
+      "fma.rn.f32x2 c, aa, %3, c;\n"
+      "mov.b64 {%0,%1}, c;\n"
+      "}"
+      : "+f"(d.lo), "+f"(d.hi)
+      : "f"(a), "l"(b));
+}
 __device__ __forceinline__ float4 ldg4_stream(const float* p) {
   float4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
@@ -112,53 +129,60 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// The per-warp operator stream: kRingChunks slots of kChunkWords 16-byte words in shared memory.
+// The per-warp operator stream: a ring of kRingChunks slots of kChunkWords 16-byte words in shared
+// memory (base aligned to the ring size), filled by 1-D bulk copies that complete on per-slot
+// mbarriers.  Readers keep a byte offset `ptr` into the ring; stream items never straddle a chunk
+// pair boundary the reader does not check (see the kernels), so the bookkeeping is one test per item.
+constexpr uint32_t kChunkBytes = kChunkWords * 16;
+constexpr uint32_t kRingBytes = kRingChunks * kChunkBytes;
 struct Ring {
   uint32_t base, bar;  // shared addresses of the slots / their mbarriers
   const int4* src;     // the warp's words in global memory
-  int32_t n_words, n_chunks;
-  int32_t pos, arrived, n_free;  // consumed words, words known to have landed, chunks whose slot was recycled
+  int32_t n_chunks;    // chunks of this warp's stream
+  int32_t chunk;       // chunks entered so far
+  uint32_t ptr;        // ring byte offset of the next word to read
 
   __device__ __forceinline__ void issue(int32_t c) const {
     const uint32_t slot = (uint32_t)c & (kRingChunks - 1);
-    mbar_expect_tx(bar + slot * 8, kChunkWords * 16);
-    bulk_copy(base + slot * (kChunkWords * 16), src + (size_t)c * kChunkWords, kChunkWords * 16, bar + slot * 8);
+    mbar_expect_tx(bar + slot * 8, kChunkBytes);
+    bulk_copy(base + slot * kChunkBytes, src + (size_t)c * kChunkWords, kChunkBytes, bar + slot * 8);
   }
-  __device__ __forceinline__ void start(uint32_t base_, uint32_t bar_, const int4* src_, int32_t n_words_, int lane) {
+  __device__ __forceinline__ void start(uint32_t base_, uint32_t bar_, const int4* src_, int32_t n_words, int lane) {
     base = base_;
     bar = bar_;
     src = src_;
-    n_words = n_words_;
-    n_chunks = (n_words_ + kChunkWords - 1) / kChunkWords;
-    pos = arrived = n_free = 0;
+    n_chunks = (n_words + kChunkWords - 1) / kChunkWords;
+    chunk = 0;
+    ptr = 0;
     if (lane == 0)
       for (int32_t c = 0; c < kRingChunks && c < n_chunks; ++c) issue(c);
   }
-  // words [pos, upto) must have landed before they are read
-  __device__ __forceinline__ void ensure(int32_t upto) {
-    while (arrived < upto) {
-      const int32_t c = arrived / kChunkWords;
-      mbar_wait(bar + ((uint32_t)c & (kRingChunks - 1)) * 8, ((uint32_t)c / kRingChunks) & 1u);
-      arrived += kChunkWords;
-    }
-  }
-  __device__ __forceinline__ uint32_t addr(int32_t word) const {
-    return base + (((uint32_t)word & (kRingChunks * kChunkWords - 1)) << 4);
-  }
-  // consume n words; slots of fully consumed chunks are refilled with the chunk kRingChunks ahead
-  __device__ __forceinline__ void advance(int32_t n, int lane) {
-    pos += n;
-    while ((n_free + 1) * kChunkWords <= pos) {
-      const int32_t c = n_free + kRingChunks;
+  // The reader is about to read the first word of the next chunk: wait until it has landed; the chunk
+  // before it is fully consumed, so its slot is refilled with the chunk kRingChunks - 1 ahead.
+  __device__ __forceinline__ void enter(int lane) {
+    const int32_t c = chunk++;
+    mbar_wait(bar + ((uint32_t)c & (kRingChunks - 1)) * 8, ((uint32_t)c / kRingChunks) & 1u);
+    if (c >= 1) {
       __syncwarp();
-      if (c < n_chunks && lane == 0) {
-        fence_proxy_async();
-        issue(c);
-      }
-      ++n_free;
+      const int32_t nc = c + kRingChunks - 1;
+      if (nc < n_chunks && lane == 0) issue(nc);
     }
   }
+  __device__ __forceinline__ bool at_chunk_start() const { return (ptr & (kChunkBytes - 1)) == 0; }
+  __device__ __forceinline__ void skip(uint32_t bytes) { ptr = (ptr + bytes) & (kRingBytes - 1); }
 };
+
+// (lo, hi) += (a.lo, a.hi) * (b.lo, b.hi)
+__device__ __forceinline__ void fma2p(P2& d, u64 a, u64 b) {
+  asm("{\n"
+      ".reg .b64 c;\n"
+      "mov.b64 c, {%0,%1};\n"
+      "fma.rn.f32x2 c, %2, %3, c;\n"
+      "mov.b64 {%0,%1}, c;\n"
+      "}"
+      : "+f"(d.lo), "+f"(d.hi)
+      : "l"(a), "l"(b));
+}
 
 // residual from LHS sum, load vector and convection, mirroring the reference's operation order:
 // precond branch  r = LHS - (F - c) ; else  r = LHS - (-F + c)
@@ -172,8 +196,9 @@ __device__ __forceinline__ float conv1(float d1, float s1, float d2, float s2) {
 }
 
 // Shared prologue: barriers, line staging, ring start.  Returns when the tile's lines have landed.
-__device__ __forceinline__ void stage_tile(const TensorMaps& maps, const TiledParams& p, uint32_t sb, int tile, int slab, int warp,
-                                           int lane, Ring& ring) {
+template <typename RingT>
+__device__ __forceinline__ int32_t stage_tile(const TensorMaps& maps, const TiledParams& p, uint32_t sb, int tile, int slab, int warp,
+                                              int lane, RingT& ring) {
   const uint32_t bar_lines = sb + p.bar_off;
   const uint32_t bar_ring = bar_lines + 8 + (uint32_t)warp * (kRingChunks * 8);
   if (threadIdx.x == 0) {
@@ -190,8 +215,9 @@ __device__ __forceinline__ void stage_tile(const TensorMaps& maps, const TiledPa
     tma_box(sb + (uint32_t)bx.line0 * kLineBytes, &maps.m[bx.src][bx.cls], slab * kSlab, bx.dof0, bar_lines);
   }
   const WarpRange wr = p.warp_range[(size_t)tile * (blockDim.x >> 5) + warp];
-  ring.start(sb + p.ring_off + (uint32_t)warp * (kRingChunks * kChunkWords * 16), bar_ring, p.stream + wr.begin, wr.n_words, lane);
+  ring.start(sb + p.ring_off + (uint32_t)warp * kRingBytes, bar_ring, p.stream + wr.begin, wr.n_words, lane);
   mbar_wait(bar_lines, 0);
+  return wr.n_words;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -204,22 +230,27 @@ __global__ void __launch_bounds__(256, 2) residual_fwd_tiled(const __grid_consta
   const int tile = blockIdx.x / p.n_slabs, slab = blockIdx.x - tile * p.n_slabs;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Ring ring;
-  stage_tile(maps, p, sb, tile, slab, warp, lane, ring);
+  const int ring_units = stage_tile(maps, p, sb, tile, slab, warp, lane, ring) / 4;
 
   const int q = lane >> 3;  // this lane's row slot in the quad
   // a lane owns samples [4l, 4l+4) and [32+4l, 32+4l+4), l = lane & 7: each LDS.128 of a quarter-warp then
   // reads 128 contiguous bytes of one line (conflict-free), the second one 128 B further
-  const uint32_t lane_off = (uint32_t)(lane & 7) * 16;
+  const uint32_t lines = sb + (uint32_t)(lane & 7) * 16;
+  const uint32_t rq = ring.base + (uint32_t)q * 16;  // this quarter's word within a 64-byte unit
   const int b0 = slab * kSlab + (lane & 7) * 4;
   const bool precond = p.precond != 0;
   float lsum = 0.f;
 
-  while (ring.pos < ring.n_words) {
-    ring.ensure(ring.pos + 4);
-    const int4 hdr = lds_word(ring.addr(ring.pos + q));
-    ring.advance(4, lane);
+  // stream = quads: [header unit][spare unit][n_steps step units], n_steps even; units are 64 B, so
+  // a pair of units never straddles a 512-byte chunk
+  int units_left = ring_units;
+  while (units_left > 0) {
+    if (ring.at_chunk_start()) ring.enter(lane);
+    const int4 hdr = lds_word(rq + ring.ptr);
+    ring.skip(128);
     const int n_steps = hdr.y;
     const int row = hdr.x;
+    units_left -= 2 + n_steps;
     // the load vector of this row is fetched now and consumed in the epilogue (hides the DRAM latency)
     float4 fv[2];
 #pragma unroll
@@ -227,62 +258,63 @@ __global__ void __launch_bounds__(256, 2) residual_fwd_tiled(const __grid_consta
       fv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (row >= 0 && b0 + 32 * k < p.ldb) fv[k] = ldg4_stream(p.fT + (int64_t)row * p.ldb + b0 + 32 * k);
     }
-    u64 accA[4], acc1[4], acc2[4];
+    P2 accA[4], acc1[4], acc2[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) accA[i] = acc1[i] = acc2[i] = 0ull;
+    for (int i = 0; i < 4; ++i) accA[i] = acc1[i] = acc2[i] = P2{0.f, 0.f};
+    // step pairs, in segments that end at a chunk boundary so that the inner loop carries no ring logic
+    for (int s = 0; s < n_steps;) {
+      if (ring.at_chunk_start()) ring.enter(lane);
+      const int seg = min(n_steps - s, (int)((kChunkBytes - (ring.ptr & (kChunkBytes - 1))) / 64));
+      s += seg;
+      const uint32_t rp = rq + ring.ptr;
+      ring.skip((uint32_t)seg * 64);
 #pragma unroll 1
-    for (int s = 0; s < n_steps; s += 2) {
-      ring.ensure(ring.pos + 8);
-      const int4 e0 = lds_word(ring.addr(ring.pos + q));
-      const int4 e1 = lds_word(ring.addr(ring.pos + 4 + q));
-      u64 x0[4], x1[4];
-      lds_pairs(sb + (uint32_t)e0.x + lane_off, x0[0], x0[1]);
-      lds_pairs(sb + (uint32_t)e0.x + lane_off + 128, x0[2], x0[3]);
-      lds_pairs(sb + (uint32_t)e1.x + lane_off, x1[0], x1[1]);
-      lds_pairs(sb + (uint32_t)e1.x + lane_off + 128, x1[2], x1[3]);
-      {
-        const u64 a = bc(__int_as_float(e0.y)), b1 = bc(__int_as_float(e0.z)), b2 = bc(__int_as_float(e0.w));
+      for (int t = 0; t < seg; t += 2) {
+        const int4 e0 = lds_word(rp + (uint32_t)t * 64);
+        const int4 e1 = lds_word(rp + (uint32_t)t * 64 + 64);
+        u64 x0[4], x1[4];
+        lds_pairs(lines + (uint32_t)e0.x, x0[0], x0[1]);
+        lds_pairs(lines + (uint32_t)e0.x + 128, x0[2], x0[3]);
+        lds_pairs(lines + (uint32_t)e1.x, x1[0], x1[1]);
+        lds_pairs(lines + (uint32_t)e1.x + 128, x1[2], x1[3]);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          fma2(accA[i], a, x0[i]);
-          fma2(acc1[i], b1, x0[i]);
-          fma2(acc2[i], b2, x0[i]);
+          fma2s(accA[i], __int_as_float(e0.y), x0[i]);
+          fma2s(acc1[i], __int_as_float(e0.z), x0[i]);
+          fma2s(acc2[i], __int_as_float(e0.w), x0[i]);
         }
-      }
-      {
-        const u64 a = bc(__int_as_float(e1.y)), b1 = bc(__int_as_float(e1.z)), b2 = bc(__int_as_float(e1.w));
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          fma2(accA[i], a, x1[i]);
-          fma2(acc1[i], b1, x1[i]);
-          fma2(acc2[i], b2, x1[i]);
+          fma2s(accA[i], __int_as_float(e1.y), x1[i]);
+          fma2s(acc1[i], __int_as_float(e1.z), x1[i]);
+          fma2s(acc2[i], __int_as_float(e1.w), x1[i]);
         }
       }
-      ring.advance(8, lane);
     }
     // epilogue: convection product, load vector, residual, loss, store
     if (row >= 0) {
       float lhs[8], c[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) unpk(accA[i], lhs[2 * i], lhs[2 * i + 1]);
+      for (int i = 0; i < 4; ++i) {
+        lhs[2 * i] = accA[i].lo;
+        lhs[2 * i + 1] = accA[i].hi;
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) c[i] = 0.f;
       if (hdr.w & 1) {
         u64 d1[4], d2[4];
         const uint32_t li = ((uint32_t)hdr.z & 0xffffu) * kLineBytes, lj = ((uint32_t)hdr.z >> 16) * kLineBytes;
-        lds_pairs(sb + li + lane_off, d1[0], d1[1]);
-        lds_pairs(sb + li + lane_off + 128, d1[2], d1[3]);
-        lds_pairs(sb + lj + lane_off, d2[0], d2[1]);
-        lds_pairs(sb + lj + lane_off + 128, d2[2], d2[3]);
+        lds_pairs(lines + li, d1[0], d1[1]);
+        lds_pairs(lines + li + 128, d1[2], d1[3]);
+        lds_pairs(lines + lj, d2[0], d2[1]);
+        lds_pairs(lines + lj + 128, d2[2], d2[3]);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          float u0, u1, v0, v1, s10, s11, s20, s21;
+          float u0, u1, v0, v1;
           unpk(d1[i], u0, u1);
           unpk(d2[i], v0, v1);
-          unpk(acc1[i], s10, s11);
-          unpk(acc2[i], s20, s21);
-          c[2 * i] = conv1(u0, s10, v0, s20);
-          c[2 * i + 1] = conv1(u1, s11, v1, s21);
+          c[2 * i] = conv1(u0, acc1[i].lo, v0, acc2[i].lo);
+          c[2 * i + 1] = conv1(u1, acc1[i].hi, v1, acc2[i].hi);
         }
       }
       float* rrow = p.outT != nullptr ? p.outT + (int64_t)row * p.ldb + b0 : nullptr;
@@ -326,114 +358,115 @@ __global__ void __launch_bounds__(256, 2) residual_bwd_tiled(const __grid_consta
   const int tile = blockIdx.x / p.n_slabs, slab = blockIdx.x - tile * p.n_slabs;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Ring ring;
-  stage_tile(maps, p, sb, tile, slab, warp, lane, ring);
+  const int n_words = stage_tile(maps, p, sb, tile, slab, warp, lane, ring);
 
-  const int h = lane >> 4;                                // this lane's pair slot in the duo
-  const uint32_t lane_off = (uint32_t)(lane & 15) * 16;   // 4 samples = 16 B of every line
+  const int h = lane >> 4;                                   // this lane's pair slot in the duo
+  const uint32_t lines = sb + (uint32_t)(lane & 15) * 16;    // 4 samples = 16 B of every line
+  const uint32_t rh = ring.base + (uint32_t)h * 16;          // this half's word within a word pair
   const int b0 = slab * kSlab + (lane & 15) * 4;
   const float g2 = 2.0f * (p.grad_loss != nullptr ? __ldg(p.grad_loss) : 1.0f);
 
-  while (ring.pos < ring.n_words) {
-    ring.ensure(ring.pos + 4);
-    const int4 h0 = lds_word(ring.addr(ring.pos + h));
-    const int4 h1 = lds_word(ring.addr(ring.pos + 2 + h));
-    ring.advance(4, lane);
+  // The stream is walked by linear word position `pos`; pieces (header 4 words, V-step 6, A-step 2,
+  // X-step 4) never straddle a 32-word chunk: when the next piece does not fit, both the plan builder
+  // and this reader skip to the next chunk.
+  int pos = 0;
+  auto place = [&](int len) {  // returns the ring address of the piece, entering a new chunk if needed
+    if ((pos & (kChunkWords - 1)) + len > kChunkWords) pos = (pos + kChunkWords - 1) & ~(kChunkWords - 1);
+    if ((pos & (kChunkWords - 1)) == 0) ring.enter(lane);
+    return rh + (((uint32_t)pos & (kRingChunks * kChunkWords - 1)) << 4);
+  };
+  while (pos < n_words) {
+    const uint32_t ha = place(4);
+    const int4 h0 = lds_word(ha);
+    const int4 h1 = lds_word(ha + 32);
+    pos += 4;
     const int nV = h0.z, nA = h0.w, nX = h1.x;
-    u64 accI[2] = {0ull, 0ull}, accJ[2] = {0ull, 0ull};
-    u64 bu1I[2] = {0ull, 0ull}, bu2I[2] = {0ull, 0ull}, bu1J[2] = {0ull, 0ull}, bu2J[2] = {0ull, 0ull};
-#pragma unroll 1
-    for (int v = 0; v < nV; ++v) {
-      ring.ensure(ring.pos + 6);
-      const int4 w0 = lds_word(ring.addr(ring.pos + h));
-      const int4 w1 = lds_word(ring.addr(ring.pos + 2 + h));
-      const int4 w2 = lds_word(ring.addr(ring.pos + 4 + h));
-      u64 d1[2], d2[2], rI[2], rJ[2];
-      lds_pairs(sb + ((uint32_t)w0.y & 0xffffu) * kLineBytes + lane_off, d1[0], d1[1]);
-      lds_pairs(sb + ((uint32_t)w0.y >> 16) * kLineBytes + lane_off, d2[0], d2[1]);
-      lds_pairs(sb + ((uint32_t)w0.x & 0xffffu) * kLineBytes + lane_off, rI[0], rI[1]);
-      lds_pairs(sb + ((uint32_t)w0.x >> 16) * kLineBytes + lane_off, rJ[0], rJ[1]);
-      const u64 aI = bc(__int_as_float(w0.z)), b1I = bc(__int_as_float(w0.w)), b2I = bc(__int_as_float(w1.x));
-      const u64 aJ = bc(__int_as_float(w1.y)), b1J = bc(__int_as_float(w1.z)), b2J = bc(__int_as_float(w1.w));
-      const u64 f1I = bc(__int_as_float(w2.x)), f2I = bc(__int_as_float(w2.y)), f1J = bc(__int_as_float(w2.z)),
-                f2J = bc(__int_as_float(w2.w));
+    P2 accI[2], accJ[2], bu1I[2], bu2I[2], bu1J[2], bu2J[2];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const u64 tI = fma2r(b2I, d2[i], fma2r(b1I, d1[i], aI));
-        const u64 tJ = fma2r(b2J, d2[i], fma2r(b1J, d1[i], aJ));
-        fma2(accI[i], tI, rI[i]);
-        fma2(accJ[i], tJ, rJ[i]);
-        fma2(bu1I[i], f1I, d1[i]);
-        fma2(bu2I[i], f2I, d1[i]);
-        fma2(bu1J[i], f1J, d2[i]);
-        fma2(bu2J[i], f2J, d2[i]);
+    for (int i = 0; i < 2; ++i) accI[i] = accJ[i] = bu1I[i] = bu2I[i] = bu1J[i] = bu2J[i] = P2{0.f, 0.f};
+    for (int v = 0; v < nV;) {
+      const uint32_t wa = place(6);
+      const int cnt = min(nV - v, (kChunkWords - (pos & (kChunkWords - 1))) / 6);
+      v += cnt;
+      pos += 6 * cnt;
+#pragma unroll 1
+      for (int t = 0; t < cnt; ++t) {
+        const int4 w0 = lds_word(wa + (uint32_t)t * 96);
+        const int4 w1 = lds_word(wa + (uint32_t)t * 96 + 32);
+        const int4 w2 = lds_word(wa + (uint32_t)t * 96 + 64);
+        u64 d1[2], d2[2], rI[2], rJ[2];
+        lds_pairs(lines + ((uint32_t)w0.y & 0xffffu) * kLineBytes, d1[0], d1[1]);
+        lds_pairs(lines + ((uint32_t)w0.y >> 16) * kLineBytes, d2[0], d2[1]);
+        lds_pairs(lines + ((uint32_t)w0.x & 0xffffu) * kLineBytes, rI[0], rI[1]);
+        lds_pairs(lines + ((uint32_t)w0.x >> 16) * kLineBytes, rJ[0], rJ[1]);
+        const u64 aI = bc(__int_as_float(w0.z)), b1I = bc(__int_as_float(w0.w)), b2I = bc(__int_as_float(w1.x));
+        const u64 aJ = bc(__int_as_float(w1.y)), b1J = bc(__int_as_float(w1.z)), b2J = bc(__int_as_float(w1.w));
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const u64 tI = fma2r(b2I, d2[i], fma2r(b1I, d1[i], aI));
+          const u64 tJ = fma2r(b2J, d2[i], fma2r(b1J, d1[i], aJ));
+          fma2p(accI[i], tI, rI[i]);
+          fma2p(accJ[i], tJ, rJ[i]);
+          fma2s(bu1I[i], __int_as_float(w2.x), d1[i]);
+          fma2s(bu2I[i], __int_as_float(w2.y), d1[i]);
+          fma2s(bu1J[i], __int_as_float(w2.z), d2[i]);
+          fma2s(bu2J[i], __int_as_float(w2.w), d2[i]);
+        }
       }
-      ring.advance(6, lane);
     }
+    for (int a = 0; a < nA;) {
+      const uint32_t wa = place(2);
+      const int cnt = min(nA - a, (kChunkWords - (pos & (kChunkWords - 1))) / 2);
+      a += cnt;
+      pos += 2 * cnt;
 #pragma unroll 1
-    for (int a = 0; a < nA; ++a) {
-      ring.ensure(ring.pos + 2);
-      const int4 w0 = lds_word(ring.addr(ring.pos + h));
-      u64 rI[2], rJ[2];
-      lds_pairs(sb + ((uint32_t)w0.x & 0xffffu) * kLineBytes + lane_off, rI[0], rI[1]);
-      lds_pairs(sb + ((uint32_t)w0.x >> 16) * kLineBytes + lane_off, rJ[0], rJ[1]);
-      const u64 aI = bc(__int_as_float(w0.y)), aJ = bc(__int_as_float(w0.z));
+      for (int t = 0; t < cnt; ++t) {
+        const int4 w0 = lds_word(wa + (uint32_t)t * 32);
+        u64 rI[2], rJ[2];
+        lds_pairs(lines + ((uint32_t)w0.x & 0xffffu) * kLineBytes, rI[0], rI[1]);
+        lds_pairs(lines + ((uint32_t)w0.x >> 16) * kLineBytes, rJ[0], rJ[1]);
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        fma2(accI[i], aI, rI[i]);
-        fma2(accJ[i], aJ, rJ[i]);
+        for (int i = 0; i < 2; ++i) {
+          fma2s(accI[i], __int_as_float(w0.y), rI[i]);
+          fma2s(accJ[i], __int_as_float(w0.z), rJ[i]);
+        }
       }
-      ring.advance(2, lane);
     }
 #pragma unroll 1
     for (int x = 0; x < nX; ++x) {
-      ring.ensure(ring.pos + 4);
-      const int4 w0 = lds_word(ring.addr(ring.pos + h));
-      const int4 w1 = lds_word(ring.addr(ring.pos + 2 + h));
+      const uint32_t wa = place(4);
+      pos += 4;
+      const int4 w0 = lds_word(wa);
+      const int4 w1 = lds_word(wa + 32);
       u64 xv[2];
-      lds_pairs(sb + (uint32_t)w0.x * kLineBytes + lane_off, xv[0], xv[1]);
-      const u64 c1I = bc(__int_as_float(w0.y)), c2I = bc(__int_as_float(w0.z)), c1J = bc(__int_as_float(w0.w)),
-                c2J = bc(__int_as_float(w1.x));
+      lds_pairs(lines + (uint32_t)w0.x * kLineBytes, xv[0], xv[1]);
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        fma2(bu1I[i], c1I, xv[i]);
-        fma2(bu2I[i], c2I, xv[i]);
-        fma2(bu1J[i], c1J, xv[i]);
-        fma2(bu2J[i], c2J, xv[i]);
+        fma2s(bu1I[i], __int_as_float(w0.y), xv[i]);
+        fma2s(bu2I[i], __int_as_float(w0.z), xv[i]);
+        fma2s(bu1J[i], __int_as_float(w0.w), xv[i]);
+        fma2s(bu2J[i], __int_as_float(w1.x), xv[i]);
       }
-      ring.advance(4, lane);
     }
     // epilogue: E-term, scale, store
+    float oI[4] = {accI[0].lo, accI[0].hi, accI[1].lo, accI[1].hi};
+    float oJ[4] = {accJ[0].lo, accJ[0].hi, accJ[1].lo, accJ[1].hi};
     if (h1.z & 1) {
-      u64 rI[2], rJ[2];
-      lds_pairs(sb + ((uint32_t)h1.y & 0xffffu) * kLineBytes + lane_off, rI[0], rI[1]);
-      lds_pairs(sb + ((uint32_t)h1.y >> 16) * kLineBytes + lane_off, rJ[0], rJ[1]);
-      const u64 es = bc(p.esign);
+      const float4 rI = *reinterpret_cast<const float4*>(smem + ((uint32_t)h1.y & 0xffffu) * kLineBytes + (lane & 15) * 16);
+      const float4 rJ = *reinterpret_cast<const float4*>(smem + ((uint32_t)h1.y >> 16) * kLineBytes + (lane & 15) * 16);
+      const float ri[4] = {rI.x, rI.y, rI.z, rI.w}, rj[4] = {rJ.x, rJ.y, rJ.z, rJ.w};
+      const float s1i[4] = {bu1I[0].lo, bu1I[0].hi, bu1I[1].lo, bu1I[1].hi}, s2i[4] = {bu2I[0].lo, bu2I[0].hi, bu2I[1].lo, bu2I[1].hi};
+      const float s1j[4] = {bu1J[0].lo, bu1J[0].hi, bu1J[1].lo, bu1J[1].hi}, s2j[4] = {bu2J[0].lo, bu2J[0].hi, bu2J[1].lo, bu2J[1].hi};
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        u64 eI = 0ull, eJ = 0ull;
-        fma2(eI, bu1I[i], rI[i]);
-        fma2(eI, bu1J[i], rJ[i]);
-        fma2(eJ, bu2I[i], rI[i]);
-        fma2(eJ, bu2J[i], rJ[i]);
-        fma2(accI[i], es, eI);
-        fma2(accJ[i], es, eJ);
+      for (int i = 0; i < 4; ++i) {
+        oI[i] = fmaf(p.esign, fmaf(s1j[i], rj[i], s1i[i] * ri[i]), oI[i]);
+        oJ[i] = fmaf(p.esign, fmaf(s2j[i], rj[i], s2i[i] * ri[i]), oJ[i]);
       }
     }
     if (b0 < p.B) {
       const int cI = h0.x, cJ = h0.y;
-      float4 o;
-      if (cI >= 0) {
-        unpk(accI[0], o.x, o.y);
-        unpk(accI[1], o.z, o.w);
-        o.x *= g2, o.y *= g2, o.z *= g2, o.w *= g2;
-        *reinterpret_cast<float4*>(p.outT + (int64_t)cI * p.ldb + b0) = o;
-      }
-      if (cJ >= 0) {
-        unpk(accJ[0], o.x, o.y);
-        unpk(accJ[1], o.z, o.w);
-        o.x *= g2, o.y *= g2, o.z *= g2, o.w *= g2;
-        *reinterpret_cast<float4*>(p.outT + (int64_t)cJ * p.ldb + b0) = o;
-      }
+      if (cI >= 0) *reinterpret_cast<float4*>(p.outT + (int64_t)cI * p.ldb + b0) = make_float4(oI[0] * g2, oI[1] * g2, oI[2] * g2, oI[3] * g2);
+      if (cJ >= 0) *reinterpret_cast<float4*>(p.outT + (int64_t)cJ * p.ldb + b0) = make_float4(oJ[0] * g2, oJ[1] * g2, oJ[2] * g2, oJ[3] * g2);
     }
   }
 }
@@ -492,8 +525,8 @@ struct SmemLayout {
 };
 SmemLayout smem_layout(const DevTilePlan& T) {
   SmemLayout L;
-  L.ring_off = (uint32_t)T.max_lines * kLineBytes;
-  L.bar_off = L.ring_off + (uint32_t)T.warps * (kRingChunks * kChunkWords * 16);
+  L.ring_off = ((uint32_t)T.max_lines * kLineBytes + kRingBytes - 1) / kRingBytes * kRingBytes;  // rings are size aligned
+  L.bar_off = L.ring_off + (uint32_t)T.warps * kRingBytes;
   L.total = L.bar_off + 8 + (uint32_t)T.warps * (kRingChunks * 8) + 8;
   return L;
 }

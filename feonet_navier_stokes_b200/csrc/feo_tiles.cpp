@@ -454,6 +454,7 @@ int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int3
 
     // 2. work items and their streams, one list of words per item
     std::vector<std::vector<Word16>> item_words;
+    std::vector<std::vector<int32_t>> item_parts;  // sizes (words) of the pieces that must not straddle a chunk
     std::vector<int64_t> item_cost;
     if (!backward) {
       std::vector<int32_t> rows;
@@ -477,6 +478,7 @@ int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int3
           const uint32_t offs = vel ? (LINE(F.pi[r], 0) | (LINE(F.pj[r], 0) << 16)) : 0u;
           w.push_back(mk((uint32_t)r, (uint32_t)n_steps, offs, vel ? 1u : 0u));
         }
+        for (int qd = 0; qd < 4; ++qd) w.push_back(mk(0u, 0u, 0u, 0u));  // spare unit: keeps step pairs 128-byte aligned
         for (int32_t s = 0; s < n_steps; ++s)
           for (int qd = 0; qd < 4; ++qd) {
             const int32_t r = r4[qd];
@@ -490,6 +492,7 @@ int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int3
             ++T.slot_entries;
           }
         item_cost.push_back(10 * (int64_t)n_steps + 12);
+        item_parts.emplace_back((size_t)(1 + n_steps / 2), 8);  // header pair, step pairs: 8 words each
         item_words.push_back(std::move(w));
       }
     } else {
@@ -571,6 +574,11 @@ int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int3
             for (int h = 0; h < 2; ++h) w.push_back(ws[h][k]);
         }
         item_cost.push_back(22 * (int64_t)nV + 10 * (int64_t)nA + 8 * (int64_t)nX + 20);
+        std::vector<int32_t> parts(1, 4);
+        parts.insert(parts.end(), nV, 6);
+        parts.insert(parts.end(), nA, 2);
+        parts.insert(parts.end(), nX, 4);
+        item_parts.push_back(std::move(parts));
         item_words.push_back(std::move(w));
       }
     }
@@ -592,8 +600,14 @@ int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int3
     for (int32_t w = 0; w < W; ++w) {
       WarpRange R{(int32_t)T.stream.size(), 0};
       for (int32_t it : mine[w]) {
-        T.stream.insert(T.stream.end(), item_words[it].begin(), item_words[it].end());
-        R.n_words += (int32_t)item_words[it].size();
+        // no piece straddles a chunk: the reader applies the same rule (skip to the next chunk when a piece does not fit)
+        size_t at = 0;
+        for (int32_t len : item_parts[it]) {
+          while ((T.stream.size() - (size_t)R.begin) % kChunkWords + (size_t)len > (size_t)kChunkWords) T.stream.push_back(mk(0u, 0u, 0u, 0u));
+          T.stream.insert(T.stream.end(), item_words[it].begin() + at, item_words[it].begin() + at + len);
+          at += (size_t)len;
+        }
+        R.n_words = (int32_t)(T.stream.size() - (size_t)R.begin);
       }
       while (T.stream.size() % kChunkWords != 0) T.stream.push_back(mk(0u, 0u, 0u, 0u));
       T.warp_range.push_back(R);
@@ -639,8 +653,13 @@ int replay_tile_plan(const TilePlan& T, int32_t ns_branch, const double* in0, co
     for (int32_t w = 0; w < W; ++w) {
       const WarpRange& R = T.warp_range[(size_t)t * W + w];
       if (R.begin % kChunkWords != 0) return fail(FEO_ERR_INVALID_ARGUMENT, "tile plan: warp stream not chunk aligned");
-      const Word16* s = T.stream.data() + R.begin;
+      const Word16* const s0 = T.stream.data() + R.begin;
+      const Word16* s = s0;
       const Word16* const end = s + R.n_words;
+      auto fit = [&](int32_t len) {  // skip to the next chunk when the next piece does not fit (as the kernels do)
+        const int32_t at = (int32_t)(s - s0) % kChunkWords;
+        if (at + len > kChunkWords) s += kChunkWords - at;
+      };
       while (s < end) {
         if (!T.backward) {
           const int32_t n_steps = (int32_t)s[0].w[1];
@@ -649,7 +668,7 @@ int replay_tile_plan(const TilePlan& T, int32_t ns_branch, const double* in0, co
             if ((int32_t)H.w[1] != n_steps) return fail(FEO_ERR_INVALID_ARGUMENT, "tile plan: quad step counts differ");
             double accA = 0, acc1 = 0, acc2 = 0;
             for (int32_t st = 0; st < n_steps; ++st) {
-              const Word16& e = s[4 + 4 * st + qd];
+              const Word16& e = s[8 + 4 * st + qd];
               if (e.w[0] % kLineBytes != 0) bad = true;
               const double x = S(e.w[0] / kLineBytes);
               accA += (double)u2f(e.w[1]) * x;
@@ -662,15 +681,21 @@ int replay_tile_plan(const TilePlan& T, int32_t ns_branch, const double* in0, co
             const double f = in1[row];
             out[row] = precond ? accA - (f - c) : accA - (-f + c);
           }
-          s += 4 + 4 * (size_t)n_steps;
+          s += 8 + 4 * (size_t)n_steps;
         } else {
+          fit(4);
           const uint32_t nV = s[0].w[2], nA = s[0].w[3], nX = s[2].w[0];
           for (int h = 0; h < 2; ++h) {
             const Word16 &H0 = s[h], &H1 = s[2 + h];
             if (H0.w[2] != nV || H0.w[3] != nA || H1.w[0] != nX) return fail(FEO_ERR_INVALID_ARGUMENT, "tile plan: duo step counts differ");
             double accI = 0, accJ = 0, bu1I = 0, bu2I = 0, bu1J = 0, bu2J = 0;
             const Word16* p = s + 4;
+            auto fitp = [&](int32_t len) {
+              const int32_t at = (int32_t)(p - s0) % kChunkWords;
+              if (at + len > kChunkWords) p += kChunkWords - at;
+            };
             for (uint32_t v = 0; v < nV; ++v, p += 6) {
+              fitp(6);
               const Word16 &w0 = p[h], &w1 = p[2 + h], &w2 = p[4 + h];
               const double rI = S(w0.w[0] & 0xffffu), rJ = S(w0.w[0] >> 16), d1 = S(w0.w[1] & 0xffffu), d2 = S(w0.w[1] >> 16);
               accI += rI * ((double)u2f(w0.w[2]) + (double)u2f(w0.w[3]) * d1 + (double)u2f(w1.w[0]) * d2);
@@ -681,11 +706,13 @@ int replay_tile_plan(const TilePlan& T, int32_t ns_branch, const double* in0, co
               bu2J += (double)u2f(w2.w[3]) * d2;
             }
             for (uint32_t a = 0; a < nA; ++a, p += 2) {
+              fitp(2);
               const Word16& w0 = p[h];
               accI += (double)u2f(w0.w[1]) * S(w0.w[0] & 0xffffu);
               accJ += (double)u2f(w0.w[2]) * S(w0.w[0] >> 16);
             }
             for (uint32_t x = 0; x < nX; ++x, p += 4) {
+              fitp(4);
               const Word16 &w0 = p[h], &w1 = p[2 + h];
               const double xv = S(w0.w[0]);
               bu1I += (double)u2f(w0.w[1]) * xv;
@@ -701,8 +728,8 @@ int replay_tile_plan(const TilePlan& T, int32_t ns_branch, const double* in0, co
             const int32_t cI = (int32_t)H0.w[0], cJ = (int32_t)H0.w[1];
             if (cI >= 0) out[cI] = accI;
             if (cJ >= 0) out[cJ] = accJ;
+            if (h == 1) s = p;  // both halves walk the same pieces
           }
-          s += 4 + 6 * (size_t)nV + 2 * (size_t)nA + 4 * (size_t)nX;
         }
       }
       if (s != end) return fail(FEO_ERR_INVALID_ARGUMENT, "tile plan: warp stream boundaries inconsistent");
