@@ -23,6 +23,7 @@ namespace feo {
 namespace {
 
 typedef unsigned long long u64;
+constexpr int kMaxWarps = 10;  // warps per CTA the kernels are compiled for (2 CTAs per SM, <= 102 registers)
 
 struct TensorMaps {
   CUtensorMap m[2][3];  // [source array][box class]
@@ -223,7 +224,7 @@ __device__ __forceinline__ int32_t stage_tile(const TensorMaps& maps, const Tile
 // ---------------------------------------------------------------------------------------------
 // forward: r = A a -/+ (F - c), loss partial = sum r^2
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2) residual_fwd_tiled(const __grid_constant__ TensorMaps maps, const TiledParams p) {
+__global__ void __launch_bounds__(kMaxWarps * 32, 2) residual_fwd_tiled(const __grid_constant__ TensorMaps maps, const TiledParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ float s_part[32];
   const uint32_t sb = smem_u32(smem);
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(256, 2) residual_fwd_tiled(const __grid_consta
 // ---------------------------------------------------------------------------------------------
 // backward: grad = 2 g [A^T r + s (B1^T (d1 r) + B2^T (d2 r) + E-term)], column-pair owned
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2) residual_bwd_tiled(const __grid_constant__ TensorMaps maps, const TiledParams p) {
+__global__ void __launch_bounds__(kMaxWarps * 32, 2) residual_bwd_tiled(const __grid_constant__ TensorMaps maps, const TiledParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sb = smem_u32(smem);
   const int tile = blockIdx.x / p.n_slabs, slab = blockIdx.x - tile * p.n_slabs;
@@ -550,6 +551,7 @@ int launch_residual_fwd(const feo_operator* op, const float* alphaT, const float
   if (int rc = make_maps(alphaT, ldb, op->n, maps.m[0])) return rc;
   for (int c = 0; c < 3; ++c) maps.m[1][c] = maps.m[0][c];
   const SmemLayout L = smem_layout(T);
+  if (T.warps > kMaxWarps) return fail(FEO_ERR_INVALID_ARGUMENT, "tile plan has more warps than the kernels are built for");
   TiledParams p{T.tile_box_ptr, T.tile_lines, T.boxes, T.warp_range, reinterpret_cast<const int4*>(T.stream), fT, rT, (float*)ws,
                 nullptr, ldb, B, n_slabs, op->ns_branch, 0.f, L.ring_off, L.bar_off};
   FEO_CUDA_CHECK(cudaFuncSetAttribute(residual_fwd_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
@@ -573,6 +575,7 @@ int launch_residual_bwd(const feo_operator* op, const float* alphaT, const float
   if (int rc = make_maps(rT, ldb, op->n, maps.m[0])) return rc;
   if (int rc = make_maps(op->has_conv ? alphaT : rT, ldb, op->n, maps.m[1])) return rc;
   const SmemLayout L = smem_layout(T);
+  if (T.warps > kMaxWarps) return fail(FEO_ERR_INVALID_ARGUMENT, "tile plan has more warps than the kernels are built for");
   TiledParams p{T.tile_box_ptr, T.tile_lines, T.boxes, T.warp_range, reinterpret_cast<const int4*>(T.stream), nullptr, gradT, nullptr,
                 grad_loss, ldb, B, n_slabs, op->ns_branch, op->ns_branch ? 1.0f : -1.0f, L.ring_off, L.bar_off};
   FEO_CUDA_CHECK(cudaFuncSetAttribute(residual_bwd_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));

@@ -26,10 +26,13 @@ namespace feo {
 
 TileTuning tile_tuning_from_env(bool backward) {
   TileTuning t;
+  // measured on B200 at cfg5 (tools/time_kernels.py): forward 10 warps x 360 lines, backward 8 warps x 376 lines
+  t.warps = backward ? 8 : 10;
+  t.max_lines = backward ? 376 : 360;
   if (const char* s = std::getenv(backward ? "FEO_TILE_LINES_BWD" : "FEO_TILE_LINES_FWD")) t.max_lines = atoi(s);
   if (const char* s = std::getenv(backward ? "FEO_TILE_WARPS_BWD" : "FEO_TILE_WARPS_FWD")) t.warps = atoi(s);
   t.max_lines = std::min(std::max(t.max_lines, 32), 800);
-  t.warps = std::min(std::max(t.warps, 1), 8);
+  t.warps = std::min(std::max(t.warps, 1), 10);
   return t;
 }
 
