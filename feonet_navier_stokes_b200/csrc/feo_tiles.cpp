@@ -256,35 +256,23 @@ void build_pair(const Front& F, int32_t cI, int32_t cJ, PairItem* out, int64_t* 
         }
     for (auto& kv : extra) P.x.push_back(kv.second);
   }
-  // plain entries: a source row feeding both columns is one step; the rest are zipped
+  // plain entries: each column walks its source rows in increasing order whatever its partner is (so the
+  // summation order, hence the result bits, do not depend on the tiling); a step takes the next entry of
+  // each column, and when both are the same source row the gather is shared
   {
     auto by_h = [](const TEnt& x, const TEnt& y) { return x.h < y.h; };
     std::stable_sort(plain[0].begin(), plain[0].end(), by_h);
     std::stable_sort(plain[1].begin(), plain[1].end(), by_h);
-    std::vector<TEnt> restI, restJ;
-    size_t i = 0, j = 0;
-    while (i < plain[0].size() || j < plain[1].size()) {
-      const bool hi = i < plain[0].size(), hj = j < plain[1].size();
-      if (hi && hj && plain[0][i].h == plain[1][j].h) {
-        P.a.push_back(AStep{plain[0][i].h, plain[1][j].h, plain[0][i].a, plain[1][j].a});
-        ++i;
-        ++j;
-      } else if (hi && (!hj || plain[0][i].h < plain[1][j].h)) {
-        restI.push_back(plain[0][i++]);
-      } else {
-        restJ.push_back(plain[1][j++]);
-      }
-    }
-    const size_t m = std::max(restI.size(), restJ.size());
+    const size_t m = std::max(plain[0].size(), plain[1].size());
     for (size_t t = 0; t < m; ++t) {
       AStep s{-1, -1, 0.f, 0.f};
-      if (t < restI.size()) {
-        s.hI = restI[t].h;
-        s.aI = restI[t].a;
+      if (t < plain[0].size()) {
+        s.hI = plain[0][t].h;
+        s.aI = plain[0][t].a;
       }
-      if (t < restJ.size()) {
-        s.hJ = restJ[t].h;
-        s.aJ = restJ[t].a;
+      if (t < plain[1].size()) {
+        s.hJ = plain[1][t].h;
+        s.aJ = plain[1][t].a;
       }
       P.a.push_back(s);
     }

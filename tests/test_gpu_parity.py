@@ -171,14 +171,69 @@ def test_ns_vs_oracle(feo, n, B, branch, ordering, native):
         assert feo.is_dof_major(grad)
 
 
-def test_ns_is_deterministic_and_blob_size_independent(feo, monkeypatch):
+def test_ns_is_deterministic_and_tile_size_independent(feo, monkeypatch):
     l1, g1, _, _, _ = _ns_case(feo, 10, 96, 1, "interleaved", True)
     l2, g2, _, _, _ = _ns_case(feo, 10, 96, 1, "interleaved", True)
     assert l1 == l2 and torch.equal(g1, g2)  # bit-reproducible: no atomics anywhere
-    monkeypatch.setenv("FEO_BLOB_ROWS", "9")
-    l3, g3, lo, go, _ = _ns_case(feo, 10, 96, 1, "interleaved", True)
-    assert torch.equal(g1, g3)  # per-row arithmetic does not depend on the walk order
-    assert abs(l3 - lo) <= LOSS_RTOL * abs(lo)
+    for lines, warps in (("96", "3"), ("160", "7")):  # many small tiles, other warp counts
+        monkeypatch.setenv("FEO_TILE_LINES_FWD", lines)
+        monkeypatch.setenv("FEO_TILE_LINES_BWD", lines)
+        monkeypatch.setenv("FEO_TILE_WARPS_FWD", warps)
+        monkeypatch.setenv("FEO_TILE_WARPS_BWD", warps)
+        l3, g3, lo, go, ns = _ns_case(feo, 10, 96, 1, "interleaved", True)
+        assert ns.operator.info.n_tiles_fwd > 4
+        assert torch.equal(g1, g3)  # per-row / per-column arithmetic does not depend on the tiling
+        assert abs(l3 - lo) <= LOSS_RTOL * abs(lo)
+
+
+def test_cfg5_full_size_properties(feo):
+    """BASELINE.json configs[4] at full size (n=333, N=1 001 334), a 128-sample batch: the fused kernels
+    against the SAME operator applied through the generic sparse kernels (feo_spmm) composed exactly as
+    SURVEY.md Appendix A.2 writes the loss and its gradient -- a size-independent consistency property --
+    plus padding-sample independence and bit-reproducibility."""
+    from feonet_navier_stokes_b200 import _lib as L
+    from feonet_navier_stokes_b200.fixtures import config_operators
+
+    fx = config_operators("steady_ns", 333, ordering="interleaved")
+    assert fx.N == 1001334
+    dev = torch.device("cuda")
+    ns = feo.SteadyNavierStokes(fx.A, fx.B1, fx.B2, fx.idx_sol, do_precond=False, device=dev)
+    op = ns.operator
+    B, ldb = 100, 128  # ragged: 100 of 128 columns used
+    gen = torch.Generator(device=dev).manual_seed(5)
+    aT = torch.empty(fx.N, ldb, device=dev).normal_(0.0, 0.3, generator=gen)
+    fT = torch.empty(fx.N, ldb, device=dev).normal_(0.0, 1.0, generator=gen)
+    loss, rT = op.residual_fwd(aT, fT, B)
+    gT = op.residual_bwd(aT, rT, B)
+    # reference composition on the device: r = A a + F - c (non-precond branch), c = d1*B1a + d2*B2a
+    I = torch.as_tensor(np.asarray(fx.idx_u1), device=dev)
+    J = torch.as_tensor(np.asarray(fx.idx_u2), device=dev)
+    Aa = op.spmm(L.FEO_MAT_A, False, aT, B)
+    Bu1 = op.spmm(L.FEO_MAT_B1, False, aT, B)
+    Bu2 = op.spmm(L.FEO_MAT_B2, False, aT, B)
+    d1 = torch.zeros_like(aT)
+    d2 = torch.zeros_like(aT)
+    d1[I] = aT[I]; d1[J] = aT[I]
+    d2[I] = aT[J]; d2[J] = aT[J]
+    r_ref = Aa + fT - (d1 * Bu1 + d2 * Bu2)
+    assert _rel(rT[:, :B].cpu().numpy(), r_ref[:, :B].cpu().numpy()) < 1e-6
+    l_ref = float((r_ref[:, :B].double() ** 2).sum())
+    assert abs(loss.item() - l_ref) <= LOSS_RTOL * l_ref
+    G = 2.0 * r_ref
+    g_ref = op.spmm(L.FEO_MAT_A, True, G, B)
+    g_ref -= op.spmm(L.FEO_MAT_B1, True, d1 * G, B) + op.spmm(L.FEO_MAT_B2, True, d2 * G, B)
+    w1, w2 = Bu1 * G, Bu2 * G
+    e = torch.zeros_like(aT)
+    e[I] = w1[I] + w1[J]
+    e[J] = w2[I] + w2[J]
+    g_ref -= e
+    assert _rel(gT[:, :B].cpu().numpy(), g_ref[:, :B].cpu().numpy()) < GRAD_RTOL
+    # padding columns (b >= B) never influence the result; the kernels are bit-reproducible
+    aT2 = aT.clone()
+    aT2[:, B:] = float("nan")
+    loss2, rT2 = op.residual_fwd(aT2, fT, B)
+    gT2 = op.residual_bwd(aT2, rT2, B)
+    assert loss2.item() == loss.item() and torch.equal(gT2[:, :B], gT[:, :B])
 
 
 def test_linear_properties_at_scale(feo):
