@@ -39,6 +39,29 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries (e.g. NCCL's version banner) write to file descriptor 1
+# behind Python's back, so fd 1 is pointed at stderr for the whole run and the line goes to a private
+# duplicate of the original stdout.
+_JSON_FD = None
+
+
+def claim_stdout():
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -174,7 +197,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -348,7 +371,7 @@ def run_ours(args):
             }
         except Exception as exc:  # pragma: no cover
             log(f"[bench] cpu_baseline failed: {exc!r}")
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -398,6 +421,7 @@ def run_e2e(args, torch, feo, ns, fx, dev, world, rank):
 
 def main():
     args = parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
