@@ -174,7 +174,7 @@ int feo_op_get_info(feo_handle_t h, feo_op_info* info) {
 size_t feo_workspace_bytes(feo_handle_t h, int32_t B, int32_t T) {
   if (h == nullptr || B <= 0) return 0;
   if (T < 1) T = 1;
-  return loss_partials_needed(h->n, h->tiles_f.n_tiles, (int64_t)B * T);
+  return loss_partials_needed(h->n, h->tiles_f.warps, (int64_t)B * T);
 }
 
 int feo_transpose(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int32_t rows, int32_t cols,

@@ -34,18 +34,20 @@ HostCsr transpose(const HostCsr& a);
 HostCsr axpy(const HostCsr& s, float dt, const HostCsr& a);  // S + dt*A
 
 // ---- tile plan of the fused residual kernels (feo_tiles.cpp / feo_tiled.cu) -----------------------
-// A CTA owns one TILE of operator rows (forward) / columns (backward) for one SLAB of 64 consecutive
-// samples.  It stages the "lines" the tile touches -- line = the 64 samples of one dof, 256 B -- in
-// shared memory with 2-D TMA boxes, then its warps walk private STREAMS of 16-byte words that are
-// double-buffered through shared memory by 1-D bulk copies.
+// A work unit = one TILE of operator rows (forward) / columns (backward) for one SLAB of 64 consecutive
+// samples.  A persistent CTA stages the "lines" the tile touches -- line = the 64 samples of one dof,
+// 256 B -- in shared memory with 2-D TMA boxes (two stages: the next unit loads while the current one is
+// processed), and its consumer warps walk private STREAMS of 16-byte words that are fed through
+// shared-memory rings by 1-D bulk copies.
 //   forward : a warp processes QUADS of rows, one row per quarter-warp, 8 samples per lane
 //   backward: a warp processes DUOS of column pairs, one pair (e.g. the velocity pair (I[k], J[k]))
 //             per half-warp, 4 samples per lane
-constexpr int kSlab = 64;                  // samples per CTA
+constexpr int kSlab = 64;                  // samples per work unit
 constexpr int kLineBytes = kSlab * 4;      // one staged dof line
 constexpr int kChunkWords = 32;            // stream words (16 B) per bulk copy: 512 B
 constexpr int kRingChunks = 4;             // chunks per warp ring (power of two)
-constexpr int kBoxRows[3] = {16, 4, 1};    // TMA box heights (dofs) available for staging
+constexpr int kBoxClasses = 5;
+constexpr int kBoxRows[kBoxClasses] = {16, 8, 4, 2, 1};  // TMA box heights (dofs) available for staging
 
 struct Word16 {
   uint32_t w[4];
@@ -87,8 +89,10 @@ struct WarpRange {  // 8 B
 //   A-step (1)  : {line(r[hI]) | line(r[hJ]) << 16, aI, aJ, 0}
 //   X-step (2)  : w0 = {line(alpha[x]), c1I, c2I, c1J}  w1 = {c2J, 0, 0, 0}: Bu1[cI] += c1I x, Bu2[cI] += c2I x, Bu1[cJ] += c1J x, ...
 struct TileTuning {
-  int32_t max_lines = 376;  // staged lines per tile (shared-memory budget: lines * 256 B)
-  int32_t warps = 8;        // warps per CTA
+  int32_t max_lines = 384;  // staged lines per tile (shared-memory budget: 2 stages x lines x 256 B), fillers included
+  int32_t fill_reserve_pct = 6;  // share of max_lines kept free for fillers while a tile grows (when fill_gap > 0)
+  int32_t fill_gap = 0;     // runs of needed dofs separated by <= fill_gap unneeded dofs are staged as one run
+  int32_t warps = 15;       // consumer warps per CTA (+ 1 producer warp)
 };
 TileTuning tile_tuning_from_env(bool backward);
 
@@ -162,7 +166,8 @@ int launch_sq_diff_sum(const float* xT, const float* yT, int32_t n, int64_t ldb,
 int launch_dense(const float* D, int32_t n, const float* XT, float* CT, int64_t ldb, int32_t B, float scale,
                  const float* scale_dev, const float* sub, float* loss_out, void* ws, size_t ws_bytes,
                  cudaStream_t st);
-size_t loss_partials_needed(int32_t n, int32_t n_tiles, int64_t cols);
+size_t loss_partials_needed(int32_t n, int32_t fused_warps, int64_t cols);
+size_t fused_partials_needed(int32_t warps);  // floats: one loss partial per (persistent CTA, consumer warp)
 int finalize_loss(float* partials, int count, float scale, float* loss_out, cudaStream_t st);
 int launch_residual_fwd(const feo_operator* op, const float* alphaT, const float* fT, int64_t ldb, int32_t B,
                         float* loss_out, float* rT, void* ws, size_t ws_bytes, cudaStream_t st);

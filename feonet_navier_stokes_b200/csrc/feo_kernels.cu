@@ -236,9 +236,9 @@ int check_layout(const void* p, int64_t ld, int32_t B, const char* what) {
 
 }  // namespace
 
-size_t loss_partials_needed(int32_t n, int32_t n_tiles, int64_t cols) {
-  // the fused forward writes one partial per (tile, 64-sample slab), the generic kernels one per (8 rows, 128 samples)
-  const int64_t fused = (int64_t)n_tiles * ((cols + kSlab - 1) / kSlab);
+size_t loss_partials_needed(int32_t n, int32_t fused_warps, int64_t cols) {
+  // the fused forward writes one partial per (persistent CTA, consumer warp), the generic kernels one per (8 rows, 128 samples)
+  const int64_t fused = (int64_t)fused_partials_needed(fused_warps);
   const int64_t generic = (int64_t)((n + 7) / 8) * ((cols + kWarpSamples - 1) / kWarpSamples);
   return (size_t)(std::max<int64_t>(std::max(fused, generic), 1024)) * sizeof(float);
 }

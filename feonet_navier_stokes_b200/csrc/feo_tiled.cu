@@ -1,11 +1,15 @@
 // sm_100a kernels of the fused sparse residual (forward: r, loss; backward: grad alpha).
 //
-// One CTA = one tile of operator rows (forward) / columns (backward) x one slab of 64 samples
-// (feo_internal.h, feo_tiles.cpp).  Data path of a CTA:
-//   1. the tile's dof lines (64 samples x 4 B each) are staged in shared memory by 2-D TMA boxes
-//      (cp.async.bulk.tensor) straight from the dof-major batch arrays -- no registers, no LSU slots;
-//   2. every warp streams its private list of 16-byte operator words through a 2 x 512 B shared
-//      memory ring filled by 1-D bulk copies (cp.async.bulk) that complete on per-slot mbarriers;
+// A work UNIT = one tile of operator rows (forward) / columns (backward) x one slab of 64 samples
+// (feo_internal.h, feo_tiles.cpp).  The kernels are PERSISTENT: one CTA per SM walks the units
+// blockIdx.x, blockIdx.x + gridDim.x, ... through a two-stage shared-memory pipeline:
+//   1. a producer warp stages the dof lines of the NEXT unit (64 samples x 4 B each) with 2-D TMA boxes
+//      (cp.async.bulk.tensor) straight from the dof-major batch arrays while the consumer warps work on
+//      the current one (full/empty mbarriers per stage; a warp may run one unit ahead of the slowest);
+//   2. every consumer warp streams its private list of 16-byte operator words through a 4 x 512 B shared
+//      memory ring filled by 1-D bulk copies (cp.async.bulk) that complete on per-slot mbarriers; the
+//      ring runs continuously across units, so the first words of the next unit are already in flight
+//      when the current one ends;
 //   3. gathers are conflict-free LDS.128 from the staged lines, the arithmetic is packed fp32
 //      (fma.rn.f32x2: two IEEE fp32 FMAs per instruction).
 // The load-store pipe (128 B/clk of shared-memory data per SM) is what bounds these kernels, so the
@@ -17,16 +21,19 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "feo_internal.h"
 
 namespace feo {
 namespace {
 
 typedef unsigned long long u64;
-constexpr int kMaxWarps = 10;  // warps per CTA the kernels are compiled for (2 CTAs per SM, <= 102 registers)
+constexpr uint32_t kSmemMax = 232448;  // opt-in dynamic shared memory per CTA (227 KB)
 
 struct TensorMaps {
-  CUtensorMap m[2][3];  // [source array][box class]
+  CUtensorMap m[2][kBoxClasses];  // [source array][box class]
 };
 
 struct TiledParams {
@@ -37,10 +44,15 @@ struct TiledParams {
   const int4* stream;
   const float* fT;         // forward: load vectors
   float* outT;             // forward: rT (may be NULL) ; backward: gradT
-  float* partials;         // forward: one loss partial per CTA
+  float* partials;         // forward: one loss partial per (CTA, consumer warp)
   const float* grad_loss;  // backward: upstream gradient (NULL = 1)
   int64_t ldb;
   int32_t B, n_slabs;
+  int32_t n_units;    // tiles x slabs
+  int32_t g_div, g_mod;  // gridDim.x / n_slabs, gridDim.x % n_slabs: (tile, slab) of a CTA's next unit without a division
+  int32_t warps;      // consumer warps (the tile plan's warp count); warp `warps` is the producer
+  uint32_t buf_bytes; // size of one line stage
+  int32_t debug;      // developer timing modes (FEO_DEBUG_MODE): 1 = stage lines only, 2 = compute only (no staging)
   int32_t precond;    // forward: 1 -> r = lhs - (f - c), 0 -> r = lhs - (-f + c)
   float esign;        // backward: +1 precond branch, -1 otherwise
   uint32_t ring_off;  // byte offset of the warp rings in dynamic shared memory
@@ -51,6 +63,9 @@ struct TiledParams {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -130,47 +145,78 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 // The per-warp operator stream: a ring of kRingChunks slots of kChunkWords 16-byte words in shared
 // memory (base aligned to the ring size), filled by 1-D bulk copies that complete on per-slot
-// mbarriers.  Readers keep a byte offset `ptr` into the ring; stream items never straddle a chunk
-// pair boundary the reader does not check (see the kernels), so the bookkeeping is one test per item.
+// mbarriers.  The ring is continuous over the units of the persistent CTA: chunk g (counted over all
+// units) lives in slot g % kRingChunks, every unit's words start at a fresh chunk.  The reader ENTERS
+// chunk g when it is about to read its first word; chunk g - 1 is then fully consumed and its slot is
+// refilled with chunk g + kRingChunks - 1, which may already belong to a later unit.
 constexpr uint32_t kChunkBytes = kChunkWords * 16;
 constexpr uint32_t kRingBytes = kRingChunks * kChunkBytes;
-struct Ring {
+struct Stream {
   uint32_t base, bar;  // shared addresses of the slots / their mbarriers
-  const int4* src;     // the warp's words in global memory
-  int32_t n_chunks;    // chunks of this warp's stream
-  int32_t chunk;       // chunks entered so far
-  uint32_t ptr;        // ring byte offset of the next word to read
+  uint32_t entered;    // chunks entered by the reader so far
+  uint32_t issued;     // chunks issued by the feeder so far
+  const int4* src;     // next chunk to issue
+  int32_t left;        // chunks left to issue in the feeder's current unit
+  int32_t u_next;      // the unit the feeder moves to next, its tile and slab
+  int32_t t_next, s_next;
+  int2 nxt;            // that unit's WarpRange {begin, n_words}, fetched one unit ahead
 
-  __device__ __forceinline__ void issue(int32_t c) const {
-    const uint32_t slot = (uint32_t)c & (kRingChunks - 1);
-    mbar_expect_tx(bar + slot * 8, kChunkBytes);
-    bulk_copy(base + slot * kChunkBytes, src + (size_t)c * kChunkWords, kChunkBytes, bar + slot * 8);
+  __device__ __forceinline__ void fetch_range(const TiledParams& p, int warp) {
+    if (u_next < p.n_units) nxt = __ldg(reinterpret_cast<const int2*>(p.warp_range + (size_t)t_next * p.warps + warp));
   }
-  __device__ __forceinline__ void start(uint32_t base_, uint32_t bar_, const int4* src_, int32_t n_words, int lane) {
+  // all lanes keep the bookkeeping, lane 0 issues the copy
+  __device__ __forceinline__ void issue_one(const TiledParams& p, int warp, int lane) {
+    while (left == 0) {
+      if (u_next >= p.n_units) return;
+      src = p.stream + nxt.x;
+      left = (nxt.y + kChunkWords - 1) / kChunkWords;
+      u_next += (int32_t)gridDim.x;
+      t_next += p.g_div;
+      s_next += p.g_mod;
+      if (s_next >= p.n_slabs) {
+        s_next -= p.n_slabs;
+        ++t_next;
+      }
+      fetch_range(p, warp);
+    }
+    if (lane == 0) {
+      const uint32_t slot = issued & (kRingChunks - 1);
+      mbar_expect_tx(bar + slot * 8, kChunkBytes);
+      bulk_copy(base + slot * kChunkBytes, src, kChunkBytes, bar + slot * 8);
+    }
+    src += kChunkWords;
+    --left;
+    ++issued;
+  }
+  __device__ __forceinline__ void start(const TiledParams& p, uint32_t base_, uint32_t bar_, int warp, int lane) {
     base = base_;
     bar = bar_;
-    src = src_;
-    n_chunks = (n_words + kChunkWords - 1) / kChunkWords;
-    chunk = 0;
-    ptr = 0;
-    if (lane == 0)
-      for (int32_t c = 0; c < kRingChunks && c < n_chunks; ++c) issue(c);
+    entered = issued = 0;
+    src = nullptr;
+    left = 0;
+    u_next = (int32_t)blockIdx.x;
+    t_next = u_next / p.n_slabs;
+    s_next = u_next - t_next * p.n_slabs;
+    nxt = make_int2(0, 0);
+    fetch_range(p, warp);
+    for (int c = 0; c < kRingChunks; ++c) issue_one(p, warp, lane);
   }
-  // The reader is about to read the first word of the next chunk: wait until it has landed; the chunk
-  // before it is fully consumed, so its slot is refilled with the chunk kRingChunks - 1 ahead.
-  __device__ __forceinline__ void enter(int lane) {
-    const int32_t c = chunk++;
-    mbar_wait(bar + ((uint32_t)c & (kRingChunks - 1)) * 8, ((uint32_t)c / kRingChunks) & 1u);
-    if (c >= 1) {
+  __device__ __forceinline__ void enter(const TiledParams& p, int warp, int lane) {
+    const uint32_t g = entered++;
+    mbar_wait(bar + (g & (kRingChunks - 1)) * 8, (g / kRingChunks) & 1u);
+    if (g >= 1) {
       __syncwarp();
-      const int32_t nc = c + kRingChunks - 1;
-      if (nc < n_chunks && lane == 0) issue(nc);
+      issue_one(p, warp, lane);
     }
   }
-  __device__ __forceinline__ bool at_chunk_start() const { return (ptr & (kChunkBytes - 1)) == 0; }
-  __device__ __forceinline__ void skip(uint32_t bytes) { ptr = (ptr + bytes) & (kRingBytes - 1); }
 };
 
 // (lo, hi) += (a.lo, a.hi) * (b.lo, b.hi)
@@ -196,279 +242,370 @@ __device__ __forceinline__ float conv1(float d1, float s1, float d2, float s2) {
   return __fadd_rn(__fmul_rn(d1, s1), __fmul_rn(d2, s2));
 }
 
-// Shared prologue: barriers, line staging, ring start.  Returns when the tile's lines have landed.
-template <typename RingT>
-__device__ __forceinline__ int32_t stage_tile(const TensorMaps& maps, const TiledParams& p, uint32_t sb, int tile, int slab, int warp,
-                                              int lane, RingT& ring) {
-  const uint32_t bar_lines = sb + p.bar_off;
-  const uint32_t bar_ring = bar_lines + 8 + (uint32_t)warp * (kRingChunks * 8);
+// Shared-memory map of a persistent CTA: [stage 0 lines][stage 1 lines][warp rings][mbarriers]
+//   mbarriers: full[2], empty[2], then kRingChunks per consumer warp
+struct Bars {
+  uint32_t full, empty, rings;
+};
+__device__ __forceinline__ Bars setup_barriers(const TiledParams& p, uint32_t sb, int warp, int lane) {
+  Bars b;
+  b.full = sb + p.bar_off;
+  b.empty = b.full + 16;
+  b.rings = b.full + 32;
   if (threadIdx.x == 0) {
-    mbar_init(bar_lines, 1);
-    mbar_expect_tx(bar_lines, (uint32_t)p.tile_lines[tile] * kLineBytes);
+    mbar_init(b.full, 1);
+    mbar_init(b.full + 8, 1);
+    mbar_init(b.empty, (uint32_t)p.warps);
+    mbar_init(b.empty + 8, (uint32_t)p.warps);
   }
-  if (lane == 0)
-    for (int c = 0; c < kRingChunks; ++c) mbar_init(bar_ring + c * 8, 1);
+  if (warp < p.warps && lane == 0)
+    for (int c = 0; c < kRingChunks; ++c) mbar_init(b.rings + (uint32_t)warp * (kRingChunks * 8) + c * 8, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
-  const int b0 = p.tile_box_ptr[tile], b1 = p.tile_box_ptr[tile + 1];
-  for (int b = b0 + (int)threadIdx.x; b < b1; b += (int)blockDim.x) {
-    const StageBox bx = p.boxes[b];
-    tma_box(sb + (uint32_t)bx.line0 * kLineBytes, &maps.m[bx.src][bx.cls], slab * kSlab, bx.dof0, bar_lines);
+  return b;
+}
+
+// (tile, slab) of the unit gridDim.x further
+__device__ __forceinline__ void next_unit(const TiledParams& p, int& tile, int& slab) {
+  tile += p.g_div;
+  slab += p.g_mod;
+  if (slab >= p.n_slabs) {
+    slab -= p.n_slabs;
+    ++tile;
   }
-  const WarpRange wr = p.warp_range[(size_t)tile * (blockDim.x >> 5) + warp];
-  ring.start(sb + p.ring_off + (uint32_t)warp * kRingBytes, bar_ring, p.stream + wr.begin, wr.n_words, lane);
-  mbar_wait(bar_lines, 0);
-  return wr.n_words;
+}
+
+// The producer warp: stages the lines of unit i into stage i & 1 as soon as every consumer warp has
+// released the unit that used the stage before (unit i - 2).
+__device__ __forceinline__ void produce_lines(const TensorMaps& maps, const TiledParams& p, uint32_t sb, const Bars& bars, int lane) {
+  int i = 0;
+  if (p.debug == 2) return;
+  int tile = (int)blockIdx.x / p.n_slabs, slab = (int)blockIdx.x - tile * p.n_slabs;
+  for (int u = (int)blockIdx.x; u < p.n_units; u += (int)gridDim.x, ++i, next_unit(p, tile, slab)) {
+    const uint32_t s = (uint32_t)i & 1u;
+    const int b0 = p.tile_box_ptr[tile], b1 = p.tile_box_ptr[tile + 1];
+    const uint32_t bytes = (uint32_t)p.tile_lines[tile] * kLineBytes;
+    if (i >= 2) mbar_wait(bars.empty + s * 8, (((uint32_t)i >> 1) - 1u) & 1u);
+    if (lane == 0) mbar_expect_tx(bars.full + s * 8, bytes);
+    __syncwarp();
+    const uint32_t dst = sb + s * p.buf_bytes;
+    for (int b = b0 + lane; b < b1; b += 32) {
+      const StageBox bx = p.boxes[b];
+      tma_box(dst + (uint32_t)bx.line0 * kLineBytes, &maps.m[bx.src][bx.cls], slab * kSlab, bx.dof0, bars.full + s * 8);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
 // forward: r = A a -/+ (F - c), loss partial = sum r^2
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kMaxWarps * 32, 2) residual_fwd_tiled(const __grid_constant__ TensorMaps maps, const TiledParams p) {
+template <int MAXW>
+__global__ void __launch_bounds__((MAXW + 1) * 32, 1) residual_fwd_tiled(const __grid_constant__ TensorMaps maps, const TiledParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ float s_part[32];
   const uint32_t sb = smem_u32(smem);
-  const int tile = blockIdx.x / p.n_slabs, slab = blockIdx.x - tile * p.n_slabs;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  Ring ring;
-  const int ring_units = stage_tile(maps, p, sb, tile, slab, warp, lane, ring) / 4;
+  const Bars bars = setup_barriers(p, sb, warp, lane);
+  if (warp == p.warps) {
+    produce_lines(maps, p, sb, bars, lane);
+    return;
+  }
+  Stream ring;
+  if (p.debug == 1) {  // staging only: wait for every unit's lines, touch nothing
+    int i = 0;
+    for (int u = (int)blockIdx.x; u < p.n_units; u += (int)gridDim.x, ++i) {
+      mbar_wait(bars.full + ((uint32_t)i & 1u) * 8, ((uint32_t)i >> 1) & 1u);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars.empty + ((uint32_t)i & 1u) * 8);
+    }
+    return;
+  }
+  ring.start(p, sb + p.ring_off + (uint32_t)warp * kRingBytes, bars.rings + (uint32_t)warp * (kRingChunks * 8), warp, lane);
 
   const int q = lane >> 3;  // this lane's row slot in the quad
   // a lane owns samples [4l, 4l+4) and [32+4l, 32+4l+4), l = lane & 7: each LDS.128 of a quarter-warp then
   // reads 128 contiguous bytes of one line (conflict-free), the second one 128 B further
-  const uint32_t lines = sb + (uint32_t)(lane & 7) * 16;
+  const uint32_t lane_off = (uint32_t)(lane & 7) * 16;
   const uint32_t rq = ring.base + (uint32_t)q * 16;  // this quarter's word within a 64-byte unit
-  const int b0 = slab * kSlab + (lane & 7) * 4;
   const bool precond = p.precond != 0;
-  float lsum = 0.f;
+  const WarpRange* my_ranges = p.warp_range + warp;
+  double dsum = 0.0;
 
-  // stream = quads: [header unit][spare unit][n_steps step units], n_steps even; units are 64 B, so
-  // a pair of units never straddles a 512-byte chunk
-  int units_left = ring_units;
-  while (units_left > 0) {
-    if (ring.at_chunk_start()) ring.enter(lane);
-    const int4 hdr = lds_word(rq + ring.ptr);
-    ring.skip(128);
-    const int n_steps = hdr.y;
-    const int row = hdr.x;
-    units_left -= 2 + n_steps;
-    // the load vector of this row is fetched now and consumed in the epilogue (hides the DRAM latency)
-    float4 fv[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      fv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row >= 0 && b0 + 32 * k < p.ldb) fv[k] = ldg4_stream(p.fT + (int64_t)row * p.ldb + b0 + 32 * k);
-    }
-    P2 accA[4], acc1[4], acc2[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) accA[i] = acc1[i] = acc2[i] = P2{0.f, 0.f};
-    // step pairs, in segments that end at a chunk boundary so that the inner loop carries no ring logic
-    for (int s = 0; s < n_steps;) {
-      if (ring.at_chunk_start()) ring.enter(lane);
-      const int seg = min(n_steps - s, (int)((kChunkBytes - (ring.ptr & (kChunkBytes - 1))) / 64));
-      s += seg;
-      const uint32_t rp = rq + ring.ptr;
-      ring.skip((uint32_t)seg * 64);
-#pragma unroll 1
-      for (int t = 0; t < seg; t += 2) {
-        const int4 e0 = lds_word(rp + (uint32_t)t * 64);
-        const int4 e1 = lds_word(rp + (uint32_t)t * 64 + 64);
-        u64 x0[4], x1[4];
-        lds_pairs(lines + (uint32_t)e0.x, x0[0], x0[1]);
-        lds_pairs(lines + (uint32_t)e0.x + 128, x0[2], x0[3]);
-        lds_pairs(lines + (uint32_t)e1.x, x1[0], x1[1]);
-        lds_pairs(lines + (uint32_t)e1.x + 128, x1[2], x1[3]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          fma2s(accA[i], __int_as_float(e0.y), x0[i]);
-          fma2s(acc1[i], __int_as_float(e0.z), x0[i]);
-          fma2s(acc2[i], __int_as_float(e0.w), x0[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          fma2s(accA[i], __int_as_float(e1.y), x1[i]);
-          fma2s(acc1[i], __int_as_float(e1.z), x1[i]);
-          fma2s(acc2[i], __int_as_float(e1.w), x1[i]);
-        }
-      }
-    }
-    // epilogue: convection product, load vector, residual, loss, store
-    if (row >= 0) {
-      float lhs[8], c[8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        lhs[2 * i] = accA[i].lo;
-        lhs[2 * i + 1] = accA[i].hi;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) c[i] = 0.f;
-      if (hdr.w & 1) {
-        u64 d1[4], d2[4];
-        const uint32_t li = ((uint32_t)hdr.z & 0xffffu) * kLineBytes, lj = ((uint32_t)hdr.z >> 16) * kLineBytes;
-        lds_pairs(lines + li, d1[0], d1[1]);
-        lds_pairs(lines + li + 128, d1[2], d1[3]);
-        lds_pairs(lines + lj, d2[0], d2[1]);
-        lds_pairs(lines + lj + 128, d2[2], d2[3]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float u0, u1, v0, v1;
-          unpk(d1[i], u0, u1);
-          unpk(d2[i], v0, v1);
-          c[2 * i] = conv1(u0, acc1[i].lo, v0, acc2[i].lo);
-          c[2 * i + 1] = conv1(u1, acc1[i].hi, v1, acc2[i].hi);
-        }
-      }
-      float* rrow = p.outT != nullptr ? p.outT + (int64_t)row * p.ldb + b0 : nullptr;
+  int tile_n = (int)blockIdx.x / p.n_slabs, slab_n = (int)blockIdx.x - tile_n * p.n_slabs;  // the unit after the current one
+  int32_t n_words_next = __ldg(&my_ranges[(size_t)tile_n * p.warps].n_words);
+  int i = 0;
+  for (int u = (int)blockIdx.x; u < p.n_units; u += (int)gridDim.x, ++i) {
+    const int32_t n_words = n_words_next;
+    const int slab = slab_n;
+    next_unit(p, tile_n, slab_n);
+    if (u + (int)gridDim.x < p.n_units) n_words_next = __ldg(&my_ranges[(size_t)tile_n * p.warps].n_words);
+    const uint32_t lines = sb + ((uint32_t)i & 1u) * p.buf_bytes + lane_off;
+    const int b0 = slab * kSlab + (lane & 7) * 4;
+    if (p.debug != 2) mbar_wait(bars.full + ((uint32_t)i & 1u) * 8, ((uint32_t)i >> 1) & 1u);
+    uint32_t ptr = (ring.entered & (kRingChunks - 1)) * kChunkBytes;  // the unit's words start at a fresh chunk
+    float lsum = 0.f;
+
+    // stream = quads: [header unit][spare unit][n_steps step units], n_steps even; units are 64 B, so
+    // a pair of units never straddles a 512-byte chunk
+    int units_left = n_words / 4;
+    while (units_left > 0) {
+      if ((ptr & (kChunkBytes - 1)) == 0) ring.enter(p, warp, lane);
+      const int4 hdr = lds_word(rq + ptr);
+      ptr = (ptr + 128) & (kRingBytes - 1);
+      const int n_steps = hdr.y;
+      const int row = hdr.x;
+      units_left -= 2 + n_steps;
+      // the load vector of this row is fetched now and consumed in the epilogue (hides the DRAM latency)
+      float4 fv[2];
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        const int b = b0 + 32 * k;
-        if (b < p.ldb) {
-          const float4 f = fv[k];
-          float4 r;
-          r.x = resid1(lhs[4 * k + 0], f.x, c[4 * k + 0], precond);
-          r.y = resid1(lhs[4 * k + 1], f.y, c[4 * k + 1], precond);
-          r.z = resid1(lhs[4 * k + 2], f.z, c[4 * k + 2], precond);
-          r.w = resid1(lhs[4 * k + 3], f.w, c[4 * k + 3], precond);
-          if (b + 0 < p.B) lsum = fmaf(r.x, r.x, lsum);
-          if (b + 1 < p.B) lsum = fmaf(r.y, r.y, lsum);
-          if (b + 2 < p.B) lsum = fmaf(r.z, r.z, lsum);
-          if (b + 3 < p.B) lsum = fmaf(r.w, r.w, lsum);
-          if (rrow != nullptr && b < p.B) *reinterpret_cast<float4*>(rrow + 32 * k) = r;
+        fv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row >= 0 && b0 + 32 * k < p.ldb) fv[k] = ldg4_stream(p.fT + (int64_t)row * p.ldb + b0 + 32 * k);
+      }
+      P2 accA[4], acc1[4], acc2[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) accA[k] = acc1[k] = acc2[k] = P2{0.f, 0.f};
+      // step pairs, in segments that end at a chunk boundary so that the inner loop carries no ring logic.
+      // (A software-pipelined variant of this loop -- gathers of pair j + 1 in flight during the FMAs of pair j --
+      // was measured SLOWER, 5.0-5.7 ms vs 4.06 ms at cfg5: the kernel is bound by the load-store pipe, not by
+      // the exposed round trips, and the extra control flow costs issue slots.)
+      for (int s = 0; s < n_steps;) {
+        if ((ptr & (kChunkBytes - 1)) == 0) ring.enter(p, warp, lane);
+        const int seg = min(n_steps - s, (int)((kChunkBytes - (ptr & (kChunkBytes - 1))) / 64));
+        s += seg;
+        const uint32_t rp = rq + ptr;
+        ptr = (ptr + (uint32_t)seg * 64) & (kRingBytes - 1);
+#pragma unroll 1
+        for (int t = 0; t < seg; t += 2) {
+          const int4 e0 = lds_word(rp + (uint32_t)t * 64);
+          const int4 e1 = lds_word(rp + (uint32_t)t * 64 + 64);
+          u64 x0[4], x1[4];
+          lds_pairs(lines + (uint32_t)e0.x, x0[0], x0[1]);
+          lds_pairs(lines + (uint32_t)e0.x + 128, x0[2], x0[3]);
+          lds_pairs(lines + (uint32_t)e1.x, x1[0], x1[1]);
+          lds_pairs(lines + (uint32_t)e1.x + 128, x1[2], x1[3]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            fma2s(accA[k], __int_as_float(e0.y), x0[k]);
+            fma2s(acc1[k], __int_as_float(e0.z), x0[k]);
+            fma2s(acc2[k], __int_as_float(e0.w), x0[k]);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            fma2s(accA[k], __int_as_float(e1.y), x1[k]);
+            fma2s(acc1[k], __int_as_float(e1.z), x1[k]);
+            fma2s(acc2[k], __int_as_float(e1.w), x1[k]);
+          }
+        }
+      }
+      // epilogue: convection product, load vector, residual, loss, store
+      if (row >= 0) {
+        float lhs[8], c[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          lhs[2 * k] = accA[k].lo;
+          lhs[2 * k + 1] = accA[k].hi;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) c[k] = 0.f;
+        if (hdr.w & 1) {
+          u64 d1[4], d2[4];
+          const uint32_t li = ((uint32_t)hdr.z & 0xffffu) * kLineBytes, lj = ((uint32_t)hdr.z >> 16) * kLineBytes;
+          lds_pairs(lines + li, d1[0], d1[1]);
+          lds_pairs(lines + li + 128, d1[2], d1[3]);
+          lds_pairs(lines + lj, d2[0], d2[1]);
+          lds_pairs(lines + lj + 128, d2[2], d2[3]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float u0, u1, v0, v1;
+            unpk(d1[k], u0, u1);
+            unpk(d2[k], v0, v1);
+            c[2 * k] = conv1(u0, acc1[k].lo, v0, acc2[k].lo);
+            c[2 * k + 1] = conv1(u1, acc1[k].hi, v1, acc2[k].hi);
+          }
+        }
+        float* rrow = p.outT != nullptr ? p.outT + (int64_t)row * p.ldb + b0 : nullptr;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int b = b0 + 32 * k;
+          if (b < p.ldb) {
+            const float4 f = fv[k];
+            float4 r;
+            r.x = resid1(lhs[4 * k + 0], f.x, c[4 * k + 0], precond);
+            r.y = resid1(lhs[4 * k + 1], f.y, c[4 * k + 1], precond);
+            r.z = resid1(lhs[4 * k + 2], f.z, c[4 * k + 2], precond);
+            r.w = resid1(lhs[4 * k + 3], f.w, c[4 * k + 3], precond);
+            if (b + 0 < p.B) lsum = fmaf(r.x, r.x, lsum);
+            if (b + 1 < p.B) lsum = fmaf(r.y, r.y, lsum);
+            if (b + 2 < p.B) lsum = fmaf(r.z, r.z, lsum);
+            if (b + 3 < p.B) lsum = fmaf(r.w, r.w, lsum);
+            if (rrow != nullptr && b < p.B) *reinterpret_cast<float4*>(rrow + 32 * k) = r;
+          }
         }
       }
     }
+    dsum += (double)lsum;  // per-unit fp32 partial, accumulated over the units in fp64
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bars.empty + ((uint32_t)i & 1u) * 8);  // this warp is done with the stage
   }
-  // fixed-order block reduction of the loss partial
-  lsum = warp_sum(lsum);
-  if (lane == 0) s_part[warp] = lsum;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    const int nw = blockDim.x >> 5;
-    for (int w = 0; w < nw; ++w) t += s_part[w];
-    p.partials[blockIdx.x] = t;
-  }
+  // fixed-order reduction: lanes -> warp; the warp partials are summed in fp64 by finalize_loss_kernel
+  dsum = warp_sum(dsum);
+  if (lane == 0) p.partials[(size_t)blockIdx.x * p.warps + warp] = (float)dsum;
 }
 
 // ---------------------------------------------------------------------------------------------
 // backward: grad = 2 g [A^T r + s (B1^T (d1 r) + B2^T (d2 r) + E-term)], column-pair owned
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kMaxWarps * 32, 2) residual_bwd_tiled(const __grid_constant__ TensorMaps maps, const TiledParams p) {
+template <int MAXW>
+__global__ void __launch_bounds__((MAXW + 1) * 32, 1) residual_bwd_tiled(const __grid_constant__ TensorMaps maps, const TiledParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sb = smem_u32(smem);
-  const int tile = blockIdx.x / p.n_slabs, slab = blockIdx.x - tile * p.n_slabs;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  Ring ring;
-  const int n_words = stage_tile(maps, p, sb, tile, slab, warp, lane, ring);
+  const Bars bars = setup_barriers(p, sb, warp, lane);
+  if (warp == p.warps) {
+    produce_lines(maps, p, sb, bars, lane);
+    return;
+  }
+  Stream ring;
+  if (p.debug == 1) {  // staging only: wait for every unit's lines, touch nothing
+    int i = 0;
+    for (int u = (int)blockIdx.x; u < p.n_units; u += (int)gridDim.x, ++i) {
+      mbar_wait(bars.full + ((uint32_t)i & 1u) * 8, ((uint32_t)i >> 1) & 1u);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars.empty + ((uint32_t)i & 1u) * 8);
+    }
+    return;
+  }
+  ring.start(p, sb + p.ring_off + (uint32_t)warp * kRingBytes, bars.rings + (uint32_t)warp * (kRingChunks * 8), warp, lane);
 
-  const int h = lane >> 4;                                   // this lane's pair slot in the duo
-  const uint32_t lines = sb + (uint32_t)(lane & 15) * 16;    // 4 samples = 16 B of every line
-  const uint32_t rh = ring.base + (uint32_t)h * 16;          // this half's word within a word pair
-  const int b0 = slab * kSlab + (lane & 15) * 4;
+  const int h = lane >> 4;                            // this lane's pair slot in the duo
+  const uint32_t lane_off = (uint32_t)(lane & 15) * 16;  // 4 samples = 16 B of every line
+  const uint32_t rh = ring.base + (uint32_t)h * 16;   // this half's word within a word pair
   const float g2 = 2.0f * (p.grad_loss != nullptr ? __ldg(p.grad_loss) : 1.0f);
+  const WarpRange* my_ranges = p.warp_range + warp;
 
-  // The stream is walked by linear word position `pos`; pieces (header 4 words, V-step 6, A-step 2,
-  // X-step 4) never straddle a 32-word chunk: when the next piece does not fit, both the plan builder
-  // and this reader skip to the next chunk.
-  int pos = 0;
-  auto place = [&](int len) {  // returns the ring address of the piece, entering a new chunk if needed
-    if ((pos & (kChunkWords - 1)) + len > kChunkWords) pos = (pos + kChunkWords - 1) & ~(kChunkWords - 1);
-    if ((pos & (kChunkWords - 1)) == 0) ring.enter(lane);
-    return rh + (((uint32_t)pos & (kRingChunks * kChunkWords - 1)) << 4);
-  };
-  while (pos < n_words) {
-    const uint32_t ha = place(4);
-    const int4 h0 = lds_word(ha);
-    const int4 h1 = lds_word(ha + 32);
-    pos += 4;
-    const int nV = h0.z, nA = h0.w, nX = h1.x;
-    P2 accI[2], accJ[2], bu1I[2], bu2I[2], bu1J[2], bu2J[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) accI[i] = accJ[i] = bu1I[i] = bu2I[i] = bu1J[i] = bu2J[i] = P2{0.f, 0.f};
-    for (int v = 0; v < nV;) {
-      const uint32_t wa = place(6);
-      const int cnt = min(nV - v, (kChunkWords - (pos & (kChunkWords - 1))) / 6);
-      v += cnt;
-      pos += 6 * cnt;
-#pragma unroll 1
-      for (int t = 0; t < cnt; ++t) {
-        const int4 w0 = lds_word(wa + (uint32_t)t * 96);
-        const int4 w1 = lds_word(wa + (uint32_t)t * 96 + 32);
-        const int4 w2 = lds_word(wa + (uint32_t)t * 96 + 64);
-        u64 d1[2], d2[2], rI[2], rJ[2];
-        lds_pairs(lines + ((uint32_t)w0.y & 0xffffu) * kLineBytes, d1[0], d1[1]);
-        lds_pairs(lines + ((uint32_t)w0.y >> 16) * kLineBytes, d2[0], d2[1]);
-        lds_pairs(lines + ((uint32_t)w0.x & 0xffffu) * kLineBytes, rI[0], rI[1]);
-        lds_pairs(lines + ((uint32_t)w0.x >> 16) * kLineBytes, rJ[0], rJ[1]);
-        const u64 aI = bc(__int_as_float(w0.z)), b1I = bc(__int_as_float(w0.w)), b2I = bc(__int_as_float(w1.x));
-        const u64 aJ = bc(__int_as_float(w1.y)), b1J = bc(__int_as_float(w1.z)), b2J = bc(__int_as_float(w1.w));
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const u64 tI = fma2r(b2I, d2[i], fma2r(b1I, d1[i], aI));
-          const u64 tJ = fma2r(b2J, d2[i], fma2r(b1J, d1[i], aJ));
-          fma2p(accI[i], tI, rI[i]);
-          fma2p(accJ[i], tJ, rJ[i]);
-          fma2s(bu1I[i], __int_as_float(w2.x), d1[i]);
-          fma2s(bu2I[i], __int_as_float(w2.y), d1[i]);
-          fma2s(bu1J[i], __int_as_float(w2.z), d2[i]);
-          fma2s(bu2J[i], __int_as_float(w2.w), d2[i]);
-        }
-      }
-    }
-    for (int a = 0; a < nA;) {
-      const uint32_t wa = place(2);
-      const int cnt = min(nA - a, (kChunkWords - (pos & (kChunkWords - 1))) / 2);
-      a += cnt;
-      pos += 2 * cnt;
-#pragma unroll 1
-      for (int t = 0; t < cnt; ++t) {
-        const int4 w0 = lds_word(wa + (uint32_t)t * 32);
-        u64 rI[2], rJ[2];
-        lds_pairs(lines + ((uint32_t)w0.x & 0xffffu) * kLineBytes, rI[0], rI[1]);
-        lds_pairs(lines + ((uint32_t)w0.x >> 16) * kLineBytes, rJ[0], rJ[1]);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          fma2s(accI[i], __int_as_float(w0.y), rI[i]);
-          fma2s(accJ[i], __int_as_float(w0.z), rJ[i]);
-        }
-      }
-    }
-#pragma unroll 1
-    for (int x = 0; x < nX; ++x) {
-      const uint32_t wa = place(4);
+  int tile_n = (int)blockIdx.x / p.n_slabs, slab_n = (int)blockIdx.x - tile_n * p.n_slabs;  // the unit after the current one
+  int32_t n_words_next = __ldg(&my_ranges[(size_t)tile_n * p.warps].n_words);
+  int i = 0;
+  for (int u = (int)blockIdx.x; u < p.n_units; u += (int)gridDim.x, ++i) {
+    const int32_t n_words = n_words_next;
+    const int slab = slab_n;
+    next_unit(p, tile_n, slab_n);
+    if (u + (int)gridDim.x < p.n_units) n_words_next = __ldg(&my_ranges[(size_t)tile_n * p.warps].n_words);
+    const uint32_t lines = sb + ((uint32_t)i & 1u) * p.buf_bytes + lane_off;
+    const int b0 = slab * kSlab + (lane & 15) * 4;
+    if (p.debug != 2) mbar_wait(bars.full + ((uint32_t)i & 1u) * 8, ((uint32_t)i >> 1) & 1u);
+
+    // The stream is walked by linear word position `pos` (counted over all units: the unit starts at a
+    // fresh chunk); pieces (header 4 words, V-step 6, A-step 2, X-step 4) never straddle a 32-word chunk:
+    // when the next piece does not fit, both the plan builder and this reader skip to the next chunk.
+    int pos = (int)(ring.entered * kChunkWords);
+    const int pos_end = pos + n_words;
+    auto place = [&](int len) {  // returns the ring address of the piece, entering a new chunk if needed
+      if ((pos & (kChunkWords - 1)) + len > kChunkWords) pos = (pos + kChunkWords - 1) & ~(kChunkWords - 1);
+      if ((pos & (kChunkWords - 1)) == 0) ring.enter(p, warp, lane);
+      return rh + (((uint32_t)pos & (kRingChunks * kChunkWords - 1)) << 4);
+    };
+    while (pos < pos_end) {
+      const uint32_t ha = place(4);
+      const int4 h0 = lds_word(ha);
+      const int4 h1 = lds_word(ha + 32);
       pos += 4;
-      const int4 w0 = lds_word(wa);
-      const int4 w1 = lds_word(wa + 32);
-      u64 xv[2];
-      lds_pairs(lines + (uint32_t)w0.x * kLineBytes, xv[0], xv[1]);
+      const int nV = h0.z, nA = h0.w, nX = h1.x;
+      P2 accI[2], accJ[2], bu1I[2], bu2I[2], bu1J[2], bu2J[2];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        fma2s(bu1I[i], __int_as_float(w0.y), xv[i]);
-        fma2s(bu2I[i], __int_as_float(w0.z), xv[i]);
-        fma2s(bu1J[i], __int_as_float(w0.w), xv[i]);
-        fma2s(bu2J[i], __int_as_float(w1.x), xv[i]);
+      for (int k = 0; k < 2; ++k) accI[k] = accJ[k] = bu1I[k] = bu2I[k] = bu1J[k] = bu2J[k] = P2{0.f, 0.f};
+      for (int v = 0; v < nV;) {
+        const uint32_t wa = place(6);
+        const int cnt = min(nV - v, (kChunkWords - (pos & (kChunkWords - 1))) / 6);
+        v += cnt;
+        pos += 6 * cnt;
+#pragma unroll 1
+        for (int t = 0; t < cnt; ++t) {
+          const int4 w0 = lds_word(wa + (uint32_t)t * 96);
+          const int4 w1 = lds_word(wa + (uint32_t)t * 96 + 32);
+          const int4 w2 = lds_word(wa + (uint32_t)t * 96 + 64);
+          u64 d1[2], d2[2], rI[2], rJ[2];
+          lds_pairs(lines + ((uint32_t)w0.y & 0xffffu) * kLineBytes, d1[0], d1[1]);
+          lds_pairs(lines + ((uint32_t)w0.y >> 16) * kLineBytes, d2[0], d2[1]);
+          lds_pairs(lines + ((uint32_t)w0.x & 0xffffu) * kLineBytes, rI[0], rI[1]);
+          lds_pairs(lines + ((uint32_t)w0.x >> 16) * kLineBytes, rJ[0], rJ[1]);
+          const u64 aI = bc(__int_as_float(w0.z)), b1I = bc(__int_as_float(w0.w)), b2I = bc(__int_as_float(w1.x));
+          const u64 aJ = bc(__int_as_float(w1.y)), b1J = bc(__int_as_float(w1.z)), b2J = bc(__int_as_float(w1.w));
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const u64 tI = fma2r(b2I, d2[k], fma2r(b1I, d1[k], aI));
+            const u64 tJ = fma2r(b2J, d2[k], fma2r(b1J, d1[k], aJ));
+            fma2p(accI[k], tI, rI[k]);
+            fma2p(accJ[k], tJ, rJ[k]);
+            fma2s(bu1I[k], __int_as_float(w2.x), d1[k]);
+            fma2s(bu2I[k], __int_as_float(w2.y), d1[k]);
+            fma2s(bu1J[k], __int_as_float(w2.z), d2[k]);
+            fma2s(bu2J[k], __int_as_float(w2.w), d2[k]);
+          }
+        }
+      }
+      for (int a = 0; a < nA;) {
+        const uint32_t wa = place(2);
+        const int cnt = min(nA - a, (kChunkWords - (pos & (kChunkWords - 1))) / 2);
+        a += cnt;
+        pos += 2 * cnt;
+#pragma unroll 1
+        for (int t = 0; t < cnt; ++t) {
+          const int4 w0 = lds_word(wa + (uint32_t)t * 32);
+          u64 rI[2], rJ[2];
+          lds_pairs(lines + ((uint32_t)w0.x & 0xffffu) * kLineBytes, rI[0], rI[1]);
+          lds_pairs(lines + ((uint32_t)w0.x >> 16) * kLineBytes, rJ[0], rJ[1]);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            fma2s(accI[k], __int_as_float(w0.y), rI[k]);
+            fma2s(accJ[k], __int_as_float(w0.z), rJ[k]);
+          }
+        }
+      }
+#pragma unroll 1
+      for (int x = 0; x < nX; ++x) {
+        const uint32_t wa = place(4);
+        pos += 4;
+        const int4 w0 = lds_word(wa);
+        const int4 w1 = lds_word(wa + 32);
+        u64 xv[2];
+        lds_pairs(lines + (uint32_t)w0.x * kLineBytes, xv[0], xv[1]);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          fma2s(bu1I[k], __int_as_float(w0.y), xv[k]);
+          fma2s(bu2I[k], __int_as_float(w0.z), xv[k]);
+          fma2s(bu1J[k], __int_as_float(w0.w), xv[k]);
+          fma2s(bu2J[k], __int_as_float(w1.x), xv[k]);
+        }
+      }
+      // epilogue: E-term, scale, store
+      float oI[4] = {accI[0].lo, accI[0].hi, accI[1].lo, accI[1].hi};
+      float oJ[4] = {accJ[0].lo, accJ[0].hi, accJ[1].lo, accJ[1].hi};
+      if (h1.z & 1) {
+        u64 pI[2], pJ[2];
+        lds_pairs(lines + ((uint32_t)h1.y & 0xffffu) * kLineBytes, pI[0], pI[1]);
+        lds_pairs(lines + ((uint32_t)h1.y >> 16) * kLineBytes, pJ[0], pJ[1]);
+        float ri[4], rj[4];
+        unpk(pI[0], ri[0], ri[1]);
+        unpk(pI[1], ri[2], ri[3]);
+        unpk(pJ[0], rj[0], rj[1]);
+        unpk(pJ[1], rj[2], rj[3]);
+        const float s1i[4] = {bu1I[0].lo, bu1I[0].hi, bu1I[1].lo, bu1I[1].hi}, s2i[4] = {bu2I[0].lo, bu2I[0].hi, bu2I[1].lo, bu2I[1].hi};
+        const float s1j[4] = {bu1J[0].lo, bu1J[0].hi, bu1J[1].lo, bu1J[1].hi}, s2j[4] = {bu2J[0].lo, bu2J[0].hi, bu2J[1].lo, bu2J[1].hi};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          oI[k] = fmaf(p.esign, fmaf(s1j[k], rj[k], s1i[k] * ri[k]), oI[k]);
+          oJ[k] = fmaf(p.esign, fmaf(s2j[k], rj[k], s2i[k] * ri[k]), oJ[k]);
+        }
+      }
+      if (b0 < p.B) {
+        const int cI = h0.x, cJ = h0.y;
+        if (cI >= 0) *reinterpret_cast<float4*>(p.outT + (int64_t)cI * p.ldb + b0) = make_float4(oI[0] * g2, oI[1] * g2, oI[2] * g2, oI[3] * g2);
+        if (cJ >= 0) *reinterpret_cast<float4*>(p.outT + (int64_t)cJ * p.ldb + b0) = make_float4(oJ[0] * g2, oJ[1] * g2, oJ[2] * g2, oJ[3] * g2);
       }
     }
-    // epilogue: E-term, scale, store
-    float oI[4] = {accI[0].lo, accI[0].hi, accI[1].lo, accI[1].hi};
-    float oJ[4] = {accJ[0].lo, accJ[0].hi, accJ[1].lo, accJ[1].hi};
-    if (h1.z & 1) {
-      const float4 rI = *reinterpret_cast<const float4*>(smem + ((uint32_t)h1.y & 0xffffu) * kLineBytes + (lane & 15) * 16);
-      const float4 rJ = *reinterpret_cast<const float4*>(smem + ((uint32_t)h1.y >> 16) * kLineBytes + (lane & 15) * 16);
-      const float ri[4] = {rI.x, rI.y, rI.z, rI.w}, rj[4] = {rJ.x, rJ.y, rJ.z, rJ.w};
-      const float s1i[4] = {bu1I[0].lo, bu1I[0].hi, bu1I[1].lo, bu1I[1].hi}, s2i[4] = {bu2I[0].lo, bu2I[0].hi, bu2I[1].lo, bu2I[1].hi};
-      const float s1j[4] = {bu1J[0].lo, bu1J[0].hi, bu1J[1].lo, bu1J[1].hi}, s2j[4] = {bu2J[0].lo, bu2J[0].hi, bu2J[1].lo, bu2J[1].hi};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        oI[i] = fmaf(p.esign, fmaf(s1j[i], rj[i], s1i[i] * ri[i]), oI[i]);
-        oJ[i] = fmaf(p.esign, fmaf(s2j[i], rj[i], s2i[i] * ri[i]), oJ[i]);
-      }
-    }
-    if (b0 < p.B) {
-      const int cI = h0.x, cJ = h0.y;
-      if (cI >= 0) *reinterpret_cast<float4*>(p.outT + (int64_t)cI * p.ldb + b0) = make_float4(oI[0] * g2, oI[1] * g2, oI[2] * g2, oI[3] * g2);
-      if (cJ >= 0) *reinterpret_cast<float4*>(p.outT + (int64_t)cJ * p.ldb + b0) = make_float4(oJ[0] * g2, oJ[1] * g2, oJ[2] * g2, oJ[3] * g2);
-    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bars.empty + ((uint32_t)i & 1u) * 8);  // this warp is done with the stage
   }
 }
 
@@ -492,7 +629,7 @@ int get_encode(EncodeTiledFn* out) {
 }
 
 // one map per box class over the dof-major array base[n][ldb]: box = kSlab samples x kBoxRows[cls] dofs
-int make_maps(const float* base, int64_t ldb, int32_t n, CUtensorMap out[3]) {
+int make_maps(const float* base, int64_t ldb, int32_t n, CUtensorMap out[kBoxClasses]) {
   EncodeTiledFn enc;
   if (int rc = get_encode(&enc)) return rc;
   // the driver entry point needs the primary context current on THIS thread (autograd runs the backward
@@ -500,7 +637,7 @@ int make_maps(const float* base, int64_t ldb, int32_t n, CUtensorMap out[3]) {
   int dev = 0;
   FEO_CUDA_CHECK(cudaGetDevice(&dev));
   FEO_CUDA_CHECK(cudaSetDevice(dev));
-  for (int cls = 0; cls < 3; ++cls) {
+  for (int cls = 0; cls < kBoxClasses; ++cls) {
     const cuuint64_t dims[2] = {(cuuint64_t)ldb, (cuuint64_t)n};
     const cuuint64_t strides[1] = {(cuuint64_t)ldb * sizeof(float)};
     const cuuint32_t box[2] = {(cuuint32_t)kSlab, (cuuint32_t)kBoxRows[cls]};
@@ -522,17 +659,50 @@ int check_layout(const void* p, int64_t ld, int32_t B, const char* what) {
 }
 
 struct SmemLayout {
-  uint32_t ring_off, bar_off, total;
+  uint32_t buf_bytes, ring_off, bar_off, total;
 };
 SmemLayout smem_layout(const DevTilePlan& T) {
   SmemLayout L;
-  L.ring_off = ((uint32_t)T.max_lines * kLineBytes + kRingBytes - 1) / kRingBytes * kRingBytes;  // rings are size aligned
+  L.buf_bytes = ((uint32_t)T.max_lines * kLineBytes + 1023u) / 1024u * 1024u;
+  L.ring_off = 2 * L.buf_bytes;
   L.bar_off = L.ring_off + (uint32_t)T.warps * kRingBytes;
-  L.total = L.bar_off + 8 + (uint32_t)T.warps * (kRingChunks * 8) + 8;
+  L.total = L.bar_off + 32 + (uint32_t)T.warps * (kRingChunks * 8);
   return L;
 }
 
+int debug_mode() {
+  const char* s = std::getenv("FEO_DEBUG_MODE");
+  return s != nullptr ? atoi(s) : 0;
+}
+
+int sm_count(int* out) {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    FEO_CUDA_CHECK(cudaGetDevice(&dev));
+    FEO_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    cached = n > 0 ? n : 1;
+  }
+  *out = cached;
+  return FEO_OK;
+}
+
+// persistent launch: one CTA per SM (or per unit when there are fewer units), `warps` consumer warps + 1 producer warp
+template <typename Kernel>
+int launch_persistent(Kernel k15, Kernel k19, const DevTilePlan& T, const SmemLayout& L, int grid, const TensorMaps& maps,
+                      const TiledParams& p, cudaStream_t st) {
+  if (T.warps > 19) return fail(FEO_ERR_INVALID_ARGUMENT, "tile plan has more warps than the kernels are built for");
+  if (L.total > kSmemMax) return fail(FEO_ERR_INVALID_ARGUMENT, "tile plan needs more shared memory than an SM has");
+  Kernel k = T.warps <= 15 ? k15 : k19;  // 16 warps x 128 registers or 20 warps x 96
+  FEO_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  k<<<(unsigned)grid, (unsigned)(T.warps + 1) * 32, L.total, st>>>(maps, p);
+  FEO_CUDA_CHECK(cudaGetLastError());
+  return FEO_OK;
+}
+
 }  // namespace
+
+size_t fused_partials_needed(int32_t warps) { return (size_t)1024 * (size_t)(warps > 0 ? warps : 1); }  // <= 1024 SMs
 
 int launch_residual_fwd(const feo_operator* op, const float* alphaT, const float* fT, int64_t ldb, int32_t B,
                         float* loss_out, float* rT, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -545,19 +715,21 @@ int launch_residual_fwd(const feo_operator* op, const float* alphaT, const float
   const DevTilePlan& T = op->tiles_f;
   const int32_t n_slabs = (B + kSlab - 1) / kSlab;
   const int64_t count = (int64_t)T.n_tiles * n_slabs;
-  if (count >= ((int64_t)1 << 31)) return fail(FEO_ERR_UNSUPPORTED, "grid too large");
-  if (ws == nullptr || ws_bytes < (size_t)count * sizeof(float)) return fail(FEO_ERR_INVALID_ARGUMENT, "workspace too small");
+  if (count >= ((int64_t)1 << 31)) return fail(FEO_ERR_UNSUPPORTED, "too many work units");
+  int sms = 1;
+  if (int rc = sm_count(&sms)) return rc;
+  const int grid = (int)std::min<int64_t>(count, sms);
+  const size_t n_partials = (size_t)grid * T.warps;
+  if (ws == nullptr || ws_bytes < n_partials * sizeof(float)) return fail(FEO_ERR_INVALID_ARGUMENT, "workspace too small");
   TensorMaps maps;
   if (int rc = make_maps(alphaT, ldb, op->n, maps.m[0])) return rc;
-  for (int c = 0; c < 3; ++c) maps.m[1][c] = maps.m[0][c];
+  for (int c = 0; c < kBoxClasses; ++c) maps.m[1][c] = maps.m[0][c];
   const SmemLayout L = smem_layout(T);
-  if (T.warps > kMaxWarps) return fail(FEO_ERR_INVALID_ARGUMENT, "tile plan has more warps than the kernels are built for");
   TiledParams p{T.tile_box_ptr, T.tile_lines, T.boxes, T.warp_range, reinterpret_cast<const int4*>(T.stream), fT, rT, (float*)ws,
-                nullptr, ldb, B, n_slabs, op->ns_branch, 0.f, L.ring_off, L.bar_off};
-  FEO_CUDA_CHECK(cudaFuncSetAttribute(residual_fwd_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-  residual_fwd_tiled<<<(unsigned)count, T.warps * 32, L.total, st>>>(maps, p);
-  FEO_CUDA_CHECK(cudaGetLastError());
-  return finalize_loss((float*)ws, (int)count, 1.0f, loss_out, st);
+                nullptr, ldb, B, n_slabs, (int32_t)count, grid / n_slabs, grid % n_slabs, T.warps, L.buf_bytes, debug_mode(), op->ns_branch, 0.f, L.ring_off,
+                L.bar_off};
+  if (int rc = launch_persistent(residual_fwd_tiled<15>, residual_fwd_tiled<19>, T, L, grid, maps, p, st)) return rc;
+  return finalize_loss((float*)ws, (int)n_partials, 1.0f, loss_out, st);
 }
 
 int launch_residual_bwd(const feo_operator* op, const float* alphaT, const float* rT, const float* grad_loss,
@@ -570,18 +742,18 @@ int launch_residual_bwd(const feo_operator* op, const float* alphaT, const float
   const DevTilePlan& T = op->tiles_b;
   const int32_t n_slabs = (B + kSlab - 1) / kSlab;
   const int64_t count = (int64_t)T.n_tiles * n_slabs;
-  if (count >= ((int64_t)1 << 31)) return fail(FEO_ERR_UNSUPPORTED, "grid too large");
+  if (count >= ((int64_t)1 << 31)) return fail(FEO_ERR_UNSUPPORTED, "too many work units");
+  int sms = 1;
+  if (int rc = sm_count(&sms)) return rc;
+  const int grid = (int)std::min<int64_t>(count, sms);
   TensorMaps maps;
   if (int rc = make_maps(rT, ldb, op->n, maps.m[0])) return rc;
   if (int rc = make_maps(op->has_conv ? alphaT : rT, ldb, op->n, maps.m[1])) return rc;
   const SmemLayout L = smem_layout(T);
-  if (T.warps > kMaxWarps) return fail(FEO_ERR_INVALID_ARGUMENT, "tile plan has more warps than the kernels are built for");
   TiledParams p{T.tile_box_ptr, T.tile_lines, T.boxes, T.warp_range, reinterpret_cast<const int4*>(T.stream), nullptr, gradT, nullptr,
-                grad_loss, ldb, B, n_slabs, op->ns_branch, op->ns_branch ? 1.0f : -1.0f, L.ring_off, L.bar_off};
-  FEO_CUDA_CHECK(cudaFuncSetAttribute(residual_bwd_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-  residual_bwd_tiled<<<(unsigned)count, T.warps * 32, L.total, st>>>(maps, p);
-  FEO_CUDA_CHECK(cudaGetLastError());
-  return FEO_OK;
+                grad_loss, ldb, B, n_slabs, (int32_t)count, grid / n_slabs, grid % n_slabs, T.warps, L.buf_bytes, debug_mode(),
+                op->ns_branch, op->ns_branch ? 1.0f : -1.0f, L.ring_off, L.bar_off};
+  return launch_persistent(residual_bwd_tiled<15>, residual_bwd_tiled<19>, T, L, grid, maps, p, st);
 }
 
 }  // namespace feo

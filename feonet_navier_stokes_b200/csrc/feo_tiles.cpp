@@ -15,6 +15,7 @@
 //   rows (the E-term of SURVEY.md Appendix A.2) from the alpha lines it gathers anyway, so the forward
 //   saves nothing but r.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
@@ -26,13 +27,18 @@ namespace feo {
 
 TileTuning tile_tuning_from_env(bool backward) {
   TileTuning t;
-  // measured on B200 at cfg5 (tools/time_kernels.py): forward 10 warps x 360 lines, backward 8 warps x 376 lines
-  t.warps = backward ? 8 : 10;
-  t.max_lines = backward ? 376 : 360;
+  // one persistent CTA per SM: 2 line stages + one 2 KB ring per consumer warp must fit 227 KB of shared memory.
+  // Measured at cfg5 (tools/time_kernels.py): forward 19 warps x 374 lines 3.74 ms (15 x 384: 3.95), backward 15 x 384
+  // 6.71 ms (19 x 374: 7.02); gap filling of the staging runs (fill_gap > 0) did not pay at any setting.
+  t.warps = backward ? 15 : 19;
+  t.max_lines = backward ? 384 : 374;
   if (const char* s = std::getenv(backward ? "FEO_TILE_LINES_BWD" : "FEO_TILE_LINES_FWD")) t.max_lines = atoi(s);
   if (const char* s = std::getenv(backward ? "FEO_TILE_WARPS_BWD" : "FEO_TILE_WARPS_FWD")) t.warps = atoi(s);
-  t.max_lines = std::min(std::max(t.max_lines, 32), 800);
-  t.warps = std::min(std::max(t.warps, 1), 10);
+  if (const char* s = std::getenv("FEO_TILE_FILL_GAP")) t.fill_gap = std::min(std::max(atoi(s), 0), 8);
+  if (const char* s = std::getenv("FEO_TILE_FILL_RESERVE")) t.fill_reserve_pct = std::min(std::max(atoi(s), 0), 50);
+  t.warps = std::min(std::max(t.warps, 1), 19);
+  const int32_t budget = (232448 - t.warps * (kRingChunks * kChunkWords * 16 + kRingChunks * 8) - 1024) / 2 / kLineBytes;
+  t.max_lines = std::min(std::max(t.max_lines, 32), budget);
   return t;
 }
 
@@ -328,6 +334,8 @@ int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int3
   };
 
   // ---- grow tiles --------------------------------------------------------------------------------
+  // the needed lines of a tile may take `grow_lines`; the rest of the budget is left for filler lines (see below)
+  const int32_t grow_lines = tune.fill_gap > 0 ? tune.max_lines - tune.max_lines * tune.fill_reserve_pct / 100 : tune.max_lines;
   std::vector<char> seen(n_units, 0);
   std::vector<int32_t> stamp((backward ? 2 : 1) * (size_t)n, -1);
   std::deque<int32_t> frontier, q;
@@ -369,11 +377,11 @@ int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int3
           }
         });
       const int32_t add = (int32_t)fresh.size();
-      if (!tile_units.back().empty() && lines + add > tune.max_lines) {
+      if (!tile_units.back().empty() && lines + add > grow_lines) {
         for (int64_t key : fresh) stamp[key] = -1;  // not staged after all
         break;
       }
-      if (add > tune.max_lines)
+      if (add > grow_lines)
         return fail(FEO_ERR_UNSUPPORTED, "a row needs more dof lines than a tile can stage; use the dense operator path");
       q.pop_front();
       tile_units.back().push_back(u);
@@ -420,6 +428,56 @@ int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int3
     }
     std::sort(keys.begin(), keys.end());
     keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    // The copy engine spends about the same time on a box whatever its height (~50 cycles per SM, tools/micro8.cu),
+    // so the number of boxes is what matters: runs separated by a few unneeded dofs are merged by staging the
+    // dofs in between as well (smallest gaps first), and run lengths are rounded up to one box where that
+    // costs at most a few extra lines.  Fillers are staged but never referenced by the streams.
+    {
+      struct Run {
+        int64_t start, len;
+      };
+      std::vector<Run> runs;
+      for (size_t i = 0; i < keys.size();) {
+        size_t j = i + 1;
+        while (j < keys.size() && keys[j] == keys[j - 1] + 1 && (keys[j] >= n) == (keys[i] >= n)) ++j;
+        runs.push_back(Run{keys[i], (int64_t)(j - i)});
+        i = j;
+      }
+      int64_t budget = (int64_t)tune.max_lines - (int64_t)keys.size();
+      auto same_src = [&](int64_t a, int64_t b) { return (a >= n) == (b >= n); };
+      for (int64_t g = 1; g <= tune.fill_gap && budget > 0; ++g) {
+        std::vector<Run> merged;
+        for (const Run& r : runs) {
+          if (!merged.empty()) {
+            Run& m = merged.back();
+            const int64_t gap = r.start - (m.start + m.len);
+            if (gap == g && gap <= budget && same_src(m.start, r.start)) {
+              m.len += gap + r.len;
+              budget -= gap;
+              continue;
+            }
+          }
+          merged.push_back(r);
+        }
+        runs.swap(merged);
+      }
+      for (size_t i = 0; i < runs.size(); ++i) {
+        Run& r = runs[i];
+        const int64_t rem = r.len % 16;
+        if (rem == 0) continue;
+        int64_t c = 1;
+        while (c < rem) c *= 2;
+        const int64_t junk = c - rem, src_end = r.start >= n ? 2 * (int64_t)n : (int64_t)n;
+        const int64_t room = (i + 1 < runs.size() && same_src(runs[i + 1].start, r.start) ? runs[i + 1].start : src_end) - (r.start + r.len);
+        if (junk > 0 && junk <= (c >= 16 ? 3 : c >= 8 ? 2 : 1) && junk <= budget && junk <= room) {
+          r.len += junk;
+          budget -= junk;
+        }
+      }
+      keys.clear();
+      for (const Run& r : runs)
+        for (int64_t k = 0; k < r.len; ++k) keys.push_back(r.start + k);
+    }
     if (keys.size() > 65535) return fail(FEO_ERR_UNSUPPORTED, "tile stages too many lines");
     T.max_lines = std::max<int32_t>(T.max_lines, (int32_t)keys.size());
     T.tile_lines.push_back((int32_t)keys.size());
@@ -428,7 +486,7 @@ int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int3
       size_t j = i + 1;
       while (j < keys.size() && keys[j] == keys[j - 1] + 1 && (keys[j] >= n) == (keys[i] >= n)) ++j;
       size_t len = j - i, pos = i;
-      for (int cls = 0; cls < 3; ++cls)
+      for (int cls = 0; cls < kBoxClasses; ++cls)
         while (len >= (size_t)kBoxRows[cls]) {
           const int64_t key = keys[pos];
           T.boxes.push_back(StageBox{(int32_t)(key >= n ? key - n : key), (uint16_t)pos, (uint8_t)cls, (uint8_t)(key >= n ? 1 : 0)});
@@ -436,6 +494,11 @@ int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int3
           len -= kBoxRows[cls];
         }
       i = j;
+    }
+    if (std::getenv("FEO_PLAN_DEBUG") && T.tile_lines.size() % 4000 == 0) {
+      long c[kBoxClasses] = {0, 0, 0, 0, 0};
+      for (const StageBox& b : T.boxes) c[b.cls]++;
+      fprintf(stderr, "[plan] boxes 16/8/4/2/1 rows: %ld %ld %ld %ld %ld over %ld tiles, %ld lines\n", c[0], c[1], c[2], c[3], c[4], (long)T.tile_lines.size(), (long)T.total_lines);
     }
     T.tile_box_ptr.push_back((int32_t)T.boxes.size());
     auto LINE = [&](int32_t dof, int32_t src) -> uint32_t {
@@ -579,14 +642,26 @@ int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int3
     std::vector<int32_t> order(item_words.size());
     for (size_t i = 0; i < order.size(); ++i) order[i] = (int32_t)i;
     std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return item_cost[x] > item_cost[y]; });
+    // Ties go to the first warp of a scan whose start and direction change from tile to tile: a consumer warp
+    // may run one unit ahead of the slowest one, so the warps that get the larger share must not be the
+    // same in consecutive units.
     std::vector<int64_t> load(W, 0);
     std::vector<std::vector<int32_t>> mine(W);
+    const uint32_t tile_no = (uint32_t)T.tile_lines.size() - 1u;
+    const uint32_t hsh = tile_no * 2654435761u;
+    const int32_t w0 = (int32_t)((hsh >> 8) % (uint32_t)W), dir = (hsh >> 7) & 1u ? 1 : W - 1;
     for (int32_t it : order) {
-      int32_t best = 0;
-      for (int32_t w = 1; w < W; ++w)
+      int32_t best = w0;
+      for (int32_t k = 1, w = (w0 + dir) % W; k < W; ++k, w = (w + dir) % W)
         if (load[w] < load[best]) best = w;
       load[best] += item_cost[it];
       mine[best].push_back(it);
+    }
+    if (std::getenv("FEO_PLAN_DEBUG")) {
+      static double sum_max = 0, sum_mean = 0; static long nt = 0;
+      int64_t mx = 0, tot = 0; for (int32_t w = 0; w < W; ++w) { mx = std::max(mx, load[w]); tot += load[w]; }
+      sum_max += (double)mx; sum_mean += (double)tot / W; ++nt;
+      if (nt % 2000 == 0) fprintf(stderr, "[plan] tiles %ld items/tile %.1f balance mean/max = %.3f\n", nt, (double)item_words.size(), sum_mean / sum_max);
     }
     for (int32_t w = 0; w < W; ++w) {
       WarpRange R{(int32_t)T.stream.size(), 0};
