@@ -80,12 +80,15 @@ struct WarpRange {  // 8 B
 // forward, per quad, quarter q reads word 4*unit + q; [header unit][spare unit][n_steps step units], n_steps even:
 //   header unit : {row (-1: idle), n_steps, line(alpha[pi]) | line(alpha[pj]) << 16, flags (bit 0: velocity row)}
 //   step unit   : {line(col) * 256, a, b1, b2}
-// backward, per duo, half h reads word 2*k + h:
-//   header      : w0 = {cI, cJ (-1: idle), nV, nA}   w1 = {nX, line(r[cI]) | line(r[cJ]) << 16, flags (bit 0: E-term), 0}
+// backward, per duo, half h reads word 2*k + h; [header][S-steps][V-steps][P-steps][A-steps][X-steps]:
+//   header      : w0 = {cI, cJ (-1: idle), nV, nA}   w1 = {nX, line(r[cI]) | line(r[cJ]) << 16, flags (bit 0: E-term), nS | nP << 16}
 //   V-step (3)  : w0 = {line(r[hI]) | line(r[hJ]) << 16, line(alpha[pi]) | line(alpha[pj]) << 16, aI, b1I}
 //                 w1 = {b2I, aJ, b1J, b2J}   w2 = {f1I, f2I, f1J, f2J}
 //       accI += r[hI] * (aI + b1I d1 + b2I d2)   accJ += r[hJ] * (aJ + b1J d1 + b2J d2)      (b* carry the branch sign)
 //       Bu1[cI] += f1I d1   Bu2[cI] += f2I d1    Bu1[cJ] += f1J d2   Bu2[cJ] += f2J d2
+//   S-step (2)  : a V-step whose two columns share the coefficients (the usual case: A's velocity block is
+//                 diag(K, K), B1 = diag(Dx, Dx), B2 = diag(Dy, Dy)):  w0 as above with a, b1;  w1 = {b2, f1, f2, 0}
+//   P-step (1)  : {line(r[h]), aI, aJ, 0}      both columns read the same source row h (one gather)
 //   A-step (1)  : {line(r[hI]) | line(r[hJ]) << 16, aI, aJ, 0}
 //   X-step (2)  : w0 = {line(alpha[x]), c1I, c2I, c1J}  w1 = {c2J, 0, 0, 0}: Bu1[cI] += c1I x, Bu2[cI] += c2I x, Bu1[cJ] += c1J x, ...
 struct TileTuning {

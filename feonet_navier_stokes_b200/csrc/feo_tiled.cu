@@ -496,7 +496,7 @@ __global__ void __launch_bounds__((MAXW + 1) * 32, 1) residual_bwd_tiled(const _
     if (p.debug != 2) mbar_wait(bars.full + ((uint32_t)i & 1u) * 8, ((uint32_t)i >> 1) & 1u);
 
     // The stream is walked by linear word position `pos` (counted over all units: the unit starts at a
-    // fresh chunk); pieces (header 4 words, V-step 6, A-step 2, X-step 4) never straddle a 32-word chunk:
+    // fresh chunk); pieces (header 4 words, S-step 4, V-step 6, P-step 2, A-step 2, X-step 4) never straddle a 32-word chunk:
     // when the next piece does not fit, both the plan builder and this reader skip to the next chunk.
     int pos = (int)(ring.entered * kChunkWords);
     const int pos_end = pos + n_words;
@@ -510,10 +510,38 @@ __global__ void __launch_bounds__((MAXW + 1) * 32, 1) residual_bwd_tiled(const _
       const int4 h0 = lds_word(ha);
       const int4 h1 = lds_word(ha + 32);
       pos += 4;
-      const int nV = h0.z, nA = h0.w, nX = h1.x;
+      const int nV = h0.z, nA = h0.w, nX = h1.x, nS = (int)((uint32_t)h1.w & 0xffffu), nP = (int)((uint32_t)h1.w >> 16);
       P2 accI[2], accJ[2], bu1I[2], bu2I[2], bu1J[2], bu2J[2];
 #pragma unroll
       for (int k = 0; k < 2; ++k) accI[k] = accJ[k] = bu1I[k] = bu2I[k] = bu1J[k] = bu2J[k] = P2{0.f, 0.f};
+      // symmetric V-steps: both columns share a, b1, b2 (one effective coefficient t) and f1, f2
+      for (int v = 0; v < nS;) {
+        const uint32_t wa = place(4);
+        const int cnt = min(nS - v, (kChunkWords - (pos & (kChunkWords - 1))) / 4);
+        v += cnt;
+        pos += 4 * cnt;
+#pragma unroll 1
+        for (int t = 0; t < cnt; ++t) {
+          const int4 w0 = lds_word(wa + (uint32_t)t * 64);
+          const int4 w1 = lds_word(wa + (uint32_t)t * 64 + 32);
+          u64 d1[2], d2[2], rI[2], rJ[2];
+          lds_pairs(lines + ((uint32_t)w0.y & 0xffffu) * kLineBytes, d1[0], d1[1]);
+          lds_pairs(lines + ((uint32_t)w0.y >> 16) * kLineBytes, d2[0], d2[1]);
+          lds_pairs(lines + ((uint32_t)w0.x & 0xffffu) * kLineBytes, rI[0], rI[1]);
+          lds_pairs(lines + ((uint32_t)w0.x >> 16) * kLineBytes, rJ[0], rJ[1]);
+          const u64 a = bc(__int_as_float(w0.z)), b1 = bc(__int_as_float(w0.w)), b2 = bc(__int_as_float(w1.x));
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const u64 tt = fma2r(b2, d2[k], fma2r(b1, d1[k], a));
+            fma2p(accI[k], tt, rI[k]);
+            fma2p(accJ[k], tt, rJ[k]);
+            fma2s(bu1I[k], __int_as_float(w1.y), d1[k]);
+            fma2s(bu2I[k], __int_as_float(w1.z), d1[k]);
+            fma2s(bu1J[k], __int_as_float(w1.y), d2[k]);
+            fma2s(bu2J[k], __int_as_float(w1.z), d2[k]);
+          }
+        }
+      }
       for (int v = 0; v < nV;) {
         const uint32_t wa = place(6);
         const int cnt = min(nV - v, (kChunkWords - (pos & (kChunkWords - 1))) / 6);
@@ -541,6 +569,24 @@ __global__ void __launch_bounds__((MAXW + 1) * 32, 1) residual_bwd_tiled(const _
             fma2s(bu2I[k], __int_as_float(w2.y), d1[k]);
             fma2s(bu1J[k], __int_as_float(w2.z), d2[k]);
             fma2s(bu2J[k], __int_as_float(w2.w), d2[k]);
+          }
+        }
+      }
+      // plain steps whose two columns read the same source row: one gather
+      for (int a = 0; a < nP;) {
+        const uint32_t wa = place(2);
+        const int cnt = min(nP - a, (kChunkWords - (pos & (kChunkWords - 1))) / 2);
+        a += cnt;
+        pos += 2 * cnt;
+#pragma unroll 1
+        for (int t = 0; t < cnt; ++t) {
+          const int4 w0 = lds_word(wa + (uint32_t)t * 32);
+          u64 rX[2];
+          lds_pairs(lines + (uint32_t)w0.x * kLineBytes, rX[0], rX[1]);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            fma2s(accI[k], __int_as_float(w0.y), rX[k]);
+            fma2s(accJ[k], __int_as_float(w0.z), rX[k]);
           }
         }
       }

@@ -161,11 +161,14 @@ struct XStep {
 struct PairItem {
   int32_t cI = -1, cJ = -1;
   bool vel = false;
+  std::vector<VStep> s;  // symmetric V-steps: both columns use the same a, b1, b2, f1, f2 (two words instead of three)
   std::vector<VStep> v;
+  std::vector<AStep> p;  // plain steps whose two columns read the SAME source row (one gather)
   std::vector<AStep> a;
   std::vector<XStep> x;
-  int64_t cost() const { return 22 * (int64_t)v.size() + 10 * (int64_t)a.size() + 8 * (int64_t)x.size() + 20; }
 };
+// load-store pipe cycles of a duo step (tools/micro5.cu, micro7.cu): gathers 4 each, half-uniform words 2 each
+constexpr int64_t kCostS = 20, kCostV = 22, kCostP = 6, kCostA = 10, kCostX = 8, kCostDuo = 24;
 
 struct TEnt {
   int32_t h;
@@ -242,7 +245,9 @@ void build_pair(const Front& F, int32_t cI, int32_t cJ, PairItem* out, int64_t* 
         take(fwd[0], s.kpi, &s.f1I, &s.f2I);
         take(fwd[1], s.kpj, &s.f1J, &s.f2J);
       }
-      P.v.push_back(s);
+      const bool sym = s.hI >= 0 && s.hJ >= 0 && f2u(s.aI) == f2u(s.aJ) && f2u(s.b1I) == f2u(s.b1J) && f2u(s.b2I) == f2u(s.b2J) &&
+                       f2u(s.f1I) == f2u(s.f1J) && f2u(s.f2I) == f2u(s.f2J);
+      (sym ? P.s : P.v).push_back(s);
     }
   }
   // forward entries of the own rows that no V-step gathers: extra steps
@@ -262,23 +267,45 @@ void build_pair(const Front& F, int32_t cI, int32_t cJ, PairItem* out, int64_t* 
         }
     for (auto& kv : extra) P.x.push_back(kv.second);
   }
-  // plain entries: each column walks its source rows in increasing order whatever its partner is (so the
-  // summation order, hence the result bits, do not depend on the tiling); a step takes the next entry of
-  // each column, and when both are the same source row the gather is shared
+  // plain entries: each column walks its source rows in increasing order.  A velocity pair (whose partner never
+  // changes) first takes the source rows BOTH columns read -- one gather serves the two of them (P-steps, e.g. the
+  // pressure rows of the divergence block) -- then the rest; two single dofs that merely share a pair slot are zipped
+  // position by position whatever their partner is, so that the summation order, hence the result bits, do not
+  // depend on the tiling.
   {
     auto by_h = [](const TEnt& x, const TEnt& y) { return x.h < y.h; };
     std::stable_sort(plain[0].begin(), plain[0].end(), by_h);
     std::stable_sort(plain[1].begin(), plain[1].end(), by_h);
-    const size_t m = std::max(plain[0].size(), plain[1].size());
+    std::vector<TEnt> rest[2];
+    if (P.vel) {
+      size_t i = 0, j = 0;
+      while (i < plain[0].size() && j < plain[1].size()) {
+        if (plain[0][i].h == plain[1][j].h) {
+          P.p.push_back(AStep{plain[0][i].h, plain[1][j].h, plain[0][i].a, plain[1][j].a});
+          ++i;
+          ++j;
+        } else if (plain[0][i].h < plain[1][j].h) {
+          rest[0].push_back(plain[0][i++]);
+        } else {
+          rest[1].push_back(plain[1][j++]);
+        }
+      }
+      rest[0].insert(rest[0].end(), plain[0].begin() + i, plain[0].end());
+      rest[1].insert(rest[1].end(), plain[1].begin() + j, plain[1].end());
+    } else {
+      rest[0] = plain[0];
+      rest[1] = plain[1];
+    }
+    const size_t m = std::max(rest[0].size(), rest[1].size());
     for (size_t t = 0; t < m; ++t) {
       AStep s{-1, -1, 0.f, 0.f};
-      if (t < plain[0].size()) {
-        s.hI = plain[0][t].h;
-        s.aI = plain[0][t].a;
+      if (t < rest[0].size()) {
+        s.hI = rest[0][t].h;
+        s.aI = rest[0][t].a;
       }
-      if (t < plain[1].size()) {
-        s.hJ = plain[1][t].h;
-        s.aJ = plain[1][t].a;
+      if (t < rest[1].size()) {
+        s.hJ = rest[1][t].h;
+        s.aJ = rest[1][t].a;
       }
       P.a.push_back(s);
     }
@@ -570,22 +597,42 @@ int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int3
         build_pair(F, pending, -1, &pairs.back(), &T.real_entries);
       }
       std::stable_sort(pairs.begin(), pairs.end(), [](const PairItem& x, const PairItem& y) {
+        if (x.s.size() != y.s.size()) return x.s.size() > y.s.size();
         if (x.v.size() != y.v.size()) return x.v.size() > y.v.size();
+        if (x.p.size() != y.p.size()) return x.p.size() > y.p.size();
         if (x.a.size() != y.a.size()) return x.a.size() > y.a.size();
         return x.x.size() > y.x.size();
       });
       const PairItem idle;
       for (size_t g = 0; g < pairs.size(); g += 2) {
         const PairItem* pp[2] = {&pairs[g], g + 1 < pairs.size() ? &pairs[g + 1] : &idle};
+        const uint32_t nS = (uint32_t)std::max(pp[0]->s.size(), pp[1]->s.size());
         const uint32_t nV = (uint32_t)std::max(pp[0]->v.size(), pp[1]->v.size());
+        const uint32_t nP = (uint32_t)std::max(pp[0]->p.size(), pp[1]->p.size());
         const uint32_t nA = (uint32_t)std::max(pp[0]->a.size(), pp[1]->a.size());
         const uint32_t nX = (uint32_t)std::max(pp[0]->x.size(), pp[1]->x.size());
+        if (nS > 65535 || nP > 65535) return fail(FEO_ERR_UNSUPPORTED, "a column has too many entries for the fused backward plan");
         std::vector<Word16> w;
         for (int h = 0; h < 2; ++h) w.push_back(mk((uint32_t)pp[h]->cI, (uint32_t)pp[h]->cJ, nV, nA));
         for (int h = 0; h < 2; ++h) {
           const PairItem& P = *pp[h];
           const uint32_t own = P.vel ? (LINE(P.cI, 0) | (LINE(P.cJ, 0) << 16)) : 0u;
-          w.push_back(mk(nX, own, P.vel ? 1u : 0u, 0u));
+          w.push_back(mk(nX, own, P.vel ? 1u : 0u, nS | (nP << 16)));
+        }
+        auto r_lines = [&](int32_t hI, int32_t hJ) { return LINE(hI >= 0 ? hI : hJ, 0) | (LINE(hJ >= 0 ? hJ : hI, 0) << 16); };
+        for (uint32_t s = 0; s < nS; ++s) {
+          Word16 ws[2][2];
+          for (int h = 0; h < 2; ++h) {
+            ws[h][0] = ws[h][1] = mk(0u, 0u, 0u, 0u);
+            if (s < pp[h]->s.size()) {
+              const VStep& v = pp[h]->s[s];
+              ws[h][0] = mk(r_lines(v.hI, v.hJ), LINE(v.kpi, 1) | (LINE(v.kpj, 1) << 16), f2u(v.aI), f2u(v.b1I));
+              ws[h][1] = mk(f2u(v.b2I), f2u(v.f1I), f2u(v.f2I), 0u);
+            }
+            T.slot_entries += 2;
+          }
+          for (int k = 0; k < 2; ++k)
+            for (int h = 0; h < 2; ++h) w.push_back(ws[h][k]);
         }
         for (uint32_t s = 0; s < nV; ++s) {
           Word16 ws[2][3];
@@ -593,8 +640,7 @@ int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int3
             ws[h][0] = ws[h][1] = ws[h][2] = mk(0u, 0u, 0u, 0u);
             if (s < pp[h]->v.size()) {
               const VStep& v = pp[h]->v[s];
-              const uint32_t lrI = LINE(v.hI >= 0 ? v.hI : v.hJ, 0), lrJ = LINE(v.hJ >= 0 ? v.hJ : v.hI, 0);
-              ws[h][0] = mk(lrI | (lrJ << 16), LINE(v.kpi, 1) | (LINE(v.kpj, 1) << 16), f2u(v.aI), f2u(v.b1I));
+              ws[h][0] = mk(r_lines(v.hI, v.hJ), LINE(v.kpi, 1) | (LINE(v.kpj, 1) << 16), f2u(v.aI), f2u(v.b1I));
               ws[h][1] = mk(f2u(v.b2I), f2u(v.aJ), f2u(v.b1J), f2u(v.b2J));
               ws[h][2] = mk(f2u(v.f1I), f2u(v.f2I), f2u(v.f1J), f2u(v.f2J));
             }
@@ -603,13 +649,22 @@ int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int3
           for (int k = 0; k < 3; ++k)
             for (int h = 0; h < 2; ++h) w.push_back(ws[h][k]);
         }
+        for (uint32_t s = 0; s < nP; ++s)
+          for (int h = 0; h < 2; ++h) {
+            Word16 x = mk(0u, 0u, 0u, 0u);
+            if (s < pp[h]->p.size()) {
+              const AStep& a = pp[h]->p[s];
+              x = mk(LINE(a.hI, 0), f2u(a.aI), f2u(a.aJ), 0u);
+            }
+            T.slot_entries += 2;
+            w.push_back(x);
+          }
         for (uint32_t s = 0; s < nA; ++s)
           for (int h = 0; h < 2; ++h) {
             Word16 x = mk(0u, 0u, 0u, 0u);
             if (s < pp[h]->a.size()) {
               const AStep& a = pp[h]->a[s];
-              const uint32_t lrI = LINE(a.hI >= 0 ? a.hI : a.hJ, 0), lrJ = LINE(a.hJ >= 0 ? a.hJ : a.hI, 0);
-              x = mk(lrI | (lrJ << 16), f2u(a.aI), f2u(a.aJ), 0u);
+              x = mk(r_lines(a.hI, a.hJ), f2u(a.aI), f2u(a.aJ), 0u);
             }
             T.slot_entries += 2;
             w.push_back(x);
@@ -627,9 +682,11 @@ int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int3
           for (int k = 0; k < 2; ++k)
             for (int h = 0; h < 2; ++h) w.push_back(ws[h][k]);
         }
-        item_cost.push_back(22 * (int64_t)nV + 10 * (int64_t)nA + 8 * (int64_t)nX + 20);
+        item_cost.push_back(kCostS * nS + kCostV * nV + kCostP * nP + kCostA * nA + kCostX * nX + kCostDuo);
         std::vector<int32_t> parts(1, 4);
+        parts.insert(parts.end(), nS, 4);
         parts.insert(parts.end(), nV, 6);
+        parts.insert(parts.end(), nP, 2);
         parts.insert(parts.end(), nA, 2);
         parts.insert(parts.end(), nX, 4);
         item_parts.push_back(std::move(parts));
@@ -750,16 +807,29 @@ int replay_tile_plan(const TilePlan& T, int32_t ns_branch, const double* in0, co
           s += 8 + 4 * (size_t)n_steps;
         } else {
           fit(4);
-          const uint32_t nV = s[0].w[2], nA = s[0].w[3], nX = s[2].w[0];
+          const uint32_t nV = s[0].w[2], nA = s[0].w[3], nX = s[2].w[0], nS = s[2].w[3] & 0xffffu, nP = s[2].w[3] >> 16;
           for (int h = 0; h < 2; ++h) {
             const Word16 &H0 = s[h], &H1 = s[2 + h];
-            if (H0.w[2] != nV || H0.w[3] != nA || H1.w[0] != nX) return fail(FEO_ERR_INVALID_ARGUMENT, "tile plan: duo step counts differ");
+            if (H0.w[2] != nV || H0.w[3] != nA || H1.w[0] != nX || H1.w[3] != s[2].w[3])
+              return fail(FEO_ERR_INVALID_ARGUMENT, "tile plan: duo step counts differ");
             double accI = 0, accJ = 0, bu1I = 0, bu2I = 0, bu1J = 0, bu2J = 0;
             const Word16* p = s + 4;
             auto fitp = [&](int32_t len) {
               const int32_t at = (int32_t)(p - s0) % kChunkWords;
               if (at + len > kChunkWords) p += kChunkWords - at;
             };
+            for (uint32_t v = 0; v < nS; ++v, p += 4) {
+              fitp(4);
+              const Word16 &w0 = p[h], &w1 = p[2 + h];
+              const double rI = S(w0.w[0] & 0xffffu), rJ = S(w0.w[0] >> 16), d1 = S(w0.w[1] & 0xffffu), d2 = S(w0.w[1] >> 16);
+              const double t = (double)u2f(w0.w[2]) + (double)u2f(w0.w[3]) * d1 + (double)u2f(w1.w[0]) * d2;
+              accI += rI * t;
+              accJ += rJ * t;
+              bu1I += (double)u2f(w1.w[1]) * d1;
+              bu2I += (double)u2f(w1.w[2]) * d1;
+              bu1J += (double)u2f(w1.w[1]) * d2;
+              bu2J += (double)u2f(w1.w[2]) * d2;
+            }
             for (uint32_t v = 0; v < nV; ++v, p += 6) {
               fitp(6);
               const Word16 &w0 = p[h], &w1 = p[2 + h], &w2 = p[4 + h];
@@ -770,6 +840,13 @@ int replay_tile_plan(const TilePlan& T, int32_t ns_branch, const double* in0, co
               bu2I += (double)u2f(w2.w[1]) * d1;
               bu1J += (double)u2f(w2.w[2]) * d2;
               bu2J += (double)u2f(w2.w[3]) * d2;
+            }
+            for (uint32_t a = 0; a < nP; ++a, p += 2) {
+              fitp(2);
+              const Word16& w0 = p[h];
+              const double rx = S(w0.w[0]);
+              accI += (double)u2f(w0.w[1]) * rx;
+              accJ += (double)u2f(w0.w[2]) * rx;
             }
             for (uint32_t a = 0; a < nA; ++a, p += 2) {
               fitp(2);
