@@ -7,6 +7,7 @@ sm_100a CUDA behind a C ABI (include/feonet_b200.h); there is no CPU fallback.
 from ._lib import FeoError, load_library  # noqa: F401
 from .functional import (DenseFn, DenseResidualLossFn, ResidualLossFn, SeqResidualLossFn, SpmmFn,  # noqa: F401
                          dof_major_empty, dof_major_zeros, is_dof_major, precond_output, to_dof_major_tensor)
+from .host_io import HostBatchPipeline  # noqa: F401
 from .operator import FEOperator  # noqa: F401
 from .train_api import (LinearStokes, SteadyNavierStokes, TimeDependentStokes, rel_L2_error,  # noqa: F401
                         sincos_forcing_grid)
