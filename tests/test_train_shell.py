@@ -1,0 +1,54 @@
+"""The training shell around the hot path (feonet_navier_stokes_b200/train_FEONet.py): flag parsing and data
+synthesis on the CPU, a short end-to-end training run on the GPU."""
+import numpy as np
+import pytest
+
+from feonet_navier_stokes_b200 import train_FEONet as T
+from oracle import feonet_oracle as orc
+
+
+def test_flags_follow_the_reference_cli():
+    args = T.build_parser().parse_args("--bc channel_flow --forcing_term sincos --train_file 1000N450 --val_file 1000N450 "
+                                       "--model UNetWithHead --optimizer Adam --do_precond 1 --resol_in 64 --blocks 4 --ks 5 "
+                                       "--filters 64 --epochs 10".split())
+    assert T.parse_file_flag(args.train_file) == (1000, 450) and T.mesh_n_from_ne(450) == 15 and T.mesh_n_from_ne(72) == 6
+    with pytest.raises(ValueError):
+        T.mesh_n_from_ne(154)
+    c = T.sample_coeff_f(50, 5)
+    assert c.shape == (50, 6) and (c[:, :2] <= 1).all() and (c[:, 2:] <= np.pi).all() and (c >= 0).all()
+
+
+@pytest.mark.parametrize("branch", [True, False])
+def test_synthetic_ns_solutions_zero_the_reference_residual(branch):
+    """The Newton solutions used as validation targets solve the algebraic system the reference's loss penalises
+    (both sign branches, steady NS train_FEONet.py:324-330): the oracle's residual loss vanishes on them."""
+    fx, data = T.synthesize("steady_ns", 5, "channel_flow", 3, 5, branch)
+    U = np.zeros((3, fx.N))
+    U[:, fx.idx_u1], U[:, fx.idx_u2], U[:, fx.idx_p] = data["fenics_u1"], data["fenics_u2"], data["fenics_p"]
+    loss, _, _ = orc.ns_loss_and_grad(U, data["load_vec_f"], fx.A, fx.B1, fx.B2, fx.idx_u1, fx.idx_u2, branch, dtype=np.float64)
+    scale = float((data["load_vec_f"] ** 2).sum())
+    assert loss < 1e-18 * scale
+
+
+def test_synthetic_stokes_solutions():
+    fx, data = T.synthesize("stokes_square", 4, "channel_flow", 2, 5, False)
+    U = np.zeros((2, fx.N))
+    U[:, fx.idx_u1], U[:, fx.idx_u2], U[:, fx.idx_p] = data["fenics_u1"], data["fenics_u2"], data["fenics_p"]
+    assert np.abs(U @ fx.A.T.toarray() - data["load_vec_f"]).max() < 1e-10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant,do_precond", [("steady_ns", 1), ("stokes_square", 0), ("stokes_square", 1)])
+def test_training_run_reduces_the_loss(tmp_path, variant, do_precond):
+    import torch
+
+    argv = ["--variant", variant, "--train_file", "32N32", "--val_file", "8N32", "--model", "FCNN", "--optimizer", "Adam",
+            "--do_precond", str(do_precond), "--epochs", "60", "--log_every", "20", "--lr", "3e-3", "--out", str(tmp_path),
+            "--spai_steps", "50"]
+    tr = T.Trainer(dict(T.build_parser().parse_args(argv).__dict__), device=torch.device("cuda"))
+    out = tr.fit()
+    assert len(tr.losses) == 3 and tr.losses[-1] < tr.losses[0] and np.isfinite(out["val_all"])
+    import os
+    assert os.path.exists(os.path.join(tr.folder, "model.pt")) and os.path.exists(os.path.join(tr.folder, "model.pth"))
+    ck = torch.load(os.path.join(tr.folder, "model.pt"), map_location="cpu")
+    assert set(ck) == {"model_state_dict", "losses", "train_rel_L2_errors", "test_rel_L2_errors"}
