@@ -117,6 +117,7 @@ int feo_op_create(const feo_operator_desc* desc, feo_handle_t* out) {
       D.n_tiles = plan.n_tiles;
       D.max_lines = plan.max_lines;
       D.warps = plan.warps;
+      D.stages = plan.stages;
       if ((rc = upload(op, plan.tile_box_ptr, &D.tile_box_ptr))) return bail(rc);
       if ((rc = upload(op, plan.tile_lines, &D.tile_lines))) return bail(rc);
       if ((rc = upload(op, plan.boxes, &D.boxes))) return bail(rc);

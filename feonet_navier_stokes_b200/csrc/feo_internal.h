@@ -96,12 +96,13 @@ struct TileTuning {
   int32_t fill_reserve_pct = 6;  // share of max_lines kept free for fillers while a tile grows (when fill_gap > 0)
   int32_t fill_gap = 0;     // runs of needed dofs separated by <= fill_gap unneeded dofs are staged as one run
   int32_t warps = 15;       // consumer warps per CTA (+ 1 producer warp)
+  int32_t stages = 2;       // line stages in shared memory (2 or 3)
 };
 TileTuning tile_tuning_from_env(bool backward);
 
 struct TilePlan {
   bool backward = false, has_conv = false;
-  int32_t n = 0, warps = 0, n_tiles = 0, max_lines = 0;
+  int32_t n = 0, warps = 0, stages = 2, n_tiles = 0, max_lines = 0;
   std::vector<int32_t> tile_box_ptr;  // [n_tiles+1]
   std::vector<int32_t> tile_lines;    // [n_tiles]
   std::vector<StageBox> boxes;
@@ -118,7 +119,7 @@ int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int3
 int replay_tile_plan(const TilePlan& T, int32_t ns_branch, const double* in0, const double* in1, double* out);
 
 struct DevTilePlan {
-  int32_t n_tiles = 0, max_lines = 0, warps = 0;
+  int32_t n_tiles = 0, max_lines = 0, warps = 0, stages = 2;
   int32_t* tile_box_ptr = nullptr;
   int32_t* tile_lines = nullptr;
   StageBox* boxes = nullptr;

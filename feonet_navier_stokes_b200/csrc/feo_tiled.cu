@@ -52,6 +52,7 @@ struct TiledParams {
   int32_t g_div, g_mod;  // gridDim.x / n_slabs, gridDim.x % n_slabs: (tile, slab) of a CTA's next unit without a division
   int32_t warps;      // consumer warps (the tile plan's warp count); warp `warps` is the producer
   uint32_t buf_bytes; // size of one line stage
+  int32_t n_stages;   // line stages in shared memory (2 or 3)
   int32_t debug;      // developer timing modes (FEO_DEBUG_MODE): 1 = stage lines only, 2 = compute only (no staging)
   int32_t precond;    // forward: 1 -> r = lhs - (f - c), 0 -> r = lhs - (-f + c)
   float esign;        // backward: +1 precond branch, -1 otherwise
@@ -242,22 +243,31 @@ __device__ __forceinline__ float conv1(float d1, float s1, float d2, float s2) {
   return __fadd_rn(__fmul_rn(d1, s1), __fmul_rn(d2, s2));
 }
 
-// Shared-memory map of a persistent CTA: [stage 0 lines][stage 1 lines][warp rings][mbarriers]
-//   mbarriers: full[2], empty[2], then kRingChunks per consumer warp
+// Shared-memory map of a persistent CTA: [stage 0 lines]...[stage n-1 lines][warp rings][mbarriers]
+//   mbarriers: full[4], empty[4] (n_stages used), then kRingChunks per consumer warp
 struct Bars {
   uint32_t full, empty, rings;
+};
+// Unit i of a CTA lives in stage i % n_stages; its barriers are in phase (i / n_stages) & 1.
+struct StageCursor {
+  uint32_t s = 0, ph = 0;
+  __device__ __forceinline__ void next(int32_t n_stages) {
+    if (++s == (uint32_t)n_stages) {
+      s = 0;
+      ph ^= 1u;
+    }
+  }
 };
 __device__ __forceinline__ Bars setup_barriers(const TiledParams& p, uint32_t sb, int warp, int lane) {
   Bars b;
   b.full = sb + p.bar_off;
-  b.empty = b.full + 16;
-  b.rings = b.full + 32;
-  if (threadIdx.x == 0) {
-    mbar_init(b.full, 1);
-    mbar_init(b.full + 8, 1);
-    mbar_init(b.empty, (uint32_t)p.warps);
-    mbar_init(b.empty + 8, (uint32_t)p.warps);
-  }
+  b.empty = b.full + 32;
+  b.rings = b.full + 64;
+  if (threadIdx.x == 0)
+    for (int k = 0; k < p.n_stages; ++k) {
+      mbar_init(b.full + k * 8, 1);
+      mbar_init(b.empty + k * 8, (uint32_t)p.warps);
+    }
   if (warp < p.warps && lane == 0)
     for (int c = 0; c < kRingChunks; ++c) mbar_init(b.rings + (uint32_t)warp * (kRingChunks * 8) + c * 8, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -281,11 +291,12 @@ __device__ __forceinline__ void produce_lines(const TensorMaps& maps, const Tile
   int i = 0;
   if (p.debug == 2) return;
   int tile = (int)blockIdx.x / p.n_slabs, slab = (int)blockIdx.x - tile * p.n_slabs;
-  for (int u = (int)blockIdx.x; u < p.n_units; u += (int)gridDim.x, ++i, next_unit(p, tile, slab)) {
-    const uint32_t s = (uint32_t)i & 1u;
+  StageCursor cur;
+  for (int u = (int)blockIdx.x; u < p.n_units; u += (int)gridDim.x, ++i, next_unit(p, tile, slab), cur.next(p.n_stages)) {
+    const uint32_t s = cur.s;
     const int b0 = p.tile_box_ptr[tile], b1 = p.tile_box_ptr[tile + 1];
     const uint32_t bytes = (uint32_t)p.tile_lines[tile] * kLineBytes;
-    if (i >= 2) mbar_wait(bars.empty + s * 8, (((uint32_t)i >> 1) - 1u) & 1u);
+    if (i >= p.n_stages) mbar_wait(bars.empty + s * 8, cur.ph ^ 1u);  // the unit that used the stage before is released
     if (lane == 0) mbar_expect_tx(bars.full + s * 8, bytes);
     __syncwarp();
     const uint32_t dst = sb + s * p.buf_bytes;
@@ -311,11 +322,11 @@ __global__ void __launch_bounds__((MAXW + 1) * 32, 1) residual_fwd_tiled(const _
   }
   Stream ring;
   if (p.debug == 1) {  // staging only: wait for every unit's lines, touch nothing
-    int i = 0;
-    for (int u = (int)blockIdx.x; u < p.n_units; u += (int)gridDim.x, ++i) {
-      mbar_wait(bars.full + ((uint32_t)i & 1u) * 8, ((uint32_t)i >> 1) & 1u);
+    StageCursor cur;
+    for (int u = (int)blockIdx.x; u < p.n_units; u += (int)gridDim.x, cur.next(p.n_stages)) {
+      mbar_wait(bars.full + cur.s * 8, cur.ph);
       __syncwarp();
-      if (lane == 0) mbar_arrive(bars.empty + ((uint32_t)i & 1u) * 8);
+      if (lane == 0) mbar_arrive(bars.empty + cur.s * 8);
     }
     return;
   }
@@ -332,15 +343,15 @@ __global__ void __launch_bounds__((MAXW + 1) * 32, 1) residual_fwd_tiled(const _
 
   int tile_n = (int)blockIdx.x / p.n_slabs, slab_n = (int)blockIdx.x - tile_n * p.n_slabs;  // the unit after the current one
   int32_t n_words_next = __ldg(&my_ranges[(size_t)tile_n * p.warps].n_words);
-  int i = 0;
-  for (int u = (int)blockIdx.x; u < p.n_units; u += (int)gridDim.x, ++i) {
+  StageCursor cur;
+  for (int u = (int)blockIdx.x; u < p.n_units; u += (int)gridDim.x, cur.next(p.n_stages)) {
     const int32_t n_words = n_words_next;
     const int slab = slab_n;
     next_unit(p, tile_n, slab_n);
     if (u + (int)gridDim.x < p.n_units) n_words_next = __ldg(&my_ranges[(size_t)tile_n * p.warps].n_words);
-    const uint32_t lines = sb + ((uint32_t)i & 1u) * p.buf_bytes + lane_off;
+    const uint32_t lines = sb + cur.s * p.buf_bytes + lane_off;
     const int b0 = slab * kSlab + (lane & 7) * 4;
-    if (p.debug != 2) mbar_wait(bars.full + ((uint32_t)i & 1u) * 8, ((uint32_t)i >> 1) & 1u);
+    if (p.debug != 2) mbar_wait(bars.full + cur.s * 8, cur.ph);
     uint32_t ptr = (ring.entered & (kRingChunks - 1)) * kChunkBytes;  // the unit's words start at a fresh chunk
     float lsum = 0.f;
 
@@ -445,7 +456,7 @@ __global__ void __launch_bounds__((MAXW + 1) * 32, 1) residual_fwd_tiled(const _
     }
     dsum += (double)lsum;  // per-unit fp32 partial, accumulated over the units in fp64
     __syncwarp();
-    if (lane == 0) mbar_arrive(bars.empty + ((uint32_t)i & 1u) * 8);  // this warp is done with the stage
+    if (lane == 0) mbar_arrive(bars.empty + cur.s * 8);  // this warp is done with the stage
   }
   // fixed-order reduction: lanes -> warp; the warp partials are summed in fp64 by finalize_loss_kernel
   dsum = warp_sum(dsum);
@@ -467,11 +478,11 @@ __global__ void __launch_bounds__((MAXW + 1) * 32, 1) residual_bwd_tiled(const _
   }
   Stream ring;
   if (p.debug == 1) {  // staging only: wait for every unit's lines, touch nothing
-    int i = 0;
-    for (int u = (int)blockIdx.x; u < p.n_units; u += (int)gridDim.x, ++i) {
-      mbar_wait(bars.full + ((uint32_t)i & 1u) * 8, ((uint32_t)i >> 1) & 1u);
+    StageCursor cur;
+    for (int u = (int)blockIdx.x; u < p.n_units; u += (int)gridDim.x, cur.next(p.n_stages)) {
+      mbar_wait(bars.full + cur.s * 8, cur.ph);
       __syncwarp();
-      if (lane == 0) mbar_arrive(bars.empty + ((uint32_t)i & 1u) * 8);
+      if (lane == 0) mbar_arrive(bars.empty + cur.s * 8);
     }
     return;
   }
@@ -485,15 +496,15 @@ __global__ void __launch_bounds__((MAXW + 1) * 32, 1) residual_bwd_tiled(const _
 
   int tile_n = (int)blockIdx.x / p.n_slabs, slab_n = (int)blockIdx.x - tile_n * p.n_slabs;  // the unit after the current one
   int32_t n_words_next = __ldg(&my_ranges[(size_t)tile_n * p.warps].n_words);
-  int i = 0;
-  for (int u = (int)blockIdx.x; u < p.n_units; u += (int)gridDim.x, ++i) {
+  StageCursor cur;
+  for (int u = (int)blockIdx.x; u < p.n_units; u += (int)gridDim.x, cur.next(p.n_stages)) {
     const int32_t n_words = n_words_next;
     const int slab = slab_n;
     next_unit(p, tile_n, slab_n);
     if (u + (int)gridDim.x < p.n_units) n_words_next = __ldg(&my_ranges[(size_t)tile_n * p.warps].n_words);
-    const uint32_t lines = sb + ((uint32_t)i & 1u) * p.buf_bytes + lane_off;
+    const uint32_t lines = sb + cur.s * p.buf_bytes + lane_off;
     const int b0 = slab * kSlab + (lane & 15) * 4;
-    if (p.debug != 2) mbar_wait(bars.full + ((uint32_t)i & 1u) * 8, ((uint32_t)i >> 1) & 1u);
+    if (p.debug != 2) mbar_wait(bars.full + cur.s * 8, cur.ph);
 
     // The stream is walked by linear word position `pos` (counted over all units: the unit starts at a
     // fresh chunk); pieces (header 4 words, S-step 4, V-step 6, P-step 2, A-step 2, X-step 4) never straddle a 32-word chunk:
@@ -651,7 +662,7 @@ __global__ void __launch_bounds__((MAXW + 1) * 32, 1) residual_bwd_tiled(const _
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(bars.empty + ((uint32_t)i & 1u) * 8);  // this warp is done with the stage
+    if (lane == 0) mbar_arrive(bars.empty + cur.s * 8);  // this warp is done with the stage
   }
 }
 
@@ -710,9 +721,9 @@ struct SmemLayout {
 SmemLayout smem_layout(const DevTilePlan& T) {
   SmemLayout L;
   L.buf_bytes = ((uint32_t)T.max_lines * kLineBytes + 1023u) / 1024u * 1024u;
-  L.ring_off = 2 * L.buf_bytes;
+  L.ring_off = (uint32_t)T.stages * L.buf_bytes;
   L.bar_off = L.ring_off + (uint32_t)T.warps * kRingBytes;
-  L.total = L.bar_off + 32 + (uint32_t)T.warps * (kRingChunks * 8);
+  L.total = L.bar_off + 64 + (uint32_t)T.warps * (kRingChunks * 8);
   return L;
 }
 
@@ -772,7 +783,7 @@ int launch_residual_fwd(const feo_operator* op, const float* alphaT, const float
   for (int c = 0; c < kBoxClasses; ++c) maps.m[1][c] = maps.m[0][c];
   const SmemLayout L = smem_layout(T);
   TiledParams p{T.tile_box_ptr, T.tile_lines, T.boxes, T.warp_range, reinterpret_cast<const int4*>(T.stream), fT, rT, (float*)ws,
-                nullptr, ldb, B, n_slabs, (int32_t)count, grid / n_slabs, grid % n_slabs, T.warps, L.buf_bytes, debug_mode(), op->ns_branch, 0.f, L.ring_off,
+                nullptr, ldb, B, n_slabs, (int32_t)count, grid / n_slabs, grid % n_slabs, T.warps, L.buf_bytes, T.stages, debug_mode(), op->ns_branch, 0.f, L.ring_off,
                 L.bar_off};
   if (int rc = launch_persistent(residual_fwd_tiled<15>, residual_fwd_tiled<19>, T, L, grid, maps, p, st)) return rc;
   return finalize_loss((float*)ws, (int)n_partials, 1.0f, loss_out, st);
@@ -797,7 +808,7 @@ int launch_residual_bwd(const feo_operator* op, const float* alphaT, const float
   if (int rc = make_maps(op->has_conv ? alphaT : rT, ldb, op->n, maps.m[1])) return rc;
   const SmemLayout L = smem_layout(T);
   TiledParams p{T.tile_box_ptr, T.tile_lines, T.boxes, T.warp_range, reinterpret_cast<const int4*>(T.stream), nullptr, gradT, nullptr,
-                grad_loss, ldb, B, n_slabs, (int32_t)count, grid / n_slabs, grid % n_slabs, T.warps, L.buf_bytes, debug_mode(),
+                grad_loss, ldb, B, n_slabs, (int32_t)count, grid / n_slabs, grid % n_slabs, T.warps, L.buf_bytes, T.stages, debug_mode(),
                 op->ns_branch, op->ns_branch ? 1.0f : -1.0f, L.ring_off, L.bar_off};
   return launch_persistent(residual_bwd_tiled<15>, residual_bwd_tiled<19>, T, L, grid, maps, p, st);
 }

@@ -36,8 +36,10 @@ TileTuning tile_tuning_from_env(bool backward) {
   if (const char* s = std::getenv(backward ? "FEO_TILE_WARPS_BWD" : "FEO_TILE_WARPS_FWD")) t.warps = atoi(s);
   if (const char* s = std::getenv("FEO_TILE_FILL_GAP")) t.fill_gap = std::min(std::max(atoi(s), 0), 8);
   if (const char* s = std::getenv("FEO_TILE_FILL_RESERVE")) t.fill_reserve_pct = std::min(std::max(atoi(s), 0), 50);
+  if (const char* s = std::getenv(backward ? "FEO_TILE_STAGES_BWD" : "FEO_TILE_STAGES_FWD")) t.stages = atoi(s);
+  t.stages = std::min(std::max(t.stages, 2), 3);
   t.warps = std::min(std::max(t.warps, 1), 19);
-  const int32_t budget = (232448 - t.warps * (kRingChunks * kChunkWords * 16 + kRingChunks * 8) - 1024) / 2 / kLineBytes;
+  const int32_t budget = ((232448 - t.warps * (kRingChunks * kChunkWords * 16 + kRingChunks * 8) - 1024) / t.stages - 1024) / kLineBytes;  // stages are 1 KB aligned
   t.max_lines = std::min(std::max(t.max_lines, 32), budget);
   return t;
 }
@@ -328,6 +330,7 @@ int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int3
   T.has_conv = F.conv;
   T.n = n;
   T.warps = W;
+  T.stages = tune.stages;
   const int32_t n_units = (int32_t)F.unit_first.size();
 
   // lines a row (forward) / column (backward) needs.  key = dof (forward) or src * n + dof (backward;

@@ -1,6 +1,6 @@
 """Developer timing of the fused residual kernels through FEOperator (no autograd): CUDA events per call.
 
-usage: time_kernels.py [n] [B] [K] [cfg ...]   with cfg = Wf,Lf,Wb,Lb (consumer warps / staged lines, forward / backward)
+usage: time_kernels.py [n] [B] [K] [cfg ...]   with cfg = Wf,Lf,Wb,Lb[,gap,reserve[,Sf,Sb]] (consumer warps / staged lines forward / backward, gap filling, line stages)
 The fixture is assembled once; one operator (one tile plan) is built per cfg.  A checksum of the loss
 and the gradient is printed per cfg so that plans can be compared with each other.
 """
@@ -31,6 +31,8 @@ for cfg in cfgs:
         os.environ.update(FEO_TILE_WARPS_FWD=wf, FEO_TILE_LINES_FWD=lf, FEO_TILE_WARPS_BWD=wb, FEO_TILE_LINES_BWD=lb)
         if rest:
             os.environ.update(FEO_TILE_FILL_GAP=rest[0], FEO_TILE_FILL_RESERVE=rest[1] if len(rest) > 1 else "6")
+        if len(rest) > 3:
+            os.environ.update(FEO_TILE_STAGES_FWD=rest[2], FEO_TILE_STAGES_BWD=rest[3])
     t0 = time.time()
     op = FEOperator(N, A=fx.A, B1=fx.B1, B2=fx.B2, idx_sol=fx.idx_sol, ns_precond_branch=True, device=dev)
     t_plan = time.time() - t0
