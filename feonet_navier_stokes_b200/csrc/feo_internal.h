@@ -80,6 +80,12 @@ struct WarpRange {  // 8 B
 // forward, per quad, quarter q reads word 4*unit + q; [header unit][spare unit][n_steps step units], n_steps even:
 //   header unit : {row (-1: idle), n_steps, line(alpha[pi]) | line(alpha[pj]) << 16, flags (bit 0: velocity row)}
 //   step unit   : {line(col) * 256, a, b1, b2}
+// forward pair quad (flags bit 1), quarter q owns the velocity rows (I[k], J[k]) of a node:
+//   header unit : {row I, row J (-1: idle), line(alpha[I]) | line(alpha[J]) << 16, 3 | nS << 8 | nP << 16 | nX << 24}
+//   spare unit, then nX X-steps (2 units), nP P-steps (nP even), nS S-steps, one pad unit if nS is odd
+//   X-step : {off(col), aI, b1I, b2I} {aJ, b1J, b2J, 0}   one column feeds both rows
+//   P-step : {off(col), aI, aJ, 0}                         the same with b1 = b2 = 0 (e.g. pressure columns)
+//   S-step : {line(I[m]) | line(J[m]) << 16, a, b1, b2}    row I takes alpha[I[m]], row J takes alpha[J[m]], same coefficients
 // backward, per duo, half h reads word 2*k + h; [header][S-steps][V-steps][P-steps][A-steps][X-steps]:
 //   header      : w0 = {cI, cJ (-1: idle), nV, nA}   w1 = {nX, line(r[cI]) | line(r[cJ]) << 16, flags (bit 0: E-term), nS | nP << 16}
 //   V-step (3)  : w0 = {line(r[hI]) | line(r[hJ]) << 16, line(alpha[pi]) | line(alpha[pj]) << 16, aI, b1I}
@@ -97,6 +103,7 @@ struct TileTuning {
   int32_t fill_gap = 0;     // runs of needed dofs separated by <= fill_gap unneeded dofs are staged as one run
   int32_t warps = 15;       // consumer warps per CTA (+ 1 producer warp)
   int32_t stages = 2;       // line stages in shared memory (2 or 3)
+  bool pair_rows = true;    // forward: walk the two velocity rows of a node together (pair quads)
 };
 TileTuning tile_tuning_from_env(bool backward);
 

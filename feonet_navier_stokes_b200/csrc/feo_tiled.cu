@@ -362,6 +362,155 @@ __global__ void __launch_bounds__((MAXW + 1) * 32, 1) residual_fwd_tiled(const _
       if ((ptr & (kChunkBytes - 1)) == 0) ring.enter(p, warp, lane);
       const int4 hdr = lds_word(rq + ptr);
       ptr = (ptr + 128) & (kRingBytes - 1);
+      if (hdr.w & 2) {
+        // ---- pair quad: each quarter owns the two velocity rows (I[k], J[k]) of a node ----------------------
+        // [header][spare][nX X-steps (2 units)][nP P-steps (unit each, nP even)][nS S-steps (unit each)][pad if nS odd]
+        const int rowI = hdr.x, rowJ = hdr.y;
+        const int nS = (hdr.w >> 8) & 255, nP = (hdr.w >> 16) & 255, nX = (int)((uint32_t)hdr.w >> 24);
+        units_left -= 2 + 2 * nX + nP + nS + (nS & 1);
+        float4 fI[2], fJ[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          fI[k] = fJ[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rowI >= 0 && b0 + 32 * k < p.ldb) {
+            fI[k] = ldg4_stream(p.fT + (int64_t)rowI * p.ldb + b0 + 32 * k);
+            fJ[k] = ldg4_stream(p.fT + (int64_t)rowJ * p.ldb + b0 + 32 * k);
+          }
+        }
+        P2 aI[4], uI[4], vI[4], aJ[4], uJ[4], vJ[4];  // A, B1, B2 sums of row I and of row J
+#pragma unroll
+        for (int k = 0; k < 4; ++k) aI[k] = uI[k] = vI[k] = aJ[k] = uJ[k] = vJ[k] = P2{0.f, 0.f};
+        // X-steps: one column feeds both rows with its own coefficients {off, aI, b1I, b2I} {aJ, b1J, b2J, 0}
+        for (int s = 0; s < nX;) {
+          if ((ptr & (kChunkBytes - 1)) == 0) ring.enter(p, warp, lane);
+          const int seg = min(nX - s, (int)((kChunkBytes - (ptr & (kChunkBytes - 1))) / 128));
+          s += seg;
+          const uint32_t rp = rq + ptr;
+          ptr = (ptr + (uint32_t)seg * 128) & (kRingBytes - 1);
+#pragma unroll 1
+          for (int t = 0; t < seg; ++t) {
+            const int4 e0 = lds_word(rp + (uint32_t)t * 128);
+            const int4 e1 = lds_word(rp + (uint32_t)t * 128 + 64);
+            u64 x[4];
+            lds_pairs(lines + (uint32_t)e0.x, x[0], x[1]);
+            lds_pairs(lines + (uint32_t)e0.x + 128, x[2], x[3]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              fma2s(aI[k], __int_as_float(e0.y), x[k]);
+              fma2s(uI[k], __int_as_float(e0.z), x[k]);
+              fma2s(vI[k], __int_as_float(e0.w), x[k]);
+              fma2s(aJ[k], __int_as_float(e1.x), x[k]);
+              fma2s(uJ[k], __int_as_float(e1.y), x[k]);
+              fma2s(vJ[k], __int_as_float(e1.z), x[k]);
+            }
+          }
+        }
+        // P-steps, two per iteration: one column with b1 = b2 = 0 feeds both rows {off, aI, aJ, 0}
+        for (int s = 0; s < nP;) {
+          if ((ptr & (kChunkBytes - 1)) == 0) ring.enter(p, warp, lane);
+          const int seg = min(nP - s, (int)((kChunkBytes - (ptr & (kChunkBytes - 1))) / 64));
+          s += seg;
+          const uint32_t rp = rq + ptr;
+          ptr = (ptr + (uint32_t)seg * 64) & (kRingBytes - 1);
+#pragma unroll 1
+          for (int t = 0; t < seg; t += 2) {
+            const int4 e0 = lds_word(rp + (uint32_t)t * 64);
+            const int4 e1 = lds_word(rp + (uint32_t)t * 64 + 64);
+            u64 x0[4], x1[4];
+            lds_pairs(lines + (uint32_t)e0.x, x0[0], x0[1]);
+            lds_pairs(lines + (uint32_t)e0.x + 128, x0[2], x0[3]);
+            lds_pairs(lines + (uint32_t)e1.x, x1[0], x1[1]);
+            lds_pairs(lines + (uint32_t)e1.x + 128, x1[2], x1[3]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              fma2s(aI[k], __int_as_float(e0.y), x0[k]);
+              fma2s(aJ[k], __int_as_float(e0.z), x0[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              fma2s(aI[k], __int_as_float(e1.y), x1[k]);
+              fma2s(aJ[k], __int_as_float(e1.z), x1[k]);
+            }
+          }
+        }
+        // S-steps: the columns (I[m], J[m]) of a neighbour node with the same coefficients for both rows
+        // {line(I[m]) | line(J[m]) << 16, a, b1, b2}: row I takes alpha[I[m]], row J takes alpha[J[m]]
+        for (int s = 0; s < nS;) {
+          if ((ptr & (kChunkBytes - 1)) == 0) ring.enter(p, warp, lane);
+          const int seg = min(nS - s, (int)((kChunkBytes - (ptr & (kChunkBytes - 1))) / 64));
+          s += seg;
+          const uint32_t rp = rq + ptr;
+          ptr = (ptr + (uint32_t)seg * 64) & (kRingBytes - 1);
+#pragma unroll 1
+          for (int t = 0; t < seg; ++t) {
+            const int4 e = lds_word(rp + (uint32_t)t * 64);
+            const uint32_t oI = ((uint32_t)e.x & 0xffffu) * kLineBytes, oJ = ((uint32_t)e.x >> 16) * kLineBytes;
+            u64 xI[4], xJ[4];
+            lds_pairs(lines + oI, xI[0], xI[1]);
+            lds_pairs(lines + oI + 128, xI[2], xI[3]);
+            lds_pairs(lines + oJ, xJ[0], xJ[1]);
+            lds_pairs(lines + oJ + 128, xJ[2], xJ[3]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              fma2s(aI[k], __int_as_float(e.y), xI[k]);
+              fma2s(uI[k], __int_as_float(e.z), xI[k]);
+              fma2s(vI[k], __int_as_float(e.w), xI[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              fma2s(aJ[k], __int_as_float(e.y), xJ[k]);
+              fma2s(uJ[k], __int_as_float(e.z), xJ[k]);
+              fma2s(vJ[k], __int_as_float(e.w), xJ[k]);
+            }
+          }
+        }
+        if (nS & 1) ptr = (ptr + 64) & (kRingBytes - 1);  // pad unit: items stay 128-byte aligned
+        if (rowI >= 0) {
+          u64 d1[4], d2[4];
+          const uint32_t li = ((uint32_t)hdr.z & 0xffffu) * kLineBytes, lj = ((uint32_t)hdr.z >> 16) * kLineBytes;
+          lds_pairs(lines + li, d1[0], d1[1]);
+          lds_pairs(lines + li + 128, d1[2], d1[3]);
+          lds_pairs(lines + lj, d2[0], d2[1]);
+          lds_pairs(lines + lj + 128, d2[2], d2[3]);
+          float cI[8], cJ[8];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float u0, u1, v0, v1;
+            unpk(d1[k], u0, u1);
+            unpk(d2[k], v0, v1);
+            cI[2 * k] = conv1(u0, uI[k].lo, v0, vI[k].lo);
+            cI[2 * k + 1] = conv1(u1, uI[k].hi, v1, vI[k].hi);
+            cJ[2 * k] = conv1(u0, uJ[k].lo, v0, vJ[k].lo);
+            cJ[2 * k + 1] = conv1(u1, uJ[k].hi, v1, vJ[k].hi);
+          }
+          float* rI = p.outT != nullptr ? p.outT + (int64_t)rowI * p.ldb + b0 : nullptr;
+          float* rJ = p.outT != nullptr ? p.outT + (int64_t)rowJ * p.ldb + b0 : nullptr;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int b = b0 + 32 * k;
+            if (b < p.ldb) {
+              float4 r, q4;
+              r.x = resid1(aI[2 * k].lo, fI[k].x, cI[4 * k + 0], precond);
+              r.y = resid1(aI[2 * k].hi, fI[k].y, cI[4 * k + 1], precond);
+              r.z = resid1(aI[2 * k + 1].lo, fI[k].z, cI[4 * k + 2], precond);
+              r.w = resid1(aI[2 * k + 1].hi, fI[k].w, cI[4 * k + 3], precond);
+              q4.x = resid1(aJ[2 * k].lo, fJ[k].x, cJ[4 * k + 0], precond);
+              q4.y = resid1(aJ[2 * k].hi, fJ[k].y, cJ[4 * k + 1], precond);
+              q4.z = resid1(aJ[2 * k + 1].lo, fJ[k].z, cJ[4 * k + 2], precond);
+              q4.w = resid1(aJ[2 * k + 1].hi, fJ[k].w, cJ[4 * k + 3], precond);
+              if (b + 0 < p.B) lsum = fmaf(q4.x, q4.x, fmaf(r.x, r.x, lsum));
+              if (b + 1 < p.B) lsum = fmaf(q4.y, q4.y, fmaf(r.y, r.y, lsum));
+              if (b + 2 < p.B) lsum = fmaf(q4.z, q4.z, fmaf(r.z, r.z, lsum));
+              if (b + 3 < p.B) lsum = fmaf(q4.w, q4.w, fmaf(r.w, r.w, lsum));
+              if (rI != nullptr && b < p.B) {
+                *reinterpret_cast<float4*>(rI + 32 * k) = r;
+                *reinterpret_cast<float4*>(rJ + 32 * k) = q4;
+              }
+            }
+          }
+        }
+        continue;
+      }
       const int n_steps = hdr.y;
       const int row = hdr.x;
       units_left -= 2 + n_steps;

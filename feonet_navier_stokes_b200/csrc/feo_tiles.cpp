@@ -30,10 +30,11 @@ TileTuning tile_tuning_from_env(bool backward) {
   // one persistent CTA per SM: 2 line stages + one 2 KB ring per consumer warp must fit 227 KB of shared memory.
   // Measured at cfg5 (tools/time_kernels.py): forward 19 warps x 374 lines 3.74 ms (15 x 384: 3.95), backward 15 x 384
   // 6.71 ms (19 x 374: 7.02); gap filling of the staging runs (fill_gap > 0) did not pay at any setting.
-  t.warps = backward ? 15 : 19;
-  t.max_lines = backward ? 384 : 374;
+  t.warps = 15;
+  t.max_lines = 384;
   if (const char* s = std::getenv(backward ? "FEO_TILE_LINES_BWD" : "FEO_TILE_LINES_FWD")) t.max_lines = atoi(s);
   if (const char* s = std::getenv(backward ? "FEO_TILE_WARPS_BWD" : "FEO_TILE_WARPS_FWD")) t.warps = atoi(s);
+  if (const char* s = std::getenv("FEO_TILE_PAIR_ROWS")) t.pair_rows = atoi(s) != 0;
   if (const char* s = std::getenv("FEO_TILE_FILL_GAP")) t.fill_gap = std::min(std::max(atoi(s), 0), 8);
   if (const char* s = std::getenv("FEO_TILE_FILL_RESERVE")) t.fill_reserve_pct = std::min(std::max(atoi(s), 0), 50);
   if (const char* s = std::getenv(backward ? "FEO_TILE_STAGES_BWD" : "FEO_TILE_STAGES_FWD")) t.stages = atoi(s);
@@ -314,6 +315,71 @@ void build_pair(const Front& F, int32_t cI, int32_t cJ, PairItem* out, int64_t* 
   }
 }
 
+// ---- forward pair description -----------------------------------------------------------------------
+// The two velocity rows (I[k], J[k]) of a node are walked together: a neighbour node whose columns (I[m], J[m])
+// carry the same coefficients in both rows is ONE stream word (S-step); any other column feeds both rows from one
+// gather (P-step when its B1/B2 coefficients vanish, e.g. pressure columns; X-step otherwise).
+struct FwdSym {
+  int32_t colI, colJ;
+  float a, b1, b2;
+};
+struct FwdCol {
+  int32_t col;
+  float aI, b1I, b2I, aJ, b1J, b2J;
+  int32_t n_entries;
+};
+struct FwdPair {
+  int32_t rI = -1, rJ = -1;
+  std::vector<FwdSym> s;
+  std::vector<FwdCol> p, x;
+};
+
+void build_fwd_pair(const Front& F, int32_t rI, int32_t rJ, FwdPair* out) {
+  FwdPair& P = *out;
+  P.rI = rI;
+  P.rJ = rJ;
+  std::map<int32_t, FwdCol> cols;  // by column, increasing
+  for (int side = 0; side < 2; ++side) {
+    const int32_t r = side == 0 ? rI : rJ;
+    for (int32_t k = F.ptr[r]; k < F.ptr[r + 1]; ++k) {
+      const UEnt& e = F.ent[k];
+      FwdCol& c = cols.emplace(e.col, FwdCol{e.col, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0}).first->second;
+      if (side == 0) {
+        c.aI = e.a;
+        c.b1I = e.b1;
+        c.b2I = e.b2;
+      } else {
+        c.aJ = e.a;
+        c.b1J = e.b1;
+        c.b2J = e.b2;
+      }
+      ++c.n_entries;
+    }
+  }
+  auto same = [](float x, float y) { return f2u(x) == f2u(y); };
+  auto zero3 = [](float a, float b, float c) { return f2u(a) == 0u && f2u(b) == 0u && f2u(c) == 0u; };
+  // S-steps: column I[m] is stored by row I alone, J[m] by row J alone, with the same coefficients
+  for (auto& kv : cols) {
+    FwdCol& c = kv.second;
+    if (F.kind[c.col] != 1 || c.n_entries != 1 || !zero3(c.aJ, c.b1J, c.b2J)) continue;
+    auto jt = cols.find(F.mate[c.col]);
+    if (jt == cols.end()) continue;
+    FwdCol& d = jt->second;
+    if (d.n_entries == 1 && zero3(d.aI, d.b1I, d.b2I) && same(c.aI, d.aJ) && same(c.b1I, d.b1J) && same(c.b2I, d.b2J)) {
+      P.s.push_back(FwdSym{c.col, d.col, c.aI, c.b1I, c.b2I});
+      c.n_entries = d.n_entries = -1;
+    }
+  }
+  for (auto& kv : cols) {
+    const FwdCol& c = kv.second;
+    if (c.n_entries < 0) continue;  // part of an S-step
+    if (f2u(c.b1I) == 0u && f2u(c.b2I) == 0u && f2u(c.b1J) == 0u && f2u(c.b2J) == 0u)
+      P.p.push_back(c);
+    else
+      P.x.push_back(c);
+  }
+}
+
 Word16 mk(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return Word16{{a, b, c, d}}; }
 
 }  // namespace
@@ -542,10 +608,91 @@ int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int3
     std::vector<int64_t> item_cost;
     if (!backward) {
       std::vector<int32_t> rows;
+      std::vector<FwdPair> fpairs;
       for (int32_t u : units) {
         int32_t rr[2];
         const int32_t nr = F.unit_rows(u, rr);
-        for (int32_t t = 0; t < nr; ++t) rows.push_back(rr[t]);
+        if (nr == 2 && F.conv && tune.pair_rows) {
+          fpairs.emplace_back();
+          build_fwd_pair(F, rr[0], rr[1], &fpairs.back());
+        } else {
+          for (int32_t t = 0; t < nr; ++t) rows.push_back(rr[t]);
+        }
+      }
+      // pair quads: four velocity pairs of similar shape, one per quarter-warp
+      std::stable_sort(fpairs.begin(), fpairs.end(), [](const FwdPair& x, const FwdPair& y) {
+        if (x.s.size() != y.s.size()) return x.s.size() > y.s.size();
+        if (x.p.size() != y.p.size()) return x.p.size() > y.p.size();
+        return x.x.size() > y.x.size();
+      });
+      for (size_t g = 0; g < fpairs.size(); g += 4) {
+        const FwdPair* q4[4];
+        size_t nS = 0, nP = 0, nX = 0;
+        for (int qd = 0; qd < 4; ++qd) {
+          q4[qd] = g + qd < fpairs.size() ? &fpairs[g + qd] : nullptr;
+          if (q4[qd] != nullptr) {
+            nS = std::max(nS, q4[qd]->s.size());
+            nP = std::max(nP, q4[qd]->p.size());
+            nX = std::max(nX, q4[qd]->x.size());
+          }
+        }
+        nP = (nP + 1) / 2 * 2;  // P-steps are consumed two by two
+        if (nS > 255 || nP > 255 || nX > 255) return fail(FEO_ERR_UNSUPPORTED, "a velocity row pair has too many entries for the fused forward plan");
+        std::vector<Word16> w;
+        for (int qd = 0; qd < 4; ++qd) {
+          const FwdPair* P = q4[qd];
+          const uint32_t flags = 3u | ((uint32_t)nS << 8) | ((uint32_t)nP << 16) | ((uint32_t)nX << 24);
+          if (P != nullptr)
+            w.push_back(mk((uint32_t)P->rI, (uint32_t)P->rJ, LINE(F.pi[P->rI], 0) | (LINE(F.pj[P->rI], 0) << 16), flags));
+          else
+            w.push_back(mk(0xffffffffu, 0xffffffffu, 0u, flags));
+        }
+        for (int qd = 0; qd < 4; ++qd) w.push_back(mk(0u, 0u, 0u, 0u));  // spare unit
+        for (size_t st = 0; st < nX; ++st) {
+          for (int half = 0; half < 2; ++half)
+            for (int qd = 0; qd < 4; ++qd) {
+              const FwdPair* P = q4[qd];
+              if (P != nullptr && st < P->x.size()) {
+                const FwdCol& c = P->x[st];
+                w.push_back(half == 0 ? mk(LINE(c.col, 0) * kLineBytes, f2u(c.aI), f2u(c.b1I), f2u(c.b2I))
+                                      : mk(f2u(c.aJ), f2u(c.b1J), f2u(c.b2J), 0u));
+                if (half == 0) T.real_entries += c.n_entries;
+              } else {
+                w.push_back(mk(0u, 0u, 0u, 0u));
+              }
+              if (half == 0) T.slot_entries += 2;
+            }
+        }
+        for (size_t st = 0; st < nP; ++st)
+          for (int qd = 0; qd < 4; ++qd) {
+            const FwdPair* P = q4[qd];
+            if (P != nullptr && st < P->p.size()) {
+              const FwdCol& c = P->p[st];
+              w.push_back(mk(LINE(c.col, 0) * kLineBytes, f2u(c.aI), f2u(c.aJ), 0u));
+              T.real_entries += c.n_entries;
+            } else {
+              w.push_back(mk(0u, 0u, 0u, 0u));
+            }
+            T.slot_entries += 2;
+          }
+        for (size_t st = 0; st < nS; ++st)
+          for (int qd = 0; qd < 4; ++qd) {
+            const FwdPair* P = q4[qd];
+            if (P != nullptr && st < P->s.size()) {
+              const FwdSym& c = P->s[st];
+              w.push_back(mk(LINE(c.colI, 0) | (LINE(c.colJ, 0) << 16), f2u(c.a), f2u(c.b1), f2u(c.b2)));
+              T.real_entries += 2;
+            } else {
+              w.push_back(mk(0u, 0u, 0u, 0u));
+            }
+            T.slot_entries += 2;
+          }
+        if (nS & 1)
+          for (int qd = 0; qd < 4; ++qd) w.push_back(mk(0u, 0u, 0u, 0u));  // pad unit: items stay 8-word aligned
+        // load-store pipe cycles per quad step: X 4 + 8, P 2 + 8, S 2 + 16; header, epilogue gathers and stores
+        item_cost.push_back(12 * (int64_t)nX + 10 * (int64_t)nP + 18 * (int64_t)nS + 40);
+        item_parts.emplace_back(w.size() / 4, 4);
+        item_words.push_back(std::move(w));
       }
       std::stable_sort(rows.begin(), rows.end(), [&](int32_t x, int32_t y) { return F.ptr[x + 1] - F.ptr[x] > F.ptr[y + 1] - F.ptr[y]; });
       for (size_t g = 0; g < rows.size(); g += 4) {
@@ -787,7 +934,51 @@ int replay_tile_plan(const TilePlan& T, int32_t ns_branch, const double* in0, co
         if (at + len > kChunkWords) s += kChunkWords - at;
       };
       while (s < end) {
-        if (!T.backward) {
+        if (!T.backward && (s[0].w[3] & 2u)) {  // pair quad
+          const uint32_t fl = s[0].w[3];
+          const uint32_t nS = (fl >> 8) & 255u, nP = (fl >> 16) & 255u, nX = fl >> 24;
+          for (int qd = 0; qd < 4; ++qd) {
+            const Word16& H = s[qd];
+            if (H.w[3] != fl) return fail(FEO_ERR_INVALID_ARGUMENT, "tile plan: pair quad step counts differ");
+            double aI = 0, uI = 0, vI = 0, aJ = 0, uJ = 0, vJ = 0;
+            const Word16* q = s + 8;
+            for (uint32_t st = 0; st < nX; ++st, q += 8) {
+              const Word16 &e0 = q[qd], &e1 = q[4 + qd];
+              if (e0.w[0] % kLineBytes != 0) bad = true;
+              const double x = S(e0.w[0] / kLineBytes);
+              aI += (double)u2f(e0.w[1]) * x;
+              uI += (double)u2f(e0.w[2]) * x;
+              vI += (double)u2f(e0.w[3]) * x;
+              aJ += (double)u2f(e1.w[0]) * x;
+              uJ += (double)u2f(e1.w[1]) * x;
+              vJ += (double)u2f(e1.w[2]) * x;
+            }
+            for (uint32_t st = 0; st < nP; ++st, q += 4) {
+              const Word16& e = q[qd];
+              if (e.w[0] % kLineBytes != 0) bad = true;
+              const double x = S(e.w[0] / kLineBytes);
+              aI += (double)u2f(e.w[1]) * x;
+              aJ += (double)u2f(e.w[2]) * x;
+            }
+            for (uint32_t st = 0; st < nS; ++st, q += 4) {
+              const Word16& e = q[qd];
+              const double xI = S(e.w[0] & 0xffffu), xJ = S(e.w[0] >> 16);
+              aI += (double)u2f(e.w[1]) * xI;
+              uI += (double)u2f(e.w[2]) * xI;
+              vI += (double)u2f(e.w[3]) * xI;
+              aJ += (double)u2f(e.w[1]) * xJ;
+              uJ += (double)u2f(e.w[2]) * xJ;
+              vJ += (double)u2f(e.w[3]) * xJ;
+            }
+            const int32_t rI = (int32_t)H.w[0], rJ = (int32_t)H.w[1];
+            if (rI < 0) continue;
+            const double d1 = S(H.w[2] & 0xffffu), d2 = S(H.w[2] >> 16);
+            const double cI = d1 * uI + d2 * vI, cJ = d1 * uJ + d2 * vJ;
+            out[rI] = precond ? aI - (in1[rI] - cI) : aI - (-in1[rI] + cI);
+            out[rJ] = precond ? aJ - (in1[rJ] - cJ) : aJ - (-in1[rJ] + cJ);
+          }
+          s += 8 + 8 * (size_t)nX + 4 * (size_t)nP + 4 * (size_t)nS + ((nS & 1u) ? 4 : 0);
+        } else if (!T.backward) {
           const int32_t n_steps = (int32_t)s[0].w[1];
           for (int qd = 0; qd < 4; ++qd) {
             const Word16& H = s[qd];
