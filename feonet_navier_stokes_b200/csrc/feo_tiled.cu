@@ -285,25 +285,52 @@ __device__ __forceinline__ void next_unit(const TiledParams& p, int& tile, int& 
   }
 }
 
-// The producer warp: stages the lines of unit i into stage i & 1 as soon as every consumer warp has
-// released the unit that used the stage before (unit i - 2).
+// The producer warp: stages the lines of unit i into stage i % n_stages as soon as every consumer warp has
+// released the unit that used the stage before.  The staging boxes of the NEXT unit are fetched into
+// registers (three per lane) right after the current unit's copies are issued, so that no dependent global
+// load sits between the release of a stage and the first TMA request into it.
+constexpr int kBoxPrefetch = 3;
+struct BoxBatch {
+  int32_t b0, b1;
+  uint32_t bytes;
+  StageBox bx[kBoxPrefetch];
+  __device__ __forceinline__ void fetch(const TiledParams& p, int tile, int lane) {
+    b0 = p.tile_box_ptr[tile];
+    b1 = p.tile_box_ptr[tile + 1];
+    bytes = (uint32_t)p.tile_lines[tile] * kLineBytes;
+#pragma unroll
+    for (int k = 0; k < kBoxPrefetch; ++k) {
+      const int b = b0 + lane + 32 * k;
+      if (b < b1) bx[k] = p.boxes[b];
+    }
+  }
+};
 __device__ __forceinline__ void produce_lines(const TensorMaps& maps, const TiledParams& p, uint32_t sb, const Bars& bars, int lane) {
-  int i = 0;
   if (p.debug == 2) return;
   int tile = (int)blockIdx.x / p.n_slabs, slab = (int)blockIdx.x - tile * p.n_slabs;
+  BoxBatch cur_boxes;
+  cur_boxes.fetch(p, tile, lane);
   StageCursor cur;
-  for (int u = (int)blockIdx.x; u < p.n_units; u += (int)gridDim.x, ++i, next_unit(p, tile, slab), cur.next(p.n_stages)) {
+  int i = 0;
+  for (int u = (int)blockIdx.x; u < p.n_units; u += (int)gridDim.x, ++i, cur.next(p.n_stages)) {
     const uint32_t s = cur.s;
-    const int b0 = p.tile_box_ptr[tile], b1 = p.tile_box_ptr[tile + 1];
-    const uint32_t bytes = (uint32_t)p.tile_lines[tile] * kLineBytes;
     if (i >= p.n_stages) mbar_wait(bars.empty + s * 8, cur.ph ^ 1u);  // the unit that used the stage before is released
-    if (lane == 0) mbar_expect_tx(bars.full + s * 8, bytes);
+    if (lane == 0) mbar_expect_tx(bars.full + s * 8, cur_boxes.bytes);
     __syncwarp();
     const uint32_t dst = sb + s * p.buf_bytes;
-    for (int b = b0 + lane; b < b1; b += 32) {
+    const int c0 = slab * kSlab;
+#pragma unroll
+    for (int k = 0; k < kBoxPrefetch; ++k)
+      if (cur_boxes.b0 + lane + 32 * k < cur_boxes.b1) {
+        const StageBox bx = cur_boxes.bx[k];
+        tma_box(dst + (uint32_t)bx.line0 * kLineBytes, &maps.m[bx.src][bx.cls], c0, bx.dof0, bars.full + s * 8);
+      }
+    for (int b = cur_boxes.b0 + lane + 32 * kBoxPrefetch; b < cur_boxes.b1; b += 32) {
       const StageBox bx = p.boxes[b];
-      tma_box(dst + (uint32_t)bx.line0 * kLineBytes, &maps.m[bx.src][bx.cls], slab * kSlab, bx.dof0, bars.full + s * 8);
+      tma_box(dst + (uint32_t)bx.line0 * kLineBytes, &maps.m[bx.src][bx.cls], c0, bx.dof0, bars.full + s * 8);
     }
+    next_unit(p, tile, slab);
+    if (u + (int)gridDim.x < p.n_units) cur_boxes.fetch(p, tile, lane);
   }
 }
 
