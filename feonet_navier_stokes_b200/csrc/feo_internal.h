@@ -45,7 +45,7 @@ HostCsr axpy(const HostCsr& s, float dt, const HostCsr& a);  // S + dt*A
 constexpr int kSlab = 64;                  // samples per work unit
 constexpr int kLineBytes = kSlab * 4;      // one staged dof line
 constexpr int kChunkWords = 32;            // stream words (16 B) per bulk copy: 512 B
-constexpr int kRingChunks = 4;             // chunks per warp ring (power of two)
+constexpr int kRingChunks = 2;             // chunks per warp ring (power of two)
 constexpr int kBoxClasses = 5;
 constexpr int kBoxRows[kBoxClasses] = {16, 8, 4, 2, 1};  // TMA box heights (dofs) available for staging
 
@@ -98,7 +98,7 @@ struct WarpRange {  // 8 B
 //   A-step (1)  : {line(r[hI]) | line(r[hJ]) << 16, aI, aJ, 0}
 //   X-step (2)  : w0 = {line(alpha[x]), c1I, c2I, c1J}  w1 = {c2J, 0, 0, 0}: Bu1[cI] += c1I x, Bu2[cI] += c2I x, Bu1[cJ] += c1J x, ...
 struct TileTuning {
-  int32_t max_lines = 384;  // staged lines per tile (shared-memory budget: 2 stages x lines x 256 B), fillers included
+  int32_t max_lines = 414;  // staged lines per tile (shared-memory budget: 2 stages x lines x 256 B), fillers included
   int32_t fill_reserve_pct = 6;  // share of max_lines kept free for fillers while a tile grows (when fill_gap > 0)
   int32_t fill_gap = 0;     // runs of needed dofs separated by <= fill_gap unneeded dofs are staged as one run
   int32_t warps = 15;       // consumer warps per CTA (+ 1 producer warp)

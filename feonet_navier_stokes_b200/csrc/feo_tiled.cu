@@ -6,7 +6,7 @@
 //   1. a producer warp stages the dof lines of the NEXT unit (64 samples x 4 B each) with 2-D TMA boxes
 //      (cp.async.bulk.tensor) straight from the dof-major batch arrays while the consumer warps work on
 //      the current one (full/empty mbarriers per stage; a warp may run one unit ahead of the slowest);
-//   2. every consumer warp streams its private list of 16-byte operator words through a 4 x 512 B shared
+//   2. every consumer warp streams its private list of 16-byte operator words through a 2 x 512 B shared
 //      memory ring filled by 1-D bulk copies (cp.async.bulk) that complete on per-slot mbarriers; the
 //      ring runs continuously across units, so the first words of the next unit are already in flight
 //      when the current one ends;

@@ -27,11 +27,11 @@ namespace feo {
 
 TileTuning tile_tuning_from_env(bool backward) {
   TileTuning t;
-  // one persistent CTA per SM: 2 line stages + one 2 KB ring per consumer warp must fit 227 KB of shared memory.
+  // one persistent CTA per SM: 2 line stages + one 1 KB ring per consumer warp must fit 227 KB of shared memory.
   // Measured at cfg5 (tools/time_kernels.py): forward 19 warps x 374 lines 3.74 ms (15 x 384: 3.95), backward 15 x 384
   // 6.71 ms (19 x 374: 7.02); gap filling of the staging runs (fill_gap > 0) did not pay at any setting.
   t.warps = 15;
-  t.max_lines = 384;
+  t.max_lines = 414;  // with 2 x 512 B rings per warp; 4-chunk rings and 384 lines: backward 6.10 ms instead of 5.89 ms
   if (const char* s = std::getenv(backward ? "FEO_TILE_LINES_BWD" : "FEO_TILE_LINES_FWD")) t.max_lines = atoi(s);
   if (const char* s = std::getenv(backward ? "FEO_TILE_WARPS_BWD" : "FEO_TILE_WARPS_FWD")) t.warps = atoi(s);
   if (const char* s = std::getenv("FEO_TILE_PAIR_ROWS")) t.pair_rows = atoi(s) != 0;
