@@ -104,6 +104,7 @@ struct TileTuning {
   int32_t warps = 15;       // consumer warps per CTA (+ 1 producer warp)
   int32_t stages = 2;       // line stages in shared memory (2 or 3)
   bool pair_rows = true;    // forward: walk the two velocity rows of a node together (pair quads)
+  bool match_singles = true;  // backward: pair single (pressure) dofs that share source rows, once, before tiling
 };
 TileTuning tile_tuning_from_env(bool backward);
 

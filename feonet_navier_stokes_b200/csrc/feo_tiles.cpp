@@ -35,6 +35,7 @@ TileTuning tile_tuning_from_env(bool backward) {
   if (const char* s = std::getenv(backward ? "FEO_TILE_LINES_BWD" : "FEO_TILE_LINES_FWD")) t.max_lines = atoi(s);
   if (const char* s = std::getenv(backward ? "FEO_TILE_WARPS_BWD" : "FEO_TILE_WARPS_FWD")) t.warps = atoi(s);
   if (const char* s = std::getenv("FEO_TILE_PAIR_ROWS")) t.pair_rows = atoi(s) != 0;
+  if (const char* s = std::getenv("FEO_TILE_MATCH_SINGLES")) t.match_singles = atoi(s) != 0;
   if (const char* s = std::getenv("FEO_TILE_FILL_GAP")) t.fill_gap = std::min(std::max(atoi(s), 0), 8);
   if (const char* s = std::getenv("FEO_TILE_FILL_RESERVE")) t.fill_reserve_pct = std::min(std::max(atoi(s), 0), 50);
   if (const char* s = std::getenv(backward ? "FEO_TILE_STAGES_BWD" : "FEO_TILE_STAGES_FWD")) t.stages = atoi(s);
@@ -57,7 +58,8 @@ struct Front {
   bool conv = false;
   float sgn = 1.f;
   std::vector<int32_t> pi, pj, kind, mate;   // per dof: partners, 0 none / 1 I-dof / 2 J-dof, the other dof of the pair
-  std::vector<int32_t> unit_of, unit_first;  // units: a velocity pair (I[k], J[k]) or a single dof
+  std::vector<int32_t> smate;                // single dofs matched two by two (they share source rows), -1: alone
+  std::vector<int32_t> unit_of, unit_first;  // units: a velocity pair (I[k], J[k]), two matched single dofs, or a single dof
   std::vector<int32_t> ptr;                  // union rows
   std::vector<UEnt> ent;
   std::vector<int32_t> tptr, trow, tsrc;     // transposed union: per column the source rows + index into ent
@@ -70,6 +72,10 @@ struct Front {
       o[1] = mate[r];
       return 2;
     }
+    if (kind[r] == 0 && smate[r] >= 0) {
+      o[1] = smate[r];
+      return 2;
+    }
     return 1;
   }
   // entry (h, c) takes part in the convective term: row h is a velocity row and B1 or B2 is stored there
@@ -77,7 +83,7 @@ struct Front {
 };
 
 int build_front(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int32_t n_u, const int32_t* idx_i,
-                const int32_t* idx_j, int32_t ns_branch, Front* out) {
+                const int32_t* idx_j, int32_t ns_branch, bool match_singles, Front* out) {
   Front& F = *out;
   const int32_t n = A.n;
   F.n = n;
@@ -102,18 +108,6 @@ int build_front(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int32_t 
       F.mate[i] = j;
       F.mate[j] = i;
     }
-  F.unit_of.assign(n, -1);
-  for (int32_t r = 0; r < n; ++r) {
-    if (F.unit_of[r] >= 0) continue;
-    const int32_t u = (int32_t)F.unit_first.size();
-    if (F.kind[r] == 0) {
-      F.unit_first.push_back(r);
-      F.unit_of[r] = u;
-    } else {
-      F.unit_first.push_back(F.pi[r]);
-      F.unit_of[F.pi[r]] = F.unit_of[F.pj[r]] = u;
-    }
-  }
   // union pattern (rows sorted by column) and its transpose
   F.ptr.assign(n + 1, 0);
   for (int32_t r = 0; r < n; ++r) {
@@ -144,6 +138,49 @@ int build_front(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int32_t 
       F.trow[p] = r;
       F.tsrc[p] = k;
     }
+  // Single dofs (pressure) are matched two by two, once and for all, with the single dof that shares the most
+  // source rows: the backward then gathers a shared row once for both columns (P-steps), and because the partner
+  // does not depend on the tiling, neither does the summation order.
+  F.smate.assign(n, -1);
+  if (match_singles) {
+    std::vector<int32_t> cnt(n, 0), touched;
+    for (int32_t a = 0; a < n; ++a) {
+      if (F.kind[a] != 0 || F.smate[a] >= 0) continue;
+      touched.clear();
+      int32_t n_src = 0;
+      for (int32_t p = F.tptr[a]; p < F.tptr[a + 1]; ++p) {
+        if (F.ent[F.tsrc[p]].a == 0.f) continue;
+        ++n_src;
+        const int32_t h = F.trow[p];
+        for (int32_t k = F.ptr[h]; k < F.ptr[h + 1]; ++k) {
+          const int32_t c = F.ent[k].col;
+          if (c != a && F.kind[c] == 0 && F.smate[c] < 0 && F.ent[k].a != 0.f && cnt[c]++ == 0) touched.push_back(c);
+        }
+      }
+      int32_t best = -1;
+      for (int32_t c : touched) {
+        if (best < 0 || cnt[c] > cnt[best] || (cnt[c] == cnt[best] && c < best)) best = c;
+      }
+      if (best >= 0 && 4 * cnt[best] >= n_src) {
+        F.smate[a] = best;
+        F.smate[best] = a;
+      }
+      for (int32_t c : touched) cnt[c] = 0;
+    }
+  }
+  F.unit_of.assign(n, -1);
+  for (int32_t r = 0; r < n; ++r) {
+    if (F.unit_of[r] >= 0) continue;
+    const int32_t u = (int32_t)F.unit_first.size();
+    if (F.kind[r] == 0) {
+      F.unit_first.push_back(r);
+      F.unit_of[r] = u;
+      if (F.smate[r] >= 0) F.unit_of[F.smate[r]] = u;
+    } else {
+      F.unit_first.push_back(F.pi[r]);
+      F.unit_of[F.pi[r]] = F.unit_of[F.pj[r]] = u;
+    }
+  }
   return FEO_OK;
 }
 
@@ -183,7 +220,7 @@ struct FEnt {
   bool used;
 };
 
-void build_pair(const Front& F, int32_t cI, int32_t cJ, PairItem* out, int64_t* real_entries) {
+void build_pair(const Front& F, int32_t cI, int32_t cJ, bool fixed_partner, PairItem* out, int64_t* real_entries) {
   PairItem& P = *out;
   P.cI = cI;
   P.cJ = cJ;
@@ -270,17 +307,17 @@ void build_pair(const Front& F, int32_t cI, int32_t cJ, PairItem* out, int64_t* 
         }
     for (auto& kv : extra) P.x.push_back(kv.second);
   }
-  // plain entries: each column walks its source rows in increasing order.  A velocity pair (whose partner never
-  // changes) first takes the source rows BOTH columns read -- one gather serves the two of them (P-steps, e.g. the
-  // pressure rows of the divergence block) -- then the rest; two single dofs that merely share a pair slot are zipped
-  // position by position whatever their partner is, so that the summation order, hence the result bits, do not
-  // depend on the tiling.
+  // plain entries: each column walks its source rows in increasing order.  A pair whose partner never changes (a
+  // velocity pair, two matched single dofs) first takes the source rows BOTH columns read -- one gather serves the
+  // two of them (P-steps, e.g. the pressure rows of the divergence block) -- then the rest; two single dofs that
+  // merely share a pair slot in this tile are zipped position by position whatever their partner is, so that the
+  // summation order, hence the result bits, do not depend on the tiling.
   {
     auto by_h = [](const TEnt& x, const TEnt& y) { return x.h < y.h; };
     std::stable_sort(plain[0].begin(), plain[0].end(), by_h);
     std::stable_sort(plain[1].begin(), plain[1].end(), by_h);
     std::vector<TEnt> rest[2];
-    if (P.vel) {
+    if (fixed_partner) {
       size_t i = 0, j = 0;
       while (i < plain[0].size() && j < plain[1].size()) {
         if (plain[0][i].h == plain[1][j].h) {
@@ -387,7 +424,7 @@ Word16 mk(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return Word16{{a, b,
 int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int32_t n_u, const int32_t* idx_i,
                     const int32_t* idx_j, int32_t ns_branch, bool backward, const TileTuning& tune, TilePlan* out) {
   Front F;
-  if (int rc = build_front(A, B1, B2, n_u, idx_i, idx_j, ns_branch, &F)) return rc;
+  if (int rc = build_front(A, B1, B2, n_u, idx_i, idx_j, ns_branch, backward && tune.match_singles, &F)) return rc;
   const int32_t n = F.n;
   const int32_t W = tune.warps;
   TilePlan& T = *out;
@@ -612,7 +649,7 @@ int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int3
       for (int32_t u : units) {
         int32_t rr[2];
         const int32_t nr = F.unit_rows(u, rr);
-        if (nr == 2 && F.conv && tune.pair_rows) {
+        if (nr == 2 && F.conv && tune.pair_rows && F.kind[rr[0]] != 0) {
           fpairs.emplace_back();
           build_fwd_pair(F, rr[0], rr[1], &fpairs.back());
         } else {
@@ -733,18 +770,18 @@ int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int3
         int32_t rr[2];
         if (F.unit_rows(u, rr) == 2) {
           pairs.emplace_back();
-          build_pair(F, rr[0], rr[1], &pairs.back(), &T.real_entries);
+          build_pair(F, rr[0], rr[1], true, &pairs.back(), &T.real_entries);
         } else if (pending < 0) {
           pending = rr[0];
         } else {
           pairs.emplace_back();
-          build_pair(F, pending, rr[0], &pairs.back(), &T.real_entries);
+          build_pair(F, pending, rr[0], false, &pairs.back(), &T.real_entries);
           pending = -1;
         }
       }
       if (pending >= 0) {
         pairs.emplace_back();
-        build_pair(F, pending, -1, &pairs.back(), &T.real_entries);
+        build_pair(F, pending, -1, false, &pairs.back(), &T.real_entries);
       }
       std::stable_sort(pairs.begin(), pairs.end(), [](const PairItem& x, const PairItem& y) {
         if (x.s.size() != y.s.size()) return x.s.size() > y.s.size();
