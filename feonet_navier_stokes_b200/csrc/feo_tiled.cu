@@ -707,26 +707,53 @@ __global__ void __launch_bounds__((MAXW + 1) * 32, 1) residual_bwd_tiled(const _
         const int cnt = min(nS - v, (kChunkWords - (pos & (kChunkWords - 1))) / 4);
         v += cnt;
         pos += 4 * cnt;
-#pragma unroll 1
-        for (int t = 0; t < cnt; ++t) {
-          const int4 w0 = lds_word(wa + (uint32_t)t * 64);
-          const int4 w1 = lds_word(wa + (uint32_t)t * 64 + 32);
+        // two steps per iteration: the kernel is bound by exposed shared-memory round trips at 15 warps per SM, so
+        // each trip (word loads, then gathers) carries the loads of two steps
+        struct SWords {
+          int4 w0, w1;
+        };
+        struct SLines {
           u64 d1[2], d2[2], rI[2], rJ[2];
-          lds_pairs(lines + ((uint32_t)w0.y & 0xffffu) * kLineBytes, d1[0], d1[1]);
-          lds_pairs(lines + ((uint32_t)w0.y >> 16) * kLineBytes, d2[0], d2[1]);
-          lds_pairs(lines + ((uint32_t)w0.x & 0xffffu) * kLineBytes, rI[0], rI[1]);
-          lds_pairs(lines + ((uint32_t)w0.x >> 16) * kLineBytes, rJ[0], rJ[1]);
-          const u64 a = bc(__int_as_float(w0.z)), b1 = bc(__int_as_float(w0.w)), b2 = bc(__int_as_float(w1.x));
+        };
+        auto s_words = [&](int t) {
+          SWords w;
+          w.w0 = lds_word(wa + (uint32_t)t * 64);
+          w.w1 = lds_word(wa + (uint32_t)t * 64 + 32);
+          return w;
+        };
+        auto s_gather = [&](const SWords& w) {
+          SLines x;
+          lds_pairs(lines + ((uint32_t)w.w0.y & 0xffffu) * kLineBytes, x.d1[0], x.d1[1]);
+          lds_pairs(lines + ((uint32_t)w.w0.y >> 16) * kLineBytes, x.d2[0], x.d2[1]);
+          lds_pairs(lines + ((uint32_t)w.w0.x & 0xffffu) * kLineBytes, x.rI[0], x.rI[1]);
+          lds_pairs(lines + ((uint32_t)w.w0.x >> 16) * kLineBytes, x.rJ[0], x.rJ[1]);
+          return x;
+        };
+        auto s_fma = [&](const SWords& w, const SLines& x) {
+          const u64 a = bc(__int_as_float(w.w0.z)), b1 = bc(__int_as_float(w.w0.w)), b2 = bc(__int_as_float(w.w1.x));
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
-            const u64 tt = fma2r(b2, d2[k], fma2r(b1, d1[k], a));
-            fma2p(accI[k], tt, rI[k]);
-            fma2p(accJ[k], tt, rJ[k]);
-            fma2s(bu1I[k], __int_as_float(w1.y), d1[k]);
-            fma2s(bu2I[k], __int_as_float(w1.z), d1[k]);
-            fma2s(bu1J[k], __int_as_float(w1.y), d2[k]);
-            fma2s(bu2J[k], __int_as_float(w1.z), d2[k]);
+            const u64 tt = fma2r(b2, x.d2[k], fma2r(b1, x.d1[k], a));
+            fma2p(accI[k], tt, x.rI[k]);
+            fma2p(accJ[k], tt, x.rJ[k]);
+            fma2s(bu1I[k], __int_as_float(w.w1.y), x.d1[k]);
+            fma2s(bu2I[k], __int_as_float(w.w1.z), x.d1[k]);
+            fma2s(bu1J[k], __int_as_float(w.w1.y), x.d2[k]);
+            fma2s(bu2J[k], __int_as_float(w.w1.z), x.d2[k]);
           }
+        };
+        int t = 0;
+#pragma unroll 1
+        for (; t + 1 < cnt; t += 2) {
+          const SWords wA = s_words(t), wB = s_words(t + 1);
+          const SLines xA = s_gather(wA), xB = s_gather(wB);
+          s_fma(wA, xA);
+          s_fma(wB, xB);
+        }
+        if (t < cnt) {
+          const SWords wA = s_words(t);
+          const SLines xA = s_gather(wA);
+          s_fma(wA, xA);
         }
       }
       for (int v = 0; v < nV;) {
@@ -759,14 +786,31 @@ __global__ void __launch_bounds__((MAXW + 1) * 32, 1) residual_bwd_tiled(const _
           }
         }
       }
-      // plain steps whose two columns read the same source row: one gather
+      // plain steps whose two columns read the same source row: one gather; four steps per iteration
       for (int a = 0; a < nP;) {
         const uint32_t wa = place(2);
         const int cnt = min(nP - a, (kChunkWords - (pos & (kChunkWords - 1))) / 2);
         a += cnt;
         pos += 2 * cnt;
+        int t = 0;
 #pragma unroll 1
-        for (int t = 0; t < cnt; ++t) {
+        for (; t + 3 < cnt; t += 4) {
+          int4 w[4];
+          u64 rX[4][2];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) w[j] = lds_word(wa + (uint32_t)(t + j) * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) lds_pairs(lines + (uint32_t)w[j].x * kLineBytes, rX[j][0], rX[j][1]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              fma2s(accI[k], __int_as_float(w[j].y), rX[j][k]);
+              fma2s(accJ[k], __int_as_float(w[j].z), rX[j][k]);
+            }
+        }
+#pragma unroll 1
+        for (; t < cnt; ++t) {
           const int4 w0 = lds_word(wa + (uint32_t)t * 32);
           u64 rX[2];
           lds_pairs(lines + (uint32_t)w0.x * kLineBytes, rX[0], rX[1]);
@@ -782,8 +826,27 @@ __global__ void __launch_bounds__((MAXW + 1) * 32, 1) residual_bwd_tiled(const _
         const int cnt = min(nA - a, (kChunkWords - (pos & (kChunkWords - 1))) / 2);
         a += cnt;
         pos += 2 * cnt;
+        int t = 0;
 #pragma unroll 1
-        for (int t = 0; t < cnt; ++t) {
+        for (; t + 1 < cnt; t += 2) {
+          int4 w[2];
+          u64 rI[2][2], rJ[2][2];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) w[j] = lds_word(wa + (uint32_t)(t + j) * 32);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            lds_pairs(lines + ((uint32_t)w[j].x & 0xffffu) * kLineBytes, rI[j][0], rI[j][1]);
+            lds_pairs(lines + ((uint32_t)w[j].x >> 16) * kLineBytes, rJ[j][0], rJ[j][1]);
+          }
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              fma2s(accI[k], __int_as_float(w[j].y), rI[j][k]);
+              fma2s(accJ[k], __int_as_float(w[j].z), rJ[j][k]);
+            }
+        }
+        if (t < cnt) {
           const int4 w0 = lds_word(wa + (uint32_t)t * 32);
           u64 rI[2], rJ[2];
           lds_pairs(lines + ((uint32_t)w0.x & 0xffffu) * kLineBytes, rI[0], rI[1]);
