@@ -80,6 +80,8 @@ struct WarpRange {  // 8 B
 // forward, per quad, quarter q reads word 4*unit + q; [header unit][spare unit][n_steps step units], n_steps even:
 //   header unit : {row (-1: idle), n_steps, line(alpha[pi]) | line(alpha[pj]) << 16, flags (bit 0: velocity row)}
 //   step unit   : {line(col) * 256, a, b1, b2}
+// forward A-quad (flags bit 2): rows whose entries all have b1 = b2 = 0; n_steps is a multiple of 4
+//   packed unit : {off(step 2j), a, off(step 2j + 1), a}
 // forward pair quad (flags bit 1), quarter q owns the velocity rows (I[k], J[k]) of a node:
 //   header unit : {row I, row J (-1: idle), line(alpha[I]) | line(alpha[J]) << 16, 3 | nS << 8 | nP << 16 | nX << 24}
 //   spare unit, then nX X-steps (2 units), nP P-steps (nP even), nS S-steps, one pad unit if nS is odd
@@ -104,6 +106,7 @@ struct TileTuning {
   int32_t warps = 15;       // consumer warps per CTA (+ 1 producer warp)
   int32_t stages = 2;       // line stages in shared memory (2 or 3)
   bool pair_rows = true;    // forward: walk the two velocity rows of a node together (pair quads)
+  bool pack_a_rows = true;  // forward: rows without B1/B2 entries use two steps per stream word (A-quads)
   bool match_singles = true;  // backward: pair single (pressure) dofs that share source rows, once, before tiling
 };
 TileTuning tile_tuning_from_env(bool backward);

@@ -540,7 +540,7 @@ __global__ void __launch_bounds__((MAXW + 1) * 32, 1) residual_fwd_tiled(const _
       }
       const int n_steps = hdr.y;
       const int row = hdr.x;
-      units_left -= 2 + n_steps;
+      units_left -= 2 + ((hdr.w & 4) ? n_steps / 2 : n_steps);
       // the load vector of this row is fetched now and consumed in the epilogue (hides the DRAM latency)
       float4 fv[2];
 #pragma unroll
@@ -555,7 +555,39 @@ __global__ void __launch_bounds__((MAXW + 1) * 32, 1) residual_fwd_tiled(const _
       // (A software-pipelined variant of this loop -- gathers of pair j + 1 in flight during the FMAs of pair j --
       // was measured SLOWER, 5.0-5.7 ms vs 4.06 ms at cfg5: the kernel is bound by the load-store pipe, not by
       // the exposed round trips, and the extra control flow costs issue slots.)
-      for (int s = 0; s < n_steps;) {
+      if (hdr.w & 4) {
+        // A-quad: rows without B1/B2 entries (pressure rows), two steps per word {off, a, off, a}; four steps
+        // (two words, four gathered lines) per iteration
+        for (int s = 0; s < n_steps;) {
+          if ((ptr & (kChunkBytes - 1)) == 0) ring.enter(p, warp, lane);
+          const int seg = min((n_steps - s) / 2, (int)((kChunkBytes - (ptr & (kChunkBytes - 1))) / 64));  // packed units
+          s += 2 * seg;
+          const uint32_t rp = rq + ptr;
+          ptr = (ptr + (uint32_t)seg * 64) & (kRingBytes - 1);
+#pragma unroll 1
+          for (int t = 0; t < seg; t += 2) {
+            const int4 e0 = lds_word(rp + (uint32_t)t * 64);
+            const int4 e1 = lds_word(rp + (uint32_t)t * 64 + 64);
+            u64 x[4][4];
+            lds_pairs(lines + (uint32_t)e0.x, x[0][0], x[0][1]);
+            lds_pairs(lines + (uint32_t)e0.x + 128, x[0][2], x[0][3]);
+            lds_pairs(lines + (uint32_t)e0.z, x[1][0], x[1][1]);
+            lds_pairs(lines + (uint32_t)e0.z + 128, x[1][2], x[1][3]);
+            lds_pairs(lines + (uint32_t)e1.x, x[2][0], x[2][1]);
+            lds_pairs(lines + (uint32_t)e1.x + 128, x[2][2], x[2][3]);
+            lds_pairs(lines + (uint32_t)e1.z, x[3][0], x[3][1]);
+            lds_pairs(lines + (uint32_t)e1.z + 128, x[3][2], x[3][3]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              fma2s(accA[k], __int_as_float(e0.y), x[0][k]);
+              fma2s(accA[k], __int_as_float(e0.w), x[1][k]);
+              fma2s(accA[k], __int_as_float(e1.y), x[2][k]);
+              fma2s(accA[k], __int_as_float(e1.w), x[3][k]);
+            }
+          }
+        }
+      }
+      for (int s = (hdr.w & 4) ? n_steps : 0; s < n_steps;) {
         if ((ptr & (kChunkBytes - 1)) == 0) ring.enter(p, warp, lane);
         const int seg = min(n_steps - s, (int)((kChunkBytes - (ptr & (kChunkBytes - 1))) / 64));
         s += seg;

@@ -35,6 +35,7 @@ TileTuning tile_tuning_from_env(bool backward) {
   if (const char* s = std::getenv(backward ? "FEO_TILE_LINES_BWD" : "FEO_TILE_LINES_FWD")) t.max_lines = atoi(s);
   if (const char* s = std::getenv(backward ? "FEO_TILE_WARPS_BWD" : "FEO_TILE_WARPS_FWD")) t.warps = atoi(s);
   if (const char* s = std::getenv("FEO_TILE_PAIR_ROWS")) t.pair_rows = atoi(s) != 0;
+  if (const char* s = std::getenv("FEO_TILE_PACK_A_ROWS")) t.pack_a_rows = atoi(s) != 0;
   if (const char* s = std::getenv("FEO_TILE_MATCH_SINGLES")) t.match_singles = atoi(s) != 0;
   if (const char* s = std::getenv("FEO_TILE_FILL_GAP")) t.fill_gap = std::min(std::max(atoi(s), 0), 8);
   if (const char* s = std::getenv("FEO_TILE_FILL_RESERVE")) t.fill_reserve_pct = std::min(std::max(atoi(s), 0), 50);
@@ -731,37 +732,65 @@ int build_tile_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int3
         item_parts.emplace_back(w.size() / 4, 4);
         item_words.push_back(std::move(w));
       }
-      std::stable_sort(rows.begin(), rows.end(), [&](int32_t x, int32_t y) { return F.ptr[x + 1] - F.ptr[x] > F.ptr[y + 1] - F.ptr[y]; });
-      for (size_t g = 0; g < rows.size(); g += 4) {
-        int32_t r4[4], n_steps = 0;
-        for (int qd = 0; qd < 4; ++qd) {
-          r4[qd] = g + qd < rows.size() ? rows[g + qd] : -1;
-          if (r4[qd] >= 0) n_steps = std::max(n_steps, F.ptr[r4[qd] + 1] - F.ptr[r4[qd]]);
-        }
-        n_steps = (n_steps + 1) / 2 * 2;  // the kernel consumes steps two by two
-        std::vector<Word16> w;
-        for (int qd = 0; qd < 4; ++qd) {
-          const int32_t r = r4[qd];
-          const bool vel = r >= 0 && F.kind[r] != 0;
-          const uint32_t offs = vel ? (LINE(F.pi[r], 0) | (LINE(F.pj[r], 0) << 16)) : 0u;
-          w.push_back(mk((uint32_t)r, (uint32_t)n_steps, offs, vel ? 1u : 0u));
-        }
-        for (int qd = 0; qd < 4; ++qd) w.push_back(mk(0u, 0u, 0u, 0u));  // spare unit: keeps step pairs 128-byte aligned
-        for (int32_t s = 0; s < n_steps; ++s)
+      // rows whose entries all have b1 = b2 = 0 (pressure rows; every row of an operator without convection) go
+      // into A-quads: two steps per stream word, one accumulator per sample
+      auto a_only = [&](int32_t r) {
+        for (int32_t k = F.ptr[r]; k < F.ptr[r + 1]; ++k)
+          if (f2u(F.ent[k].b1) != 0u || f2u(F.ent[k].b2) != 0u) return false;
+        return true;
+      };
+      std::vector<int32_t> rows_a, rows_g;
+      for (int32_t r : rows) (tune.pack_a_rows && a_only(r) ? rows_a : rows_g).push_back(r);
+      auto by_len = [&](int32_t x, int32_t y) { return F.ptr[x + 1] - F.ptr[x] > F.ptr[y + 1] - F.ptr[y]; };
+      std::stable_sort(rows_a.begin(), rows_a.end(), by_len);
+      std::stable_sort(rows_g.begin(), rows_g.end(), by_len);
+      for (int packed = 1; packed >= 0; --packed) {
+        const std::vector<int32_t>& rws = packed ? rows_a : rows_g;
+        for (size_t g = 0; g < rws.size(); g += 4) {
+          int32_t r4[4], n_steps = 0;
+          for (int qd = 0; qd < 4; ++qd) {
+            r4[qd] = g + qd < rws.size() ? rws[g + qd] : -1;
+            if (r4[qd] >= 0) n_steps = std::max(n_steps, F.ptr[r4[qd] + 1] - F.ptr[r4[qd]]);
+          }
+          const int32_t group = packed ? 4 : 2;  // steps consumed per loop iteration
+          n_steps = (n_steps + group - 1) / group * group;
+          std::vector<Word16> w;
           for (int qd = 0; qd < 4; ++qd) {
             const int32_t r = r4[qd];
-            if (r >= 0 && F.ptr[r] + s < F.ptr[r + 1]) {
-              const UEnt& e = F.ent[F.ptr[r] + s];
-              w.push_back(mk(LINE(e.col, 0) * kLineBytes, f2u(e.a), f2u(e.b1), f2u(e.b2)));
-              ++T.real_entries;
-            } else {
-              w.push_back(mk(0u, 0u, 0u, 0u));  // padding: line 0 of the tile with zero coefficients
-            }
-            ++T.slot_entries;
+            const bool vel = r >= 0 && F.kind[r] != 0;
+            const uint32_t offs = vel ? (LINE(F.pi[r], 0) | (LINE(F.pj[r], 0) << 16)) : 0u;
+            w.push_back(mk((uint32_t)r, (uint32_t)n_steps, offs, packed ? 4u : (vel ? 1u : 0u)));  // A-quads have no convection
           }
-        item_cost.push_back(10 * (int64_t)n_steps + 12);
-        item_parts.emplace_back((size_t)(1 + n_steps / 2), 8);  // header pair, step pairs: 8 words each
-        item_words.push_back(std::move(w));
+          for (int qd = 0; qd < 4; ++qd) w.push_back(mk(0u, 0u, 0u, 0u));  // spare unit: keeps step groups 128-byte aligned
+          auto ENT = [&](int32_t r, int32_t st) -> const UEnt* { return r >= 0 && F.ptr[r] + st < F.ptr[r + 1] ? &F.ent[F.ptr[r] + st] : nullptr; };
+          if (packed) {
+            for (int32_t st = 0; st < n_steps; st += 2)
+              for (int qd = 0; qd < 4; ++qd) {
+                const UEnt *e0 = ENT(r4[qd], st), *e1 = ENT(r4[qd], st + 1);
+                w.push_back(mk(e0 ? LINE(e0->col, 0) * kLineBytes : 0u, e0 ? f2u(e0->a) : 0u, e1 ? LINE(e1->col, 0) * kLineBytes : 0u,
+                               e1 ? f2u(e1->a) : 0u));
+                T.real_entries += (e0 ? 1 : 0) + (e1 ? 1 : 0);
+                T.slot_entries += 2;
+              }
+            item_cost.push_back(9 * (int64_t)n_steps + 12);
+            item_parts.emplace_back((size_t)(1 + n_steps / 4), 8);  // header pair, groups of two packed units: 8 words each
+          } else {
+            for (int32_t st = 0; st < n_steps; ++st)
+              for (int qd = 0; qd < 4; ++qd) {
+                const UEnt* e = ENT(r4[qd], st);
+                if (e != nullptr) {
+                  w.push_back(mk(LINE(e->col, 0) * kLineBytes, f2u(e->a), f2u(e->b1), f2u(e->b2)));
+                  ++T.real_entries;
+                } else {
+                  w.push_back(mk(0u, 0u, 0u, 0u));  // padding: line 0 of the tile with zero coefficients
+                }
+                ++T.slot_entries;
+              }
+            item_cost.push_back(10 * (int64_t)n_steps + 12);
+            item_parts.emplace_back((size_t)(1 + n_steps / 2), 8);  // header pair, step pairs: 8 words each
+          }
+          item_words.push_back(std::move(w));
+        }
       }
     } else {
       std::vector<PairItem> pairs;
@@ -1015,6 +1044,24 @@ int replay_tile_plan(const TilePlan& T, int32_t ns_branch, const double* in0, co
             out[rJ] = precond ? aJ - (in1[rJ] - cJ) : aJ - (-in1[rJ] + cJ);
           }
           s += 8 + 8 * (size_t)nX + 4 * (size_t)nP + 4 * (size_t)nS + ((nS & 1u) ? 4 : 0);
+        } else if (!T.backward && (s[0].w[3] & 4u)) {  // A-quad: two steps per word, coefficients of A only
+          const int32_t n_steps = (int32_t)s[0].w[1];
+          for (int qd = 0; qd < 4; ++qd) {
+            const Word16& H = s[qd];
+            if ((int32_t)H.w[1] != n_steps || !(H.w[3] & 4u)) return fail(FEO_ERR_INVALID_ARGUMENT, "tile plan: quad step counts differ");
+            double accA = 0;
+            for (int32_t st = 0; st < n_steps; ++st) {
+              const Word16& e = s[8 + 4 * (st / 2) + qd];
+              const uint32_t off = e.w[2 * (st & 1)];
+              if (off % kLineBytes != 0) bad = true;
+              accA += (double)u2f(e.w[2 * (st & 1) + 1]) * S(off / kLineBytes);
+            }
+            const int32_t row = (int32_t)H.w[0];
+            if (row < 0) continue;
+            const double f = in1[row];
+            out[row] = precond ? accA - (f - 0.0) : accA - (-f + 0.0);
+          }
+          s += 8 + 2 * (size_t)n_steps;
         } else if (!T.backward) {
           const int32_t n_steps = (int32_t)s[0].w[1];
           for (int qd = 0; qd < 4; ++qd) {
