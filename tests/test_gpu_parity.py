@@ -369,3 +369,32 @@ def test_host_batch_pipeline_matches_one_shot(feo):
         l2 = pipe.step(a_host, f_host, grad_out=grad)
         assert abs(l2 - loss.item()) <= LOSS_RTOL * abs(loss.item())
         assert torch.equal(grad, g_ref)
+
+
+@pytest.mark.parametrize("branch", [True, False])
+def test_ns_noncolocated_pairs_and_cross_terms_on_device(feo, branch):
+    """I, J are opaque lists: shuffled pairing plus B1/B2 entries that couple the two
+    components and the pressure columns, so that the generic step kinds of the fused kernels (forward X-steps and
+    row quads, backward V-, A- and X-steps) run on the device, not only in the host replay."""
+    import scipy.sparse as sp
+    from feonet_navier_stokes_b200.fixtures import config_operators
+
+    fx = config_operators("steady_ns", 7, ordering="interleaved")
+    rng = np.random.default_rng(11)
+    idx_i = np.asarray(fx.idx_u1).copy()
+    idx_j = np.asarray(fx.idx_u2).copy()[rng.permutation(len(fx.idx_u2))]
+    noise = sp.random(fx.N, fx.N, density=0.01, random_state=5, data_rvs=rng.standard_normal).tocsr()
+    B1, B2 = (fx.B1 + noise).tocsr(), (fx.B2 + noise.T).tocsr()
+    idx_sol = np.empty(3, dtype=object)
+    idx_sol[0], idx_sol[1], idx_sol[2] = idx_i.tolist(), idx_j.tolist(), list(fx.idx_p)
+    B = 70
+    alpha = (0.3 * rng.standard_normal((B, fx.N))).astype(np.float32)
+    F = rng.standard_normal((B, fx.N)).astype(np.float32)
+    dev = torch.device("cuda")
+    ns = feo.SteadyNavierStokes(fx.A, B1, B2, idx_sol, do_precond=branch, precond=None, device=dev)
+    a = torch.tensor(alpha, device=dev).requires_grad_(True)
+    loss = ns.residual_loss(a, torch.tensor(F, device=dev), fx.A, B1, B2, idx_sol)
+    (grad,) = torch.autograd.grad(loss, a)
+    lo, go, _ = orc.ns_loss_and_grad(alpha, F, fx.A, B1, B2, idx_i, idx_j, branch, dtype=np.float64)
+    assert abs(loss.item() - lo) <= LOSS_RTOL * abs(lo)
+    assert _rel(grad.cpu().numpy(), go) < GRAD_RTOL and _relmax(grad.cpu().numpy(), go) < GRAD_RTOL
