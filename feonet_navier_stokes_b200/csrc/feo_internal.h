@@ -39,7 +39,8 @@ HostCsr axpy(const HostCsr& s, float dt, const HostCsr& a);  // S + dt*A
 // 256 B -- in shared memory with 2-D TMA boxes (two stages: the next unit loads while the current one is
 // processed), and its consumer warps walk private STREAMS of 16-byte words that are fed through
 // shared-memory rings by 1-D bulk copies.
-//   forward : a warp processes QUADS of rows, one row per quarter-warp, 8 samples per lane
+//   forward : a warp processes QUADS, one velocity row pair (pair quad) or one row (row quad, A-quad) per
+//             quarter-warp, 8 samples per lane
 //   backward: a warp processes DUOS of column pairs, one pair (e.g. the velocity pair (I[k], J[k]))
 //             per half-warp, 4 samples per lane
 constexpr int kSlab = 64;                  // samples per work unit

@@ -12,10 +12,11 @@
 //      when the current one ends;
 //   3. gathers are conflict-free LDS.128 from the staged lines, the arithmetic is packed fp32
 //      (fma.rn.f32x2: two IEEE fp32 FMAs per instruction).
-// The load-store pipe (128 B/clk of shared-memory data per SM) is what bounds these kernels, so the
-// mapping minimises its use: forward = one row per quarter-warp, 2 x 4 samples per lane (10 LSU cycles per
-// 4 row entries); backward = one column PAIR per half-warp, 4 samples per lane, so that the gathers of
-// r[I], r[J], alpha[I], alpha[J] of a neighbour node serve both columns.
+// The load-store pipe (128 B/clk of shared-memory data per SM) and the exposed shared-memory round trips of the
+// 15 consumer warps are what bound these kernels, so the mapping minimises the gathers and batches them:
+// forward = one velocity row PAIR (pair quads) or one row (row / A-quads) per quarter-warp, 2 x 4 samples per
+// lane; backward = one column PAIR per half-warp, 4 samples per lane, so that the gathers of r[I], r[J],
+// alpha[I], alpha[J] of a neighbour node serve both columns; several steps' loads per loop iteration.
 // Everything is row-/column-owned with a fixed summation order: no atomics, bit-reproducible.
 #include <cuda.h>
 #include <cuda_runtime.h>
