@@ -241,6 +241,10 @@ int feo_assemble_u_init(feo_handle_t h, const float* init_x, const float* init_y
   return launch_transpose(init_y, h->n_u, u0T, ldb, B, h->n_u, h->idx_j, st);
 }
 
+int feo_sincos_forcing_grid(const float* coeff_f, int32_t B, int32_t resol_in, float* value_f, void* stream) {
+  return launch_sincos_grid(coeff_f, B, resol_in, value_f, (cudaStream_t)stream);
+}
+
 int feo_sq_diff_sum(const float* xT, const float* yT, int32_t n, int64_t ldb, int32_t B, float scale, float* loss_out,
                     void* workspace, size_t workspace_bytes, void* stream) {
   return launch_sq_diff_sum(xT, yT, n, ldb, B, scale, loss_out, workspace, workspace_bytes, (cudaStream_t)stream);

@@ -182,6 +182,7 @@ int launch_sq_diff_sum(const float* xT, const float* yT, int32_t n, int64_t ldb,
 int launch_dense(const float* D, int32_t n, const float* XT, float* CT, int64_t ldb, int32_t B, float scale,
                  const float* scale_dev, const float* sub, float* loss_out, void* ws, size_t ws_bytes,
                  cudaStream_t st);
+int launch_sincos_grid(const float* coeff, int32_t B, int32_t resol, float* out, cudaStream_t st);
 size_t loss_partials_needed(int32_t n, int32_t fused_warps, int64_t cols);
 size_t fused_partials_needed(int32_t warps);  // floats: one loss partial per (persistent CTA, consumer warp)
 int finalize_loss(float* partials, int count, float scale, float* loss_out, cudaStream_t st);

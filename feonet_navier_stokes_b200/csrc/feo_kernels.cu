@@ -299,6 +299,36 @@ int launch_seq(const DevCsr& M, const DevCsr& S, int32_t n, bool backward, const
   return FEO_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// input synthesis of `closure` (FEONet_steady_Navier-Stokes/train_FEONet.py:337-345): the sin/cos forcing of every
+// sample on the resol x resol grid cartesian_prod(linspace(-1, 1, resol)), one kernel instead of ~10 eager ops
+//   out[b][0][i][j] = m0 sin(n0 x_i + n1 y_j),  out[b][1][i][j] = m1 cos(n2 x_i + n3 y_j)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sincos_grid_kernel(const float* __restrict__ coeff, int32_t B, int32_t resol,
+                                                          float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B || cell >= resol * resol) return;
+  const float* c = coeff + (size_t)b * 6;
+  const int i = cell / resol, j = cell - i * resol;
+  // torch.linspace(-1, 1, n): start + k * step for the first half, end - (n - 1 - k) * step for the second
+  const float step = 2.0f / (float)(resol - 1);
+  auto lin = [&](int k) { return k < resol / 2 ? -1.0f + step * (float)k : 1.0f - step * (float)(resol - 1 - k); };
+  const float x = resol > 1 ? lin(i) : -1.0f, y = resol > 1 ? lin(j) : -1.0f;
+  const size_t base = (size_t)b * 2 * resol * resol + cell;
+  out[base] = c[0] * sinf(__fadd_rn(__fmul_rn(c[2], x), __fmul_rn(c[3], y)));
+  out[base + (size_t)resol * resol] = c[1] * cosf(__fadd_rn(__fmul_rn(c[4], x), __fmul_rn(c[5], y)));
+}
+
+int launch_sincos_grid(const float* coeff, int32_t B, int32_t resol, float* out, cudaStream_t st) {
+  if (coeff == nullptr || out == nullptr || B <= 0 || resol <= 0) return fail(FEO_ERR_INVALID_ARGUMENT, "sincos_grid: bad arguments");
+  if (B > 65535) return fail(FEO_ERR_UNSUPPORTED, "sincos_grid: batch too large for one launch");
+  dim3 grid((resol * resol + 255) / 256, B);
+  sincos_grid_kernel<<<grid, 256, 0, st>>>(coeff, B, resol, out);
+  FEO_CUDA_CHECK(cudaGetLastError());
+  return FEO_OK;
+}
+
 int launch_sq_diff_sum(const float* xT, const float* yT, int32_t n, int64_t ldb, int32_t B, float scale,
                        float* loss_out, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (xT == nullptr || loss_out == nullptr || n <= 0 || B <= 0) return fail(FEO_ERR_INVALID_ARGUMENT, "sq_diff_sum: bad arguments");

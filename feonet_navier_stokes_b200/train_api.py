@@ -33,7 +33,18 @@ def rel_L2_error(pred: torch.Tensor, true: torch.Tensor) -> torch.Tensor:
 
 
 def sincos_forcing_grid(coeff: torch.Tensor, resol_in: int) -> torch.Tensor:
-    """Input synthesis of `closure` (steady NS :337-345; Stokes :277-283)."""
+    """Input synthesis of `closure` (steady NS :337-345; Stokes :277-283): one fused kernel
+    (`feo_sincos_forcing_grid`) on CUDA tensors; the reference's eager formula elsewhere (tests, CPU set-up)."""
+    if coeff.is_cuda:
+        import ctypes as C
+
+        lib = L.load_library()
+        c = coeff.detach().to(torch.float32).contiguous()
+        out = torch.empty((c.shape[0], 2, resol_in, resol_in), dtype=torch.float32, device=c.device)
+        with torch.cuda.device(c.device):
+            L.check(lib.feo_sincos_forcing_grid(C.c_void_p(c.data_ptr()), c.shape[0], int(resol_in), C.c_void_p(out.data_ptr()),
+                                                C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return out
     device = coeff.device
     m0, m1, n0, n1, n2, n3 = (coeff[:, [k]] for k in range(6))
     grid_x = torch.linspace(-1, 1, resol_in)

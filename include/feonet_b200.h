@@ -161,6 +161,11 @@ int feo_seq_bwd(feo_handle_t h, const float* rT, const float* grad_loss, float* 
 int feo_assemble_u_init(feo_handle_t h, const float* init_x, const float* init_y, float* u0T, int64_t ldb,
                         int32_t B, void* stream);
 
+/* Input synthesis of `closure` (FEONet_steady_Navier-Stokes/train_FEONet.py:337-345, FEONet_Stokes_square
+ * :277-283): value_f[b] = [m0 sin(n0 x + n1 y), m1 cos(n2 x + n3 y)] on cartesian_prod(linspace(-1, 1, resol_in)),
+ * coeff_f row-major [B, 6] = (m0, m1, n0, n1, n2, n3), value_f row-major [B, 2, resol_in, resol_in]. */
+int feo_sincos_forcing_grid(const float* coeff_f, int32_t B, int32_t resol_in, float* value_f, void* stream);
+
 /* Elementwise sum-of-squares of (x - y) over an [n][ldb] dof-major pair, first B columns:
  * the loss block of closure applied to materialised (LHS, RHS). y may be NULL. */
 int feo_sq_diff_sum(const float* xT, const float* yT, int32_t n, int64_t ldb, int32_t B, float scale,

@@ -398,3 +398,18 @@ def test_ns_noncolocated_pairs_and_cross_terms_on_device(feo, branch):
     lo, go, _ = orc.ns_loss_and_grad(alpha, F, fx.A, B1, B2, idx_i, idx_j, branch, dtype=np.float64)
     assert abs(loss.item() - lo) <= LOSS_RTOL * abs(lo)
     assert _rel(grad.cpu().numpy(), go) < GRAD_RTOL and _relmax(grad.cpu().numpy(), go) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("resol", [20, 64, 7])
+def test_sincos_forcing_grid_kernel(feo, resol):
+    """Fused input synthesis (feo_sincos_forcing_grid) vs the reference's eager formula in `closure`
+    (FEONet_steady_Navier-Stokes/train_FEONet.py:337-345) evaluated by torch on the CPU; fp32 sin/cos of the
+    two libraries differ by a few ulp."""
+    gen = torch.Generator().manual_seed(resol)
+    coeff = torch.rand(33, 6, generator=gen)
+    coeff[:, 2:] *= np.pi
+    ref = feo.sincos_forcing_grid(coeff, resol)  # CPU tensor -> the reference's torch formula
+    out = feo.sincos_forcing_grid(coeff.cuda(), resol)
+    assert out.shape == ref.shape == (33, 2, resol, resol)
+    assert torch.allclose(out.cpu(), ref, rtol=0, atol=2e-6)
+    assert np.allclose(ref.numpy(), orc.sincos_forcing_grid(coeff.numpy(), resol), atol=2e-6)
