@@ -64,6 +64,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--spai_steps", type=int, default=200, help="minimal-residual iterations of the SPAI preconditioner")
     p.add_argument("--dof_major_head", type=int, default=1, help="let the last layer write the coefficients dof-major")
+    p.add_argument("--npz", type=str, default=None,
+                   help="an assemble_fenics.py npz (data_ordered/P2x1_ne..._BC[_force].npz) to train on instead of synthesised data")
     return p
 
 
@@ -180,9 +182,23 @@ class Trainer:
             raise ValueError("train and validation files must use the same mesh")
         n = mesh_n_from_ne(ne, strict=variant != "hole")  # the hole stand-in mesh is Delaunay: ne only sets its resolution
         do_precond = int(gparams["do_precond"]) > 0
-        # data (seeds 5 / 10: create_data.py:30-33)
-        self.fx, train = synthesize(variant, n, gparams["bc"], n_train, 5, do_precond)
-        _, val = synthesize(variant, n, gparams["bc"], n_val, 10, do_precond)
+        if gparams.get("npz"):
+            # the reference's own file: dense operators -> CSR, the first NUM_DATA samples of each split (:69-85, :218-245)
+            from types import SimpleNamespace
+
+            from .data_io import load_reference_npz
+
+            z = load_reference_npz(gparams["npz"])
+            i_, j_, k_ = z["idx_sol"]
+            self.fx = SimpleNamespace(N=z["N"], A=z["A"] if "A" in z else z["matrix"], B1=z.get("B1"), B2=z.get("B2"),
+                                      idx_u1=np.asarray(i_), idx_u2=np.asarray(j_), idx_p=np.asarray(k_), idx_sol=z["idx_sol"])
+            train = {k: v[:n_train] for k, v in z["train"].items() if k != "forcing_term"}
+            val = {k: v[:n_val] for k, v in z["validate"].items() if k != "forcing_term"}
+            n_train, n_val = len(train["coeff_f"]), len(val["coeff_f"])
+        else:
+            # data (seeds 5 / 10: create_data.py:30-33)
+            self.fx, train = synthesize(variant, n, gparams["bc"], n_train, 5, do_precond)
+            _, val = synthesize(variant, n, gparams["bc"], n_val, 10, do_precond)
         t = lambda a: torch.tensor(np.asarray(a), dtype=torch.float32)  # noqa: E731
         lo, hi = parallel.shard_bounds(n_train, self.rank, self.world)
         self.train = {k: t(v[lo:hi]).to(self.device) for k, v in train.items()}

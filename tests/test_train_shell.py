@@ -52,3 +52,20 @@ def test_training_run_reduces_the_loss(tmp_path, variant, do_precond):
     assert os.path.exists(os.path.join(tr.folder, "model.pt")) and os.path.exists(os.path.join(tr.folder, "model.pth"))
     ck = torch.load(os.path.join(tr.folder, "model.pt"), map_location="cpu")
     assert set(ck) == {"model_state_dict", "losses", "train_rel_L2_errors", "test_rel_L2_errors"}
+
+
+@pytest.mark.gpu
+def test_training_from_a_reference_npz(tmp_path):
+    """The shell trains from an `assemble_fenics.py`-schema npz (dense float64 operators, object idx_sol)."""
+    import torch
+
+    from feonet_navier_stokes_b200 import data_io as D
+
+    fx, train = T.synthesize("steady_ns", 4, "channel_flow", 16, 5, True)
+    _, val = T.synthesize("steady_ns", 4, "channel_flow", 4, 10, True)
+    path = D.save_reference_npz(str(tmp_path / D.npz_name(fx.mesh.ne, "channel_flow", "sincos")), fx, train, val, "steady_ns")
+    argv = ["--variant", "steady_ns", "--train_file", "16N32", "--val_file", "4N32", "--model", "FCNN", "--optimizer", "Adam", "--do_precond", "1",
+            "--epochs", "40", "--log_every", "20", "--lr", "3e-3", "--out", str(tmp_path), "--npz", path]
+    tr = T.Trainer(dict(T.build_parser().parse_args(argv).__dict__), device=torch.device("cuda"))
+    tr.fit()
+    assert len(tr.losses) == 2 and tr.losses[-1] < tr.losses[0]
