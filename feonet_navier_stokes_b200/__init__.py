@@ -9,6 +9,7 @@ from .functional import (DenseFn, DenseResidualLossFn, ResidualLossFn, SeqResidu
                          dof_major_empty, dof_major_zeros, is_dof_major, precond_output, to_dof_major_tensor)
 from .host_io import HostBatchPipeline  # noqa: F401
 from .operator import FEOperator  # noqa: F401
+from .precond import spai_device  # noqa: F401
 from .train_api import (LinearStokes, SteadyNavierStokes, TimeDependentStokes, rel_L2_error,  # noqa: F401
                         sincos_forcing_grid)
 

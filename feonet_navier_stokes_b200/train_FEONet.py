@@ -215,9 +215,7 @@ class Trainer:
             self.closure_args = lambda b: (b["coeff_f"], None, b["load_vec_f"], A, self.fx.B1, self.fx.B2, gparams["resol_in"])  # noqa: E731
         else:
             if do_precond:
-                from .fixtures import spai
-
-                self.P = torch.tensor(spai(np.asarray(A.todense()), gparams["spai_steps"]), dtype=torch.float32)
+                self.P = feo.spai_device(A, gparams["spai_steps"], self.device).to(torch.float32).cpu()
             hole = variant == "hole"
             self.problem = feo.LinearStokes(A, self.P, do_precond=do_precond, model_name=gparams["model"], force=gparams["forcing_term"],
                                             hole_signature=hole, device=self.device)

@@ -413,3 +413,17 @@ def test_sincos_forcing_grid_kernel(feo, resol):
     assert out.shape == ref.shape == (33, 2, resol, resol)
     assert torch.allclose(out.cpu(), ref, rtol=0, atol=2e-6)
     assert np.allclose(ref.numpy(), orc.sincos_forcing_grid(coeff.numpy(), resol), atol=2e-6)
+
+
+def test_spai_on_device_matches_the_host_iteration(feo):
+    """feo.spai_device runs the reference's SPAI recurrence (FEONet_Stokes_square/train_FEONet.py:104-121) on the GPU;
+    same steps as the host restatement, and the residual ||I - A M||_F decreases (minimal-residual iteration)."""
+    from feonet_navier_stokes_b200.fixtures import config_operators, spai
+
+    fx = config_operators("stokes_square", 6)
+    A = np.asarray(fx.A.todense())
+    P_host = spai(A, 60)
+    P_dev = feo.spai_device(A, 60).cpu().numpy()
+    assert np.allclose(P_dev, P_host, rtol=1e-9, atol=1e-12)
+    eye = np.eye(A.shape[0])
+    assert np.linalg.norm(eye - A @ P_dev) < np.linalg.norm(eye - A @ feo.spai_device(A, 0).cpu().numpy())
