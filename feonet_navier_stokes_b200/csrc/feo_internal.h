@@ -182,6 +182,10 @@ int launch_sq_diff_sum(const float* xT, const float* yT, int32_t n, int64_t ldb,
 int launch_dense(const float* D, int32_t n, const float* XT, float* CT, int64_t ldb, int32_t B, float scale,
                  const float* scale_dev, const float* sub, float* loss_out, void* ws, size_t ws_bytes,
                  cudaStream_t st);
+// tcgen05 3xTF32 tile GEMM behind launch_dense (feo_dense_tc.cu); writes one loss partial per 128 x 128 tile
+int launch_dense_tc(const float* D, int32_t n, int32_t ldd, const float* XT, float* CT, int64_t ldb, int32_t B,
+                    float scale, const float* scale_dev, const float* sub, float* partials, int* count_out,
+                    cudaStream_t st);
 int launch_sincos_grid(const float* coeff, int32_t B, int32_t resol, float* out, cudaStream_t st);
 size_t loss_partials_needed(int32_t n, int32_t fused_warps, int64_t cols);
 size_t fused_partials_needed(int32_t warps);  // floats: one loss partial per (persistent CTA, consumer warp)

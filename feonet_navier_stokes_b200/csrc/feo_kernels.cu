@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 #include "feo_internal.h"
 
 namespace feo {
@@ -431,14 +433,23 @@ int launch_dense(const float* D, int32_t n, const float* XT, float* CT, int64_t 
     if (int rc = check_layout(sub, ldb, B, "sub")) return rc;
   const int32_t ldd = (n + 3) / 4 * 4;
   dim3 grid((int)((((B + 3) / 4 * 4) + GBN - 1) / GBN), (n + GBM - 1) / GBM);
-  const int count = grid.x * grid.y;
+  int count = grid.x * grid.y;
   float* partials = nullptr;
   if (loss_out != nullptr) {
     if (ws == nullptr || ws_bytes < (size_t)count * sizeof(float)) return fail(FEO_ERR_INVALID_ARGUMENT, "workspace too small");
     partials = (float*)ws;
   }
-  dense_apply_kernel<<<grid, 256, 0, st>>>(D, n, ldd, XT, CT, ldb, B, scale, scale_dev, sub, partials);
-  FEO_CUDA_CHECK(cudaGetLastError());
+  // product path: tcgen05 3xTF32 (feo_dense_tc.cu); FEO_DENSE_SIMT=1 selects the fp32 FMA kernel (developer comparison)
+  static const bool simt = [] {
+    const char* e = std::getenv("FEO_DENSE_SIMT");
+    return e != nullptr && atoi(e) != 0;
+  }();
+  if (!simt) {
+    if (int rc = launch_dense_tc(D, n, ldd, XT, CT, ldb, B, scale, scale_dev, sub, partials, &count, st)) return rc;
+  } else {
+    dense_apply_kernel<<<grid, 256, 0, st>>>(D, n, ldd, XT, CT, ldb, B, scale, scale_dev, sub, partials);
+    FEO_CUDA_CHECK(cudaGetLastError());
+  }
   if (loss_out != nullptr) return finalize(partials, count, 1.0f, loss_out, st);
   return FEO_OK;
 }

@@ -316,6 +316,37 @@ def test_dense_precond_cfg1_vs_oracle(feo):
     assert _rel(grad.cpu().numpy(), go) < GRAD_RTOL and _relmax(grad.cpu().numpy(), go) < GRAD_RTOL
 
 
+@pytest.mark.parametrize("n,B", [(72, 5), (200, 130), (387, 1000), (813, 257), (2549, 1024)])
+def test_dense_apply_tensor_core_vs_fp64(feo, n, B):
+    """feo_dense_apply (tcgen05 3xTF32, feo_dense_tc.cu) against the fp64 product: ragged n (not a multiple of the
+    128 x 128 x 16 tile) and B, all epilogues (scale, device scale, subtract, sum of squares).  The split must be
+    fp32-grade: every element within 2e-6 of the row's |D||x| bound (plain TF32 would sit near 5e-4)."""
+    from feonet_navier_stokes_b200 import _lib as L
+
+    dev = torch.device("cuda")
+    rng = np.random.default_rng(n + B)
+    D = (rng.standard_normal((n, n)) / np.sqrt(n)).astype(np.float32)
+    D[rng.random((n, n)) < 0.1] = 0.0
+    op = feo.FEOperator(n, dense_m=D, device=dev)
+    x = rng.standard_normal((B, n)).astype(np.float32)
+    f = rng.standard_normal((B, n)).astype(np.float32)
+    xT, fT = op.to_dof_major(torch.tensor(x, device=dev)), op.to_dof_major(torch.tensor(f, device=dev))
+    D64, x64, f64 = D.astype(np.float64), x.astype(np.float64), f.astype(np.float64)
+    bound = (np.abs(D64) @ np.abs(x64).T)  # [n, B]
+    # plain product, then the transposed operator
+    for which, M in ((L.FEO_DENSE_M, D64), (L.FEO_DENSE_MT, D64.T)):
+        cT = op.dense_apply(which, xT, B)
+        err = np.abs(cT[:, :B].cpu().numpy().astype(np.float64) - M @ x64.T)
+        bnd = bound if which == L.FEO_DENSE_M else (np.abs(D64.T) @ np.abs(x64).T)
+        assert (err <= 2e-6 * bnd + 1e-30).all(), (which, float((err / (bnd + 1e-30)).max()))
+    # fused residual epilogue: r = 0.5 * s * D x - f, loss = sum r^2
+    sdev = torch.tensor([3.0], device=dev)
+    rT, loss = op.dense_apply(L.FEO_DENSE_M, xT, B, scale=0.5, scale_dev=sdev, sub=fT, want_loss=True)
+    r64 = 1.5 * (D64 @ x64.T) - f64.T
+    assert np.abs(rT[:, :B].cpu().numpy() - r64).max() <= 4e-6 * max(1.0, bound.max())
+    assert abs(loss.item() - (r64 ** 2).sum()) <= LOSS_RTOL * (r64 ** 2).sum()
+
+
 def test_time_dep_cfg4_vs_oracle(feo):
     from feonet_navier_stokes_b200.fixtures import config_operators
 
