@@ -76,6 +76,7 @@ def parse_args():
     ap.add_argument("--cpu-samples", type=int, default=8, help="samples per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-precond-gemm", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-chunk", type=int, default=256, help="samples per host->device chunk of the end-to-end leg")
     return ap.parse_args()
@@ -363,6 +364,11 @@ def run_ours(args):
         out["value_row_major_layout"] = alt_value
     if e2e is not None:
         out["e2e"] = e2e
+    if world == 1 and not args.no_precond_gemm:
+        try:
+            out["precond_gemm"] = run_precond_gemm(torch, feo, dev)
+        except Exception as exc:  # pragma: no cover
+            log(f"[bench] precond_gemm leg failed: {exc!r}")
     if not args.no_cpu_baseline and world == 1:
         try:
             rate, threads, ms = cpu_port_rate(fx, args, 3, 1)
@@ -375,6 +381,49 @@ def run_ours(args):
     emit(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_precond_gemm(torch, feo, dev, n=2549, B=1024, iters=30):
+    """The dense preconditioned apply r = (A P) alpha - F with its loss (SURVEY 8a a7, cfg2b size N=2549, B=1024):
+    tcgen05 3xTF32 kernel behind feo_dense_apply, CUDA events.  Tensor-pipe work = three TF32 products per fp32 product;
+    the peak beside it is MEASURED_PEAKS.json's dense bf16 figure halved (TF32 runs at half the bf16 rate)."""
+    from feonet_navier_stokes_b200 import _lib as L
+    import numpy as np
+
+    rng = np.random.default_rng(0)
+    D = (rng.standard_normal((n, n)) / np.sqrt(n)).astype(np.float32)
+    op = feo.FEOperator(n, dense_m=D, device=dev)
+    xT = torch.randn(n, B, device=dev)
+    fT = torch.randn(n, B, device=dev)
+    for _ in range(3):
+        op.dense_apply(L.FEO_DENSE_M, xT, B, sub=fT, want_loss=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        rT, loss = op.dense_apply(L.FEO_DENSE_M, xT, B, sub=fT, want_loss=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    ref = torch.tensor(D, device=dev, dtype=torch.float64) @ xT.double() - fT.double()
+    loss_ref = float((ref ** 2).sum())
+    bf16_peak = None
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        bf16_peak = float(pk["bf16_tflops"])  # burst figure: the kernel is timed alone
+    except Exception:
+        pass
+    tensor_tf = 6.0 * n * n * B / (ms * 1e-3) / 1e12
+    out = {
+        "kernel": "dense_apply_tc_kernel (tcgen05 kind::tf32, 3xTF32 split, TMEM accumulator)", "n": n, "batch": B,
+        "ms_per_apply": ms, "fp32_equivalent_tflops": 2.0 * n * n * B / (ms * 1e-3) / 1e12, "tensor_pipe_tflops": tensor_tf,
+        "loss_rel_err_vs_fp64": abs(loss.item() - loss_ref) / loss_ref,
+        "max_abs_err_vs_fp64": float((rT[:, :B].double() - ref).abs().max()),
+    }
+    if bf16_peak:
+        out["tf32_peak_tflops"] = bf16_peak / 2.0
+        out["tensor_pipe_frac"] = tensor_tf / (bf16_peak / 2.0)
+    return out
 
 
 def run_e2e(args, torch, feo, ns, fx, dev, world, rank):
