@@ -77,6 +77,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-precond-gemm", action="store_true")
+    ap.add_argument("--configs", action="store_true", help="time cfg1-4 (parity-test cases) on cuda:0 beside the CPU port; not the bench line")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-chunk", type=int, default=256, help="samples per host->device chunk of the end-to-end leg")
     return ap.parse_args()
@@ -426,6 +427,142 @@ def run_precond_gemm(torch, feo, dev, n=2549, B=1024, iters=30):
     return out
 
 
+def run_configs(args):
+    """--configs: the reference's own configurations (SURVEY 8 size table cfg1-4; parity-test cases, NOT the bench
+    line) through the reference-facing API on cuda:0 -- residual loss + backward to grad alpha, row-major [B, N]
+    inputs as the reference passes them -- with the oracle's CPU port (numpy/scipy, fp32) timed beside it.
+    Prints one JSON object; `tools/...` summarise it into profiles/."""
+    import torch
+    import feonet_navier_stokes_b200 as feo
+    from feonet_navier_stokes_b200.fixtures import config_operators
+    from oracle import feonet_oracle as orc
+
+    feo.load_library(build_if_missing=False)
+    dev = torch.device("cuda:0")
+    B, T, dt = 1000, 10, 0.1
+    rng = np.random.default_rng(0)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def time_gpu(fn, iters=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    def time_cpu(fn, reps=3):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            out = fn()
+        return 1e3 * (time.perf_counter() - t0) / reps, out
+
+    def dense_precond(n):  # a dense, well-conditioned stand-in for the missing precond_{ne}.npy blobs
+        return (np.eye(n) + 0.3 * rng.standard_normal((n, n)) / np.sqrt(n)).astype(np.float32)
+
+    rows = []
+
+    def report(name, N, gpu_ms, cpu_ms, loss_gpu, loss_cpu, grad_gpu, grad_cpu, note):
+        g, c = np.asarray(grad_gpu, dtype=np.float64), np.asarray(grad_cpu, dtype=np.float64)
+        rows.append({"config": name, "N": N, "batch": B, "gpu_ms_fwd_bwd": gpu_ms, "gpu_samples_per_s": B / (gpu_ms * 1e-3),
+                     "cpu_port_ms_fwd_bwd": cpu_ms, "cpu_port_samples_per_s": B / (cpu_ms * 1e-3), "speedup": cpu_ms / gpu_ms,
+                     "loss_rel_diff": abs(loss_gpu - loss_cpu) / abs(loss_cpu),
+                     "grad_rel_diff": float(np.linalg.norm(g - c) / np.linalg.norm(c)), "note": note})
+        log(f"[configs] {rows[-1]}")
+
+    # cfg1 / cfg2: linear Stokes, preconditioned (dense apply on the tensor cores)
+    for name, fxname, n in (("cfg1 Stokes_square precond N=387", "stokes_square", 6), ("cfg2a square-with-hole precond", "hole", 10),
+                             ("cfg2b square-with-hole precond", "hole", 18)):
+        fx = config_operators(fxname, n)
+        A = np.asarray(fx.A.todense(), dtype=np.float32)
+        P = dense_precond(fx.N)
+        alpha = (0.3 * rng.standard_normal((B, fx.N))).astype(np.float32)
+        F = rng.standard_normal((B, fx.N)).astype(np.float32)
+        At, Pt = torch.tensor(A, device=dev), torch.tensor(P, device=dev)
+        st = feo.LinearStokes(At, Pt, do_precond=True, device=dev)
+        a = torch.tensor(alpha, device=dev, requires_grad=True)
+        Ft = torch.tensor(F, device=dev)
+        box = {}
+
+        def step():
+            loss = st.residual_loss(a, Ft, At, Pt)
+            (box["g"],) = torch.autograd.grad(loss, a)
+            box["l"] = loss
+
+        gpu_ms = time_gpu(step)
+        cpu_ms, (lo, go, _) = time_cpu(lambda: orc.stokes_loss_and_grad(alpha, F, A, P, True, dtype=np.float32))
+        report(name + (f" N={fx.N}" if "N=" not in name else ""), fx.N, gpu_ms, cpu_ms,
+               box["l"].item(), float(lo), box["g"].cpu().numpy(), go, "dense A.P folded at set-up, tcgen05 3xTF32 apply")
+
+    # cfg3: steady Navier-Stokes, both sign branches (fused sparse kernels)
+    fx = config_operators("steady_ns", 15)
+    alpha = (0.3 * rng.standard_normal((B, fx.N))).astype(np.float32)
+    F = rng.standard_normal((B, fx.N)).astype(np.float32)
+    for precond in (True, False):
+        nsm = feo.SteadyNavierStokes(fx.A, fx.B1, fx.B2, fx.idx_sol, do_precond=precond, device=dev)
+        a = torch.tensor(alpha, device=dev, requires_grad=True)
+        Ft = torch.tensor(F, device=dev)
+        box = {}
+
+        def step():
+            loss = nsm.residual_loss(a, Ft, fx.A, fx.B1, fx.B2, fx.idx_sol)
+            (box["g"],) = torch.autograd.grad(loss, a)
+            box["l"] = loss
+
+        gpu_ms = time_gpu(step)
+        cpu_ms, (lo, go, _) = time_cpu(lambda: orc.ns_loss_and_grad(alpha, F, fx.A, fx.B1, fx.B2, fx.idx_u1, fx.idx_u2, precond, dtype=np.float32))
+        report(f"cfg3 steady NS N={fx.N} ({'precond=I' if precond else 'no precond'} sign branch)", fx.N, gpu_ms, cpu_ms,
+               box["l"].item(), float(lo), box["g"].cpu().numpy(), go, "fused residual_fwd/bwd_tiled incl. row-major <-> dof-major transposes")
+
+    # cfg4: time-dependent Stokes, T = 10
+    fx = config_operators("time_dep", 10)
+    pred = (0.3 * rng.standard_normal((B, T, fx.N))).astype(np.float32)
+    u0 = rng.standard_normal((B, fx.N)).astype(np.float32)
+    F = np.repeat(rng.standard_normal((1, fx.N)).astype(np.float32), B, axis=0)
+    td = feo.TimeDependentStokes(fx.S, fx.A, fx.idx_sol, dt=dt, do_precond=False, device=dev)
+    pt = torch.tensor(pred, device=dev, requires_grad=True)
+    Ft, u0t = torch.tensor(F, device=dev), torch.tensor(u0, device=dev)
+    box = {}
+
+    def step():
+        loss = td.residual_loss(pt, Ft, fx.S, fx.A, None, dt, u0t)
+        (box["g"],) = torch.autograd.grad(loss, pt)
+        box["l"] = loss
+
+    gpu_ms = time_gpu(step)
+    cpu_ms, (lo, go, _) = time_cpu(lambda: orc.seq_loss_and_grad(pred, F, fx.S, fx.A, None, dt, u0, False, dtype=np.float32))
+    report(f"cfg4 time-dependent Stokes N={fx.N} T={T}", fx.N, gpu_ms, cpu_ms, box["l"].item(), float(lo),
+           box["g"].cpu().numpy(), go, "seq_kernel fwd/bwd, one sample = T rows")
+    # the linear Stokes operator (no convective term: A-quads forward, 20 N B algorithmic bytes) at the cfg5 mesh size
+    large = None
+    try:
+        from feonet_navier_stokes_b200.operator import FEOperator
+
+        fx = config_operators("stokes_square", args.n, ordering=args.ordering)
+        Bl, Nl = 1024, fx.N
+        op = FEOperator(Nl, A=fx.A, device=dev)
+        aT = torch.empty(Nl, Bl, device=dev).normal_(0, 0.1)
+        fT = torch.empty(Nl, Bl, device=dev).normal_(0, 1.0)
+        gT = torch.empty(Nl, Bl, device=dev)
+        tf = time_gpu(lambda: op.residual_fwd(aT, fT, Bl), 10)
+        _, rT = op.residual_fwd(aT, fT, Bl)
+        tb = time_gpu(lambda: op.residual_bwd(aT, rT, Bl, out=gT), 10)
+        peak, _ = measured_peak_gbs()
+        large = {"config": f"linear Stokes at the cfg5 mesh (N={Nl}, B={Bl}, dof-major)", "fwd_ms": tf, "bwd_ms": tb,
+                 "samples_per_s": Bl / ((tf + tb) * 1e-3), "fwd_algorithmic_GBs": 12.0 * Nl * Bl / (tf * 1e-3) / 1e9,
+                 "bwd_algorithmic_GBs": 8.0 * Nl * Bl / (tb * 1e-3) / 1e9, "hbm_peak_GBs": peak}
+        log(f"[configs] {large}")
+    except Exception as exc:  # pragma: no cover
+        log(f"[configs] large linear case failed: {exc!r}")
+    emit({"configs": rows, "linear_large": large, "cores": os.cpu_count(), "cpu_kind": "port (oracle numpy/scipy, fp32)",
+          "reference_own_code": "SURVEY 8a: 5.0 s at N=387, 9.2 s at N=2178 per step (B=1000, 8 threads, torch CPU, reference loops)"})
+
+
 def run_e2e(args, torch, feo, ns, fx, dev, world, rank):
     """Public-API call with host inputs: alpha and F start in pinned host memory in the reference's
     row-major [B,N] layout, are copied to the device, go through residual_loss + backward, and the
@@ -472,7 +609,9 @@ def run_e2e(args, torch, feo, ns, fx, dev, world, rank):
 def main():
     args = parse_args()
     claim_stdout()
-    if args.impl == "reference":
+    if args.configs:
+        run_configs(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
