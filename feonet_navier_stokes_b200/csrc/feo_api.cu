@@ -135,9 +135,13 @@ int feo_op_create(const feo_operator_desc* desc, feo_handle_t* out) {
   if (desc->dense_m != nullptr) {
     if ((rc = upload_dense(op, desc->dense_m, desc->n, false, &op->dM))) return bail(rc);
     if ((rc = upload_dense(op, desc->dense_m, desc->n, true, &op->dMT))) return bail(rc);
+    if ((rc = upload(op, dense_split_tiles(desc->dense_m, desc->n, false), &op->dMs))) return bail(rc);
+    if ((rc = upload(op, dense_split_tiles(desc->dense_m, desc->n, true), &op->dMTs))) return bail(rc);
   }
-  if (desc->dense_p != nullptr)
+  if (desc->dense_p != nullptr) {
     if ((rc = upload_dense(op, desc->dense_p, desc->n, false, &op->dP))) return bail(rc);
+    if ((rc = upload(op, dense_split_tiles(desc->dense_p, desc->n, false), &op->dPs))) return bail(rc);
+  }
   if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(FEO_ERR_CUDA, "device synchronize failed after upload"));
   *out = op;
   return FEO_OK;
@@ -211,7 +215,8 @@ int feo_dense_apply(feo_handle_t h, int32_t which, const float* XT, float* CT, i
   if (int rc = check_handle(h)) return rc;
   const float* D = which == FEO_DENSE_M ? h->dM : which == FEO_DENSE_MT ? h->dMT : which == FEO_DENSE_P ? h->dP : nullptr;
   if (which < 0 || which > FEO_DENSE_P) return fail(FEO_ERR_INVALID_ARGUMENT, "dense_apply: unknown matrix id");
-  return launch_dense(D, h->n, XT, CT, ldb, B, scale, scale_dev, sub, loss_out, workspace, workspace_bytes,
+  const float* Ds = which == FEO_DENSE_M ? h->dMs : which == FEO_DENSE_MT ? h->dMTs : which == FEO_DENSE_P ? h->dPs : nullptr;
+  return launch_dense(D, Ds, h->n, XT, CT, ldb, B, scale, scale_dev, sub, loss_out, workspace, workspace_bytes,
                       (cudaStream_t)stream);
 }
 
@@ -283,3 +288,26 @@ int feo_debug_tile_replay(const feo_operator_desc* desc, int32_t backward, int32
 }
 
 }  // extern "C"
+
+int64_t feo_debug_dense_split_replay(const float* dense, int32_t n, int32_t transposed, const double* x, double* out_hi,
+                                     double* out_lo) {
+  if (dense == nullptr || n <= 0) return feo::fail(FEO_ERR_INVALID_ARGUMENT, "dense_split_replay: bad arguments");
+  const std::vector<float> t = feo::dense_split_tiles(dense, n, transposed != 0);
+  if (x != nullptr && out_hi != nullptr && out_lo != nullptr) {
+    // decode exactly as dense_apply_tc_kernel addresses a stage: block (row tile, k-block) = [hi 8 KB | lo 8 KB],
+    // element (r, k) at (k / 4) * 2048 + r * 16 + (k % 4) * 4 bytes
+    const int64_t nkb = (n + 15) / 16;
+    for (int32_t r = 0; r < n; ++r) {
+      double hi = 0.0, lo = 0.0;
+      for (int64_t k = 0; k < nkb * 16; ++k) {
+        const size_t at = ((size_t)(r / 128) * nkb + k / 16) * 4096 + (size_t)((k % 16) / 4) * 512 + (size_t)(r % 128) * 4 + k % 4;
+        const double xv = k < n ? x[k] : 1.0;  // padding columns must hold zeros: x = 1 there exposes a leak
+        hi += (double)t[at] * xv;
+        lo += (double)t[at + 2048] * xv;
+      }
+      out_hi[r] = hi;
+      out_lo[r] = lo;
+    }
+  }
+  return (int64_t)t.size();
+}

@@ -9,13 +9,16 @@
 // relative per product and unbiased, i.e. fp32-grade, which plain TF32 (2^-11) is not: the north-star
 // tolerance on the loss is 1e-5 relative.
 //
-// One CTA = one 128 x 128 tile of CT (UMMA M = 128, N = 128, K = 8), k-blocks of 16, two shared-memory
-// stages.  The operands come straight from global memory through registers (the split needs a register
-// pass anyway, and XT is sample-contiguous, i.e. MN-major: the register pass also transposes it into the
-// K-major core-matrix layout), so there is no TMA here; the stage hand-over is
-//   generic stores -> fence.proxy.async -> bar.sync -> one thread issues 6 MMAs -> tcgen05.commit -> mbarrier
-// and the loads of the next k-block are in flight while the tensor core works.  64 KB of shared memory and
-// 128 TMEM columns per CTA: two CTAs per SM overlap each other's load latency.
+// One CTA = one 128 x 64 (or 128 x 128) tile of CT (UMMA M = 128, N = 64 | 128, K = 8), k-blocks of 16.
+//  * D operand: split ONCE at set-up (dense_split_tiles: per (row tile, k-block) a 16 KB block [hi | lo] already in
+//    the shared-memory operand layout), so a stage is one cp.async.bulk (UBLKCP) onto an mbarrier: three stages,
+//    the copy of k-block kb + 1 is issued as soon as the MMAs of kb - 2 have released its stage.
+//  * XT operand (the activations: split at run time; sample-contiguous, i.e. MN-major): through registers --
+//    coalesced row reads, cvt.rna.tf32 split, STS.128 straight into the K-major core-matrix layout, which also
+//    transposes it; two stages, two register sets (k-blocks kb + 1 and kb + 2 in flight).
+// Hand-over per k-block: generic stores -> fence.proxy.async -> bar.sync -> one thread waits for the D stage, issues
+// 6 MMAs -> tcgen05.commit -> mbarrier.  64 KB (BN = 64) of shared memory and BN TMEM columns per CTA: three CTAs
+// per SM overlap each other's latencies.
 //
 // The tensor core aligns and TRUNCATES when it adds a K = 8 product group to the fp32 accumulator, which biases a
 // long accumulation towards zero (measured: 3e-6 of |D||x| at n = 2549, against 1e-7 for the split itself).  The
@@ -29,6 +32,7 @@
 #include <stdint.h>
 
 #include <cstdlib>
+#include <vector>
 
 #include "feo_internal.h"
 
@@ -38,8 +42,10 @@ namespace {
 constexpr int TBM = 128, TBK = 16;                      // CT tile rows, k-block; tile columns BN = 128 or 64 (template)
 constexpr int kTcThreads = 256;
 constexpr uint32_t kABytes = TBM * TBK * 4;              // 8 KB: A_hi or A_lo of a stage
-__host__ __device__ constexpr uint32_t stage_bytes(int BN) { return 2 * kABytes + 2 * (uint32_t)BN * TBK * 4; }  // A_hi, A_lo, B_hi, B_lo
-constexpr int kTcStages = 2;
+constexpr int kAStages = 3;                              // D operand ring (bulk copies)
+constexpr int kTcStages = 2;                             // XT operand stages (register pass)
+__host__ __device__ constexpr uint32_t b_stage_bytes(int BN) { return 2 * (uint32_t)BN * TBK * 4; }  // B_hi, B_lo
+__host__ __device__ constexpr uint32_t smem_bytes_for(int BN) { return kAStages * 2 * kABytes + kTcStages * b_stage_bytes(BN); }
 constexpr int kFlushDefault = 4;                         // k-blocks between drains of the TMEM accumulator (FEO_DENSE_FLUSH)
 constexpr uint32_t kLboA = TBM * 16;                     // 2048 B between the k-chunks (4 k each) of an A tile; BN * 16 for B
 constexpr uint32_t kSbo = 128;                           // 8-row groups are contiguous
@@ -70,6 +76,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar),
       "r"(parity)
       : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -113,14 +127,15 @@ __device__ __forceinline__ void store_split(uint8_t* hi_base, uint8_t* lo_base, 
 }
 
 template <int BN>
-__global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_kernel(const float* __restrict__ D, int32_t n, int32_t ldd,
+__global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_kernel(const float* __restrict__ Dsplit, int32_t n,
                                                                     const float* __restrict__ XT, float* __restrict__ CT,
                                                                     int64_t ldb, int32_t B, float scale,
                                                                     const float* __restrict__ scale_dev,
                                                                     const float* __restrict__ sub,
                                                                     float* __restrict__ partials, int32_t flush) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t s_bar[kTcStages];
+  __shared__ __align__(8) uint64_t s_bar[kTcStages];   // commit barriers: MMAs of a k-block done (by k-block parity)
+  __shared__ __align__(8) uint64_t s_full[kAStages];   // D operand stage landed
   __shared__ uint32_t s_tmem;
   __shared__ float s_part[kTcThreads / 32];
 
@@ -128,7 +143,9 @@ __global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_
   const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * BN;
   constexpr uint32_t kTmemCols = BN;                      // fp32 accumulator columns (power of two >= 32)
   constexpr uint32_t kBBytes = (uint32_t)BN * TBK * 4;    // B_hi or B_lo of a stage
-  constexpr uint32_t kStage = stage_bytes(BN);
+  constexpr uint32_t kAStage = 2 * kABytes;               // [hi | lo]
+  constexpr uint32_t kBStage = b_stage_bytes(BN);
+  constexpr uint32_t kBBase = kAStages * kAStage;
   constexpr uint32_t kLboB = BN * 16;
   constexpr uint32_t kIdesc = instr_desc(BN);
   constexpr int CB = BN / 64;                             // k-chunks of the B tile per thread
@@ -140,6 +157,7 @@ __global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_
   }
   if (tid == 32) {
     for (int s = 0; s < kTcStages; ++s) mbar_init(smem_u32(&s_bar[s]), 1);
+    for (int s = 0; s < kAStages; ++s) mbar_init(smem_u32(&s_full[s]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -147,23 +165,23 @@ __global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = s_tmem;
 
-  // loader coordinates.  A tile: thread -> (row, pair of k-chunks) = 32 contiguous bytes of a row of D;
-  // B tile: thread -> (sample column, CB k-chunks): four coalesced row reads of XT per chunk.
-  const int a_r = tid & 127, a_c = (tid >> 7) * 2;      // k-chunks a_c, a_c + 1
-  const int b_c = tid % BN, b_q = (tid / BN) * CB;      // k-chunks b_q .. b_q + CB - 1
-  const bool a_row_ok = m0 + a_r < n;
-  const bool b_col_ok = n0 + b_c < ldb;
-  const float* a_src = D + (int64_t)(m0 + a_r) * ldd + a_c * 4;
-  const float* b_src = XT + n0 + b_c;
+  const int nkb = (n + TBK - 1) / TBK;
+  // D operand: block (row tile, kb) of Dsplit -> A stage kb % 3, one bulk copy
+  const float* a_src = Dsplit + (size_t)blockIdx.y * nkb * (kAStage / 4);
+  auto copy_a = [&](int kb) {
+    const uint32_t bar = smem_u32(&s_full[kb % kAStages]);
+    mbar_expect_tx(bar, kAStage);
+    bulk_copy(smem_u32(smem) + (uint32_t)(kb % kAStages) * kAStage, a_src + (size_t)kb * (kAStage / 4), kAStage, bar);
+  };
+  if (tid == 0) copy_a(0);
 
+  // XT operand: thread -> (sample column, CB k-chunks): four coalesced row reads of XT per chunk
+  const int b_c = tid % BN, b_q = (tid / BN) * CB;      // k-chunks b_q .. b_q + CB - 1
+  const bool b_col_ok = n0 + b_c < ldb;
+  const float* b_src = XT + n0 + b_c;
   // two register sets: the loads of k-blocks kb + 1 and kb + 2 are in flight while kb is split and multiplied
-  float4 av0[2], bv0[CB], av1[2], bv1[CB];
-  auto load_block = [&](int k0, float4 (&av)[2], float4 (&bv)[CB]) {
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int k = k0 + (a_c + j) * 4;
-      av[j] = (a_row_ok && k < ldd) ? __ldg(reinterpret_cast<const float4*>(a_src + k0 + j * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+  float4 bv0[CB], bv1[CB];
+  auto load_block = [&](int k0, float4 (&bv)[CB]) {
 #pragma unroll
     for (int j = 0; j < CB; ++j) {
       const int k = k0 + (b_q + j) * 4;
@@ -180,29 +198,27 @@ __global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_
 #pragma unroll
   for (int i = 0; i < WC; ++i) acc[i] = 0.f;
 
-  const int nkb = (n + TBK - 1) / TBK;
-  auto k_block = [&](int kb, float4 (&av)[2], float4 (&bv)[CB]) {
+  auto k_block = [&](int kb, float4 (&bv)[CB]) {
     const int s = kb & 1;
-    uint8_t* stage = smem + s * kStage;
-    // the MMAs that read this stage two k-blocks ago have completed (use j waits for commit j - 1)
+    uint8_t* stage_b = smem + kBBase + s * kBStage;
+    // the MMAs of k-block kb - 2 have completed (use j of a commit barrier waits for commit j - 1): B stage s and
+    // A stage (kb + 1) % 3 are free
     if (kb >= kTcStages) mbar_wait(smem_u32(&s_bar[s]), ((kb >> 1) - 1) & 1);
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-      store_split(stage, stage + kABytes, (uint32_t)(a_c + j) * kLboA + (uint32_t)a_r * 16, av[j]);
+    if (tid == 0 && kb + 1 < nkb) copy_a(kb + 1);
 #pragma unroll
     for (int j = 0; j < CB; ++j)
-      store_split(stage + 2 * kABytes, stage + 2 * kABytes + kBBytes, (uint32_t)(b_q + j) * kLboB + (uint32_t)b_c * 16, bv[j]);
-    if (kb + 2 < nkb) load_block((kb + 2) * TBK, av, bv);  // this register set is free again
+      store_split(stage_b, stage_b + kBBytes, (uint32_t)(b_q + j) * kLboB + (uint32_t)b_c * 16, bv[j]);
+    if (kb + 2 < nkb) load_block((kb + 2) * TBK, bv);  // this register set is free again
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> tensor-core (async proxy) reads
     __syncthreads();
     if (tid == 0) {
+      mbar_wait(smem_u32(&s_full[kb % kAStages]), (kb / kAStages) & 1);  // the D stage has landed
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t base = smem_u32(stage);
+      const uint32_t a_base = smem_u32(smem) + (uint32_t)(kb % kAStages) * kAStage, b_base = smem_u32(stage_b);
 #pragma unroll
       for (int ks = 0; ks < TBK / 8; ++ks) {
-        const uint64_t a_hi = smem_desc(base + ks * 2 * kLboA, kLboA), a_lo = smem_desc(base + kABytes + ks * 2 * kLboA, kLboA);
-        const uint64_t b_hi = smem_desc(base + 2 * kABytes + ks * 2 * kLboB, kLboB);
-        const uint64_t b_lo = smem_desc(base + 2 * kABytes + kBBytes + ks * 2 * kLboB, kLboB);
+        const uint64_t a_hi = smem_desc(a_base + ks * 2 * kLboA, kLboA), a_lo = smem_desc(a_base + kABytes + ks * 2 * kLboA, kLboA);
+        const uint64_t b_hi = smem_desc(b_base + ks * 2 * kLboB, kLboB), b_lo = smem_desc(b_base + kBBytes + ks * 2 * kLboB, kLboB);
         umma_tf32(tmem, a_lo, b_hi, kIdesc, ((kb % flush) | ks) != 0);  // first product of a chunk overwrites
         umma_tf32(tmem, a_hi, b_lo, kIdesc, 1);
         umma_tf32(tmem, a_hi, b_hi, kIdesc, 1);
@@ -225,11 +241,11 @@ __global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
   };
-  load_block(0, av0, bv0);
-  if (nkb > 1) load_block(TBK, av1, bv1);
+  load_block(0, bv0);
+  if (nkb > 1) load_block(TBK, bv1);
   for (int kb = 0; kb < nkb; kb += 2) {
-    k_block(kb, av0, bv0);
-    if (kb + 1 < nkb) k_block(kb + 1, av1, bv1);
+    k_block(kb, bv0);
+    if (kb + 1 < nkb) k_block(kb + 1, bv1);
   }
 
   // epilogue
@@ -274,15 +290,15 @@ __global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_
 }
 
 template <int BN>
-int launch_tc(dim3 grid, const float* D, int32_t n, int32_t ldd, const float* XT, float* CT, int64_t ldb, int32_t B, float scale,
+int launch_tc(dim3 grid, const float* Dsplit, int32_t n, const float* XT, float* CT, int64_t ldb, int32_t B, float scale,
               const float* scale_dev, const float* sub, float* partials, int flush, cudaStream_t st) {
   static bool configured = false;
-  const int smem_bytes = kTcStages * stage_bytes(BN);
+  const int smem_bytes = (int)smem_bytes_for(BN);
   if (!configured) {
     FEO_CUDA_CHECK(cudaFuncSetAttribute(dense_apply_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = true;
   }
-  dense_apply_tc_kernel<BN><<<grid, kTcThreads, smem_bytes, st>>>(D, n, ldd, XT, CT, ldb, B, scale, scale_dev, sub, partials, flush);
+  dense_apply_tc_kernel<BN><<<grid, kTcThreads, smem_bytes, st>>>(Dsplit, n, XT, CT, ldb, B, scale, scale_dev, sub, partials, flush);
   FEO_CUDA_CHECK(cudaGetLastError());
   return FEO_OK;
 }
@@ -291,23 +307,49 @@ int env_int(const char* name, int dflt) {
   const int v = e != nullptr ? atoi(e) : dflt;
   return v > 0 ? v : dflt;
 }
+// cvt.rna.tf32.f32 on the host: round to nearest, ties away from zero, to 10 mantissa bits
+float rna_tf32(float x) {
+  uint32_t u = f2u(x);
+  if ((u & 0x7f800000u) == 0x7f800000u) return x;  // inf / nan
+  u = (u + 0x1000u) & 0xffffe000u;
+  float r;
+  __builtin_memcpy(&r, &u, 4);
+  return r;
+}
 }  // namespace
 
-int launch_dense_tc(const float* D, int32_t n, int32_t ldd, const float* XT, float* CT, int64_t ldb, int32_t B,
+std::vector<float> dense_split_tiles(const float* src, int32_t n, bool transposed) {
+  const int64_t row_tiles = (n + TBM - 1) / TBM, nkb = (n + TBK - 1) / TBK;
+  const size_t block = 2 * kABytes / 4;  // floats per (row tile, k-block): [hi | lo]
+  std::vector<float> out((size_t)row_tiles * nkb * block, 0.f);
+  for (int32_t r = 0; r < n; ++r)
+    for (int32_t k = 0; k < n; ++k) {
+      const float x = transposed ? src[(size_t)k * n + r] : src[(size_t)r * n + k];
+      const float hi = rna_tf32(x), lo = rna_tf32(x - hi);
+      const int32_t rr = r % TBM, kk = k % TBK;
+      const size_t at = ((size_t)(r / TBM) * nkb + k / TBK) * block + (size_t)(kk / 4) * (kLboA / 4) + (size_t)rr * 4 + kk % 4;
+      out[at] = hi;
+      out[at + kABytes / 4] = lo;
+    }
+  return out;
+}
+
+int launch_dense_tc(const float* Dsplit, int32_t n, const float* XT, float* CT, int64_t ldb, int32_t B,
                     float scale, const float* scale_dev, const float* sub, float* partials, int* count_out,
                     cudaStream_t st) {
   static const int flush = env_int("FEO_DENSE_FLUSH", kFlushDefault);
   static const int bn_env = env_int("FEO_DENSE_BN", 0);
+  if (Dsplit == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, "dense operator not present in this handle");
   const int64_t cols = (B + 3) / 4 * 4;
   const int64_t row_tiles = (n + TBM - 1) / TBM;
   // 128-column tiles halve the reads of D per flop; 64-column tiles put several CTAs on every SM, which is what hides
-  // the global-load latency of a k-block while the problem is small
+  // the latencies of a k-block while the problem is small
   int bn = row_tiles * ((cols + 127) / 128) >= 4 * 148 ? 128 : 64;
   if (bn_env == 64 || bn_env == 128) bn = bn_env;
   dim3 grid((unsigned)((cols + bn - 1) / bn), (unsigned)row_tiles);
   *count_out = (int)(grid.x * grid.y);
-  if (bn == 128) return launch_tc<128>(grid, D, n, ldd, XT, CT, ldb, B, scale, scale_dev, sub, partials, flush, st);
-  return launch_tc<64>(grid, D, n, ldd, XT, CT, ldb, B, scale, scale_dev, sub, partials, flush, st);
+  if (bn == 128) return launch_tc<128>(grid, Dsplit, n, XT, CT, ldb, B, scale, scale_dev, sub, partials, flush, st);
+  return launch_tc<64>(grid, Dsplit, n, XT, CT, ldb, B, scale, scale_dev, sub, partials, flush, st);
 }
 
 }  // namespace feo

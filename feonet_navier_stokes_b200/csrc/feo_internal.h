@@ -160,6 +160,7 @@ struct feo_operator {
   feo::DevTilePlan tiles_f, tiles_b;
   // dense
   float *dM = nullptr, *dMT = nullptr, *dP = nullptr;
+  float *dMs = nullptr, *dMTs = nullptr, *dPs = nullptr;  // the same matrices pre-split into TF32 hi/lo operand tiles (feo_dense_tc.cu)
   // bookkeeping
   int64_t nnz[5] = {0, 0, 0, 0, 0};
   int64_t nnz_union = 0;
@@ -179,11 +180,14 @@ int launch_seq(const DevCsr& M, const DevCsr& S, int32_t n, bool backward, const
                float* outT, float* loss_out, void* ws, size_t ws_bytes, cudaStream_t st);
 int launch_sq_diff_sum(const float* xT, const float* yT, int32_t n, int64_t ldb, int32_t B, float scale,
                        float* loss_out, void* ws, size_t ws_bytes, cudaStream_t st);
-int launch_dense(const float* D, int32_t n, const float* XT, float* CT, int64_t ldb, int32_t B, float scale,
+int launch_dense(const float* D, const float* Dsplit, int32_t n, const float* XT, float* CT, int64_t ldb, int32_t B, float scale,
                  const float* scale_dev, const float* sub, float* loss_out, void* ws, size_t ws_bytes,
                  cudaStream_t st);
-// tcgen05 3xTF32 tile GEMM behind launch_dense (feo_dense_tc.cu); writes one loss partial per 128 x 128 tile
-int launch_dense_tc(const float* D, int32_t n, int32_t ldd, const float* XT, float* CT, int64_t ldb, int32_t B,
+// tcgen05 3xTF32 tile GEMM behind launch_dense (feo_dense_tc.cu); writes one loss partial per CT tile.
+// Dsplit = dense_split_tiles(D): per (128-row tile, 16-column k-block) one 16 KB block [hi | lo] in the kernel's
+// shared-memory operand layout, so that a stage of the D operand is ONE bulk copy.
+std::vector<float> dense_split_tiles(const float* src, int32_t n, bool transposed);
+int launch_dense_tc(const float* Dsplit, int32_t n, const float* XT, float* CT, int64_t ldb, int32_t B,
                     float scale, const float* scale_dev, const float* sub, float* partials, int* count_out,
                     cudaStream_t st);
 int launch_sincos_grid(const float* coeff, int32_t B, int32_t resol, float* out, cudaStream_t st);

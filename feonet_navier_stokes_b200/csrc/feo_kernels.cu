@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(256) dense_apply_kernel(const float* __restric
 }
 }  // namespace
 
-int launch_dense(const float* D, int32_t n, const float* XT, float* CT, int64_t ldb, int32_t B, float scale,
+int launch_dense(const float* D, const float* Dsplit, int32_t n, const float* XT, float* CT, int64_t ldb, int32_t B, float scale,
                  const float* scale_dev, const float* sub, float* loss_out, void* ws, size_t ws_bytes,
                  cudaStream_t st) {
   if (D == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, "dense operator not present in this handle");
@@ -445,7 +445,7 @@ int launch_dense(const float* D, int32_t n, const float* XT, float* CT, int64_t 
     return e != nullptr && atoi(e) != 0;
   }();
   if (!simt) {
-    if (int rc = launch_dense_tc(D, n, ldd, XT, CT, ldb, B, scale, scale_dev, sub, partials, &count, st)) return rc;
+    if (int rc = launch_dense_tc(Dsplit, n, XT, CT, ldb, B, scale, scale_dev, sub, partials, &count, st)) return rc;
   } else {
     dense_apply_kernel<<<grid, 256, 0, st>>>(D, n, ldd, XT, CT, ldb, B, scale, scale_dev, sub, partials);
     FEO_CUDA_CHECK(cudaGetLastError());

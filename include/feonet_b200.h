@@ -180,6 +180,13 @@ int feo_sq_diff_sum(const float* xT, const float* yT, int32_t n, int64_t ldb, in
 int feo_debug_tile_replay(const feo_operator_desc* desc, int32_t backward, int32_t max_lines, int32_t warps,
                           const double* in0, const double* in1, double* out, int64_t* stats);
 
+/* Test hook (HOST ONLY): splits a dense [n,n] row-major operator into the TF32 hi/lo operand tiles of the
+ * tensor-core apply (feo_dense_apply) and replays them as the kernel reads them -- per 128-row tile and 16-column
+ * k-block, K-major core matrices -- for one vector x: out_hi = sum hi*x, out_lo = sum lo*x in fp64, so that
+ * out_hi + out_lo = D x (or D^T x) up to the 2^-22 split error.  Returns the number of floats of the tiled array. */
+int64_t feo_debug_dense_split_replay(const float* dense, int32_t n, int32_t transposed, const double* x,
+                                     double* out_hi, double* out_lo);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_exports_every_declared_symbol():
     lib = L.load_library()
     header = open(os.path.join(ROOT, "include", "feonet_b200.h")).read()
-    declared = set(re.findall(r"^(?:int|size_t|const char\*)\s+(feo_\w+)\(", header, flags=re.M))
+    declared = set(re.findall(r"^(?:int|int64_t|size_t|const char\*)\s+(feo_\w+)\(", header, flags=re.M))
     assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name)
@@ -117,3 +117,28 @@ def test_bad_inputs_are_rejected():
     # a row that touches more lines than a tile can stage is refused, not mis-computed
     desc, keep = build_desc(op.N, np.ones((op.N, op.N)))
     assert lib.feo_debug_tile_replay(C.byref(desc), 0, 32, 0, None, None, None, None) == -3
+
+
+@pytest.mark.parametrize("n,transposed", [(5, 0), (72, 1), (130, 0), (387, 1)])
+def test_dense_split_tiles_replay(n, transposed):
+    """Set-up of the tensor-core preconditioner GEMM (feo_dense_tc.cu): the operator is split into TF32 hi/lo halves
+    and laid out per (128-row tile, 16-column k-block) in the kernel's shared-memory operand layout.  Decoded the way
+    the kernel addresses it: hi + lo reproduces D x to the split error (2^-22 per entry), hi alone only to TF32
+    (2^-11), both halves are exact TF32 numbers, and the zero padding of ragged tiles holds zeros."""
+    lib = L.load_library()
+    rng = np.random.default_rng(n)
+    D = rng.standard_normal((n, n)).astype(np.float32)
+    D[rng.random((n, n)) < 0.2] = 0.0
+    x = rng.standard_normal(n)
+    hi, lo = np.empty(n), np.empty(n)
+    size = lib.feo_debug_dense_split_replay(D.ctypes.data_as(L.f32p), n, transposed, x.ctypes.data_as(L.f64p),
+                                            hi.ctypes.data_as(L.f64p), lo.ctypes.data_as(L.f64p))
+    assert size == ((n + 127) // 128) * ((n + 15) // 16) * 4096
+    M = (D.T if transposed else D).astype(np.float64)
+    bound = np.abs(M) @ np.abs(x)
+    assert (np.abs(hi + lo - M @ x) <= 2.0 ** -21 * bound + 1e-300).all()
+    assert np.abs(hi - M @ x).max() > 2.0 ** -16 * bound.max() or n < 8  # the lo half matters
+    assert (np.abs(hi - M @ x) <= 2.0 ** -11 * bound + 1e-300).all()
+    # statistics-only call and argument errors
+    assert lib.feo_debug_dense_split_replay(D.ctypes.data_as(L.f32p), n, 0, None, None, None) == size
+    assert lib.feo_debug_dense_split_replay(None, n, 0, None, None, None) < 0
