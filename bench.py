@@ -430,7 +430,8 @@ def run_precond_gemm(torch, feo, dev, n=2549, B=1024, iters=30):
 def run_configs(args):
     """--configs: the reference's own configurations (SURVEY 8 size table cfg1-4; parity-test cases, NOT the bench
     line) through the reference-facing API on cuda:0 -- residual loss + backward to grad alpha, row-major [B, N]
-    inputs as the reference passes them -- with the oracle's CPU port (numpy/scipy, fp32) timed beside it.
+    inputs as the reference passes them -- with the oracle's CPU port (numpy/scipy, fp32) timed beside it; the loss / gradient differences are taken against
+    the oracle evaluated in fp64.
     Prints one JSON object; `tools/...` summarise it into profiles/."""
     import torch
     import feonet_navier_stokes_b200 as feo
@@ -471,8 +472,8 @@ def run_configs(args):
         g, c = np.asarray(grad_gpu, dtype=np.float64), np.asarray(grad_cpu, dtype=np.float64)
         rows.append({"config": name, "N": N, "batch": B, "gpu_ms_fwd_bwd": gpu_ms, "gpu_samples_per_s": B / (gpu_ms * 1e-3),
                      "cpu_port_ms_fwd_bwd": cpu_ms, "cpu_port_samples_per_s": B / (cpu_ms * 1e-3), "speedup": cpu_ms / gpu_ms,
-                     "loss_rel_diff": abs(loss_gpu - loss_cpu) / abs(loss_cpu),
-                     "grad_rel_diff": float(np.linalg.norm(g - c) / np.linalg.norm(c)), "note": note})
+                     "loss_rel_diff_vs_fp64": abs(loss_gpu - loss_cpu) / abs(loss_cpu),
+                     "grad_rel_diff_vs_fp64": float(np.linalg.norm(g - c) / np.linalg.norm(c)), "note": note})
         log(f"[configs] {rows[-1]}")
 
     # cfg1 / cfg2: linear Stokes, preconditioned (dense apply on the tensor cores)
@@ -495,7 +496,8 @@ def run_configs(args):
             box["l"] = loss
 
         gpu_ms = time_gpu(step)
-        cpu_ms, (lo, go, _) = time_cpu(lambda: orc.stokes_loss_and_grad(alpha, F, A, P, True, dtype=np.float32))
+        cpu_ms, _ = time_cpu(lambda: orc.stokes_loss_and_grad(alpha, F, A, P, True, dtype=np.float32))
+        lo, go, _ = orc.stokes_loss_and_grad(alpha, F, A, P, True, dtype=np.float64)  # yardstick for the differences
         report(name + (f" N={fx.N}" if "N=" not in name else ""), fx.N, gpu_ms, cpu_ms,
                box["l"].item(), float(lo), box["g"].cpu().numpy(), go, "dense A.P folded at set-up, tcgen05 3xTF32 apply")
 
@@ -515,7 +517,8 @@ def run_configs(args):
             box["l"] = loss
 
         gpu_ms = time_gpu(step)
-        cpu_ms, (lo, go, _) = time_cpu(lambda: orc.ns_loss_and_grad(alpha, F, fx.A, fx.B1, fx.B2, fx.idx_u1, fx.idx_u2, precond, dtype=np.float32))
+        cpu_ms, _ = time_cpu(lambda: orc.ns_loss_and_grad(alpha, F, fx.A, fx.B1, fx.B2, fx.idx_u1, fx.idx_u2, precond, dtype=np.float32))
+        lo, go, _ = orc.ns_loss_and_grad(alpha, F, fx.A, fx.B1, fx.B2, fx.idx_u1, fx.idx_u2, precond, dtype=np.float64)
         report(f"cfg3 steady NS N={fx.N} ({'precond=I' if precond else 'no precond'} sign branch)", fx.N, gpu_ms, cpu_ms,
                box["l"].item(), float(lo), box["g"].cpu().numpy(), go, "fused residual_fwd/bwd_tiled incl. row-major <-> dof-major transposes")
 
@@ -535,7 +538,8 @@ def run_configs(args):
         box["l"] = loss
 
     gpu_ms = time_gpu(step)
-    cpu_ms, (lo, go, _) = time_cpu(lambda: orc.seq_loss_and_grad(pred, F, fx.S, fx.A, None, dt, u0, False, dtype=np.float32))
+    cpu_ms, _ = time_cpu(lambda: orc.seq_loss_and_grad(pred, F, fx.S, fx.A, None, dt, u0, False, dtype=np.float32))
+    lo, go, _ = orc.seq_loss_and_grad(pred, F, fx.S, fx.A, None, dt, u0, False, dtype=np.float64)
     report(f"cfg4 time-dependent Stokes N={fx.N} T={T}", fx.N, gpu_ms, cpu_ms, box["l"].item(), float(lo),
            box["g"].cpu().numpy(), go, "seq_kernel fwd/bwd, one sample = T rows")
     # the linear Stokes operator (no convective term: A-quads forward, 20 N B algorithmic bytes) at the cfg5 mesh size

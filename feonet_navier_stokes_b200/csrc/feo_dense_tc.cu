@@ -11,8 +11,9 @@
 //
 // One CTA = one 128 x 64 (or 128 x 128) tile of CT (UMMA M = 128, N = 64 | 128, K = 8), k-blocks of 16.
 //  * D operand: split ONCE at set-up (dense_split_tiles: per (row tile, k-block) a 16 KB block [hi | lo] already in
-//    the shared-memory operand layout), so a stage is one cp.async.bulk (UBLKCP) onto an mbarrier: three stages,
-//    the copy of k-block kb + 1 is issued as soon as the MMAs of kb - 2 have released its stage.
+//    the shared-memory operand layout), so a stage is one cp.async.bulk (UBLKCP) onto an mbarrier:
+//    SA stages (default 3),
+//    the copy of k-block kb + SA - 2 is issued as soon as the MMAs of kb - 2 have released its stage.
 //  * XT operand (the activations: split at run time; sample-contiguous, i.e. MN-major): through registers --
 //    coalesced row reads, cvt.rna.tf32 split, STS.128 straight into the K-major core-matrix layout, which also
 //    transposes it; two stages, two register sets (k-blocks kb + 1 and kb + 2 in flight).
@@ -42,10 +43,9 @@ namespace {
 constexpr int TBM = 128, TBK = 16;                      // CT tile rows, k-block; tile columns BN = 128 or 64 (template)
 constexpr int kTcThreads = 256;
 constexpr uint32_t kABytes = TBM * TBK * 4;              // 8 KB: A_hi or A_lo of a stage
-constexpr int kAStages = 3;                              // D operand ring (bulk copies)
 constexpr int kTcStages = 2;                             // XT operand stages (register pass)
 __host__ __device__ constexpr uint32_t b_stage_bytes(int BN) { return 2 * (uint32_t)BN * TBK * 4; }  // B_hi, B_lo
-__host__ __device__ constexpr uint32_t smem_bytes_for(int BN) { return kAStages * 2 * kABytes + kTcStages * b_stage_bytes(BN); }
+__host__ __device__ constexpr uint32_t smem_bytes_for(int BN, int SA) { return SA * 2 * kABytes + kTcStages * b_stage_bytes(BN); }
 constexpr int kFlushDefault = 4;                         // k-blocks between drains of the TMEM accumulator (FEO_DENSE_FLUSH)
 constexpr uint32_t kLboA = TBM * 16;                     // 2048 B between the k-chunks (4 k each) of an A tile; BN * 16 for B
 constexpr uint32_t kSbo = 128;                           // 8-row groups are contiguous
@@ -126,16 +126,16 @@ __device__ __forceinline__ void store_split(uint8_t* hi_base, uint8_t* lo_base, 
   *reinterpret_cast<float4*>(lo_base + off) = l;
 }
 
-template <int BN>
+template <int BN, int SA>  // CT tile columns; stages of the D operand ring (its copies run SA - 2 k-blocks ahead)
 __global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_kernel(const float* __restrict__ Dsplit, int32_t n,
                                                                     const float* __restrict__ XT, float* __restrict__ CT,
                                                                     int64_t ldb, int32_t B, float scale,
                                                                     const float* __restrict__ scale_dev,
                                                                     const float* __restrict__ sub,
-                                                                    float* __restrict__ partials, int32_t flush) {
+                                                                    float* __restrict__ partials, int32_t flush, int32_t debug) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t s_bar[kTcStages];   // commit barriers: MMAs of a k-block done (by k-block parity)
-  __shared__ __align__(8) uint64_t s_full[kAStages];   // D operand stage landed
+  __shared__ __align__(8) uint64_t s_full[SA];   // D operand stage landed
   __shared__ uint32_t s_tmem;
   __shared__ float s_part[kTcThreads / 32];
 
@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_
   constexpr uint32_t kBBytes = (uint32_t)BN * TBK * 4;    // B_hi or B_lo of a stage
   constexpr uint32_t kAStage = 2 * kABytes;               // [hi | lo]
   constexpr uint32_t kBStage = b_stage_bytes(BN);
-  constexpr uint32_t kBBase = kAStages * kAStage;
+  constexpr uint32_t kBBase = SA * kAStage;
+  constexpr int kAhead = SA - 2;                          // the stage of k-block kb + kAhead was last read by kb - 2
   constexpr uint32_t kLboB = BN * 16;
   constexpr uint32_t kIdesc = instr_desc(BN);
   constexpr int CB = BN / 64;                             // k-chunks of the B tile per thread
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_
   }
   if (tid == 32) {
     for (int s = 0; s < kTcStages; ++s) mbar_init(smem_u32(&s_bar[s]), 1);
-    for (int s = 0; s < kAStages; ++s) mbar_init(smem_u32(&s_full[s]), 1);
+    for (int s = 0; s < SA; ++s) mbar_init(smem_u32(&s_full[s]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -166,14 +167,15 @@ __global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_
   const uint32_t tmem = s_tmem;
 
   const int nkb = (n + TBK - 1) / TBK;
-  // D operand: block (row tile, kb) of Dsplit -> A stage kb % 3, one bulk copy
+  // D operand: block (row tile, kb) of Dsplit -> A stage kb % SA, one bulk copy
   const float* a_src = Dsplit + (size_t)blockIdx.y * nkb * (kAStage / 4);
   auto copy_a = [&](int kb) {
-    const uint32_t bar = smem_u32(&s_full[kb % kAStages]);
+    const uint32_t bar = smem_u32(&s_full[kb % SA]);
     mbar_expect_tx(bar, kAStage);
-    bulk_copy(smem_u32(smem) + (uint32_t)(kb % kAStages) * kAStage, a_src + (size_t)kb * (kAStage / 4), kAStage, bar);
+    bulk_copy(smem_u32(smem) + (uint32_t)(kb % SA) * kAStage, a_src + (size_t)kb * (kAStage / 4), kAStage, bar);
   };
-  if (tid == 0) copy_a(0);
+  if (tid == 0)
+    for (int kb = 0; kb < kAhead && kb < nkb; ++kb) copy_a(kb);
 
   // XT operand: thread -> (sample column, CB k-chunks): four coalesced row reads of XT per chunk
   const int b_c = tid % BN, b_q = (tid / BN) * CB;      // k-chunks b_q .. b_q + CB - 1
@@ -202,9 +204,9 @@ __global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_
     const int s = kb & 1;
     uint8_t* stage_b = smem + kBBase + s * kBStage;
     // the MMAs of k-block kb - 2 have completed (use j of a commit barrier waits for commit j - 1): B stage s and
-    // A stage (kb + 1) % 3 are free
+    // A stage (kb + kAhead) % SA are free
     if (kb >= kTcStages) mbar_wait(smem_u32(&s_bar[s]), ((kb >> 1) - 1) & 1);
-    if (tid == 0 && kb + 1 < nkb) copy_a(kb + 1);
+    if (tid == 0 && kb + kAhead < nkb) copy_a(kb + kAhead);
 #pragma unroll
     for (int j = 0; j < CB; ++j)
       store_split(stage_b, stage_b + kBBytes, (uint32_t)(b_q + j) * kLboB + (uint32_t)b_c * 16, bv[j]);
@@ -212,16 +214,16 @@ __global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> tensor-core (async proxy) reads
     __syncthreads();
     if (tid == 0) {
-      mbar_wait(smem_u32(&s_full[kb % kAStages]), (kb / kAStages) & 1);  // the D stage has landed
+      mbar_wait(smem_u32(&s_full[kb % SA]), (kb / SA) & 1);  // the D stage has landed
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_base = smem_u32(smem) + (uint32_t)(kb % kAStages) * kAStage, b_base = smem_u32(stage_b);
+      const uint32_t a_base = smem_u32(smem) + (uint32_t)(kb % SA) * kAStage, b_base = smem_u32(stage_b);
 #pragma unroll
       for (int ks = 0; ks < TBK / 8; ++ks) {
         const uint64_t a_hi = smem_desc(a_base + ks * 2 * kLboA, kLboA), a_lo = smem_desc(a_base + kABytes + ks * 2 * kLboA, kLboA);
         const uint64_t b_hi = smem_desc(b_base + ks * 2 * kLboB, kLboB), b_lo = smem_desc(b_base + kBBytes + ks * 2 * kLboB, kLboB);
-        umma_tf32(tmem, a_lo, b_hi, kIdesc, ((kb % flush) | ks) != 0);  // first product of a chunk overwrites
-        umma_tf32(tmem, a_hi, b_lo, kIdesc, 1);
-        umma_tf32(tmem, a_hi, b_hi, kIdesc, 1);
+        if (debug < 2) umma_tf32(tmem, a_lo, b_hi, kIdesc, ((kb % flush) | ks) != 0);  // first product of a chunk overwrites
+        if (debug < 1) umma_tf32(tmem, a_hi, b_lo, kIdesc, 1);
+        if (debug < 1) umma_tf32(tmem, a_hi, b_hi, kIdesc, 1);
       }
       umma_commit(smem_u32(&s_bar[s]));
     }
@@ -289,23 +291,24 @@ __global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_
   }
 }
 
-template <int BN>
-int launch_tc(dim3 grid, const float* Dsplit, int32_t n, const float* XT, float* CT, int64_t ldb, int32_t B, float scale,
-              const float* scale_dev, const float* sub, float* partials, int flush, cudaStream_t st) {
-  static bool configured = false;
-  const int smem_bytes = (int)smem_bytes_for(BN);
-  if (!configured) {
-    FEO_CUDA_CHECK(cudaFuncSetAttribute(dense_apply_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured = true;
-  }
-  dense_apply_tc_kernel<BN><<<grid, kTcThreads, smem_bytes, st>>>(Dsplit, n, XT, CT, ldb, B, scale, scale_dev, sub, partials, flush);
-  FEO_CUDA_CHECK(cudaGetLastError());
-  return FEO_OK;
-}
 int env_int(const char* name, int dflt) {
   const char* e = std::getenv(name);
   const int v = e != nullptr ? atoi(e) : dflt;
   return v > 0 ? v : dflt;
+}
+template <int BN, int SA>
+int launch_tc(dim3 grid, const float* Dsplit, int32_t n, const float* XT, float* CT, int64_t ldb, int32_t B, float scale,
+              const float* scale_dev, const float* sub, float* partials, int flush, cudaStream_t st) {
+  static bool configured = false;
+  static const int debug = env_int("FEO_DENSE_DEBUG", 0);  // developer timing: 1 = one product of three, 2 = no MMAs (results are garbage)
+  const int smem_bytes = (int)smem_bytes_for(BN, SA);
+  if (!configured) {
+    FEO_CUDA_CHECK(cudaFuncSetAttribute(dense_apply_tc_kernel<BN, SA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured = true;
+  }
+  dense_apply_tc_kernel<BN, SA><<<grid, kTcThreads, smem_bytes, st>>>(Dsplit, n, XT, CT, ldb, B, scale, scale_dev, sub, partials, flush, debug);
+  FEO_CUDA_CHECK(cudaGetLastError());
+  return FEO_OK;
 }
 // cvt.rna.tf32.f32 on the host: round to nearest, ties away from zero, to 10 mantissa bits
 float rna_tf32(float x) {
@@ -348,8 +351,20 @@ int launch_dense_tc(const float* Dsplit, int32_t n, const float* XT, float* CT, 
   if (bn_env == 64 || bn_env == 128) bn = bn_env;
   dim3 grid((unsigned)((cols + bn - 1) / bn), (unsigned)row_tiles);
   *count_out = (int)(grid.x * grid.y);
-  if (bn == 128) return launch_tc<128>(grid, Dsplit, n, XT, CT, ldb, B, scale, scale_dev, sub, partials, flush, st);
-  return launch_tc<64>(grid, Dsplit, n, XT, CT, ldb, B, scale, scale_dev, sub, partials, flush, st);
+  static const int sa_env = env_int("FEO_DENSE_ASTAGES", 0);
+  // 3 stages keep three 64-column CTAs on an SM; deeper rings were measured slower (fewer resident CTAs) -- the kernel
+  // is paced by L2 -> SM traffic (every 16 KB stage of the split operator is re-read by all column tiles), not by latency
+  const int sa = sa_env >= 3 && sa_env <= 5 ? sa_env : 3;
+#define FEO_TC_CASE(BN_, SA_) \
+  if (bn == BN_ && sa == SA_) return launch_tc<BN_, SA_>(grid, Dsplit, n, XT, CT, ldb, B, scale, scale_dev, sub, partials, flush, st)
+  FEO_TC_CASE(64, 3);
+  FEO_TC_CASE(64, 4);
+  FEO_TC_CASE(64, 5);
+  FEO_TC_CASE(128, 3);
+  FEO_TC_CASE(128, 4);
+  FEO_TC_CASE(128, 5);
+#undef FEO_TC_CASE
+  return fail(FEO_ERR_INVALID_ARGUMENT, "dense_apply: no kernel for this tile configuration");
 }
 
 }  // namespace feo
