@@ -77,6 +77,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// one lane of a converged warp (CUTLASS' elect_one_sync): the compiler keeps the guarded code on the uniform datapath,
+// where tcgen05.mma / cp.async.bulk take their descriptors from -- a per-thread `tid == 0` guard makes it broadcast
+// every operand with an ELECT / R2UR loop instead (measured: ~110 cycles per MMA issued)
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred;
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -140,6 +154,7 @@ __global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_
   __shared__ float s_part[kTcThreads / 32];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool warp0 = __shfl_sync(0xffffffffu, warp, 0) == 0;  // warp-uniform by construction: keeps warp 0's issue code uniform
   const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * BN;
   constexpr uint32_t kTmemCols = BN;                      // fp32 accumulator columns (power of two >= 32)
   constexpr uint32_t kBBytes = (uint32_t)BN * TBK * 4;    // B_hi or B_lo of a stage
@@ -174,7 +189,7 @@ __global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_
     mbar_expect_tx(bar, kAStage);
     bulk_copy(smem_u32(smem) + (uint32_t)(kb % SA) * kAStage, a_src + (size_t)kb * (kAStage / 4), kAStage, bar);
   };
-  if (tid == 0)
+  if (warp0 && elect_one())
     for (int kb = 0; kb < kAhead && kb < nkb; ++kb) copy_a(kb);
 
   // XT operand: thread -> (sample column, CB k-chunks): four coalesced row reads of XT per chunk
@@ -206,16 +221,17 @@ __global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_
     // the MMAs of k-block kb - 2 have completed (use j of a commit barrier waits for commit j - 1): B stage s and
     // A stage (kb + kAhead) % SA are free
     if (kb >= kTcStages) mbar_wait(smem_u32(&s_bar[s]), ((kb >> 1) - 1) & 1);
-    if (tid == 0 && kb + kAhead < nkb) copy_a(kb + kAhead);
+    if (warp0 && kb + kAhead < nkb && elect_one()) copy_a(kb + kAhead);
 #pragma unroll
     for (int j = 0; j < CB; ++j)
       store_split(stage_b, stage_b + kBBytes, (uint32_t)(b_q + j) * kLboB + (uint32_t)b_c * 16, bv[j]);
     if (kb + 2 < nkb) load_block((kb + 2) * TBK, bv);  // this register set is free again
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> tensor-core (async proxy) reads
     __syncthreads();
-    if (tid == 0) {
+    if (warp0) {
       mbar_wait(smem_u32(&s_full[kb % SA]), (kb / SA) & 1);  // the D stage has landed
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
       const uint32_t a_base = smem_u32(smem) + (uint32_t)(kb % SA) * kAStage, b_base = smem_u32(stage_b);
 #pragma unroll
       for (int ks = 0; ks < TBK / 8; ++ks) {
@@ -226,6 +242,8 @@ __global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_
         if (debug < 1) umma_tf32(tmem, a_hi, b_hi, kIdesc, 1);
       }
       umma_commit(smem_u32(&s_bar[s]));
+      }
+      __syncwarp();
     }
     if ((kb + 1) % flush == 0 || kb + 1 == nkb) {
       // drain: this k-block's commit covers every MMA issued so far
