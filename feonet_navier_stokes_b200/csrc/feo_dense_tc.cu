@@ -17,9 +17,13 @@
 //  * XT operand (the activations: split at run time; sample-contiguous, i.e. MN-major): through registers --
 //    coalesced row reads, cvt.rna.tf32 split, STS.128 straight into the K-major core-matrix layout, which also
 //    transposes it; two stages, two register sets (k-blocks kb + 1 and kb + 2 in flight).
-// Hand-over per k-block: generic stores -> fence.proxy.async -> bar.sync -> one thread waits for the D stage, issues
-// 6 MMAs -> tcgen05.commit -> mbarrier.  64 KB (BN = 64) of shared memory and BN TMEM columns per CTA: three CTAs
-// per SM overlap each other's latencies.
+// Warp roles (288 threads): eight loader / epilogue warps and one ISSUER warp.  Loaders: wait until the MMAs of
+// k-block kb - 2 have released XT stage kb % 2 (commit mbarrier), split + STS, fence.proxy.async, arrive on the
+// stage's "written" mbarrier, issue the loads of kb + 2.  Issuer (all descriptor arithmetic on the uniform datapath,
+// one elected lane issues): bulk copy of the D stage SA - 2 k-blocks ahead, wait for "written" and for the D stage,
+// six tcgen05.mma, tcgen05.commit onto the commit mbarrier.  Neither side waits for the other's instruction issue:
+// measured per k-block before the split, with one thread doing both, ~480 cycles of MMA issue sat on top of ~500
+// cycles of loader work.  80 KB.. of shared memory: 64 KB (BN = 64) and BN TMEM columns per CTA, three CTAs per SM.
 //
 // The tensor core aligns and TRUNCATES when it adds a K = 8 product group to the fp32 accumulator, which biases a
 // long accumulation towards zero (measured: 3e-6 of |D||x| at n = 2549, against 1e-7 for the split itself).  The
@@ -41,7 +45,8 @@ namespace feo {
 namespace {
 
 constexpr int TBM = 128, TBK = 16;                      // CT tile rows, k-block; tile columns BN = 128 or 64 (template)
-constexpr int kTcThreads = 256;
+constexpr int kTcThreads = 256;                         // loader / epilogue threads (8 warps)
+constexpr int kTcBlock = kTcThreads + 32;                // + the issuer warp
 constexpr uint32_t kABytes = TBM * TBK * 4;              // 8 KB: A_hi or A_lo of a stage
 constexpr int kTcStages = 2;                             // XT operand stages (register pass)
 __host__ __device__ constexpr uint32_t b_stage_bytes(int BN) { return 2 * (uint32_t)BN * TBK * 4; }  // B_hi, B_lo
@@ -63,6 +68,9 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo) {
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -141,7 +149,7 @@ __device__ __forceinline__ void store_split(uint8_t* hi_base, uint8_t* lo_base, 
 }
 
 template <int BN, int SA>  // CT tile columns; stages of the D operand ring (its copies run SA - 2 k-blocks ahead)
-__global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_kernel(const float* __restrict__ Dsplit, int32_t n,
+__global__ void __launch_bounds__(kTcBlock, BN == 128 ? 2 : 3) dense_apply_tc_kernel(const float* __restrict__ Dsplit, int32_t n,
                                                                     const float* __restrict__ XT, float* __restrict__ CT,
                                                                     int64_t ldb, int32_t B, float scale,
                                                                     const float* __restrict__ scale_dev,
@@ -149,12 +157,14 @@ __global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_
                                                                     float* __restrict__ partials, int32_t flush, int32_t debug) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t s_bar[kTcStages];   // commit barriers: MMAs of a k-block done (by k-block parity)
-  __shared__ __align__(8) uint64_t s_full[SA];   // D operand stage landed
+  __shared__ __align__(8) uint64_t s_full[SA];          // D operand stage landed
+  __shared__ __align__(8) uint64_t s_bfull[kTcStages];  // XT stage written by all loader threads
+  __shared__ __align__(8) uint64_t s_drained;           // accumulator chunk read back by all loader threads
   __shared__ uint32_t s_tmem;
   __shared__ float s_part[kTcThreads / 32];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool warp0 = __shfl_sync(0xffffffffu, warp, 0) == 0;  // warp-uniform by construction: keeps warp 0's issue code uniform
+  const bool is_issuer = __shfl_sync(0xffffffffu, warp, 0) == kTcThreads / 32;  // warp-uniform by construction: keeps the issue code uniform
   const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * BN;
   constexpr uint32_t kTmemCols = BN;                      // fp32 accumulator columns (power of two >= 32)
   constexpr uint32_t kBBytes = (uint32_t)BN * TBK * 4;    // B_hi or B_lo of a stage
@@ -174,6 +184,8 @@ __global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_
   if (tid == 32) {
     for (int s = 0; s < kTcStages; ++s) mbar_init(smem_u32(&s_bar[s]), 1);
     for (int s = 0; s < SA; ++s) mbar_init(smem_u32(&s_full[s]), 1);
+    for (int s = 0; s < kTcStages; ++s) mbar_init(smem_u32(&s_bfull[s]), kTcThreads);
+    mbar_init(smem_u32(&s_drained), kTcThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -189,8 +201,6 @@ __global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_
     mbar_expect_tx(bar, kAStage);
     bulk_copy(smem_u32(smem) + (uint32_t)(kb % SA) * kAStage, a_src + (size_t)kb * (kAStage / 4), kAStage, bar);
   };
-  if (warp0 && elect_one())
-    for (int kb = 0; kb < kAhead && kb < nkb; ++kb) copy_a(kb);
 
   // XT operand: thread -> (sample column, CB k-chunks): four coalesced row reads of XT per chunk
   const int b_c = tid % BN, b_q = (tid / BN) * CB;      // k-chunks b_q .. b_q + CB - 1
@@ -215,57 +225,71 @@ __global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_
 #pragma unroll
   for (int i = 0; i < WC; ++i) acc[i] = 0.f;
 
-  auto k_block = [&](int kb, float4 (&bv)[CB]) {
-    const int s = kb & 1;
-    uint8_t* stage_b = smem + kBBase + s * kBStage;
-    // the MMAs of k-block kb - 2 have completed (use j of a commit barrier waits for commit j - 1): B stage s and
-    // A stage (kb + kAhead) % SA are free
-    if (kb >= kTcStages) mbar_wait(smem_u32(&s_bar[s]), ((kb >> 1) - 1) & 1);
-    if (warp0 && kb + kAhead < nkb && elect_one()) copy_a(kb + kAhead);
-#pragma unroll
-    for (int j = 0; j < CB; ++j)
-      store_split(stage_b, stage_b + kBBytes, (uint32_t)(b_q + j) * kLboB + (uint32_t)b_c * 16, bv[j]);
-    if (kb + 2 < nkb) load_block((kb + 2) * TBK, bv);  // this register set is free again
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> tensor-core (async proxy) reads
-    __syncthreads();
-    if (warp0) {
-      mbar_wait(smem_u32(&s_full[kb % SA]), (kb / SA) & 1);  // the D stage has landed
+  // ---- issuer warp: operator stages (bulk copies) and the MMAs --------------------------------------------------
+  if (is_issuer) {
+    if (elect_one())
+      for (int kb = 0; kb < kAhead && kb < nkb; ++kb) copy_a(kb);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb & 1;
+      // the MMAs of k-block kb - 2 have completed (use j of a commit barrier waits for commit j - 1):
+      // A stage (kb + kAhead) % SA is free
+      if (kb >= kTcStages) mbar_wait(smem_u32(&s_bar[s]), ((kb >> 1) - 1) & 1);
+      if (kb + kAhead < nkb && elect_one()) copy_a(kb + kAhead);
+      mbar_wait(smem_u32(&s_bfull[s]), (kb >> 1) & 1);                   // the loaders have written XT stage s
+      mbar_wait(smem_u32(&s_full[kb % SA]), (kb / SA) & 1);              // the D stage has landed
+      const bool first = kb % flush == 0;
+      if (first && kb > 0) mbar_wait(smem_u32(&s_drained), ((kb / flush) - 1) & 1);  // accumulator read back by everyone
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
-      const uint32_t a_base = smem_u32(smem) + (uint32_t)(kb % SA) * kAStage, b_base = smem_u32(stage_b);
+        const uint32_t a_base = smem_u32(smem) + (uint32_t)(kb % SA) * kAStage, b_base = smem_u32(smem) + kBBase + s * kBStage;
 #pragma unroll
-      for (int ks = 0; ks < TBK / 8; ++ks) {
-        const uint64_t a_hi = smem_desc(a_base + ks * 2 * kLboA, kLboA), a_lo = smem_desc(a_base + kABytes + ks * 2 * kLboA, kLboA);
-        const uint64_t b_hi = smem_desc(b_base + ks * 2 * kLboB, kLboB), b_lo = smem_desc(b_base + kBBytes + ks * 2 * kLboB, kLboB);
-        if (debug < 2) umma_tf32(tmem, a_lo, b_hi, kIdesc, ((kb % flush) | ks) != 0);  // first product of a chunk overwrites
-        if (debug < 1) umma_tf32(tmem, a_hi, b_lo, kIdesc, 1);
-        if (debug < 1) umma_tf32(tmem, a_hi, b_hi, kIdesc, 1);
-      }
-      umma_commit(smem_u32(&s_bar[s]));
+        for (int ks = 0; ks < TBK / 8; ++ks) {
+          const uint64_t a_hi = smem_desc(a_base + ks * 2 * kLboA, kLboA), a_lo = smem_desc(a_base + kABytes + ks * 2 * kLboA, kLboA);
+          const uint64_t b_hi = smem_desc(b_base + ks * 2 * kLboB, kLboB), b_lo = smem_desc(b_base + kBBytes + ks * 2 * kLboB, kLboB);
+          if (debug < 2) umma_tf32(tmem, a_lo, b_hi, kIdesc, !(first && ks == 0));  // first product of a chunk overwrites
+          if (debug < 1) umma_tf32(tmem, a_hi, b_lo, kIdesc, 1);
+          if (debug < 1) umma_tf32(tmem, a_hi, b_hi, kIdesc, 1);
+        }
+        umma_commit(smem_u32(&s_bar[s]));
       }
       __syncwarp();
     }
-    if ((kb + 1) % flush == 0 || kb + 1 == nkb) {
-      // drain: this k-block's commit covers every MMA issued so far
-      mbar_wait(smem_u32(&s_bar[s]), (kb >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  } else {
+    // ---- loader warps: XT stages through registers, accumulator drains -----------------------------------------
+    auto k_block = [&](int kb, float4 (&bv)[CB]) {
+      const int s = kb & 1;
+      uint8_t* stage_b = smem + kBBase + s * kBStage;
+      // XT stage s was last read by the MMAs of k-block kb - 2
+      if (kb >= kTcStages) mbar_wait(smem_u32(&s_bar[s]), ((kb >> 1) - 1) & 1);
 #pragma unroll
-      for (int j = 0; j < WC / 16; ++j) {
-        uint32_t v[16];
-        tmem_ld16(t_own + (uint32_t)(j * 16), v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int j = 0; j < CB; ++j)
+        store_split(stage_b, stage_b + kBBytes, (uint32_t)(b_q + j) * kLboB + (uint32_t)b_c * 16, bv[j]);
+      if (kb + 2 < nkb) load_block((kb + 2) * TBK, bv);  // this register set is free again
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> tensor-core (async proxy) reads
+      mbar_arrive(smem_u32(&s_bfull[s]));
+      if ((kb + 1) % flush == 0 || kb + 1 == nkb) {
+        // drain: this k-block's commit covers every MMA issued so far
+        mbar_wait(smem_u32(&s_bar[s]), (kb >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[j * 16 + i] += __uint_as_float(v[i]);
+        for (int j = 0; j < WC / 16; ++j) {
+          uint32_t v[16];
+          tmem_ld16(t_own + (uint32_t)(j * 16), v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[j * 16 + i] += __uint_as_float(v[i]);
+        }
+        // orders these TMEM reads before the next chunk's overwrite: the issuer waits for all 256 arrivals
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(smem_u32(&s_drained));
       }
-      // orders these TMEM reads before the next chunk's overwrite (next k-block: bar.sync, then the issuing thread's fence)
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    };
+    load_block(0, bv0);
+    if (nkb > 1) load_block(TBK, bv1);
+    for (int kb = 0; kb < nkb; kb += 2) {
+      k_block(kb, bv0);
+      if (kb + 1 < nkb) k_block(kb + 1, bv1);
     }
-  };
-  load_block(0, bv0);
-  if (nkb > 1) load_block(TBK, bv1);
-  for (int kb = 0; kb < nkb; kb += 2) {
-    k_block(kb, bv0);
-    if (kb + 1 < nkb) k_block(kb + 1, bv1);
   }
 
   // epilogue
@@ -276,7 +300,7 @@ __global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_
 #pragma unroll
   for (int q = 0; q < WC / 4; ++q) {
     const int c = n0 + cbase + q * 4;
-    if (m < n && c < ldb) {
+    if (!is_issuer && m < n && c < ldb) {
       float4 o = make_float4(sc * acc[q * 4 + 0], sc * acc[q * 4 + 1], sc * acc[q * 4 + 2], sc * acc[q * 4 + 3]);
       if (sub != nullptr) {
         const float4 sv = __ldg(reinterpret_cast<const float4*>(sub + (int64_t)m * ldb + c));
@@ -295,7 +319,7 @@ __global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 3) dense_apply_tc_
   // fixed-order CTA reduction of the loss partial
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-  if (lane == 0) s_part[warp] = lsum;
+  if (lane == 0 && !is_issuer) s_part[warp] = lsum;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (tid == 0 && partials != nullptr) {
@@ -324,7 +348,7 @@ int launch_tc(dim3 grid, const float* Dsplit, int32_t n, const float* XT, float*
     FEO_CUDA_CHECK(cudaFuncSetAttribute(dense_apply_tc_kernel<BN, SA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = true;
   }
-  dense_apply_tc_kernel<BN, SA><<<grid, kTcThreads, smem_bytes, st>>>(Dsplit, n, XT, CT, ldb, B, scale, scale_dev, sub, partials, flush, debug);
+  dense_apply_tc_kernel<BN, SA><<<grid, kTcBlock, smem_bytes, st>>>(Dsplit, n, XT, CT, ldb, B, scale, scale_dev, sub, partials, flush, debug);
   FEO_CUDA_CHECK(cudaGetLastError());
   return FEO_OK;
 }
@@ -363,9 +387,9 @@ int launch_dense_tc(const float* Dsplit, int32_t n, const float* XT, float* CT, 
   if (Dsplit == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, "dense operator not present in this handle");
   const int64_t cols = (B + 3) / 4 * 4;
   const int64_t row_tiles = (n + TBM - 1) / TBM;
-  // 128-column tiles halve the reads of D per flop; 64-column tiles put several CTAs on every SM, which is what hides
-  // the latencies of a k-block while the problem is small
-  int bn = row_tiles * ((cols + 127) / 128) >= 4 * 148 ? 128 : 64;
+  // 64-column tiles put three CTAs on every SM and were the fastest at every measured size (N = 387 .. 2549,
+  // B = 1024 .. 8192); 128-column tiles (half the operator re-reads, 128 registers) stay selectable for experiments
+  int bn = 64;
   if (bn_env == 64 || bn_env == 128) bn = bn_env;
   dim3 grid((unsigned)((cols + bn - 1) / bn), (unsigned)row_tiles);
   *count_out = (int)(grid.x * grid.y);
