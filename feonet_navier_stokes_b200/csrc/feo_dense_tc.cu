@@ -107,6 +107,20 @@ __device__ __forceinline__ void bulk_copy(uint32_t dst, const void* src, uint32_
                "r"(bytes), "r"(bar)
                : "memory");
 }
+// the same 1-D bulk copy delivered to the same CTA-relative address (and mbarrier) of every CTA in `mask`
+__device__ __forceinline__ void bulk_copy_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -120,6 +134,11 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint
 // the mbarrier receives one arrival when every tcgen05.mma issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// the arrival goes to the same mbarrier of every CTA in `mask` (the cluster's CTAs release shared operand stages together)
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -148,7 +167,8 @@ __device__ __forceinline__ void store_split(uint8_t* hi_base, uint8_t* lo_base, 
   *reinterpret_cast<float4*>(lo_base + off) = l;
 }
 
-template <int BN, int SA>  // CT tile columns; stages of the D operand ring (its copies run SA - 2 k-blocks ahead)
+template <int BN, int SA, int CL>  // CT tile columns; stages of the D operand ring (its copies run SA - 2 k-blocks ahead);
+                                   // CL = 2: two column tiles form a cluster and share every D stage (each CTA fetches one half, multicast)
 __global__ void __launch_bounds__(kTcBlock, BN == 128 ? 2 : 3) dense_apply_tc_kernel(const float* __restrict__ Dsplit, int32_t n,
                                                                     const float* __restrict__ XT, float* __restrict__ CT,
                                                                     int64_t ldb, int32_t B, float scale,
@@ -182,7 +202,7 @@ __global__ void __launch_bounds__(kTcBlock, BN == 128 ? 2 : 3) dense_apply_tc_ke
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 32) {
-    for (int s = 0; s < kTcStages; ++s) mbar_init(smem_u32(&s_bar[s]), 1);
+    for (int s = 0; s < kTcStages; ++s) mbar_init(smem_u32(&s_bar[s]), CL);  // one commit per CTA of the cluster
     for (int s = 0; s < SA; ++s) mbar_init(smem_u32(&s_full[s]), 1);
     for (int s = 0; s < kTcStages; ++s) mbar_init(smem_u32(&s_bfull[s]), kTcThreads);
     mbar_init(smem_u32(&s_drained), kTcThreads);
@@ -190,17 +210,13 @@ __global__ void __launch_bounds__(kTcBlock, BN == 128 ? 2 : 3) dense_apply_tc_ke
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CL > 1) cluster_sync();  // the peer's mbarriers exist before anything is multicast to them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = s_tmem;
 
   const int nkb = (n + TBK - 1) / TBK;
   // D operand: block (row tile, kb) of Dsplit -> A stage kb % SA, one bulk copy
   const float* a_src = Dsplit + (size_t)blockIdx.y * nkb * (kAStage / 4);
-  auto copy_a = [&](int kb) {
-    const uint32_t bar = smem_u32(&s_full[kb % SA]);
-    mbar_expect_tx(bar, kAStage);
-    bulk_copy(smem_u32(smem) + (uint32_t)(kb % SA) * kAStage, a_src + (size_t)kb * (kAStage / 4), kAStage, bar);
-  };
 
   // XT operand: thread -> (sample column, CB k-chunks): four coalesced row reads of XT per chunk
   const int b_c = tid % BN, b_q = (tid / BN) * CB;      // k-chunks b_q .. b_q + CB - 1
@@ -227,32 +243,62 @@ __global__ void __launch_bounds__(kTcBlock, BN == 128 ? 2 : 3) dense_apply_tc_ke
 
   // ---- issuer warp: operator stages (bulk copies) and the MMAs --------------------------------------------------
   if (is_issuer) {
+    // Everything below is warp-uniform and kept incremental (stage indices, phases, descriptor low words advance by
+    // additions): the uniform datapath that feeds UTCHMMA / UBLKCP is narrow, and rebuilding descriptors from byte
+    // addresses (shift, mask, or; `% SA`) cost more cycles per k-block than the six MMAs take to run.
+    const uint32_t half = CL == 1 ? 0u : cluster_ctarank() * kABytes;        // cluster: this CTA's half of a D stage
+    const uint32_t copy_bytes = CL == 1 ? kAStage : kABytes;
+    auto copy_a = [&](int stage, int kb) {  // D block kb of this row tile -> stage
+      const uint32_t bar = smem_u32(&s_full[0]) + (uint32_t)stage * 8;
+      mbar_expect_tx(bar, kAStage);
+      const uint32_t dst = smem_u32(smem) + (uint32_t)stage * kAStage + half;
+      const float* src = a_src + (size_t)kb * (kAStage / 4) + half / 4;
+      if (CL == 1) bulk_copy(dst, src, copy_bytes, bar);
+      else bulk_copy_multicast(dst, src, copy_bytes, bar, (uint16_t)3);
+    };
     if (elect_one())
-      for (int kb = 0; kb < kAhead && kb < nkb; ++kb) copy_a(kb);
+      for (int kb = 0; kb < kAhead && kb < nkb; ++kb) copy_a(kb, kb);  // kAhead < SA: stage = kb
+    int c_stage = kAhead;  // stage of the next copy (k-block kAhead)
+    // descriptor words: lo = (address >> 4) | (LBO >> 4) << 16, hi = (SBO >> 4) | version 1 << 14
+    constexpr uint32_t kDescHi = (kSbo >> 4) | (1u << 14);
+    const uint32_t a_lo0 = ((smem_u32(smem) & 0x3ffffu) >> 4) | ((kLboA >> 4) << 16);
+    const uint32_t b_lo0 = (((smem_u32(smem) + kBBase) & 0x3ffffu) >> 4) | ((kLboB >> 4) << 16);
+    auto desc = [&](uint32_t lo) { return ((uint64_t)kDescHi << 32) | (uint64_t)lo; };
+    int a_stage = 0, a_phase = 0, chunk_pos = 0, drain_phase = 0;
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb & 1;
+      const uint32_t bar_s = smem_u32(&s_bar[0]) + (uint32_t)s * 8;
       // the MMAs of k-block kb - 2 have completed (use j of a commit barrier waits for commit j - 1):
       // A stage (kb + kAhead) % SA is free
-      if (kb >= kTcStages) mbar_wait(smem_u32(&s_bar[s]), ((kb >> 1) - 1) & 1);
-      if (kb + kAhead < nkb && elect_one()) copy_a(kb + kAhead);
-      mbar_wait(smem_u32(&s_bfull[s]), (kb >> 1) & 1);                   // the loaders have written XT stage s
-      mbar_wait(smem_u32(&s_full[kb % SA]), (kb / SA) & 1);              // the D stage has landed
-      const bool first = kb % flush == 0;
-      if (first && kb > 0) mbar_wait(smem_u32(&s_drained), ((kb / flush) - 1) & 1);  // accumulator read back by everyone
+      if (kb >= kTcStages) mbar_wait(bar_s, ((kb >> 1) - 1) & 1);
+      if (kb + kAhead < nkb) {
+        if (elect_one()) copy_a(c_stage, kb + kAhead);
+        if (++c_stage == SA) c_stage = 0;
+      }
+      mbar_wait(smem_u32(&s_bfull[0]) + (uint32_t)s * 8, (kb >> 1) & 1);    // the loaders have written XT stage s
+      mbar_wait(smem_u32(&s_full[0]) + (uint32_t)a_stage * 8, a_phase);     // the D stage has landed
+      const bool first = chunk_pos == 0;
+      if (first && kb > 0) {
+        mbar_wait(smem_u32(&s_drained), drain_phase);                       // accumulator read back by everyone
+        drain_phase ^= 1;
+      }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
-        const uint32_t a_base = smem_u32(smem) + (uint32_t)(kb % SA) * kAStage, b_base = smem_u32(smem) + kBBase + s * kBStage;
+        const uint32_t la = a_lo0 + (uint32_t)a_stage * (kAStage >> 4), lb = b_lo0 + (uint32_t)s * (kBStage >> 4);
 #pragma unroll
         for (int ks = 0; ks < TBK / 8; ++ks) {
-          const uint64_t a_hi = smem_desc(a_base + ks * 2 * kLboA, kLboA), a_lo = smem_desc(a_base + kABytes + ks * 2 * kLboA, kLboA);
-          const uint64_t b_hi = smem_desc(b_base + ks * 2 * kLboB, kLboB), b_lo = smem_desc(b_base + kBBytes + ks * 2 * kLboB, kLboB);
+          const uint64_t a_hi = desc(la + ks * (2 * kLboA >> 4)), a_lo = desc(la + (kABytes >> 4) + ks * (2 * kLboA >> 4));
+          const uint64_t b_hi = desc(lb + ks * (2 * kLboB >> 4)), b_lo = desc(lb + (kBBytes >> 4) + ks * (2 * kLboB >> 4));
           if (debug < 2) umma_tf32(tmem, a_lo, b_hi, kIdesc, !(first && ks == 0));  // first product of a chunk overwrites
           if (debug < 1) umma_tf32(tmem, a_hi, b_lo, kIdesc, 1);
           if (debug < 1) umma_tf32(tmem, a_hi, b_hi, kIdesc, 1);
         }
-        umma_commit(smem_u32(&s_bar[s]));
+        if (CL == 1) umma_commit(bar_s);
+        else umma_commit_multicast(bar_s, (uint16_t)3);
       }
       __syncwarp();
+      if (++a_stage == SA) a_stage = 0, a_phase ^= 1;
+      if (++chunk_pos == flush) chunk_pos = 0;
     }
   } else {
     // ---- loader warps: XT stages through registers, accumulator drains -----------------------------------------
@@ -264,9 +310,11 @@ __global__ void __launch_bounds__(kTcBlock, BN == 128 ? 2 : 3) dense_apply_tc_ke
 #pragma unroll
       for (int j = 0; j < CB; ++j)
         store_split(stage_b, stage_b + kBBytes, (uint32_t)(b_q + j) * kLboB + (uint32_t)b_c * 16, bv[j]);
-      if (kb + 2 < nkb) load_block((kb + 2) * TBK, bv);  // this register set is free again
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> tensor-core (async proxy) reads
       mbar_arrive(smem_u32(&s_bfull[s]));
+      // this register set is free again; the loads go out AFTER the proxy fence, which otherwise holds the thread until
+      // they have returned from L2
+      if (kb + 2 < nkb) load_block((kb + 2) * TBK, bv);
       if ((kb + 1) % flush == 0 || kb + 1 == nkb) {
         // drain: this k-block's commit covers every MMA issued so far
         mbar_wait(smem_u32(&s_bar[s]), (kb >> 1) & 1);
@@ -331,6 +379,7 @@ __global__ void __launch_bounds__(kTcBlock, BN == 128 ? 2 : 3) dense_apply_tc_ke
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
   }
+  if (CL > 1) cluster_sync();  // no CTA leaves while its peer may still signal it
 }
 
 int env_int(const char* name, int dflt) {
@@ -338,18 +387,30 @@ int env_int(const char* name, int dflt) {
   const int v = e != nullptr ? atoi(e) : dflt;
   return v > 0 ? v : dflt;
 }
-template <int BN, int SA>
+template <int BN, int SA, int CL>
 int launch_tc(dim3 grid, const float* Dsplit, int32_t n, const float* XT, float* CT, int64_t ldb, int32_t B, float scale,
               const float* scale_dev, const float* sub, float* partials, int flush, cudaStream_t st) {
   static bool configured = false;
   static const int debug = env_int("FEO_DENSE_DEBUG", 0);  // developer timing: 1 = one product of three, 2 = no MMAs (results are garbage)
   const int smem_bytes = (int)smem_bytes_for(BN, SA);
   if (!configured) {
-    FEO_CUDA_CHECK(cudaFuncSetAttribute(dense_apply_tc_kernel<BN, SA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    FEO_CUDA_CHECK(cudaFuncSetAttribute(dense_apply_tc_kernel<BN, SA, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = true;
   }
-  dense_apply_tc_kernel<BN, SA><<<grid, kTcBlock, smem_bytes, st>>>(Dsplit, n, XT, CT, ldb, B, scale, scale_dev, sub, partials, flush, debug);
-  FEO_CUDA_CHECK(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kTcBlock);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  FEO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dense_apply_tc_kernel<BN, SA, CL>, Dsplit, n, XT, CT, ldb, B, scale, scale_dev, sub, partials,
+                                    (int32_t)flush, (int32_t)debug));
   return FEO_OK;
 }
 // cvt.rna.tf32.f32 on the host: round to nearest, ties away from zero, to 10 mantissa bits
@@ -391,20 +452,27 @@ int launch_dense_tc(const float* Dsplit, int32_t n, const float* XT, float* CT, 
   // B = 1024 .. 8192); 128-column tiles (half the operator re-reads, 128 registers) stay selectable for experiments
   int bn = 64;
   if (bn_env == 64 || bn_env == 128) bn = bn_env;
-  dim3 grid((unsigned)((cols + bn - 1) / bn), (unsigned)row_tiles);
+  // FEO_DENSE_CLUSTER=2: pairs of column tiles share every operator stage through cluster multicast (each CTA fetches one
+  // half).  Measured equal to the plain launch (0.164 vs 0.162 ms at N = 2549, B = 1024; 0.90 vs 0.89 ms at B = 8192):
+  // the crossbar traffic it halves is not what paces the kernel, so the plain launch stays the default.
+  static const int cl_env = env_int("FEO_DENSE_CLUSTER", 0);
+  const int cl = cl_env == 2 ? 2 : 1;
+  // cluster launches need a grid that is a multiple of the cluster: a padding column tile runs the protocol and stores nothing
+  const unsigned col_tiles = (unsigned)((cols + bn - 1) / bn);
+  dim3 grid((col_tiles + cl - 1) / cl * cl, (unsigned)row_tiles);
   *count_out = (int)(grid.x * grid.y);
   static const int sa_env = env_int("FEO_DENSE_ASTAGES", 0);
-  // 3 stages keep three 64-column CTAs on an SM; deeper rings were measured slower (fewer resident CTAs): the
-  // copy latency is not what paces the kernel (a run without any MMA takes 0.144 of the 0.183 ms at N = 2549, B = 1024)
   const int sa = sa_env >= 3 && sa_env <= 5 ? sa_env : 3;
-#define FEO_TC_CASE(BN_, SA_) \
-  if (bn == BN_ && sa == SA_) return launch_tc<BN_, SA_>(grid, Dsplit, n, XT, CT, ldb, B, scale, scale_dev, sub, partials, flush, st)
-  FEO_TC_CASE(64, 3);
-  FEO_TC_CASE(64, 4);
-  FEO_TC_CASE(64, 5);
-  FEO_TC_CASE(128, 3);
-  FEO_TC_CASE(128, 4);
-  FEO_TC_CASE(128, 5);
+#define FEO_TC_CASE(BN_, SA_, CL_) \
+  if (bn == BN_ && sa == SA_ && cl == CL_) \
+  return launch_tc<BN_, SA_, CL_>(grid, Dsplit, n, XT, CT, ldb, B, scale, scale_dev, sub, partials, flush, st)
+  FEO_TC_CASE(64, 3, 2);
+  FEO_TC_CASE(64, 4, 2);
+  FEO_TC_CASE(64, 5, 2);
+  FEO_TC_CASE(128, 3, 2);
+  FEO_TC_CASE(64, 3, 1);
+  FEO_TC_CASE(64, 4, 1);
+  FEO_TC_CASE(128, 3, 1);
 #undef FEO_TC_CASE
   return fail(FEO_ERR_INVALID_ARGUMENT, "dense_apply: no kernel for this tile configuration");
 }
