@@ -9,26 +9,29 @@
 // relative per product and unbiased, i.e. fp32-grade, which plain TF32 (2^-11) is not: the north-star
 // tolerance on the loss is 1e-5 relative.
 //
-// One CTA = one 128 x 64 (or 128 x 128) tile of CT (UMMA M = 128, N = 64 | 128, K = 8), k-blocks of 16.
+// One CTA = one 128 x 64 tile of CT (UMMA M = 128, N = 64, K = 8; 128-column tiles selectable), k-blocks of 16.
 //  * D operand: split ONCE at set-up (dense_split_tiles: per (row tile, k-block) a 16 KB block [hi | lo] already in
-//    the shared-memory operand layout), so a stage is one cp.async.bulk (UBLKCP) onto an mbarrier:
-//    SA stages (default 3),
-//    the copy of k-block kb + SA - 2 is issued as soon as the MMAs of kb - 2 have released its stage.
+//    the shared-memory operand layout), so a stage is one cp.async.bulk (UBLKCP) onto an mbarrier; SA = 3 stages, the
+//    copy of k-block kb + SA - 2 is issued as soon as the MMAs of kb - 2 have released its stage.
 //  * XT operand (the activations: split at run time; sample-contiguous, i.e. MN-major): through registers --
 //    coalesced row reads, cvt.rna.tf32 split, STS.128 straight into the K-major core-matrix layout, which also
 //    transposes it; two stages, two register sets (k-blocks kb + 1 and kb + 2 in flight).
 // Warp roles (288 threads): eight loader / epilogue warps and one ISSUER warp.  Loaders: wait until the MMAs of
 // k-block kb - 2 have released XT stage kb % 2 (commit mbarrier), split + STS, fence.proxy.async, arrive on the
-// stage's "written" mbarrier, issue the loads of kb + 2.  Issuer (all descriptor arithmetic on the uniform datapath,
-// one elected lane issues): bulk copy of the D stage SA - 2 k-blocks ahead, wait for "written" and for the D stage,
-// six tcgen05.mma, tcgen05.commit onto the commit mbarrier.  Neither side waits for the other's instruction issue:
-// measured per k-block before the split, with one thread doing both, ~480 cycles of MMA issue sat on top of ~500
-// cycles of loader work.  80 KB.. of shared memory: 64 KB (BN = 64) and BN TMEM columns per CTA, three CTAs per SM.
+// stage's "written" mbarrier, issue the loads of kb + 2.  Issuer (warp-uniform code, incremental stage / phase /
+// descriptor state on the uniform datapath, one elected lane issues): bulk copy of the D stage SA - 2 k-blocks
+// ahead, wait for "written" and for the D stage, six tcgen05.mma, tcgen05.commit onto the commit mbarrier.  With one
+// thread doing both jobs behind a bar.sync, ~480 cycles of MMA issue per k-block (ELECT / R2UR broadcast loops around
+// every UTCHMMA under a `tid == 0` guard, descriptors rebuilt from byte addresses) sat on top of ~500 cycles of
+// loader work.  64 KB of shared memory and 64 TMEM columns per CTA: three CTAs per SM.
+// Optional (FEO_DENSE_CLUSTER=2): two column tiles form a cluster, each CTA fetches one half of every D stage and
+// multicasts it, commits are multicast to both CTAs' barriers (stages are released together).
 //
 // The tensor core aligns and TRUNCATES when it adds a K = 8 product group to the fp32 accumulator, which biases a
 // long accumulation towards zero (measured: 3e-6 of |D||x| at n = 2549, against 1e-7 for the split itself).  The
-// accumulator is therefore drained every `flush` k-blocks (default 4 = 64 k, 24 accumulations; costs nothing measurable) into fp32 registers with round-to-nearest adds
-// -- 64 registers per thread, the epilogue's own TMEM mapping -- and restarted with accumulate = 0.
+// accumulator is therefore drained every `flush` k-blocks (default 4 = 64 k, 24 accumulations; 7 % of the run time at
+// N = 2549) into fp32 registers with round-to-nearest adds -- the epilogue's own TMEM mapping, 32 registers per
+// thread -- and restarted with accumulate = 0 once every loader thread has arrived on the "drained" mbarrier.
 //
 // Shared-memory operand layout (canonical K-major, SWIZZLE_NONE): element (r, k) of a [128 x 16] tile lives at
 //   (k / 4) * 2048 + r * 16 + (k % 4) * 4   bytes,
