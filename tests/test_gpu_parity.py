@@ -347,6 +347,39 @@ def test_dense_apply_tensor_core_vs_fp64(feo, n, B):
     assert abs(loss.item() - (r64 ** 2).sum()) <= LOSS_RTOL * (r64 ** 2).sum()
 
 
+@pytest.mark.parametrize("env", [{"FEO_DENSE_CLUSTER": "2"}, {"FEO_DENSE_BN": "128"}, {"FEO_DENSE_SIMT": "1"}])
+def test_dense_apply_optional_paths_subprocess(feo, env):
+    """The dense apply reads its tuning knobs once per process: the optional paths (cluster multicast of the operator stages,
+    128-column tiles, the fp32 FMA comparison kernel) are exercised in a child process, ragged sizes, against fp64."""
+    import subprocess
+    import sys
+
+    code = r"""
+import numpy as np, torch
+import feonet_navier_stokes_b200 as feo
+from feonet_navier_stokes_b200 import _lib as L
+feo.load_library(build_if_missing=False)
+dev = torch.device("cuda")
+rng = np.random.default_rng(7)
+for n, B in ((813, 257), (200, 130), (72, 5)):
+    D = (rng.standard_normal((n, n)) / np.sqrt(n)).astype(np.float32)
+    op = feo.FEOperator(n, dense_m=D, device=dev)
+    x = rng.standard_normal((B, n)).astype(np.float32); f = rng.standard_normal((B, n)).astype(np.float32)
+    xT, fT = op.to_dof_major(torch.tensor(x, device=dev)), op.to_dof_major(torch.tensor(f, device=dev))
+    rT, loss = op.dense_apply(L.FEO_DENSE_M, xT, B, sub=fT, want_loss=True)
+    r64 = D.astype(np.float64) @ x.astype(np.float64).T - f.astype(np.float64).T
+    bound = np.abs(D.astype(np.float64)) @ np.abs(x.astype(np.float64)).T + np.abs(f.astype(np.float64).T)
+    err = np.abs(rT[:, :B].cpu().numpy() - r64)
+    assert (err <= 3e-6 * bound + 1e-30).all(), (n, B, float((err / bound).max()))
+    assert abs(loss.item() - (r64 ** 2).sum()) <= 1e-5 * (r64 ** 2).sum()
+print("OK")
+"""
+    child_env = dict(os.environ, **env)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, env=child_env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
 def test_time_dep_cfg4_vs_oracle(feo):
     from feonet_navier_stokes_b200.fixtures import config_operators
 
