@@ -33,6 +33,44 @@ int canonicalize(const feo_csr& in, int32_t n, const char* name, HostCsr* out);
 HostCsr transpose(const HostCsr& a);
 HostCsr axpy(const HostCsr& s, float dt, const HostCsr& a);  // S + dt*A
 
+// ---- union pattern of A, B1, B2 with the pair structure of idx_sol (feo_tiles.cpp), shared by the tile and patch planners ----
+struct UEnt {
+  int32_t col;
+  float a, b1, b2;
+};
+
+struct Front {
+  int32_t n = 0;
+  bool conv = false;
+  float sgn = 1.f;
+  std::vector<int32_t> pi, pj, kind, mate;   // per dof: partners, 0 none / 1 I-dof / 2 J-dof, the other dof of the pair
+  std::vector<int32_t> smate;                // single dofs matched two by two (they share source rows), -1: alone
+  std::vector<int32_t> unit_of, unit_first;  // units: a velocity pair (I[k], J[k]), two matched single dofs, or a single dof
+  std::vector<int32_t> ptr;                  // union rows
+  std::vector<UEnt> ent;
+  std::vector<int32_t> tptr, trow, tsrc;     // transposed union: per column the source rows + index into ent
+  int32_t max_row_nnz = 0;
+
+  int unit_rows(int32_t u, int32_t o[2]) const {
+    const int32_t r = unit_first[u];
+    o[0] = r;
+    if (kind[r] == 1) {
+      o[1] = mate[r];
+      return 2;
+    }
+    if (kind[r] == 0 && smate[r] >= 0) {
+      o[1] = smate[r];
+      return 2;
+    }
+    return 1;
+  }
+  // entry (h, c) takes part in the convective term: row h is a velocity row and B1 or B2 is stored there
+  bool is_conv(int32_t h, const UEnt& e) const { return conv && kind[h] != 0 && (e.b1 != 0.f || e.b2 != 0.f); }
+};
+
+int build_front(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int32_t n_u, const int32_t* idx_i,
+                const int32_t* idx_j, int32_t ns_branch, bool match_singles, Front* out);
+
 // ---- tile plan of the fused residual kernels (feo_tiles.cpp / feo_tiled.cu) -----------------------
 // A work unit = one TILE of operator rows (forward) / columns (backward) for one SLAB of 64 consecutive
 // samples.  A persistent CTA stages the "lines" the tile touches -- line = the 64 samples of one dof,

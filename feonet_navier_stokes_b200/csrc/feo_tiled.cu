@@ -1005,14 +1005,17 @@ int debug_mode() {
 }
 
 int sm_count(int* out) {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    FEO_CUDA_CHECK(cudaGetDevice(&dev));
+  static int cached[64] = {0};  // per device ordinal: handles of several devices may live in one process
+  int dev = 0, n = 0;
+  FEO_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || cached[dev] == 0) {
     FEO_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    cached = n > 0 ? n : 1;
+    n = n > 0 ? n : 1;
+    if (dev >= 0 && dev < 64) cached[dev] = n;
+    *out = n;
+    return FEO_OK;
   }
-  *out = cached;
+  *out = cached[dev];
   return FEO_OK;
 }
 

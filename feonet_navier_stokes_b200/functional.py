@@ -46,18 +46,22 @@ def _prep(op: FEOperator, x: torch.Tensor, ldb: Optional[int] = None) -> torch.T
 
 
 class _TransposeCache:
-    """Load vectors are data: the same tensor comes back every epoch (full-batch training is the
-    reference default, train_FEONet.py:109-112).  Cache its dof-major copy keyed on identity."""
+    """Load vectors are data: in full-batch training the same tensor OBJECT comes back every epoch, so its
+    dof-major copy is cached.  The key is the identity of the tensor (a strong reference is kept, so its storage
+    cannot be recycled for another tensor while the entry lives) plus its version counter: a loop that makes a
+    fresh device tensor per step (`v.to(device)` on a shuffled DataLoader batch, as the reference epoch loop does)
+    never hits, whatever address the caching allocator hands back."""
 
     def __init__(self):
-        self.key = None
+        self.src = None
+        self.version = -1
+        self.ldb = -1
         self.val = None
 
     def get(self, op: FEOperator, f: torch.Tensor, ldb: int) -> torch.Tensor:
-        key = (f.data_ptr(), f._version, tuple(f.shape), tuple(f.stride()), ldb)
-        if self.key != key:
-            self.val = _prep(op, f, ldb)
-            self.key = key
+        if self.src is not f or self.version != f._version or self.ldb != ldb:
+            self.val = _prep(op, f.detach(), ldb)
+            self.src, self.version, self.ldb = f, f._version, ldb
         return self.val
 
 
@@ -73,7 +77,7 @@ class ResidualLossFn(torch.autograd.Function):
         native = is_dof_major(alpha)
         aT = _prep(op, alpha.detach())
         ldb = aT.shape[1]
-        fT = fcache.get(op, F.detach(), ldb) if fcache is not None else _prep(op, F.detach(), ldb)
+        fT = fcache.get(op, F, ldb) if fcache is not None else _prep(op, F.detach(), ldb)
         need = bool(ctx.needs_input_grad[0])
         loss, rT = op.residual_fwd(aT, fT, B, save=need)
         ctx.op, ctx.B, ctx.native = op, B, native
@@ -100,7 +104,7 @@ class DenseResidualLossFn(torch.autograd.Function):
         native = is_dof_major(alpha)
         aT = _prep(op, alpha.detach())
         ldb = aT.shape[1]
-        fT = fcache.get(op, F.detach(), ldb) if fcache is not None else _prep(op, F.detach(), ldb)
+        fT = fcache.get(op, F, ldb) if fcache is not None else _prep(op, F.detach(), ldb)
         rT, loss = op.dense_apply(L.FEO_DENSE_M, aT, B, sub=fT, want_loss=True)
         ctx.op, ctx.B, ctx.native = op, B, native
         ctx.save_for_backward(rT)

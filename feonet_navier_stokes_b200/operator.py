@@ -149,9 +149,15 @@ class FEOperator:
             self._handle = C.c_void_p()
 
     # -- helpers ------------------------------------------------------------------------------
-    @staticmethod
-    def _stream() -> C.c_void_p:
-        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    def _stream(self) -> C.c_void_p:
+        # the stream of THIS handle's device: the caller's current device may be another one
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _call(self, fn, *args) -> None:
+        """Every launch runs with the handle's device current (the library sizes grids, encodes tensor maps and
+        launches on the current device) and on that device's current stream."""
+        with torch.cuda.device(self.device):
+            L.check(fn(*args))
 
     @staticmethod
     def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
@@ -184,7 +190,7 @@ class FEOperator:
         if x.stride(1) != 1:
             x = x.contiguous()
         out = torch.empty((N, want), dtype=torch.float32, device=x.device)
-        L.check(self.lib.feo_transpose(self._p(x), x.stride(0), self._p(out), want, B, N, None, self._stream()))
+        self._call(self.lib.feo_transpose, self._p(x), x.stride(0), self._p(out), want, B, N, None, self._stream())
         self.launches += 1
         return out
 
@@ -194,7 +200,7 @@ class FEOperator:
             return xT[:, :B].t()
         N, ldb = xT.shape
         out = torch.empty((B, N), dtype=torch.float32, device=xT.device)
-        L.check(self.lib.feo_transpose(self._p(xT), ldb, self._p(out), N, N, B, None, self._stream()))
+        self._call(self.lib.feo_transpose, self._p(xT), ldb, self._p(out), N, N, B, None, self._stream())
         self.launches += 1
         return out
 
@@ -207,16 +213,16 @@ class FEOperator:
         loss = torch.empty((), dtype=torch.float32, device=self.device)
         rT = self.new(ldb) if save else None
         ws = self.workspace(B)
-        L.check(self.lib.feo_residual_fwd(self._handle, self._p(aT), self._p(fT), ldb, B, self._p(loss), self._p(rT),
-                                          self._p(ws), ws.numel() * 4, self._stream()))
+        self._call(self.lib.feo_residual_fwd, self._handle, self._p(aT), self._p(fT), ldb, B, self._p(loss), self._p(rT),
+                                          self._p(ws), ws.numel() * 4, self._stream())
         self.launches += 2
         return loss, rT
 
     def residual_bwd(self, aT, rT, B: int, grad_loss: Optional[torch.Tensor] = None, out=None) -> torch.Tensor:
         ldb = rT.shape[1]
         gT = self.new(ldb) if out is None else out
-        L.check(self.lib.feo_residual_bwd(self._handle, self._p(aT), self._p(rT), self._p(grad_loss),
-                                          self._p(gT), ldb, B, self._stream()))
+        self._call(self.lib.feo_residual_bwd, self._handle, self._p(aT), self._p(rT), self._p(grad_loss),
+                                          self._p(gT), ldb, B, self._stream())
         self.launches += 1
         return gT
 
@@ -225,8 +231,8 @@ class FEOperator:
              accumulate: bool = False) -> torch.Tensor:
         self._check(xT, self.n)
         yT = self.new(xT.shape[1]) if out is None else out
-        L.check(self.lib.feo_spmm(self._handle, which, int(transpose), self._p(xT), self._p(yT), xT.shape[1], B,
-                                  float(scale), int(accumulate), self._stream()))
+        self._call(self.lib.feo_spmm, self._handle, which, int(transpose), self._p(xT), self._p(yT), xT.shape[1], B,
+                                  float(scale), int(accumulate), self._stream())
         self.launches += 1
         return yT
 
@@ -237,17 +243,17 @@ class FEOperator:
         cT = self.new(ldb)
         loss = torch.empty((), dtype=torch.float32, device=self.device) if want_loss else None
         ws = self.workspace(B)
-        L.check(self.lib.feo_dense_apply(self._handle, which, self._p(xT), self._p(cT), ldb, B, float(scale),
+        self._call(self.lib.feo_dense_apply, self._handle, which, self._p(xT), self._p(cT), ldb, B, float(scale),
                                          self._p(scale_dev), self._p(sub), self._p(loss), self._p(ws), ws.numel() * 4,
-                                         self._stream()))
+                                         self._stream())
         self.launches += 2 if want_loss else 1
         return (cT, loss) if want_loss else cT
 
     def sq_diff_sum(self, xT, yT, B: int, scale: float = 1.0) -> torch.Tensor:
         loss = torch.empty((), dtype=torch.float32, device=self.device)
         ws = self.workspace(B)
-        L.check(self.lib.feo_sq_diff_sum(self._p(xT), self._p(yT), xT.shape[0], xT.shape[1], B, float(scale),
-                                         self._p(loss), self._p(ws), ws.numel() * 4, self._stream()))
+        self._call(self.lib.feo_sq_diff_sum, self._p(xT), self._p(yT), xT.shape[0], xT.shape[1], B, float(scale),
+                                         self._p(loss), self._p(ws), ws.numel() * 4, self._stream())
         self.launches += 2
         return loss
 
@@ -258,15 +264,15 @@ class FEOperator:
         loss = torch.empty((), dtype=torch.float32, device=self.device)
         rT = self.new(ldj)
         ws = self.workspace(B, T)
-        L.check(self.lib.feo_seq_fwd(self._handle, self._p(pT), self._p(u0T), self._p(fT), ldj, ldb, B, T, self._p(loss),
-                                     self._p(rT), self._p(ws), ws.numel() * 4, self._stream()))
+        self._call(self.lib.feo_seq_fwd, self._handle, self._p(pT), self._p(u0T), self._p(fT), ldj, ldb, B, T, self._p(loss),
+                                     self._p(rT), self._p(ws), ws.numel() * 4, self._stream())
         self.launches += 2
         return loss, rT
 
     def seq_bwd(self, rT, B: int, T: int, grad_loss=None) -> torch.Tensor:
         gT = self.new(rT.shape[1])
-        L.check(self.lib.feo_seq_bwd(self._handle, self._p(rT), self._p(grad_loss), self._p(gT), rT.shape[1], B, T,
-                                     self._stream()))
+        self._call(self.lib.feo_seq_bwd, self._handle, self._p(rT), self._p(grad_loss), self._p(gT), rT.shape[1], B, T,
+                                     self._stream())
         self.launches += 1
         return gT
 
@@ -276,7 +282,7 @@ class FEOperator:
         init_x = init_x.reshape(B, -1).contiguous().float()
         init_y = init_y.reshape(B, -1).contiguous().float()
         u0T = self.new(ceil4(B))
-        L.check(self.lib.feo_assemble_u_init(self._handle, self._p(init_x), self._p(init_y), self._p(u0T), u0T.shape[1], B,
-                                             self._stream()))
+        self._call(self.lib.feo_assemble_u_init, self._handle, self._p(init_x), self._p(init_y), self._p(u0T), u0T.shape[1], B,
+                                             self._stream())
         self.launches += 3
         return u0T
