@@ -1,10 +1,12 @@
 // extern "C" entry points of libfeonet_b200.so (declared in include/feonet_b200.h).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
 #include "feo_internal.h"
+#include "feo_patch.h"
 
 namespace feo {
 namespace {
@@ -107,8 +109,43 @@ int feo_op_create(const feo_operator_desc* desc, feo_handle_t* out) {
     if ((rc = upload(op, jj, &op->idx_j))) return bail(rc);
   }
   if (A.present()) {
+    // Plan of the fused residual kernels.  FEO_PLAN = auto (default): the patch plan (feo_patch.h) when the operator fits its
+    // model, else the tile plan; tile / patch force one of them.  Both are device code paths.
+    const char* plan_env = std::getenv("FEO_PLAN");
+    const std::string want = plan_env != nullptr ? plan_env : "auto";
+    bool use_patch = false;
+    if (want != "tile" && want != "auto") {  // auto = tile until the patch kernels are the faster ones (profiles/r02_*)
+      Front F;
+      if ((rc = build_front(A, B1, B2, desc->n_u, desc->idx_i, desc->idx_j, op->ns_branch, false, &F))) return bail(rc);
+      PatchPlan pf, pb;
+      int rf = build_patch_plan(F, false, patch_tuning_from_env(false), &pf);
+      int rb = rf == FEO_OK && pf.applicable ? build_patch_plan(F, true, patch_tuning_from_env(true), &pb) : rf;
+      use_patch = rf == FEO_OK && rb == FEO_OK && pf.applicable && pb.applicable;
+      if (!use_patch && want == "patch")
+        return bail(fail(FEO_ERR_UNSUPPORTED, "FEO_PLAN=patch but the operator does not fit the patch plan: " +
+                                                  (rf != FEO_OK || rb != FEO_OK ? last_error() : (pf.applicable ? pb.why_not : pf.why_not))));
+      if (use_patch) {
+        for (int bw = 0; bw < 2; ++bw) {
+          const PatchPlan& H = bw ? pb : pf;
+          DevPatchPlan& D = bw ? op->patch_b : op->patch_f;
+          D.warps = H.warps;
+          D.producers = H.producers;
+          D.pool_lines = H.pool_lines;
+          D.stream_cap = H.stream_cap;
+          D.n_segments = H.n_segments();
+          D.n_rounds = (int32_t)H.rounds.size();
+          if ((rc = upload(op, H.seg_ptr, &D.seg_ptr))) return bail(rc);
+          if ((rc = upload(op, H.rounds, &D.rounds))) return bail(rc);
+          if ((rc = upload(op, H.loads, &D.loads))) return bail(rc);
+          if ((rc = upload(op, H.stream, &D.stream))) return bail(rc);
+          D.present = true;
+        }
+        op->has_conv = F.conv;
+        op->nnz_union = pf.real_entries;
+      }
+    }
     // tile plans of the fused residual kernels (forward: row-owned, backward: column-pair-owned)
-    for (int bw = 0; bw < 2; ++bw) {
+    for (int bw = 0; bw < 2 && !use_patch; ++bw) {
       TilePlan plan;
       if ((rc = build_tile_plan(A, B1, B2, desc->n_u, desc->idx_i, desc->idx_j, op->ns_branch, bw != 0,
                                 tile_tuning_from_env(bw != 0), &plan)))
@@ -169,8 +206,8 @@ int feo_op_get_info(feo_handle_t h, feo_op_info* info) {
   info->nnz_b2 = h->nnz[2];
   info->nnz_s = h->nnz[3];
   info->nnz_union = h->nnz_union;
-  info->n_tiles_fwd = h->tiles_f.n_tiles;
-  info->n_tiles_bwd = h->tiles_b.n_tiles;
+  info->n_tiles_fwd = h->patch_f.present ? h->patch_f.n_rounds : h->tiles_f.n_tiles;  // patch plan: rounds
+  info->n_tiles_bwd = h->patch_b.present ? h->patch_b.n_rounds : h->tiles_b.n_tiles;
   info->max_row_nnz = h->max_row_nnz;
   info->device_bytes = h->device_bytes;
   return FEO_OK;
@@ -179,7 +216,7 @@ int feo_op_get_info(feo_handle_t h, feo_op_info* info) {
 size_t feo_workspace_bytes(feo_handle_t h, int32_t B, int32_t T) {
   if (h == nullptr || B <= 0) return 0;
   if (T < 1) T = 1;
-  return loss_partials_needed(h->n, h->tiles_f.warps, (int64_t)B * T);
+  return loss_partials_needed(h->n, std::max(h->tiles_f.warps, h->patch_f.warps), (int64_t)B * T);
 }
 
 int feo_transpose(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int32_t rows, int32_t cols,
@@ -285,6 +322,37 @@ int feo_debug_tile_replay(const feo_operator_desc* desc, int32_t backward, int32
   }
   if (in0 == nullptr || in1 == nullptr || out == nullptr) return FEO_OK;
   return replay_tile_plan(T, branch, in0, in1, out);
+}
+
+int feo_debug_patch_replay(const feo_operator_desc* desc, int32_t backward, int32_t warps, int32_t pool_lines, int32_t seg_rounds,
+                           const double* in0, const double* in1, double* out, int64_t* stats) {
+  HostCsr A, B1, B2, S;
+  if (int rc = prepare(desc, &A, &B1, &B2, &S)) return rc;
+  if (!A.present()) return fail(FEO_ERR_INVALID_ARGUMENT, "patch replay needs A");
+  const int32_t branch = desc->ns_precond_branch ? 1 : 0;
+  Front F;
+  if (int rc = build_front(A, B1, B2, desc->n_u, desc->idx_i, desc->idx_j, branch, false, &F)) return rc;
+  PatchTuning tune = patch_tuning_from_env(backward != 0);
+  if (warps > 0) tune.warps = warps;
+  if (pool_lines > 0) tune.pool_lines = pool_lines;
+  if (seg_rounds > 0) tune.seg_rounds = seg_rounds;
+  PatchPlan P;
+  if (int rc = build_patch_plan(F, backward != 0, tune, &P)) return rc;
+  if (stats != nullptr) {
+    stats[0] = P.applicable ? 1 : 0;
+    stats[1] = P.n_patches;
+    stats[2] = (int64_t)P.rounds.size();
+    stats[3] = P.applicable ? P.n_segments() : 0;
+    stats[4] = (int64_t)P.loads.size();
+    stats[5] = P.n_gathers;
+    stats[6] = P.real_entries;
+    stats[7] = P.slot_entries;
+    stats[8] = (int64_t)P.stream.size() / 4;
+    stats[9] = P.max_union_lines;
+  }
+  if (!P.applicable) return fail(FEO_ERR_UNSUPPORTED, "patch plan not applicable: " + P.why_not);
+  if (in0 == nullptr || in1 == nullptr || out == nullptr) return FEO_OK;
+  return replay_patch_plan(P, F.conv, branch, in0, in1, out);
 }
 
 }  // extern "C"

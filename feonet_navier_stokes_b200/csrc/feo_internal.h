@@ -177,6 +177,18 @@ struct DevTilePlan {
   Word16* stream = nullptr;
 };
 
+// device copy of a patch plan (feo_patch.h): the second-generation plan of the fused residual kernels
+struct LineLoad;
+struct RoundInfo;
+struct DevPatchPlan {
+  bool present = false;
+  int32_t warps = 0, producers = 1, pool_lines = 0, stream_cap = 0, n_segments = 0, n_rounds = 0;
+  int32_t* seg_ptr = nullptr;
+  RoundInfo* rounds = nullptr;
+  LineLoad* loads = nullptr;
+  uint32_t* stream = nullptr;  // 32-bit slots, rounds start on 16-byte words
+};
+
 // ---- device-side operator ---------------------------------------------------------------------
 struct DevCsr {
   int32_t* rowptr = nullptr;
@@ -196,6 +208,7 @@ struct feo_operator {
   feo::DevCsr csr[5], csrT[5];
   int32_t *idx_i = nullptr, *idx_j = nullptr;
   feo::DevTilePlan tiles_f, tiles_b;
+  feo::DevPatchPlan patch_f, patch_b;  // used instead of the tile plans when both are present
   // dense
   float *dM = nullptr, *dMT = nullptr, *dP = nullptr;
   float *dMs = nullptr, *dMTs = nullptr, *dPs = nullptr;  // the same matrices pre-split into TF32 hi/lo operand tiles (feo_dense_tc.cu)

@@ -26,6 +26,7 @@
 #include <cstdlib>
 
 #include "feo_internal.h"
+#include "feo_patch.h"
 
 namespace feo {
 namespace {
@@ -1004,6 +1005,7 @@ int debug_mode() {
   return s != nullptr ? atoi(s) : 0;
 }
 
+}  // namespace
 int sm_count(int* out) {
   static int cached[64] = {0};  // per device ordinal: handles of several devices may live in one process
   int dev = 0, n = 0;
@@ -1018,6 +1020,7 @@ int sm_count(int* out) {
   *out = cached[dev];
   return FEO_OK;
 }
+namespace {
 
 // persistent launch: one CTA per SM (or per unit when there are fewer units), `warps` consumer warps + 1 producer warp
 template <typename Kernel>
@@ -1038,6 +1041,7 @@ size_t fused_partials_needed(int32_t warps) { return (size_t)1024 * (size_t)(war
 
 int launch_residual_fwd(const feo_operator* op, const float* alphaT, const float* fT, int64_t ldb, int32_t B,
                         float* loss_out, float* rT, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (op->patch_f.present) return launch_patch_fwd(op, op->patch_f, alphaT, fT, ldb, B, loss_out, rT, ws, ws_bytes, st);
   if (B <= 0) return fail(FEO_ERR_INVALID_ARGUMENT, "B must be positive");
   if (int rc = check_layout(alphaT, ldb, B, "alphaT")) return rc;
   if (int rc = check_layout(fT, ldb, B, "fT")) return rc;
@@ -1066,6 +1070,7 @@ int launch_residual_fwd(const feo_operator* op, const float* alphaT, const float
 
 int launch_residual_bwd(const feo_operator* op, const float* alphaT, const float* rT, const float* grad_loss,
                         float* gradT, int64_t ldb, int32_t B, cudaStream_t st) {
+  if (op->patch_b.present) return launch_patch_bwd(op, op->patch_b, alphaT, rT, grad_loss, gradT, ldb, B, st);
   if (B <= 0) return fail(FEO_ERR_INVALID_ARGUMENT, "B must be positive");
   if (int rc = check_layout(rT, ldb, B, "rT")) return rc;
   if (int rc = check_layout(gradT, ldb, B, "gradT")) return rc;

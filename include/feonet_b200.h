@@ -180,6 +180,16 @@ int feo_sq_diff_sum(const float* xT, const float* yT, int32_t n, int64_t ldb, in
 int feo_debug_tile_replay(const feo_operator_desc* desc, int32_t backward, int32_t max_lines, int32_t warps,
                           const double* in0, const double* in1, double* out, int64_t* stats);
 
+/* Test hook (HOST ONLY): builds the PATCH plan of the fused residual kernels (second-generation plan: one warp evaluates a
+ * patch of up to 4 velocity nodes + 1 single dof from one gather per column; lines stay resident in a shared-memory
+ * pool from round to round) and replays its line loads, pool slots and operator streams in fp64 for one sample, as the
+ * kernels decode them.  Arguments as feo_debug_tile_replay; warps / pool_lines / seg_rounds <= 0: defaults.
+ * Returns FEO_ERR_UNSUPPORTED when the operator does not fit the patch model (the tile plan is used then).
+ * stats[0..9] = {applicable, n_patches, n_rounds, n_segments, n_loads, n_gathers, real_entries, slot_entries,
+ *               stream_units, max_union_lines}. */
+int feo_debug_patch_replay(const feo_operator_desc* desc, int32_t backward, int32_t warps, int32_t pool_lines,
+                           int32_t seg_rounds, const double* in0, const double* in1, double* out, int64_t* stats);
+
 /* Test hook (HOST ONLY): splits a dense [n,n] row-major operator into the TF32 hi/lo operand tiles of the
  * tensor-core apply (feo_dense_apply) and replays them as the kernel reads them -- per 128-row tile and 16-column
  * k-block, K-major core matrices -- for one vector x: out_hi = sum hi*x, out_lo = sum lo*x in fp64, so that
