@@ -67,6 +67,7 @@ struct PatchTuning {
   int32_t seg_rounds = 48;    // rounds per segment
   int32_t stream_cap = 0;     // bytes of one round-stream buffer (0: warps * 1536 / 2048, rounded up to 1 KB)
   int32_t pool_lines = 0;     // 0: whatever 227 KB leave after the stream buffers
+  int32_t merge_pad = 2;        // run classes of a patch are merged while that pads at most this many target slots per merge
   int32_t round_fill_pct = 64;  // lines one round may hold, in percent of the pool
 };
 PatchTuning patch_tuning_from_env(bool backward);

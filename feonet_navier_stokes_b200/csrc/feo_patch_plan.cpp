@@ -23,6 +23,7 @@ PatchTuning patch_tuning_from_env(bool backward) {
   if (const char* s = std::getenv(backward ? "FEO_PATCH_WARPS_BWD" : "FEO_PATCH_WARPS_FWD")) t.warps = atoi(s);
   if (const char* s = std::getenv(backward ? "FEO_PATCH_PRODUCERS_BWD" : "FEO_PATCH_PRODUCERS_FWD")) t.producers = atoi(s);
   if (const char* s = std::getenv("FEO_PATCH_SEG_ROUNDS")) t.seg_rounds = atoi(s);
+  if (const char* s = std::getenv("FEO_PATCH_MERGE_PAD")) t.merge_pad = std::max(atoi(s), 0);
   if (const char* s = std::getenv("FEO_PATCH_ROUND_FILL")) t.round_fill_pct = std::min(std::max(atoi(s), 10), 100);
   if (const char* s = std::getenv(backward ? "FEO_PATCH_STREAM_CAP_BWD" : "FEO_PATCH_STREAM_CAP_FWD")) t.stream_cap = atoi(s);
   if (const char* s = std::getenv(backward ? "FEO_PATCH_POOL_BWD" : "FEO_PATCH_POOL_FWD")) t.pool_lines = atoi(s);
@@ -458,6 +459,33 @@ int build_patch_plan(const Front& F, bool backward, const PatchTuning& tune, Pat
     }
     for (auto& kv : ps) pt.pair.push_back(kv.second);
     for (auto& kv : pl) pt.plain.push_back(kv.second);
+    // Runs cost latency (header read, dispatch), so classes are merged while that pads at most `merge_pad` target slots:
+    // the cheapest pair of classes is merged into the union of their masks (padding slots carry zero coefficients).
+    auto merge_classes = [&](auto& steps) {
+      while (tune.merge_pad > 0) {
+        int cnt[16] = {0};
+        for (const auto& st : steps) cnt[st.mask & 15u]++;
+        int best_a = -1, best_b = -1, best_cost = 1 << 30;
+        for (int a = 0; a < 16; ++a)
+          for (int b = a + 1; b < 16; ++b) {
+            if (cnt[a] == 0 || cnt[b] == 0) continue;
+            const int u = a | b;
+            int cost = (popc4(u) - popc4(a)) * cnt[a] + (popc4(u) - popc4(b)) * cnt[b];
+            if (u != a && u != b && cnt[u] > 0) cost += 0;  // joins an existing class
+            if (cost < best_cost) {
+              best_cost = cost;
+              best_a = a;
+              best_b = b;
+            }
+          }
+        if (best_a < 0 || best_cost > tune.merge_pad) break;
+        const uint32_t u = (uint32_t)(best_a | best_b);
+        for (auto& st : steps)
+          if ((int)st.mask == best_a || (int)st.mask == best_b) st.mask = u;
+      }
+    };
+    merge_classes(pt.pair);
+    merge_classes(pt.plain);
     // runs: steps sorted by (mask, source)
     std::stable_sort(pt.pair.begin(), pt.pair.end(), [](const Patch::PairStep& x, const Patch::PairStep& y) { return x.mask < y.mask; });
     std::stable_sort(pt.plain.begin(), pt.plain.end(), [](const Patch::PlainStep& x, const Patch::PlainStep& y) { return x.mask < y.mask; });

@@ -94,6 +94,107 @@ def allreduce_gradients(module: torch.nn.Module, bucket_mb: float = 64.0, async_
             off += n
 
 
+class GradientReducer:
+    """Asynchronous SUM all-reduce of gradient pieces as they become available during backward.
+
+    `launch(t)` enqueues an NCCL all-reduce of `t` (in place) behind the work already queued on the current stream and
+    returns at once; the collective runs on the process group's own stream, so the GEMMs the caller queues next overlap
+    it.  `finish()` makes the current stream wait for every launched piece (call it before the optimizer step)."""
+
+    def __init__(self, enabled: bool = True):
+        self.enabled = bool(enabled) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.work = []
+        self.bytes = 0
+
+    def launch(self, t: torch.Tensor) -> None:
+        if not self.enabled:
+            return
+        self.bytes += t.numel() * t.element_size()
+        self.work.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True))
+
+    def finish(self) -> int:
+        for h in self.work:
+            h.wait()  # stream-level wait for NCCL work: the host does not block
+        n, self.work, self.bytes = self.bytes, [], 0
+        return n
+
+
+class _OverlappedLinearTFn(torch.autograd.Function):
+    """y = x W^T + b with a dof-major result (as network.LinearT); the backward forms dW in `chunks` row blocks (dof
+    ranges) and hands each block to the reducer as soon as its GEMM is queued, so the all-reduce of block k runs while the
+    GEMMs of the blocks after it (and dx) execute."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, chunks: int, reducer: GradientReducer):
+        B = x.shape[0]
+        pad = (-B) % 4
+        xt = (torch.nn.functional.pad(x, (0, 0, 0, pad)) if pad else x).t()  # [in, ceil4(B)]
+        yt = torch.addmm(bias.unsqueeze(1), weight, xt) if bias is not None else weight @ xt
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias, ctx.chunks, ctx.reducer = bias is not None, int(chunks), reducer
+        return yt[:, :B].t()
+
+    @staticmethod
+    def backward(ctx, g):  # g: [B, out]
+        x, weight = ctx.saved_tensors
+        gT = g.t()  # [out, B]; a plain strided view when g is dof-major
+        out_f = weight.shape[0]
+        dW = torch.empty_like(weight)
+        step = (out_f + ctx.chunks - 1) // ctx.chunks
+        for r0 in range(0, out_f, step):
+            r1 = min(out_f, r0 + step)
+            torch.mm(gT[r0:r1], x, out=dW[r0:r1])
+            ctx.reducer.launch(dW[r0:r1])
+        db = None
+        if ctx.has_bias:
+            db = gT.sum(dim=1)
+            ctx.reducer.launch(db)
+        dx = g @ weight if ctx.needs_input_grad[0] else None
+        return dx, dW, db, None, None
+
+
+class OverlappedLinearT(torch.nn.Linear):
+    """Drop-in for the final `nn.Linear` / `network.LinearT` of a FEONet model under data parallelism (same parameters
+    and state_dict keys): dof-major output, gradient all-reduce overlapped with its own backward GEMMs."""
+
+    def __init__(self, in_features, out_features, bias=True, chunks: int = 8, reducer: Optional[GradientReducer] = None):
+        super().__init__(in_features, out_features, bias=bias)
+        self.chunks = chunks
+        self.reducer = reducer if reducer is not None else GradientReducer()
+
+    @classmethod
+    def from_linear(cls, lin: torch.nn.Linear, chunks: int = 8, reducer: Optional[GradientReducer] = None):
+        m = cls.__new__(cls)
+        torch.nn.Module.__init__(m)
+        m.in_features, m.out_features = lin.in_features, lin.out_features
+        m.weight, m.bias = lin.weight, lin.bias
+        m.chunks = chunks
+        m.reducer = reducer if reducer is not None else GradientReducer()
+        return m
+
+    def forward(self, x):
+        if x.dim() != 2:
+            return super().forward(x)
+        return _OverlappedLinearTFn.apply(x, self.weight, self.bias, self.chunks, self.reducer)
+
+
+def allreduce_remaining(module: torch.nn.Module, skip: Iterable[torch.nn.Parameter], reducer: GradientReducer) -> None:
+    """Gradients that were not reduced during backward (everything but the overlapped head): one flat bucket."""
+    if not reducer.enabled:
+        return
+    skip_ids = {id(p) for p in skip}
+    ps = [p for p in module.parameters() if p.grad is not None and id(p) not in skip_ids]
+    if not ps:
+        return
+    flat = torch.cat([p.grad.reshape(-1) for p in ps])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    off = 0
+    for p in ps:
+        n = p.grad.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n
+
+
 def allreduce_loss(loss: torch.Tensor) -> torch.Tensor:
     """Summed loss over ranks (for logging; matches the reference's full-batch SUM loss)."""
     out = loss.detach().clone()

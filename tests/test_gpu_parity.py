@@ -236,6 +236,38 @@ def test_cfg5_full_size_properties(feo):
     assert loss2.item() == loss.item() and torch.equal(gT2[:, :B], gT[:, :B])
 
 
+@pytest.mark.parametrize("branch", [1, 0])
+def test_cfg5_full_size_vs_oracle(feo, branch):
+    """BASELINE.json configs[4] -- the benchmarked operator (n=333, N=1 001 334) -- against the fp64 oracle with scipy CSR
+    (oracle.ns_loss_and_grad restates FEONet_steady_Navier-Stokes/train_FEONet.py:301-365) on 6 samples, through the public
+    autograd API in BOTH layouts: the reference's row-major [B,1,N] network output and the dof-major native tensor.
+    Tolerances as north_star: loss 1e-5, gradient 1e-4 (2-norm and max-norm)."""
+    from feonet_navier_stokes_b200.fixtures import config_operators
+
+    fx = config_operators("steady_ns", 333, ordering="interleaved")
+    assert fx.N == 1001334
+    dev = torch.device("cuda")
+    rng = np.random.default_rng(50 + branch)
+    B = 6
+    alpha = (0.1 * rng.standard_normal((B, fx.N))).astype(np.float32)
+    F = rng.standard_normal((B, fx.N)).astype(np.float32)
+    lo, go, _ = orc.ns_loss_and_grad(alpha, F, fx.A, fx.B1, fx.B2, fx.idx_u1, fx.idx_u2, bool(branch), dtype=np.float64)
+    ns = feo.SteadyNavierStokes(fx.A, fx.B1, fx.B2, fx.idx_sol, do_precond=bool(branch), device=dev)
+    Fd = torch.tensor(F, device=dev)
+    for native in (False, True):
+        a = torch.tensor(alpha, device=dev)
+        if native:
+            a = feo.to_dof_major_tensor(a)
+        else:
+            a = a.unsqueeze(1)  # [B,1,N], as the reference networks emit it
+        a.requires_grad_(True)
+        loss = ns.residual_loss(a, Fd, fx.A, fx.B1, fx.B2, fx.idx_sol)
+        (grad,) = torch.autograd.grad(loss, a)
+        g = grad.reshape(B, fx.N).cpu().numpy()
+        assert abs(loss.item() - lo) <= LOSS_RTOL * abs(lo), (native, loss.item(), lo)
+        assert _rel(g, go) < GRAD_RTOL and _relmax(g, go) < GRAD_RTOL, (native, _rel(g, go), _relmax(g, go))
+
+
 def test_linear_properties_at_scale(feo):
     """Size-independent properties on a larger operator (n=64, N=37 442): linearity of the residual
     in (alpha, F) and gradient = 2 A^T r checked against the generic sparse apply."""
