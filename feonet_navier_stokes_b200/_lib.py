@@ -66,6 +66,7 @@ SIGNATURES = {
     "feo_sq_diff_sum": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _f32, _vp, _vp, _sz, _vp]),
     "feo_debug_tile_replay": (C.c_int, [C.POINTER(FeoOperatorDesc), _i32, _i32, _i32, f64p, f64p, f64p, i64p]),
     "feo_debug_patch_replay": (C.c_int, [C.POINTER(FeoOperatorDesc), _i32, _i32, _i32, _i32, f64p, f64p, f64p, i64p]),
+    "feo_debug_lattice_replay": (C.c_int, [C.POINTER(FeoOperatorDesc), _i32, f64p, f64p, f64p, i64p]),
     "feo_debug_dense_split_replay": (C.c_int64, [f32p, _i32, _i32, f64p, f64p, f64p]),
 }
 

@@ -10,7 +10,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libfeonet_b200.so")
-SOURCES = ["feo_host.cpp", "feo_tiles.cpp", "feo_patch_plan.cpp", "feo_kernels.cu", "feo_tiled.cu", "feo_patch.cu", "feo_dense_tc.cu", "feo_api.cu"]
+SOURCES = ["feo_host.cpp", "feo_tiles.cpp", "feo_patch_plan.cpp", "feo_lattice_plan.cpp", "feo_kernels.cu", "feo_tiled.cu", "feo_patch.cu", "feo_lattice.cu", "feo_dense_tc.cu", "feo_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3", "-shared", "--use_fast_math=false", "-x", "cu",

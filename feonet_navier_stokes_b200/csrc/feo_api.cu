@@ -7,6 +7,7 @@
 
 #include "feo_internal.h"
 #include "feo_patch.h"
+#include "feo_lattice.h"
 
 namespace feo {
 namespace {
@@ -109,12 +110,37 @@ int feo_op_create(const feo_operator_desc* desc, feo_handle_t* out) {
     if ((rc = upload(op, jj, &op->idx_j))) return bail(rc);
   }
   if (A.present()) {
-    // Plan of the fused residual kernels.  FEO_PLAN = auto (default): the patch plan (feo_patch.h) when the operator fits its
-    // model, else the tile plan; tile / patch force one of them.  Both are device code paths.
+    // Plan of the fused residual kernels.  FEO_PLAN = auto (default): the lattice plan (feo_lattice.h) when the operator is a
+    // structured P2-P1 lattice it models, else the tile plan; tile / patch / lattice force one of them (patch and lattice
+    // fail when the operator does not fit).  All are device code paths.
     const char* plan_env = std::getenv("FEO_PLAN");
     const std::string want = plan_env != nullptr ? plan_env : "auto";
+    bool use_lattice = false;
+    if (want == "auto" || want == "lattice") {
+      LatticePlan lp;
+      const int32_t branch = (op->ns_branch || !(B1.present() || B2.present())) ? 1 : 0;
+      if ((rc = build_lattice_plan(A, B1, B2, desc->n_u, desc->idx_i, desc->idx_j, branch, &lp))) return bail(rc);
+      use_lattice = lp.applicable;
+      if (!use_lattice && want == "lattice")
+        return bail(fail(FEO_ERR_UNSUPPORTED, "FEO_PLAN=lattice but the operator is not a lattice the plan models: " + lp.why_not));
+      if (use_lattice) {
+        DevLatticePlan& D = op->lattice;
+        D.n = lp.n;
+        D.nc = lp.nc;
+        D.has_conv = lp.has_conv;
+        for (int dir = 0; dir < 2; ++dir) {
+          D.n_classes[dir] = lp.n_classes[dir];
+          D.exist[dir] = lp.exist[dir];
+          D.tab[dir] = lp.tab[dir];
+          if ((rc = upload(op, lp.cls[dir], &D.cls[dir]))) return bail(rc);
+        }
+        D.present = true;
+        op->has_conv = lp.has_conv;
+        op->nnz_union = lp.real_entries;
+      }
+    }
     bool use_patch = false;
-    if (want != "tile" && want != "auto") {  // auto = tile until the patch kernels are the faster ones (profiles/r02_*)
+    if (want == "patch") {  // never chosen automatically: slower than the tile plan at cfg5
       Front F;
       if ((rc = build_front(A, B1, B2, desc->n_u, desc->idx_i, desc->idx_j, op->ns_branch, false, &F))) return bail(rc);
       PatchPlan pf, pb;
@@ -145,7 +171,7 @@ int feo_op_create(const feo_operator_desc* desc, feo_handle_t* out) {
       }
     }
     // tile plans of the fused residual kernels (forward: row-owned, backward: column-pair-owned)
-    for (int bw = 0; bw < 2 && !use_patch; ++bw) {
+    for (int bw = 0; bw < 2 && !use_patch && !use_lattice; ++bw) {
       TilePlan plan;
       if ((rc = build_tile_plan(A, B1, B2, desc->n_u, desc->idx_i, desc->idx_j, op->ns_branch, bw != 0,
                                 tile_tuning_from_env(bw != 0), &plan)))
@@ -206,8 +232,9 @@ int feo_op_get_info(feo_handle_t h, feo_op_info* info) {
   info->nnz_b2 = h->nnz[2];
   info->nnz_s = h->nnz[3];
   info->nnz_union = h->nnz_union;
-  info->n_tiles_fwd = h->patch_f.present ? h->patch_f.n_rounds : h->tiles_f.n_tiles;  // patch plan: rounds
-  info->n_tiles_bwd = h->patch_b.present ? h->patch_b.n_rounds : h->tiles_b.n_tiles;
+  // patch plan: rounds; lattice plan: cells
+  info->n_tiles_fwd = h->lattice.present ? h->lattice.nc * h->lattice.nc : h->patch_f.present ? h->patch_f.n_rounds : h->tiles_f.n_tiles;
+  info->n_tiles_bwd = h->lattice.present ? h->lattice.nc * h->lattice.nc : h->patch_b.present ? h->patch_b.n_rounds : h->tiles_b.n_tiles;
   info->max_row_nnz = h->max_row_nnz;
   info->device_bytes = h->device_bytes;
   return FEO_OK;
@@ -216,7 +243,8 @@ int feo_op_get_info(feo_handle_t h, feo_op_info* info) {
 size_t feo_workspace_bytes(feo_handle_t h, int32_t B, int32_t T) {
   if (h == nullptr || B <= 0) return 0;
   if (T < 1) T = 1;
-  return loss_partials_needed(h->n, std::max(h->tiles_f.warps, h->patch_f.warps), (int64_t)B * T);
+  return loss_partials_needed(h->n, std::max(std::max(h->tiles_f.warps, h->patch_f.warps), h->lattice.present ? lattice_fwd_warps() : 0),
+                              (int64_t)B * T);
 }
 
 int feo_transpose(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int32_t rows, int32_t cols,
@@ -353,6 +381,27 @@ int feo_debug_patch_replay(const feo_operator_desc* desc, int32_t backward, int3
   if (!P.applicable) return fail(FEO_ERR_UNSUPPORTED, "patch plan not applicable: " + P.why_not);
   if (in0 == nullptr || in1 == nullptr || out == nullptr) return FEO_OK;
   return replay_patch_plan(P, F.conv, branch, in0, in1, out);
+}
+
+int feo_debug_lattice_replay(const feo_operator_desc* desc, int32_t backward, const double* in0, const double* in1, double* out,
+                             int64_t* stats) {
+  HostCsr A, B1, B2, S;
+  if (int rc = prepare(desc, &A, &B1, &B2, &S)) return rc;
+  if (!A.present()) return fail(FEO_ERR_INVALID_ARGUMENT, "lattice replay needs A");
+  const int32_t branch = (desc->ns_precond_branch || !(B1.present() || B2.present())) ? 1 : 0;
+  LatticePlan P;
+  if (int rc = build_lattice_plan(A, B1, B2, desc->n_u, desc->idx_i, desc->idx_j, branch, &P)) return rc;
+  if (stats != nullptr) {
+    stats[0] = P.applicable ? 1 : 0;
+    stats[1] = P.n;
+    stats[2] = P.n_classes[0];
+    stats[3] = P.n_classes[1];
+    stats[4] = P.n_coef[0];
+    stats[5] = P.n_coef[1];
+  }
+  if (!P.applicable) return fail(FEO_ERR_UNSUPPORTED, "lattice plan not applicable: " + P.why_not);
+  if (in0 == nullptr || in1 == nullptr || out == nullptr) return FEO_OK;
+  return replay_lattice_plan(P, backward != 0, branch, in0, in1, out);
 }
 
 }  // extern "C"

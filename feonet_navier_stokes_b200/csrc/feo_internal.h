@@ -189,6 +189,16 @@ struct DevPatchPlan {
   uint32_t* stream = nullptr;  // 32-bit slots, rounds start on 16-byte words
 };
 
+// device side of a lattice plan (feo_lattice.h): the third-generation plan for structured P2-P1 lattices
+struct DevLatticePlan {
+  bool present = false, has_conv = false;
+  int32_t n = 0, nc = 0;
+  uint8_t* cls[2] = {nullptr, nullptr};  // [nc * nc] cell classes, forward / backward
+  int32_t n_classes[2] = {0, 0};
+  std::vector<uint8_t> exist[2];         // host copies: the class tables travel as kernel parameters
+  std::vector<float> tab[2];
+};
+
 // ---- device-side operator ---------------------------------------------------------------------
 struct DevCsr {
   int32_t* rowptr = nullptr;
@@ -209,6 +219,7 @@ struct feo_operator {
   int32_t *idx_i = nullptr, *idx_j = nullptr;
   feo::DevTilePlan tiles_f, tiles_b;
   feo::DevPatchPlan patch_f, patch_b;  // used instead of the tile plans when both are present
+  feo::DevLatticePlan lattice;         // used instead of either when present
   // dense
   float *dM = nullptr, *dMT = nullptr, *dP = nullptr;
   float *dMs = nullptr, *dMTs = nullptr, *dPs = nullptr;  // the same matrices pre-split into TF32 hi/lo operand tiles (feo_dense_tc.cu)

@@ -1,0 +1,565 @@
+// sm_100a kernels of the fused sparse residual, lattice formulation (plan: feo_lattice.h, feo_lattice_plan.cpp; the cell
+// bodies are generated: tools/gen_lattice_stencil.py -> feo_lattice_gen.inc).
+//
+// One persistent CTA per SM sweeps STRIPS of W cells upwards through the lattice, one slab of 64 samples at a time:
+//   * shared memory = a ring of R lattice rows; a row slot holds the contiguous dof run of the strip's nodes (2W + 3 lattice
+//     columns: the strip and its halo) as 256-byte lines (64 samples of one dof); backward: the r run and the alpha run;
+//   * the producer warp stages the two lattice rows that enter the 5-row window of the next step(s) with ONE 2-D TMA box per
+//     row and source array (cp.async.bulk.tensor, completion on the step's `full` mbarrier); rows above / below the lattice
+//     are fetched from out-of-bounds coordinates, i.e. zero filled;
+//   * consumer warp w evaluates cell (strip * W + w, cj) for the 64 samples, 2 samples per lane: 45 (forward) / 83 (backward)
+//     conflict-free LDS.64 gathers feed all 9 rows / columns of the cell; every accumulator lives in registers; the
+//     arithmetic is packed fp32 (FFMA2) whose coefficient operand comes straight from the constant bank (kernel parameters:
+//     one table per cell class, class 0 -- the interior -- at compile-time offsets, the boundary classes indexed);
+//   * row-/column-owned with a fixed summation order: no atomics, bit-reproducible on a given device.
+// Work = (strip, slab, cj) steps, cut into gridDim.x equal contiguous chunks.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "feo_lattice.h"
+#include "feo_lattice_gen.inc"
+
+namespace feo {
+int make_box_map(const float* base, int64_t ldb, int32_t n, int32_t box_rows, CUtensorMap* out);  // feo_tiled.cu
+int sm_count(int* out);                                                                            // feo_tiled.cu
+
+namespace {
+
+typedef unsigned long long u64;
+constexpr uint32_t kSmemMax = 232448;
+constexpr int kStagesMax = 4;
+
+struct LatMaps {
+  CUtensorMap m[2][2];  // [source array][row parity]: box = 64 samples x (5W + 8 | 4W + 6) dofs
+};
+
+template <int NCOEF>
+struct LatParams {
+  const uint8_t* cls;      // [nc * nc]
+  const float* fT;         // forward: load vectors
+  float* outT;             // forward: rT (may be NULL) ; backward: gradT
+  float* partials;         // forward: one loss partial per (CTA, consumer warp)
+  const float* grad_loss;  // backward: upstream gradient (NULL = 1)
+  int64_t ldb;
+  int32_t B, n_slabs;
+  int32_t n, nc, N;        // mesh cells per side, cell origins per side, dofs
+  int32_t W, n_strips;     // consumer warps = cells per strip, strips
+  int32_t total_steps;     // n_strips * n_slabs * nc
+  int32_t R, K;            // ring rows (7 or 9), barrier stages = prefetch distance in steps ((R - 3) / 2)
+  int32_t he, ho;          // lines of an even / odd lattice row run
+  uint32_t slot_bytes, bar_off;
+  int32_t debug;           // FEO_DEBUG_MODE: 1 = staging only, 2 = compute only (results are garbage)
+  int32_t precond;         // forward: 1 -> r = lhs - (f - c), 0 -> r = lhs - (-f + c)
+  float esign;             // backward: +1 precond branch, -1 otherwise
+  uint8_t exist[kLatMaxClasses];
+  float tab[kLatMaxClasses * NCOEF];
+};
+
+// ---- PTX helpers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_box(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ u64 lds64(uint32_t a) {
+  u64 v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ u64 pk(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk(u64 v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+// acc += c * x on two packed fp32 lanes, c a scalar (a constant-bank / uniform-register operand of FFMA2)
+__device__ __forceinline__ void fmac(u64& acc, float c, u64 x) { acc = fma2(pk(c, c), x, acc); }
+__device__ __forceinline__ float2 ldg2_stream(const float* p) {
+  float2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// residual from LHS sum, load vector and convection in the reference's operation order:
+// precond branch  r = LHS - (F - c) ; else  r = LHS - (-F + c)   (FEONet_steady_Navier-Stokes/train_FEONet.py:324-330, :356)
+__device__ __forceinline__ float resid1(float lhs, float f, float c, bool precond) {
+  return precond ? __fsub_rn(lhs, __fsub_rn(f, c)) : __fsub_rn(lhs, __fadd_rn(-f, c));
+}
+// c = u_i*Bu1 + u_j*Bu2 as two rounded products and one rounded add (train_FEONet.py:317-322)
+__device__ __forceinline__ float conv1(float d1, float s1, float d2, float s2) { return __fadd_rn(__fmul_rn(d1, s1), __fmul_rn(d2, s2)); }
+
+// ---- the walk over a CTA's chunk of (column, cj) steps; column = (strip, slab) ---------------------------
+struct Walk {
+  int32_t s, s_end, strip, slab, cj, local;
+  int32_t st, ph;  // barrier stage of the step (step index mod K) and its phase parity
+  template <typename P>
+  __device__ __forceinline__ void start(const P& p) {
+    s = (int32_t)(((int64_t)blockIdx.x * p.total_steps) / (int64_t)gridDim.x);
+    s_end = (int32_t)(((int64_t)(blockIdx.x + 1) * p.total_steps) / (int64_t)gridDim.x);
+    const int32_t col = s / p.nc;
+    cj = s - col * p.nc;
+    strip = col / p.n_slabs;
+    slab = col - strip * p.n_slabs;
+    local = 0;
+    st = 0;
+    ph = 0;
+  }
+  __device__ __forceinline__ bool done() const { return s >= s_end; }
+  template <typename P>
+  __device__ __forceinline__ void next(const P& p) {
+    ++s;
+    ++cj;
+    ++local;
+    if (cj == p.nc) {
+      cj = 0;
+      local = 0;
+      if (++slab == p.n_slabs) {
+        slab = 0;
+        ++strip;
+      }
+    }
+    if (++st == p.K) {
+      st = 0;
+      ph ^= 1;
+    }
+  }
+};
+
+// dof of u1 at node (0, y) in the interleaved lattice numbering; rows off the lattice map past the end (TMA zero fill)
+template <typename P>
+__device__ __forceinline__ int32_t row_dof0(const P& p, int y) {
+  if (y < 0 || y > 2 * p.n) return p.N + 4096;
+  return (y >> 1) * (9 * p.n + 5) + (y & 1) * (5 * p.n + 3);
+}
+
+// ---- producer warp ---------------------------------------------------------------------------------------
+template <bool BWD, typename P>
+__device__ __forceinline__ void produce(const LatMaps& maps, const P& p, uint32_t sb, uint32_t full, uint32_t done, int lane) {
+  if (p.debug == 2) return;
+  Walk w;
+  w.start(p);
+  const uint32_t bytes_e = (uint32_t)p.he * kLineBytes * (BWD ? 2u : 1u), bytes_o = (uint32_t)p.ho * kLineBytes * (BWD ? 2u : 1u);
+  int32_t st_prev = 0, ph_prev = 0;
+  uint32_t slot0 = 0;  // ring slot of the window's first row = (2 * local) mod R
+  for (int32_t g = 0; !w.done(); ++g, st_prev = w.st, ph_prev = w.ph, w.next(p)) {
+    if (w.local == 0) {
+      slot0 = 0;
+      if (g > 0) mbar_wait(done + (uint32_t)st_prev * 8, (uint32_t)ph_prev);  // the new segment overwrites the whole ring
+    } else {
+      slot0 += 2;
+      if (slot0 >= (uint32_t)p.R) slot0 -= (uint32_t)p.R;
+      if (w.local >= p.K) mbar_wait(done + (uint32_t)w.st * 8, (uint32_t)w.ph ^ 1u);  // step g - K has released the two slots
+    }
+    if (lane == 0) {
+      const int32_t c0 = w.slab * kSlab, ci0 = w.strip * p.W;
+      // the segment's first step brings its whole window (rows 2cj-2 .. 2cj+2 -> slots 0..4), later steps the two new rows
+      const int first = w.local == 0 ? 0 : 3;
+      const uint32_t bar = full + (uint32_t)w.st * 8;
+      // row 2cj - 2 + i has the parity of i: rows 0..4 = three even and two odd ones, rows 3..4 = one of each
+      mbar_expect_tx(bar, first == 0 ? 3u * bytes_e + 2u * bytes_o : bytes_e + bytes_o);
+      for (int i = first; i < 5; ++i) {
+        const int y = 2 * w.cj - 2 + i, odd = i & 1;
+        uint32_t slot = slot0 + (uint32_t)i;
+        if (slot >= (uint32_t)p.R) slot -= (uint32_t)p.R;
+        const int32_t d0 = row_dof0(p, y) + (ci0 - 1) * (odd ? 4 : 5);
+        const uint32_t dst = sb + slot * p.slot_bytes;
+        tma_box(dst, &maps.m[0][odd], c0, d0, bar);
+        if (BWD) tma_box(dst + (uint32_t)p.he * kLineBytes, &maps.m[1][odd], c0, d0, bar);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---- cell bodies -------------------------------------------------------------------------------------------
+// byte offset of the line of (node dx, comp) within the row run, relative to the warp's cell (dx = -2 .. 2)
+__device__ __forceinline__ constexpr uint32_t lat_off(int dx, int dy, int comp) {
+  return (uint32_t)(lat_pos(dx + 2, dy & 1) + comp) * (uint32_t)kLineBytes;
+}
+// targets 0..3 = V (0,0), H (1,0), T (0,1), D (1,1)
+__host__ __device__ constexpr int tgt_x(int t) { return t & 1; }
+__host__ __device__ constexpr int tgt_y(int t) { return t >> 1; }
+
+#define BEGIN {
+#define END }
+#define C(i) (FAST ? p.tab[(i)] : p.tab[cbase + (i)])
+
+// forward: r = A a -/+ (F - c) for the 9 rows of a cell, loss partial
+template <bool FAST, typename P>
+__device__ __forceinline__ void fwd_cell(const P& p, const uint32_t (&Bx)[5], int cbase, uint32_t ex, int32_t dE, int32_t dO, int b0,
+                                         bool precond, float& lsum) {
+  // element offsets of the cell's rows in the dof-major arrays: V = (dE, dE + 1), P = dE + 2, H = dE + 3, T = dO, D = dO + 2
+  const bool in_ld = b0 < p.ldb, in_b = b0 < p.B;
+  const int64_t oE = (int64_t)dE * p.ldb + b0, oO = (int64_t)dO * p.ldb + b0;
+  const int64_t offs[kLatTargets] = {oE, oE + 3 * p.ldb, oO, oO + 2 * p.ldb};
+  float2 fv[kLatTargets][2], fp = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int t = 0; t < kLatTargets; ++t) fv[t][0] = fv[t][1] = make_float2(0.f, 0.f);
+  if (in_ld) {
+#pragma unroll
+    for (int t = 0; t < kLatTargets; ++t)
+      if (FAST || ((ex >> t) & 1u)) {
+        fv[t][0] = ldg2_stream(p.fT + offs[t]);
+        fv[t][1] = ldg2_stream(p.fT + offs[t] + p.ldb);
+      }
+    fp = ldg2_stream(p.fT + oE + 2 * p.ldb);
+  }
+  u64 acc[3][kLatTargets][2], sacc = 0ull;
+#pragma unroll
+  for (int m = 0; m < 3; ++m)
+#pragma unroll
+    for (int t = 0; t < kLatTargets; ++t) acc[m][t][0] = acc[m][t][1] = 0ull;
+#define LDX(v, dx, dy, comp) const u64 v = lds64(Bx[(dy) + 2] + lat_off(dx, dy, comp));
+#define FV(mat, t, i) fmac(acc[mat][t][0], C(i), xI); fmac(acc[mat][t][1], C(i), xJ);
+#define FSI(i) fmac(sacc, C(i), xI);
+#define FSJ(i) fmac(sacc, C(i), xJ);
+#define FP(t, tc, i) fmac(acc[0][t][tc], C(i), xP);
+#define FSP(i) fmac(sacc, C(i), xP);
+  FEO_LAT_FWD_BODY
+#undef LDX
+#undef FV
+#undef FSI
+#undef FSJ
+#undef FP
+#undef FSP
+#pragma unroll
+  for (int t = 0; t < kLatTargets; ++t) {
+    if (!FAST && !((ex >> t) & 1u)) continue;
+    float d1[2], d2[2];
+    unpk(lds64(Bx[tgt_y(t) + 2] + lat_off(tgt_x(t), tgt_y(t), 0)), d1[0], d1[1]);
+    unpk(lds64(Bx[tgt_y(t) + 2] + lat_off(tgt_x(t), tgt_y(t), 1)), d2[0], d2[1]);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float a[2], u[2], v[2];
+      unpk(acc[0][t][c], a[0], a[1]);
+      unpk(acc[1][t][c], u[0], u[1]);
+      unpk(acc[2][t][c], v[0], v[1]);
+      float2 r;
+      r.x = resid1(a[0], fv[t][c].x, conv1(d1[0], u[0], d2[0], v[0]), precond);
+      r.y = resid1(a[1], fv[t][c].y, conv1(d1[1], u[1], d2[1], v[1]), precond);
+      if (in_b) lsum = fmaf(r.x, r.x, lsum);
+      if (b0 + 1 < p.B) lsum = fmaf(r.y, r.y, lsum);
+      if (p.outT != nullptr && in_b) *reinterpret_cast<float2*>(p.outT + offs[t] + (c ? p.ldb : 0)) = r;
+    }
+  }
+  {
+    float a[2];
+    unpk(sacc, a[0], a[1]);
+    float2 r;
+    r.x = resid1(a[0], fp.x, 0.f, precond);
+    r.y = resid1(a[1], fp.y, 0.f, precond);
+    if (in_b) lsum = fmaf(r.x, r.x, lsum);
+    if (b0 + 1 < p.B) lsum = fmaf(r.y, r.y, lsum);
+    if (p.outT != nullptr && in_b) *reinterpret_cast<float2*>(p.outT + oE + 2 * p.ldb) = r;
+  }
+}
+
+// backward: grad = 2 g [A^T r + s (B1^T (d1 r) + B2^T (d2 r) + E-term)] for the 9 columns of a cell
+template <bool FAST, typename P>
+__device__ __forceinline__ void bwd_cell(const P& p, const uint32_t (&Br)[5], const uint32_t (&Ba)[5], int cbase, uint32_t ex, int32_t dE,
+                                         int32_t dO, int b0, float g2) {
+  const int64_t oE = (int64_t)dE * p.ldb + b0, oO = (int64_t)dO * p.ldb + b0;
+  const int64_t offs[kLatTargets] = {oE, oE + 3 * p.ldb, oO, oO + 2 * p.ldb};
+  u64 g[kLatTargets][2], bu[3][kLatTargets][2], sacc = 0ull;  // bu[1] = Bu1, bu[2] = Bu2 of the own rows ([0] unused)
+#pragma unroll
+  for (int t = 0; t < kLatTargets; ++t) {
+    g[t][0] = g[t][1] = 0ull;
+    bu[1][t][0] = bu[1][t][1] = bu[2][t][0] = bu[2][t][1] = 0ull;
+  }
+#define LDR(v, dx, dy, comp) const u64 v = lds64(Br[(dy) + 2] + lat_off(dx, dy, comp));
+#define LDA(v, dx, dy, comp) const u64 v = lds64(Ba[(dy) + 2] + lat_off(dx, dy, comp));
+#define BTA(t, ia) fmac(g[t][0], C(ia), rI); fmac(g[t][1], C(ia), rJ);
+#define BTB(t, ia, ib1, ib2)                                        \
+  {                                                                 \
+    u64 T = 0ull;                                                   \
+    if ((ia) >= 0) {                                                \
+      const float ca = C((ia) >= 0 ? (ia) : 0);                     \
+      T = pk(ca, ca);                                               \
+    }                                                               \
+    if ((ib1) >= 0) fmac(T, C((ib1) >= 0 ? (ib1) : 0), d1);         \
+    if ((ib2) >= 0) fmac(T, C((ib2) >= 0 ? (ib2) : 0), d2);         \
+    g[t][0] = fma2(rI, T, g[t][0]);                                 \
+    g[t][1] = fma2(rJ, T, g[t][1]);                                 \
+  }
+#define BF(mat, t, i) fmac(bu[mat][t][0], C(i), d1); fmac(bu[mat][t][1], C(i), d2);
+#define BSI(i) fmac(sacc, C(i), rI);
+#define BSJ(i) fmac(sacc, C(i), rJ);
+#define BP(t, tc, i) fmac(g[t][tc], C(i), rP);
+#define BSP(i) fmac(sacc, C(i), rP);
+  FEO_LAT_BWD_BODY
+#undef LDR
+#undef LDA
+#undef BTA
+#undef BTB
+#undef BF
+#undef BSI
+#undef BSJ
+#undef BP
+#undef BSP
+  const bool st = b0 < p.B;
+#pragma unroll
+  for (int t = 0; t < kLatTargets; ++t) {
+    if (!FAST && !((ex >> t) & 1u)) continue;
+    float rI[2], rJ[2], gI[2], gJ[2], s1i[2], s1j[2], s2i[2], s2j[2];
+    unpk(lds64(Br[tgt_y(t) + 2] + lat_off(tgt_x(t), tgt_y(t), 0)), rI[0], rI[1]);
+    unpk(lds64(Br[tgt_y(t) + 2] + lat_off(tgt_x(t), tgt_y(t), 1)), rJ[0], rJ[1]);
+    unpk(g[t][0], gI[0], gI[1]);
+    unpk(g[t][1], gJ[0], gJ[1]);
+    unpk(bu[1][t][0], s1i[0], s1i[1]);
+    unpk(bu[1][t][1], s1j[0], s1j[1]);
+    unpk(bu[2][t][0], s2i[0], s2i[1]);
+    unpk(bu[2][t][1], s2j[0], s2j[1]);
+    float2 oI, oJ;
+    oI.x = fmaf(p.esign, fmaf(s1j[0], rJ[0], s1i[0] * rI[0]), gI[0]) * g2;
+    oI.y = fmaf(p.esign, fmaf(s1j[1], rJ[1], s1i[1] * rI[1]), gI[1]) * g2;
+    oJ.x = fmaf(p.esign, fmaf(s2j[0], rJ[0], s2i[0] * rI[0]), gJ[0]) * g2;
+    oJ.y = fmaf(p.esign, fmaf(s2j[1], rJ[1], s2i[1] * rI[1]), gJ[1]) * g2;
+    if (st) {
+      *reinterpret_cast<float2*>(p.outT + offs[t]) = oI;
+      *reinterpret_cast<float2*>(p.outT + offs[t] + p.ldb) = oJ;
+    }
+  }
+  if (st) {
+    float a[2];
+    unpk(sacc, a[0], a[1]);
+    *reinterpret_cast<float2*>(p.outT + oE + 2 * p.ldb) = make_float2(a[0] * g2, a[1] * g2);
+  }
+}
+#undef C
+#undef BEGIN
+#undef END
+
+// ---- the kernel ---------------------------------------------------------------------------------------------
+template <bool BWD, int NT>
+__global__ void __launch_bounds__(NT, 1)
+    residual_lattice_kernel(const __grid_constant__ LatMaps maps, const __grid_constant__ LatParams<BWD ? FEO_LAT_BWD_NCOEF : FEO_LAT_FWD_NCOEF> p) {
+  constexpr int NCOEF = BWD ? FEO_LAT_BWD_NCOEF : FEO_LAT_FWD_NCOEF;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t sb = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t full = sb + p.bar_off, done = full + kStagesMax * 8;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < p.K; ++k) {
+      mbar_init(full + k * 8, 1);
+      mbar_init(done + k * 8, (uint32_t)p.W);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == p.W) {
+    produce<BWD>(maps, p, sb, full, done, lane);
+    return;
+  }
+  if (warp > p.W) return;
+  const bool precond = p.precond != 0;
+  float g2 = 2.0f;
+  if (BWD && p.grad_loss != nullptr) g2 = 2.0f * __ldg(p.grad_loss);
+  double dsum = 0.0;
+  const uint32_t lane_base = sb + (uint32_t)lane * 8u;
+  const uint32_t cell_off[2] = {(uint32_t)warp * 5u * kLineBytes, (uint32_t)warp * 4u * kLineBytes};
+  const uint32_t a_off = (uint32_t)p.he * kLineBytes;
+  Walk w;
+  w.start(p);
+  uint32_t cls_next = 0, slot0 = 0;
+  if (!w.done() && w.strip * p.W + warp < p.nc) cls_next = __ldg(p.cls + (size_t)w.cj * p.nc + w.strip * p.W + warp);
+  while (!w.done()) {
+    const int32_t ci = w.strip * p.W + warp, cj = w.cj, slab = w.slab;
+    const uint32_t cls = cls_next, st = (uint32_t)w.st, ph = (uint32_t)w.ph;
+    if (w.local == 0) {
+      slot0 = 0;
+    } else {
+      slot0 += 2;
+      if (slot0 >= (uint32_t)p.R) slot0 -= (uint32_t)p.R;
+    }
+    w.next(p);
+    if (!w.done()) {  // class of this warp's next cell, one step ahead
+      const int32_t ci_n = w.strip * p.W + warp;
+      if (ci_n < p.nc) cls_next = __ldg(p.cls + (size_t)w.cj * p.nc + ci_n);
+    }
+    if (p.debug != 2) mbar_wait(full + st * 8, ph);
+    if (p.debug != 1 && ci < p.nc) {
+      uint32_t Bx[5], Ba[5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        uint32_t slot = slot0 + (uint32_t)i;
+        if (slot >= (uint32_t)p.R) slot -= (uint32_t)p.R;
+        Bx[i] = lane_base + slot * p.slot_bytes + cell_off[i & 1];
+        Ba[i] = Bx[i] + a_off;
+      }
+      const int32_t dE = cj * (9 * p.n + 5) + 5 * ci, dO = cj * (9 * p.n + 5) + (5 * p.n + 3) + 4 * ci;
+      const int b0 = slab * kSlab + lane * 2;
+      if (!BWD) {
+        float lsum = 0.f;
+        if (cls == 0)
+          fwd_cell<true>(p, Bx, 0, 15u, dE, dO, b0, precond, lsum);
+        else
+          fwd_cell<false>(p, Bx, (int)cls * NCOEF, p.exist[cls], dE, dO, b0, precond, lsum);
+        dsum += (double)lsum;
+      } else {
+        if (cls == 0)
+          bwd_cell<true>(p, Bx, Ba, 0, 15u, dE, dO, b0, g2);
+        else
+          bwd_cell<false>(p, Bx, Ba, (int)cls * NCOEF, p.exist[cls], dE, dO, b0, g2);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(done + st * 8);
+  }
+  if (!BWD) {
+    dsum = warp_sum(dsum);
+    if (lane == 0) p.partials[(size_t)blockIdx.x * p.W + warp] = (float)dsum;
+  }
+}
+
+int check_layout(const void* ptr, int64_t ld, int32_t B, const char* what) {
+  if (ptr == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, std::string(what) + " is NULL");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0) return fail(FEO_ERR_INVALID_ARGUMENT, std::string(what) + " not 16-byte aligned");
+  if (ld % 4 != 0 || ld < ((B + 3) / 4) * 4)
+    return fail(FEO_ERR_INVALID_ARGUMENT, std::string(what) + ": ldb must be a multiple of 4 and >= ceil4(B)");
+  return FEO_OK;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* s = std::getenv(name);
+  return s != nullptr ? atoi(s) : dflt;
+}
+
+// strip width: as many consumer warps as the register file / the ring allow, preferring widths that fill the last strip
+int pick_width(int nc, int w_max) {
+  int best = std::min(w_max, nc), best_waste = 1 << 30;
+  for (int w = std::min(w_max, nc); w >= std::max(1, std::min(w_max, nc) - 3); --w) {
+    const int waste = (nc + w - 1) / w * w - nc;
+    if (waste * 100 < best_waste * 100 - 2 * nc) {  // accept a narrower strip only if it saves > 2 % of the cells
+      best = w;
+      best_waste = waste;
+    }
+  }
+  return best;
+}
+
+template <bool BWD>
+int launch(const feo_operator* op, const DevLatticePlan& L, const float* src0, const float* src1, const float* fT, float* outT,
+           float* partials, size_t partial_cap, const float* grad_loss, int64_t ldb, int32_t B, int* n_partials, cudaStream_t st) {
+  constexpr int NCOEF = BWD ? FEO_LAT_BWD_NCOEF : FEO_LAT_FWD_NCOEF;
+  constexpr int NT = BWD ? 384 : 512;
+  const int dir = BWD ? 1 : 0;
+  LatParams<NCOEF> p;  // 20-30 KB of kernel parameters (the class tables)
+  p.cls = L.cls[dir];
+  p.fT = fT;
+  p.outT = outT;
+  p.partials = partials;
+  p.grad_loss = grad_loss;
+  p.ldb = ldb;
+  p.B = B;
+  p.n_slabs = (B + kSlab - 1) / kSlab;
+  p.n = L.n;
+  p.nc = L.nc;
+  p.N = op->n;
+  const int w_max = BWD ? 11 : 15;
+  p.W = env_int(BWD ? "FEO_LAT_W_BWD" : "FEO_LAT_W_FWD", pick_width(L.nc, w_max));
+  if (p.W < 1 || p.W > w_max) return fail(FEO_ERR_INVALID_ARGUMENT, "lattice kernel: strip width out of range");
+  p.n_strips = (L.nc + p.W - 1) / p.W;
+  const int64_t total = (int64_t)p.n_strips * p.n_slabs * L.nc;
+  if (total >= ((int64_t)1 << 31)) return fail(FEO_ERR_UNSUPPORTED, "too many work items");
+  p.total_steps = (int32_t)total;
+  p.he = 5 * p.W + 8;
+  p.ho = 4 * p.W + 6;
+  p.slot_bytes = (uint32_t)p.he * kLineBytes * (BWD ? 2u : 1u);
+  p.R = env_int(BWD ? "FEO_LAT_R_BWD" : "FEO_LAT_R_FWD", BWD ? 7 : 9);
+  if (p.R != 7 && p.R != 9 && p.R != 11) return fail(FEO_ERR_INVALID_ARGUMENT, "lattice kernel: ring rows must be 7, 9 or 11");
+  while (p.R > 7 && (uint64_t)p.R * p.slot_bytes + 64 > kSmemMax) p.R -= 2;
+  p.K = (p.R - 3) / 2;
+  p.bar_off = (uint32_t)p.R * p.slot_bytes;
+  const uint32_t smem = p.bar_off + 2 * kStagesMax * 8;
+  if (smem > kSmemMax) return fail(FEO_ERR_INVALID_ARGUMENT, "lattice kernel: the row ring does not fit shared memory");
+  p.debug = env_int("FEO_DEBUG_MODE", 0);
+  p.precond = op->ns_branch;
+  p.esign = op->ns_branch ? 1.0f : -1.0f;
+  if (L.n_classes[dir] > kLatMaxClasses || L.tab[dir].size() != (size_t)L.n_classes[dir] * NCOEF)
+    return fail(FEO_ERR_INVALID_ARGUMENT, "lattice plan: class tables do not match the kernels");
+  std::fill(p.exist, p.exist + kLatMaxClasses, (uint8_t)0);
+  std::copy(L.exist[dir].begin(), L.exist[dir].end(), p.exist);
+  std::copy(L.tab[dir].begin(), L.tab[dir].end(), p.tab);
+  int sms = 1;
+  if (int rc = sm_count(&sms)) return rc;
+  const int grid = (int)std::min<int64_t>(total, sms);
+  if (n_partials != nullptr) {
+    *n_partials = grid * p.W;
+    if ((size_t)*n_partials > partial_cap) return fail(FEO_ERR_INVALID_ARGUMENT, "workspace too small");
+  }
+  LatMaps maps;
+  for (int a = 0; a < 2; ++a) {
+    const float* base = a == 0 ? src0 : src1;
+    if (int rc = make_box_map(base, ldb, op->n, p.he, &maps.m[a][0])) return rc;
+    if (int rc = make_box_map(base, ldb, op->n, p.ho, &maps.m[a][1])) return rc;
+  }
+  auto kern = residual_lattice_kernel<BWD, NT>;
+  FEO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)grid, (unsigned)(p.W + 1) * 32, smem, st>>>(maps, p);
+  FEO_CUDA_CHECK(cudaGetLastError());
+  return FEO_OK;
+}
+
+}  // namespace
+
+int lattice_fwd_warps() { return 15; }
+
+int launch_lattice_fwd(const feo_operator* op, const DevLatticePlan& L, const float* alphaT, const float* fT, int64_t ldb, int32_t B,
+                       float* loss_out, float* rT, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (B <= 0) return fail(FEO_ERR_INVALID_ARGUMENT, "B must be positive");
+  if (int rc = check_layout(alphaT, ldb, B, "alphaT")) return rc;
+  if (int rc = check_layout(fT, ldb, B, "fT")) return rc;
+  if (rT != nullptr)
+    if (int rc = check_layout(rT, ldb, B, "rT")) return rc;
+  if (loss_out == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, "loss_out is NULL");
+  if (ws == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, "workspace too small");
+  int n_partials = 0;
+  if (int rc = launch<false>(op, L, alphaT, alphaT, fT, rT, (float*)ws, ws_bytes / sizeof(float), nullptr, ldb, B, &n_partials, st)) return rc;
+  return finalize_loss((float*)ws, n_partials, 1.0f, loss_out, st);
+}
+
+int launch_lattice_bwd(const feo_operator* op, const DevLatticePlan& L, const float* alphaT, const float* rT, const float* grad_loss,
+                       float* gradT, int64_t ldb, int32_t B, cudaStream_t st) {
+  if (B <= 0) return fail(FEO_ERR_INVALID_ARGUMENT, "B must be positive");
+  if (int rc = check_layout(rT, ldb, B, "rT")) return rc;
+  if (int rc = check_layout(gradT, ldb, B, "gradT")) return rc;
+  const float* a = L.has_conv ? alphaT : rT;  // linear operators: the alpha tables are all zero, any finite source will do
+  if (int rc = check_layout(a, ldb, B, "alphaT")) return rc;
+  return launch<true>(op, L, rT, a, nullptr, gradT, nullptr, 0, grad_loss, ldb, B, nullptr, st);
+}
+
+}  // namespace feo

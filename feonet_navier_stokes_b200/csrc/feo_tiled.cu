@@ -27,6 +27,7 @@
 
 #include "feo_internal.h"
 #include "feo_patch.h"
+#include "feo_lattice.h"
 
 namespace feo {
 namespace {
@@ -1020,6 +1021,24 @@ int sm_count(int* out) {
   *out = cached[dev];
   return FEO_OK;
 }
+// one map over the dof-major array base[n][ldb] with a box of kSlab samples x box_rows dofs (lattice plan: one box per lattice row)
+int make_box_map(const float* base, int64_t ldb, int32_t n, int32_t box_rows, CUtensorMap* out) {
+  EncodeTiledFn enc;
+  if (int rc = get_encode(&enc)) return rc;
+  int dev = 0;
+  FEO_CUDA_CHECK(cudaGetDevice(&dev));
+  FEO_CUDA_CHECK(cudaSetDevice(dev));
+  if (box_rows < 1 || box_rows > 256) return fail(FEO_ERR_INVALID_ARGUMENT, "TMA box height out of range");
+  const cuuint64_t dims[2] = {(cuuint64_t)ldb, (cuuint64_t)n};
+  const cuuint64_t strides[1] = {(cuuint64_t)ldb * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)kSlab, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FEO_ERR_CUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+  return FEO_OK;
+}
 namespace {
 
 // persistent launch: one CTA per SM (or per unit when there are fewer units), `warps` consumer warps + 1 producer warp
@@ -1041,6 +1060,7 @@ size_t fused_partials_needed(int32_t warps) { return (size_t)1024 * (size_t)(war
 
 int launch_residual_fwd(const feo_operator* op, const float* alphaT, const float* fT, int64_t ldb, int32_t B,
                         float* loss_out, float* rT, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (op->lattice.present) return launch_lattice_fwd(op, op->lattice, alphaT, fT, ldb, B, loss_out, rT, ws, ws_bytes, st);
   if (op->patch_f.present) return launch_patch_fwd(op, op->patch_f, alphaT, fT, ldb, B, loss_out, rT, ws, ws_bytes, st);
   if (B <= 0) return fail(FEO_ERR_INVALID_ARGUMENT, "B must be positive");
   if (int rc = check_layout(alphaT, ldb, B, "alphaT")) return rc;
@@ -1070,6 +1090,7 @@ int launch_residual_fwd(const feo_operator* op, const float* alphaT, const float
 
 int launch_residual_bwd(const feo_operator* op, const float* alphaT, const float* rT, const float* grad_loss,
                         float* gradT, int64_t ldb, int32_t B, cudaStream_t st) {
+  if (op->lattice.present) return launch_lattice_bwd(op, op->lattice, alphaT, rT, grad_loss, gradT, ldb, B, st);
   if (op->patch_b.present) return launch_patch_bwd(op, op->patch_b, alphaT, rT, grad_loss, gradT, ldb, B, st);
   if (B <= 0) return fail(FEO_ERR_INVALID_ARGUMENT, "B must be positive");
   if (int rc = check_layout(rT, ldb, B, "rT")) return rc;

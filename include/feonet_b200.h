@@ -190,6 +190,15 @@ int feo_debug_tile_replay(const feo_operator_desc* desc, int32_t backward, int32
 int feo_debug_patch_replay(const feo_operator_desc* desc, int32_t backward, int32_t warps, int32_t pool_lines,
                            int32_t seg_rounds, const double* in0, const double* in1, double* out, int64_t* stats);
 
+/* Test hook (HOST ONLY): builds the LATTICE plan of the fused residual kernels (third-generation plan for structured
+ * right-diagonal P2-P1 meshes in lattice order: one warp evaluates a cell -- a vertex node, its three edge nodes and the
+ * vertex's pressure dof -- from one gather per window line, coefficients per cell class as kernel parameters) and replays
+ * the generated cell bodies over the class tables in fp64 for one sample.  Arguments as feo_debug_tile_replay.
+ * Returns FEO_ERR_UNSUPPORTED when the operator is not such a lattice (the tile plan is used then).
+ * stats[0..5] = {applicable, n (cells per side), classes forward, classes backward, coefficients forward, coefficients backward}. */
+int feo_debug_lattice_replay(const feo_operator_desc* desc, int32_t backward, const double* in0, const double* in1,
+                             double* out, int64_t* stats);
+
 /* Test hook (HOST ONLY): splits a dense [n,n] row-major operator into the TF32 hi/lo operand tiles of the
  * tensor-core apply (feo_dense_apply) and replays them as the kernel reads them -- per 128-row tile and 16-column
  * k-block, K-major core matrices -- for one vector x: out_hi = sum hi*x, out_lo = sum lo*x in fp64, so that

@@ -142,3 +142,69 @@ def test_dense_split_tiles_replay(n, transposed):
     # statistics-only call and argument errors
     assert lib.feo_debug_dense_split_replay(D.ctypes.data_as(L.f32p), n, 0, None, None, None) == size
     assert lib.feo_debug_dense_split_replay(None, n, 0, None, None, None) < 0
+
+
+def _lattice_replay(lib, desc, backward, in0, in1, n):
+    out = np.full(n, np.nan)
+    stats = (C.c_int64 * 8)()
+    rc = lib.feo_debug_lattice_replay(C.byref(desc), int(backward), in0.ctypes.data_as(L.f64p), in1.ctypes.data_as(L.f64p),
+                                      out.ctypes.data_as(L.f64p), stats)
+    return rc, out, list(stats)
+
+
+@pytest.mark.parametrize("n,branch,variant", [(2, 1, "steady_ns"), (3, 0, "steady_ns"), (6, 1, "steady_ns"), (9, 0, "steady_ns"),
+                                              (5, 1, "stokes_square")])
+def test_lattice_replay_matches_oracle(n, branch, variant):
+    """Lattice plan (feo_lattice.h): the class tables filled from the CSR and the GENERATED cell bodies (the same macro lists
+    the CUDA kernels compile), run in fp64 on the host, reproduce the oracle's residual and gradient -- interior, edge and
+    corner cells, identity Dirichlet rows, both sign branches, and the linear Stokes operator (no B1 / B2)."""
+    lib = L.load_library()
+    op = config_operators(variant, n, ordering="interleaved")
+    has_b = op.B1 is not None
+    desc, keep = build_desc(op.N, op.A, op.B1, op.B2, None, op.idx_u1, op.idx_u2, bool(branch))
+    rng = np.random.default_rng(100 + n)
+    alpha = rng.standard_normal(op.N)
+    f = rng.standard_normal(op.N)
+    A32 = op.A.astype(np.float32).astype(np.float64)
+    if has_b:
+        B132, B232 = (K.astype(np.float32).astype(np.float64) for K in (op.B1, op.B2))
+        lo, go, ro = orc.ns_loss_and_grad(alpha[None], f[None], A32, B132, B232, op.idx_u1, op.idx_u2, bool(branch), dtype=np.float64)
+        ro, go = ro[0], go[0]
+    else:
+        ro = A32 @ alpha - f
+        go = 2.0 * (A32.T @ ro)
+    rc, r, st = _lattice_replay(lib, desc, False, alpha, f, op.N)
+    assert rc == 0 and st[0] == 1 and st[1] == n, (rc, st, lib.feo_last_error_string())
+    assert st[2] <= 9 and st[3] <= 32
+    assert np.allclose(r, ro, rtol=1e-11, atol=1e-12)
+    rc, g, _ = _lattice_replay(lib, desc, True, ro, alpha, op.N)
+    assert rc == 0
+    assert np.allclose(2.0 * g, go, rtol=1e-10, atol=1e-11)
+
+
+def test_lattice_plan_rejects_what_it_does_not_model():
+    """Blocked dof order, shuffled (I, J) pairings, an unstructured mesh and a perturbed entry outside the stencil are not
+    lattices: the planner says so (the tile plan is used for them), it never mis-evaluates."""
+    lib = L.load_library()
+    x = np.zeros(1)
+
+    def applicable(op, idx_i=None, idx_j=None, A=None):
+        desc, keep = build_desc(op.N, op.A if A is None else A, op.B1, op.B2, None, op.idx_u1 if idx_i is None else idx_i,
+                                op.idx_u2 if idx_j is None else idx_j, True)
+        stats = (C.c_int64 * 8)()
+        rc = lib.feo_debug_lattice_replay(C.byref(desc), 0, None, None, None, stats)
+        return rc == 0 and stats[0] == 1
+
+    good = config_operators("steady_ns", 4, ordering="interleaved")
+    assert applicable(good)
+    assert not applicable(config_operators("steady_ns", 4, ordering="blocked"))
+    rng = np.random.default_rng(3)
+    assert not applicable(good, idx_j=np.asarray(good.idx_u2)[rng.permutation(len(good.idx_u2))])
+    assert not applicable(config_operators("hole", None, ordering="interleaved"))
+    A = good.A.tolil(copy=True)
+    A[int(good.idx_u1[0]), int(good.idx_u1[-1])] = 0.5  # couples two far-away nodes
+    assert not applicable(good, A=A.tocsr())
+    A = good.A.tolil(copy=True)
+    k = len(good.idx_u1) // 2
+    A[int(good.idx_u1[k]), int(good.idx_u2[k])] = 0.25  # cross-component entry
+    assert not applicable(good, A=A.tocsr())
