@@ -132,7 +132,7 @@ int feo_op_create(const feo_operator_desc* desc, feo_handle_t* out) {
           D.n_classes[dir] = lp.n_classes[dir];
           D.exist[dir] = lp.exist[dir];
           D.tab[dir] = lp.tab[dir];
-          if ((rc = upload(op, lp.cls[dir], &D.cls[dir]))) return bail(rc);
+          std::memcpy(D.cat_cls[dir], lp.cat_cls[dir], 25);
         }
         D.present = true;
         op->has_conv = lp.has_conv;

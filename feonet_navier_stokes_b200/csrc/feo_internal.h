@@ -193,7 +193,7 @@ struct DevPatchPlan {
 struct DevLatticePlan {
   bool present = false, has_conv = false;
   int32_t n = 0, nc = 0;
-  uint8_t* cls[2] = {nullptr, nullptr};  // [nc * nc] cell classes, forward / backward
+  uint8_t cat_cls[2][25];                // class of a cell by boundary-layer category (feo_lattice.h), forward / backward
   int32_t n_classes[2] = {0, 0};
   std::vector<uint8_t> exist[2];         // host copies: the class tables travel as kernel parameters
   std::vector<float> tab[2];

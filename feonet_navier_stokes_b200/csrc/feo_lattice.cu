@@ -35,11 +35,11 @@ constexpr int kStagesMax = 4;
 
 struct LatMaps {
   CUtensorMap m[2][2];  // [source array][row parity]: box = 64 samples x (5W + 8 | 4W + 6) dofs
+  CUtensorMap f[2];     // forward: load vectors, [row parity]: box = 64 samples x (5W | 4W) dofs -- the strip's own rows (L2 prefetch)
 };
 
 template <int NCOEF>
 struct LatParams {
-  const uint8_t* cls;      // [nc * nc]
   const float* fT;         // forward: load vectors
   float* outT;             // forward: rT (may be NULL) ; backward: gradT
   float* partials;         // forward: one loss partial per (CTA, consumer warp)
@@ -49,12 +49,13 @@ struct LatParams {
   int32_t n, nc, N;        // mesh cells per side, cell origins per side, dofs
   int32_t W, n_strips;     // consumer warps = cells per strip, strips
   int32_t total_steps;     // n_strips * n_slabs * nc
-  int32_t R, K;            // ring rows (7 or 9), barrier stages = prefetch distance in steps ((R - 3) / 2)
+  int32_t R, D, K;         // ring rows (7 or 9); a step's new rows reuse the slots step - D released, D = (R - 3) / 2; K = D + 1 barrier stages
   int32_t he, ho;          // lines of an even / odd lattice row run
   uint32_t slot_bytes, bar_off;
   int32_t debug;           // FEO_DEBUG_MODE: 1 = staging only, 2 = compute only (results are garbage)
   int32_t precond;         // forward: 1 -> r = lhs - (f - c), 0 -> r = lhs - (-f + c)
   float esign;             // backward: +1 precond branch, -1 otherwise
+  uint8_t cat_cls[25];     // class of a cell by the boundary-layer categories of (cj, ci): lat_cat(cj) * 5 + lat_cat(ci)
   uint8_t exist[kLatMaxClasses];
   float tab[kLatMaxClasses * NCOEF];
 };
@@ -167,6 +168,13 @@ __device__ __forceinline__ int32_t row_dof0(const P& p, int y) {
 }
 
 // ---- producer warp ---------------------------------------------------------------------------------------
+// Step g of a CTA receives its rows on full[g % K] and releases them on done[g % K].  A step's two new rows go to the ring
+// slots that step g - D released; consumers release the two oldest rows of a step EARLY (after part A of the body, see
+// fwd_cell / bwd_cell) unless the step ends a segment, and wait for the new rows LATE (before part C), so a fetch has about
+// two step times of slack with a 7-row ring.
+__device__ __forceinline__ void tma_prefetch_l2(const CUtensorMap* map, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 template <bool BWD, typename P>
 __device__ __forceinline__ void produce(const LatMaps& maps, const P& p, uint32_t sb, uint32_t full, uint32_t done, int lane) {
   if (p.debug == 2) return;
@@ -182,7 +190,15 @@ __device__ __forceinline__ void produce(const LatMaps& maps, const P& p, uint32_
     } else {
       slot0 += 2;
       if (slot0 >= (uint32_t)p.R) slot0 -= (uint32_t)p.R;
-      if (w.local >= p.K) mbar_wait(done + (uint32_t)w.st * 8, (uint32_t)w.ph ^ 1u);  // step g - K has released the two slots
+      if (w.local >= p.D) {
+        // step g - D = g + 1 - K used the stage of step g + 1 one phase earlier
+        int32_t st_n = w.st + 1, ph_n = w.ph;
+        if (st_n == p.K) {
+          st_n = 0;
+          ph_n ^= 1;
+        }
+        mbar_wait(done + (uint32_t)st_n * 8, (uint32_t)ph_n ^ 1u);
+      }
     }
     if (lane == 0) {
       const int32_t c0 = w.slab * kSlab, ci0 = w.strip * p.W;
@@ -199,6 +215,10 @@ __device__ __forceinline__ void produce(const LatMaps& maps, const P& p, uint32_
         const uint32_t dst = sb + slot * p.slot_bytes;
         tma_box(dst, &maps.m[0][odd], c0, d0, bar);
         if (BWD) tma_box(dst + (uint32_t)p.he * kLineBytes, &maps.m[1][odd], c0, d0, bar);
+      }
+      if (!BWD) {  // the load vectors of the step's own rows are wanted in its epilogue: bring them to L2 now
+        tma_prefetch_l2(&maps.f[0], c0, row_dof0(p, 2 * w.cj) + 5 * ci0);
+        tma_prefetch_l2(&maps.f[1], c0, row_dof0(p, 2 * w.cj + 1) + 4 * ci0);
       }
     }
     __syncwarp();
@@ -218,10 +238,26 @@ __host__ __device__ constexpr int tgt_y(int t) { return t >> 1; }
 #define END }
 #define C(i) (FAST ? p.tab[(i)] : p.tab[cbase + (i)])
 
+// what a consumer warp does between the parts of a cell body
+struct StepSync {
+  uint32_t full_bar, full_ph, done_bar;
+  bool wait_late;      // wait for the step's new rows before part C (else they were waited for at the start)
+  bool release_early;  // release the step's two oldest rows after part A (else at the end of the step)
+  __device__ __forceinline__ void after_a(int lane) const {
+    if (release_early) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(done_bar);
+    }
+  }
+  __device__ __forceinline__ void before_c() const {
+    if (wait_late) mbar_wait(full_bar, full_ph);
+  }
+};
+
 // forward: r = A a -/+ (F - c) for the 9 rows of a cell, loss partial
 template <bool FAST, typename P>
-__device__ __forceinline__ void fwd_cell(const P& p, const uint32_t (&Bx)[5], int cbase, uint32_t ex, int32_t dE, int32_t dO, int b0,
-                                         bool precond, float& lsum) {
+__device__ __forceinline__ void fwd_cell(const P& p, const StepSync& sy, int lane, const uint32_t (&Bx)[5], int cbase, uint32_t ex,
+                                         int32_t dE, int32_t dO, int b0, bool precond, float& lsum) {
   // element offsets of the cell's rows in the dof-major arrays: V = (dE, dE + 1), P = dE + 2, H = dE + 3, T = dO, D = dO + 2
   const bool in_ld = b0 < p.ldb, in_b = b0 < p.B;
   const int64_t oE = (int64_t)dE * p.ldb + b0, oO = (int64_t)dO * p.ldb + b0;
@@ -249,7 +285,11 @@ __device__ __forceinline__ void fwd_cell(const P& p, const uint32_t (&Bx)[5], in
 #define FSJ(i) fmac(sacc, C(i), xJ);
 #define FP(t, tc, i) fmac(acc[0][t][tc], C(i), xP);
 #define FSP(i) fmac(sacc, C(i), xP);
-  FEO_LAT_FWD_BODY
+  FEO_LAT_FWD_BODY_A
+  sy.after_a(lane);
+  FEO_LAT_FWD_BODY_B
+  sy.before_c();
+  FEO_LAT_FWD_BODY_C
 #undef LDX
 #undef FV
 #undef FSI
@@ -290,8 +330,8 @@ __device__ __forceinline__ void fwd_cell(const P& p, const uint32_t (&Bx)[5], in
 
 // backward: grad = 2 g [A^T r + s (B1^T (d1 r) + B2^T (d2 r) + E-term)] for the 9 columns of a cell
 template <bool FAST, typename P>
-__device__ __forceinline__ void bwd_cell(const P& p, const uint32_t (&Br)[5], const uint32_t (&Ba)[5], int cbase, uint32_t ex, int32_t dE,
-                                         int32_t dO, int b0, float g2) {
+__device__ __forceinline__ void bwd_cell(const P& p, const StepSync& sy, int lane, const uint32_t (&Br)[5], const uint32_t (&Ba)[5], int cbase,
+                                         uint32_t ex, int32_t dE, int32_t dO, int b0, float g2) {
   const int64_t oE = (int64_t)dE * p.ldb + b0, oO = (int64_t)dO * p.ldb + b0;
   const int64_t offs[kLatTargets] = {oE, oE + 3 * p.ldb, oO, oO + 2 * p.ldb};
   u64 g[kLatTargets][2], bu[3][kLatTargets][2], sacc = 0ull;  // bu[1] = Bu1, bu[2] = Bu2 of the own rows ([0] unused)
@@ -320,7 +360,11 @@ __device__ __forceinline__ void bwd_cell(const P& p, const uint32_t (&Br)[5], co
 #define BSJ(i) fmac(sacc, C(i), rJ);
 #define BP(t, tc, i) fmac(g[t][tc], C(i), rP);
 #define BSP(i) fmac(sacc, C(i), rP);
-  FEO_LAT_BWD_BODY
+  FEO_LAT_BWD_BODY_A
+  sy.after_a(lane);
+  FEO_LAT_BWD_BODY_B
+  sy.before_c();
+  FEO_LAT_BWD_BODY_C
 #undef LDR
 #undef LDA
 #undef BTA
@@ -394,24 +438,27 @@ __global__ void __launch_bounds__(NT, 1)
   const uint32_t a_off = (uint32_t)p.he * kLineBytes;
   Walk w;
   w.start(p);
-  uint32_t cls_next = 0, slot0 = 0;
-  if (!w.done() && w.strip * p.W + warp < p.nc) cls_next = __ldg(p.cls + (size_t)w.cj * p.nc + w.strip * p.W + warp);
+  uint32_t slot0 = 0;
   while (!w.done()) {
     const int32_t ci = w.strip * p.W + warp, cj = w.cj, slab = w.slab;
-    const uint32_t cls = cls_next, st = (uint32_t)w.st, ph = (uint32_t)w.ph;
-    if (w.local == 0) {
+    const bool first = w.local == 0;
+    StepSync sy;
+    sy.full_bar = full + (uint32_t)w.st * 8;
+    sy.full_ph = (uint32_t)w.ph;
+    sy.done_bar = done + (uint32_t)w.st * 8;
+    if (first) {
       slot0 = 0;
     } else {
       slot0 += 2;
       if (slot0 >= (uint32_t)p.R) slot0 -= (uint32_t)p.R;
     }
     w.next(p);
-    if (!w.done()) {  // class of this warp's next cell, one step ahead
-      const int32_t ci_n = w.strip * p.W + warp;
-      if (ci_n < p.nc) cls_next = __ldg(p.cls + (size_t)w.cj * p.nc + ci_n);
-    }
-    if (p.debug != 2) mbar_wait(full + st * 8, ph);
-    if (p.debug != 1 && ci < p.nc) {
+    const bool last = w.done() || w.local == 0;  // the step ends a segment: the producer may overwrite the whole ring after it
+    const bool active = p.debug != 1 && ci < p.nc;
+    sy.wait_late = p.debug != 2 && !first && active;
+    sy.release_early = !last && active;
+    if (p.debug != 2 && !sy.wait_late) mbar_wait(sy.full_bar, sy.full_ph);
+    if (active) {
       uint32_t Bx[5], Ba[5];
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
@@ -422,22 +469,25 @@ __global__ void __launch_bounds__(NT, 1)
       }
       const int32_t dE = cj * (9 * p.n + 5) + 5 * ci, dO = cj * (9 * p.n + 5) + (5 * p.n + 3) + 4 * ci;
       const int b0 = slab * kSlab + lane * 2;
+      const uint32_t cls = p.cat_cls[lat_cat(cj, p.nc) * 5 + lat_cat(ci, p.nc)];
       if (!BWD) {
         float lsum = 0.f;
         if (cls == 0)
-          fwd_cell<true>(p, Bx, 0, 15u, dE, dO, b0, precond, lsum);
+          fwd_cell<true>(p, sy, lane, Bx, 0, 15u, dE, dO, b0, precond, lsum);
         else
-          fwd_cell<false>(p, Bx, (int)cls * NCOEF, p.exist[cls], dE, dO, b0, precond, lsum);
+          fwd_cell<false>(p, sy, lane, Bx, (int)cls * NCOEF, p.exist[cls], dE, dO, b0, precond, lsum);
         dsum += (double)lsum;
       } else {
         if (cls == 0)
-          bwd_cell<true>(p, Bx, Ba, 0, 15u, dE, dO, b0, g2);
+          bwd_cell<true>(p, sy, lane, Bx, Ba, 0, 15u, dE, dO, b0, g2);
         else
-          bwd_cell<false>(p, Bx, Ba, (int)cls * NCOEF, p.exist[cls], dE, dO, b0, g2);
+          bwd_cell<false>(p, sy, lane, Bx, Ba, (int)cls * NCOEF, p.exist[cls], dE, dO, b0, g2);
       }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(done + st * 8);
+    if (!sy.release_early) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sy.done_bar);
+    }
   }
   if (!BWD) {
     dsum = warp_sum(dsum);
@@ -478,7 +528,6 @@ int launch(const feo_operator* op, const DevLatticePlan& L, const float* src0, c
   constexpr int NT = BWD ? 384 : 512;
   const int dir = BWD ? 1 : 0;
   LatParams<NCOEF> p;  // 20-30 KB of kernel parameters (the class tables)
-  p.cls = L.cls[dir];
   p.fT = fT;
   p.outT = outT;
   p.partials = partials;
@@ -500,9 +549,10 @@ int launch(const feo_operator* op, const DevLatticePlan& L, const float* src0, c
   p.ho = 4 * p.W + 6;
   p.slot_bytes = (uint32_t)p.he * kLineBytes * (BWD ? 2u : 1u);
   p.R = env_int(BWD ? "FEO_LAT_R_BWD" : "FEO_LAT_R_FWD", BWD ? 7 : 9);
-  if (p.R != 7 && p.R != 9 && p.R != 11) return fail(FEO_ERR_INVALID_ARGUMENT, "lattice kernel: ring rows must be 7, 9 or 11");
+  if (p.R != 7 && p.R != 9) return fail(FEO_ERR_INVALID_ARGUMENT, "lattice kernel: ring rows must be 7 or 9");
   while (p.R > 7 && (uint64_t)p.R * p.slot_bytes + 64 > kSmemMax) p.R -= 2;
-  p.K = (p.R - 3) / 2;
+  p.D = (p.R - 3) / 2;
+  p.K = p.D + 1;
   p.bar_off = (uint32_t)p.R * p.slot_bytes;
   const uint32_t smem = p.bar_off + 2 * kStagesMax * 8;
   if (smem > kSmemMax) return fail(FEO_ERR_INVALID_ARGUMENT, "lattice kernel: the row ring does not fit shared memory");
@@ -511,6 +561,7 @@ int launch(const feo_operator* op, const DevLatticePlan& L, const float* src0, c
   p.esign = op->ns_branch ? 1.0f : -1.0f;
   if (L.n_classes[dir] > kLatMaxClasses || L.tab[dir].size() != (size_t)L.n_classes[dir] * NCOEF)
     return fail(FEO_ERR_INVALID_ARGUMENT, "lattice plan: class tables do not match the kernels");
+  std::copy(L.cat_cls[dir], L.cat_cls[dir] + 25, p.cat_cls);
   std::fill(p.exist, p.exist + kLatMaxClasses, (uint8_t)0);
   std::copy(L.exist[dir].begin(), L.exist[dir].end(), p.exist);
   std::copy(L.tab[dir].begin(), L.tab[dir].end(), p.tab);
@@ -526,6 +577,11 @@ int launch(const feo_operator* op, const DevLatticePlan& L, const float* src0, c
     const float* base = a == 0 ? src0 : src1;
     if (int rc = make_box_map(base, ldb, op->n, p.he, &maps.m[a][0])) return rc;
     if (int rc = make_box_map(base, ldb, op->n, p.ho, &maps.m[a][1])) return rc;
+  }
+  maps.f[0] = maps.f[1] = maps.m[0][0];
+  if (!BWD) {
+    if (int rc = make_box_map(fT, ldb, op->n, 5 * p.W, &maps.f[0])) return rc;
+    if (int rc = make_box_map(fT, ldb, op->n, 4 * p.W, &maps.f[1])) return rc;
   }
   auto kern = residual_lattice_kernel<BWD, NT>;
   FEO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -35,7 +35,8 @@ struct LatticePlan {
   // per direction (0 forward, 1 backward)
   int32_t n_classes[2] = {0, 0};
   int32_t n_coef[2] = {0, 0};
-  std::vector<uint8_t> cls[2];    // [nc * nc] class of cell (ci, cj) at cj * nc + ci; class 0 = the most frequent one
+  std::vector<uint8_t> cls[2];    // [nc * nc] class of cell (ci, cj) at cj * nc + ci; class 0 = the most frequent complete one
+  uint8_t cat_cls[2][25];         // the same by boundary-layer categories: cls = cat_cls[lat_cat(cj) * 5 + lat_cat(ci)] (verified)
   std::vector<uint8_t> exist[2];  // [n_classes] bit t: target node t exists (bit 0 is always set, the pressure dof exists with V)
   std::vector<float> tab[2];      // [n_classes][n_coef]
   int64_t real_entries = 0;
@@ -56,6 +57,10 @@ int lattice_fwd_warps();  // consumer warps of the forward kernel (loss partials
 
 // lattice geometry shared by the planner, the replay and the kernels: position (in lines) of node x within the staged run
 // of a lattice row; even rows hold (u1, u2, p) at even x and (u1, u2) at odd x, odd rows (u1, u2) everywhere
+// boundary-layer category of a cell index: 0, 1 = the first two, 3, 4 = the last two, 2 = everything between.  A cell's class
+// depends on (lat_cat(cj), lat_cat(ci)) only: boundary conditions change the rows of boundary dofs, which reach two layers
+// of cells through the transposed (backward) stencils.
+__host__ __device__ constexpr int lat_cat(int i, int nc) { return i < 2 ? i : (i >= nc - 2 ? 4 - (nc - 1 - i) : 2); }
 __host__ __device__ constexpr int lat_pos(int x, int odd_row) { return odd_row ? 2 * x : (x >> 1) * 5 + (x & 1) * 3; }
 
 }  // namespace feo

@@ -165,6 +165,17 @@ int build_lattice_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, i
     if (L->exist[dir][0] != 15) return not_applicable(L, "no complete cell");
     L->cls[dir].resize((size_t)nc * nc);
     for (size_t i = 0; i < cell_cls.size(); ++i) L->cls[dir][i] = (uint8_t)rank[(size_t)cell_cls[i]];
+    // the kernels find a cell's class from its boundary-layer categories: that must reproduce the map
+    std::memset(L->cat_cls[dir], 0xff, 25);
+    for (int cj = 0; cj < nc; ++cj)
+      for (int ci = 0; ci < nc; ++ci) {
+        uint8_t& slot = L->cat_cls[dir][lat_cat(cj, nc) * 5 + lat_cat(ci, nc)];
+        const uint8_t c = L->cls[dir][(size_t)cj * nc + ci];
+        if (slot == 0xff) slot = c;
+        if (slot != c) return not_applicable(L, "cell classes are not a function of the boundary layer (non-uniform mesh?)");
+      }
+    for (int i = 0; i < 25; ++i)
+      if (L->cat_cls[dir][i] == 0xff) L->cat_cls[dir][i] = 0;
   }
   // ---- coverage: every stored entry of A, and of the velocity rows of B1 / B2, is held by exactly one table slot.
   // Forward slots hold distinct entries of the cell's own rows, so equal counts mean full coverage; the backward tables hold
@@ -221,7 +232,7 @@ int replay_lattice_plan(const LatticePlan& L, bool backward, int32_t ns_branch, 
 #define FSJ(i) sacc += C(i) * xJ;
 #define FP(t, tc, i) acc[0][t][tc] += C(i) * xP;
 #define FSP(i) sacc += C(i) * xP;
-        FEO_LAT_FWD_BODY
+        FEO_LAT_FWD_BODY_A FEO_LAT_FWD_BODY_B FEO_LAT_FWD_BODY_C
 #undef LDX
 #undef FV
 #undef FSI
@@ -257,7 +268,7 @@ int replay_lattice_plan(const LatticePlan& L, bool backward, int32_t ns_branch, 
 #define BSJ(i) sacc += C(i) * rJ;
 #define BP(t, tc, i) g[t][tc] += C(i) * rP;
 #define BSP(i) sacc += C(i) * rP;
-        FEO_LAT_BWD_BODY
+        FEO_LAT_BWD_BODY_A FEO_LAT_BWD_BODY_B FEO_LAT_BWD_BODY_C
 #undef LDR
 #undef LDA
 #undef BTA

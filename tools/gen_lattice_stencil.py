@@ -117,8 +117,11 @@ class Table:
         return len(self.desc) - 1
 
 
-def window_nodes():
-    return [(dx, dy) for dy in range(-2, 3) for dx in range(-2, 3)]
+PARTS = (("A", (-2, -1)), ("B", (0,)), ("C", (1, 2)))  # window rows of the three body parts (see emit())
+
+
+def window_nodes(rows):
+    return [(dx, dy) for dy in rows for dx in range(-2, 3)]
 
 
 def gen_forward(keys):
@@ -126,8 +129,10 @@ def gen_forward(keys):
     the SAME coefficient (A's velocity block is diag(K, K), B1 = diag(Dx, Dx), B2 = diag(Dy, Dy)); pressure columns feed the
     A sums; the pressure row of the vertex takes both components."""
     T = Table()
-    body = []
-    for (dx, dy) in window_nodes():
+    parts = {}
+    for part, rows in PARTS:
+      body = parts.setdefault(part, [])
+      for (dx, dy) in window_nodes(rows):
         stmts, use = [], [False, False]
         for ti, (tx, ty) in enumerate(TARGETS):
             for mi, name in enumerate(MATS):
@@ -143,7 +148,7 @@ def gen_forward(keys):
         if stmts:
             loads = [f"LDX(x{'IJ'[c]}, {dx}, {dy}, {c})" for c in (0, 1) if use[c]]
             body.append("  BEGIN " + " ".join(loads + stmts) + " END")
-    for (dx, dy) in window_nodes():
+      for (dx, dy) in window_nodes(rows):
         if dx % 2 or dy % 2:
             continue
         stmts = []
@@ -157,7 +162,7 @@ def gen_forward(keys):
             stmts.append(f"FSP({i})")
         if stmts:
             body.append(f"  BEGIN LDX(xP, {dx}, {dy}, 2) " + " ".join(stmts) + " END")
-    return T, body
+    return T, parts
 
 
 def gen_backward(keys):
@@ -167,8 +172,10 @@ def gen_backward(keys):
          pressure column of the vertex:  g_P += A[I_m, P] rI + A[J_m, P] rJ
        per source pressure ROW q: rP = r[p_q]:  g_c[t] += A[p_q, c_t] rP,  g_P += A[p_q, P] rP."""
     T = Table()
-    body = []
-    for (dx, dy) in window_nodes():
+    parts = {}
+    for part, rows in PARTS:
+      body = parts.setdefault(part, [])
+      for (dx, dy) in window_nodes(rows):
         stmts, use_r, use_d = [], False, False
         for ti, (tx, ty) in enumerate(TARGETS):
             idx = []
@@ -198,7 +205,7 @@ def gen_backward(keys):
             if use_d:
                 loads += [f"LDA(d1, {dx}, {dy}, 0)", f"LDA(d2, {dx}, {dy}, 1)"]
             body.append("  BEGIN " + " ".join(loads + stmts) + " END")
-    for (dx, dy) in window_nodes():
+      for (dx, dy) in window_nodes(rows):
         if dx % 2 or dy % 2:
             continue
         stmts = []
@@ -212,7 +219,7 @@ def gen_backward(keys):
             stmts.append(f"BSP({i})")
         if stmts:
             body.append(f"  BEGIN LDR(rP, {dx}, {dy}, 2) " + " ".join(stmts) + " END")
-    return T, body
+    return T, parts
 
 
 def emit(keys):
@@ -229,6 +236,8 @@ def emit(keys):
         "//   backward: BTA(target, ia) BTB(target, ia, ib1, ib2) BF(matrix, target, i) BSI(i) BSJ(i) BP(target, comp, i) BSP(i)",
         "//   (an index of -1 = entry absent);",
         "//   targets 0..3 = the cell's nodes V (0,0), H (1,0), T (0,1), D (1,1).",
+        "// Each body comes in three parts by window row: A = rows -2, -1 (the rows a step releases first), B = row 0,",
+        "//   C = rows 1, 2 (the rows a step receives last) -- the kernels release / wait for staged rows between the parts.",
     ]
     for tag, gen in (("FWD", gen_forward), ("BWD", gen_backward)):
         T, body = gen(keys)
@@ -239,10 +248,11 @@ def emit(keys):
                 f"  DESC({i}, {mat_id[mat]}, {row[0]}, {row[1]}, {row[2]}, {col[0]}, {col[1]}, {col[2]}, {int(signed)}, {int(twin)}) \\"
             )
         lines.append("")
-        lines.append(f"#define FEO_LAT_{tag}_BODY \\")
-        for b in body:
-            lines.append(b + " \\")
-        lines.append("")
+        for part, _ in PARTS:
+            lines.append(f"#define FEO_LAT_{tag}_BODY_{part} \\")
+            for b in body[part]:
+                lines.append(b + " \\")
+            lines.append("")
     with open(OUT, "w") as f:
         f.write("\n".join(lines) + "\n")
     return lines

@@ -1,6 +1,6 @@
 """Developer timing of the fused residual kernels through FEOperator (no autograd): CUDA events per call.
 
-usage: time_kernels.py [n] [B] [K] [cfg ...]   with cfg = Wf,Lf,Wb,Lb[,gap,reserve[,Sf,Sb]] (consumer warps / staged lines forward / backward, gap filling, line stages)
+usage: time_kernels.py [n] [B] [K] [cfg ...]   with cfg = env:K=V,... (environment knobs, sticky; K= unsets) or Wf,Lf,Wb,Lb[,gap,reserve[,Sf,Sb]] (consumer warps / staged lines forward / backward, gap filling, line stages)
 The fixture is assembled once; one operator (one tile plan) is built per cfg.  A checksum of the loss
 and the gradient is printed per cfg so that plans can be compared with each other.
 """
@@ -26,7 +26,15 @@ fT = torch.empty(N, ldb, device=dev).normal_(0, 1.0)
 gT = torch.empty(N, ldb, device=dev)
 ev = lambda: torch.cuda.Event(enable_timing=True)
 for cfg in cfgs:
-    if cfg != "default":
+    if cfg.startswith("env:"):  # env:K=V,K=V -- any FEO_* knob (plan choice, lattice widths, debug modes); "env:" alone resets nothing
+        for kv in cfg[4:].split(","):
+            if kv:
+                k, v = kv.split("=")
+                if v == "":
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+    elif cfg != "default":
         wf, lf, wb, lb, *rest = cfg.split(",")
         os.environ.update(FEO_TILE_WARPS_FWD=wf, FEO_TILE_LINES_FWD=lf, FEO_TILE_WARPS_BWD=wb, FEO_TILE_LINES_BWD=lb)
         if rest:
