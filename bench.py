@@ -77,6 +77,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-precond-gemm", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the DP training-step arm (FCNN head + gradient all-reduce)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity check against the fp64 oracle")
+    ap.add_argument("--train-steps", type=int, default=6)
     ap.add_argument("--configs", action="store_true", help="time cfg1-4 (parity-test cases) on cuda:0 beside the CPU port; not the bench line")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-chunk", type=int, default=256, help="samples per host->device chunk of the end-to-end leg")
@@ -188,12 +191,12 @@ def run_reference(args):
     if rank != 0:
         return
     fx = build_fixture(args)
-    steps = min(args.steps, 10)
-    rate, threads, ms = cpu_port_rate(fx, args, steps, min(args.warmup, 2))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)  # one step = one pass of the bounded sample (about 0.1 s)
+    rate, threads, ms = cpu_port_rate(fx, args, steps, warmup)
     sample = f"{args.cpu_samples} of the {args.batch} samples per step, full N={fx.N} operator, fp32, torch CPU sparse-CSR"
     out = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args, fx.N), "device": "host CPU"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
@@ -245,14 +248,15 @@ def run_ours(args):
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
+    loss_sum = torch.zeros((), device=dev, dtype=torch.float64)
+
     def step(e_mid=None):
         alpha.grad = None
         loss = ns.residual_loss(alpha, F, fx.A, fx.B1, fx.B2, fx.idx_sol)
         if e_mid is not None:
             e_mid.record()
         loss.backward()
-        if world > 1:  # DP bookkeeping: summed loss over ranks (the only collective; parameters are not part of this path)
-            dist.all_reduce(loss.detach(), op=dist.ReduceOp.SUM)
+        loss_sum.add_(loss.detach())  # logging: the summed loss is all-reduced ONCE per reporting interval, not per step
         return loss
 
     for _ in range(max(args.warmup, 3)):
@@ -269,10 +273,15 @@ def run_ours(args):
     marks = [(ev(), ev(), ev()) for _ in range(K)]
     launches0 = op.launches
     t_wall = time.perf_counter()
+    loss_sum.zero_()
     for k in range(K):
         marks[k][0].record()
         loss = step(marks[k][1])
         marks[k][2].record()
+    if world > 1:  # DP bookkeeping inside the timed region: one scalar all-reduce for the K steps (the reference logs every 100 epochs)
+        dist.all_reduce(loss_sum, op=dist.ReduceOp.SUM)
+    e_end = ev()
+    e_end.record()
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall
     if world > 1:
@@ -281,7 +290,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     launches = op.launches - launches0
 
-    total_ms = marks[0][0].elapsed_time(marks[-1][2])
+    total_ms = marks[0][0].elapsed_time(e_end)
     fwd_ms = sum(m[0].elapsed_time(m[1]) for m in marks) / K
     bwd_ms = sum(m[1].elapsed_time(m[2]) for m in marks) / K
     if world > 1:
@@ -322,22 +331,39 @@ def run_ours(args):
             log(f"[bench] e2e leg failed: {exc!r}")
             e2e = None
 
+    train = None
+    if not args.no_train_step:
+        try:
+            train = run_train_step(args, torch, feo, ns, fx, dev, world, rank)
+        except Exception as exc:  # pragma: no cover
+            log(f"[bench] train_step leg failed: {exc!r}")
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
+    parity = None
+    if not args.no_parity and world == 1:
+        try:
+            parity = run_parity(args, torch, feo, ns, fx, dev)
+        except Exception as exc:  # pragma: no cover
+            log(f"[bench] parity leg failed: {exc!r}")
+
     peak, peak_src = measured_peak_gbs()
     alg_fwd = 12.0 * N * B  # read alpha, F; write r
     alg_bwd = 12.0 * N * B  # read r, alpha; write grad
-    dom = "residual_bwd_tiled" if bwd_ms >= fwd_ms else "residual_fwd_tiled"
+    lattice = op.info.n_tiles_fwd == (args.n + 1) ** 2  # the lattice plan reports its cells as "tiles"
+    names = ("residual_lattice_kernel<fwd>", "residual_lattice_kernel<bwd>") if lattice else ("residual_fwd_tiled", "residual_bwd_tiled")
+    dom = names[1] if bwd_ms >= fwd_ms else names[0]
     dom_ms, dom_alg = (bwd_ms, alg_bwd) if bwd_ms >= fwd_ms else (fwd_ms, alg_fwd)
     achieved = dom_alg / (dom_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    if os.path.exists(tpath):
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic_r02.json")
+    if os.path.exists(tpath):  # dram__bytes of one `ncu --set full` capture (static: ncu cannot run inside the timed bench)
         try:
-            traffic = json.load(open(tpath)).get(dom)
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj.get(dom), f"profiles/traffic_r02.json ({tj.get('source', 'ncu --set full')}; static, not measured in this run)"
         except Exception:
             traffic = None
     out = {
@@ -347,22 +373,30 @@ def run_ours(args):
         "config": {
             "workload": workload_name(args, N), "N": N, "batch_per_gpu": B, "layout": args.layout,
             "l2": "alpha and F are 4.1 GB each per GPU: every step streams far more than the 126 MB L2",
-            "parallelism": f"dp{world} (batch sharded, operator replicated, loss all-reduce only)",
+            "parallelism": f"dp{world} (batch sharded, operator replicated; `value` = the loss path: no data-path collective, one scalar "
+                           f"loss all-reduce per {K} steps; the gradient all-reduce of a training step is measured in `train_step`)",
+            "plan": "lattice" if lattice else "tile",
         },
         "clocks": clocks,
         "gpu_launches": launches,
         "roofline": {
             "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "peak_source": peak_src,
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
             "algorithmic_bytes_per_launch": dom_alg, "ms_per_launch": dom_ms,
             "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
             "step_algorithmic_GBs": 24.0 * N * B / (total_ms / K * 1e-3) / 1e9,
+            "step_frac_of_measured": 24.0 * N * B / (total_ms / K * 1e-3) / 1e9 / peak,
+            "step_frac_of_nominal_8TBs": 24.0 * N * B / (total_ms / K * 1e-3) / 1e9 / 8000.0,
         },
         "loss": loss_val,
         "wall_ms_per_step": 1e3 * t_wall / K,
     }
     if alt_value is not None:
         out["value_row_major_layout"] = alt_value
+    if parity is not None:
+        out["parity"] = parity
+    if train is not None:
+        out["train_step"] = train
     if e2e is not None:
         out["e2e"] = e2e
     if world == 1 and not args.no_precond_gemm:
@@ -382,6 +416,145 @@ def run_ours(args):
     emit(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_parity(args, torch, feo, ns, fx, dev):
+    """The benchmarked operator against the fp64 oracle (oracle.ns_loss_and_grad, scipy CSR) on the cpu_baseline's samples,
+    through the public autograd API in both layouts (FEONet_steady_Navier-Stokes/train_FEONet.py:301-365)."""
+    from oracle import feonet_oracle as orc
+
+    rng = np.random.default_rng(0)
+    bs = args.cpu_samples
+    alpha = (0.1 * rng.standard_normal((bs, fx.N))).astype(np.float32)
+    F = rng.standard_normal((bs, fx.N)).astype(np.float32)
+    lo, go, _ = orc.ns_loss_and_grad(alpha, F, fx.A, fx.B1, fx.B2, fx.idx_u1, fx.idx_u2, True, dtype=np.float64)
+    out = {"samples": bs, "against": "oracle fp64 (scipy CSR), same samples as cpu_baseline", "tolerance": {"loss": 1e-5, "grad": 1e-4}}
+    Fd = torch.tensor(F, device=dev)
+    for name, native in (("dof_major", True), ("row_major", False)):
+        a = torch.tensor(alpha, device=dev)
+        a = feo.to_dof_major_tensor(a) if native else a.unsqueeze(1)
+        a.requires_grad_(True)
+        loss = ns.residual_loss(a, Fd, fx.A, fx.B1, fx.B2, fx.idx_sol)
+        (g,) = torch.autograd.grad(loss, a)
+        g = g.reshape(bs, fx.N).double().cpu().numpy()
+        out[name] = {"rel_loss": abs(loss.item() - lo) / abs(lo), "rel_grad": float(np.linalg.norm(g - go) / np.linalg.norm(go)),
+                     "rel_grad_max": float(np.abs(g - go).max() / np.abs(go).max())}
+    out["ok"] = all(out[k]["rel_loss"] < 1e-5 and out[k]["rel_grad"] < 1e-4 and out[k]["rel_grad_max"] < 1e-4 for k in ("dof_major", "row_major"))
+    log(f"[bench] parity {out}")
+    return out
+
+
+def run_train_step(args, torch, feo, ns, fx, dev, world, rank):
+    """The data-parallel TRAINING step the loss path sits in (FEONet_steady_Navier-Stokes/train_FEONet.py:453-473 with the only
+    model that is feasible at 1M dofs, FCNN(6 -> 16 -> 32 -> 64 -> 128 -> 256 -> N), :178-179): closure() = network forward +
+    residual loss, loss.backward(), NCCL all-reduce(SUM) of the ~1.03 GB of parameter gradients, fused Adam step.  The head's
+    weight gradient is formed in dof-range chunks and each chunk's all-reduce is launched while the later chunks' GEMMs run
+    (parallel.OverlappedLinearT).  Reported per N: step time with / without the collective, the collective alone, the exposed
+    fraction, weak (1024 samples per GPU) and strong (1024 / N samples per GPU) scaling, and -- at one GPU -- closure() with the
+    reference's row-major nn.Linear head beside the dof-major head."""
+    import torch.distributed as dist
+    from feonet_navier_stokes_b200 import network, parallel
+
+    N = fx.N
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    K = max(2, args.train_steps)
+
+    def build(dof_major, overlapped):
+        torch.manual_seed(7)
+        model = network.FCNN(6, N, [16, 32, 64, 128, 256], dof_major_head=dof_major).to(dev)
+        reducer = parallel.GradientReducer(enabled=overlapped)
+        if overlapped:
+            model.model[-1] = parallel.OverlappedLinearT.from_linear(model.model[-1], chunks=8, reducer=reducer)
+        return model, reducer, torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+
+    def time_steps(model, reducer, optim, B, reduce_grads):
+        gen = torch.Generator(device=dev).manual_seed(99 + rank)
+        coeff = torch.rand(B, 6, device=dev, generator=gen)
+        F = feo.dof_major_empty(B, N, dev)
+        F.normal_(0.0, 1.0, generator=gen)
+        head = list(model.model[-1].parameters())
+
+        def step():
+            optim.zero_grad(set_to_none=True)
+            loss, _ = ns.closure(model, coeff, None, F, fx.A, fx.B1, fx.B2, 64)
+            loss.backward()
+            if reduce_grads and world > 1:
+                parallel.allreduce_remaining(model, head, reducer)
+                reducer.finish()
+            optim.step()
+            return loss
+
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(K):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / K
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        del coeff, F
+        return ms, float(loss.item())
+
+    B = args.batch
+    out = {"model": "FCNN(6,[16,32,64,128,256],N) tanh MLP, dropout 0.2, fp32 (TF32 off, torch default), fused Adam",
+           "grad_bytes": None, "steps": K}
+    model, reducer, optim = build(True, world > 1)
+    out["params"] = sum(p.numel() for p in model.parameters())
+    out["grad_bytes"] = 4 * out["params"]
+    ms_full, loss = time_steps(model, reducer, optim, B, True)
+    out["weak"] = {"batch_per_gpu": B, "ms_per_step": ms_full, "samples_per_s": world * B / (ms_full * 1e-3), "loss": loss}
+    if world > 1:
+        reducer.enabled = False
+        ms_noar, _ = time_steps(model, reducer, optim, B, False)
+        reducer.enabled = True
+        # the collective alone: the same chunks, nothing to overlap with
+        w = model.model[-1].weight
+        bufs = list(torch.empty_like(w).chunk(8, dim=0))
+        rest = torch.empty(out["params"] - w.numel(), device=dev)
+        for _ in range(2):
+            for b_ in bufs + [rest]:
+                dist.all_reduce(b_)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(3):
+            for b_ in bufs + [rest]:
+                dist.all_reduce(b_)
+        e1.record()
+        torch.cuda.synchronize()
+        ar_ms = e0.elapsed_time(e1) / 3
+        t = torch.tensor([ar_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ar_ms = float(t.item())
+        del bufs, rest
+        out["weak"].update({"ms_per_step_without_allreduce": ms_noar, "allreduce_alone_ms": ar_ms,
+                            "allreduce_busbw_GBs": 2.0 * (world - 1) / world * out["grad_bytes"] / (ar_ms * 1e-3) / 1e9,
+                            "allreduce_exposed_ms": max(0.0, ms_full - ms_noar),
+                            "allreduce_exposed_frac": max(0.0, ms_full - ms_noar) / ar_ms,
+                            "limiting_collective": "NCCL all-reduce(SUM) of the head weight gradient (256 x N fp32), 8 dof-range chunks"})
+        Bs = max(1, B // world)
+        ms_strong, _ = time_steps(model, reducer, optim, Bs, True)
+        out["strong"] = {"batch_per_gpu": Bs, "global_batch": Bs * world, "ms_per_step": ms_strong,
+                         "samples_per_s": world * Bs / (ms_strong * 1e-3)}
+    del model, optim
+    if world == 1:  # the drop-in question: what does closure() cost with the reference's row-major nn.Linear head?
+        model, reducer, optim = build(False, False)
+        ms_rm, _ = time_steps(model, reducer, optim, B, False)
+        out["closure_row_major_head"] = {"ms_per_step": ms_rm, "samples_per_s": B / (ms_rm * 1e-3),
+                                         "note": "network.FCNN with the reference's nn.Linear head ([B,1,N] row-major): the loss op transposes in and out"}
+        del model, optim
+    torch.cuda.empty_cache()
+    log(f"[bench] train_step {out}")
+    return out
 
 
 def run_precond_gemm(torch, feo, dev, n=2549, B=1024, iters=30):
@@ -467,6 +640,8 @@ def run_configs(args):
         return (np.eye(n) + 0.3 * rng.standard_normal((n, n)) / np.sqrt(n)).astype(np.float32)
 
     rows = []
+    # the reference's own execution plan (dense operators, per-sample / per-dof Python loops, autograd) on this host's cores
+    loops = orc.TorchReferenceLoops(os.cpu_count())
 
     def report(name, N, gpu_ms, cpu_ms, loss_gpu, loss_cpu, grad_gpu, grad_cpu, note):
         g, c = np.asarray(grad_gpu, dtype=np.float64), np.asarray(grad_cpu, dtype=np.float64)
@@ -500,6 +675,9 @@ def run_configs(args):
         lo, go, _ = orc.stokes_loss_and_grad(alpha, F, A, P, True, dtype=np.float64)  # yardstick for the differences
         report(name + (f" N={fx.N}" if "N=" not in name else ""), fx.N, gpu_ms, cpu_ms,
                box["l"].item(), float(lo), box["g"].cpu().numpy(), go, "dense A.P folded at set-up, tcgen05 3xTF32 apply")
+        ref_ms, (l_ref, g_ref) = time_cpu(lambda: loops.linear_stokes_step(alpha, F, A, P, True), reps=1)
+        rows[-1].update(reference_loops_ms_fwd_bwd=ref_ms, reference_loops_samples_per_s=B / (ref_ms * 1e-3),
+                        speedup_vs_reference_loops=ref_ms / gpu_ms, loss_rel_diff_vs_reference_loops=abs(box["l"].item() - l_ref) / abs(l_ref))
 
     # cfg3: steady Navier-Stokes, both sign branches (fused sparse kernels)
     fx = config_operators("steady_ns", 15)
@@ -520,7 +698,11 @@ def run_configs(args):
         cpu_ms, _ = time_cpu(lambda: orc.ns_loss_and_grad(alpha, F, fx.A, fx.B1, fx.B2, fx.idx_u1, fx.idx_u2, precond, dtype=np.float32))
         lo, go, _ = orc.ns_loss_and_grad(alpha, F, fx.A, fx.B1, fx.B2, fx.idx_u1, fx.idx_u2, precond, dtype=np.float64)
         report(f"cfg3 steady NS N={fx.N} ({'precond=I' if precond else 'no precond'} sign branch)", fx.N, gpu_ms, cpu_ms,
-               box["l"].item(), float(lo), box["g"].cpu().numpy(), go, "fused residual_fwd/bwd_tiled incl. row-major <-> dof-major transposes")
+               box["l"].item(), float(lo), box["g"].cpu().numpy(), go, "fused residual kernels incl. row-major <-> dof-major transposes")
+        dense = [np.asarray(K.todense(), dtype=np.float32) for K in (fx.A, fx.B1, fx.B2)]
+        ref_ms, (l_ref, g_ref) = time_cpu(lambda: loops.steady_ns_step(alpha, F, *dense, fx.idx_u1, fx.idx_u2, precond), reps=1)
+        rows[-1].update(reference_loops_ms_fwd_bwd=ref_ms, reference_loops_samples_per_s=B / (ref_ms * 1e-3),
+                        speedup_vs_reference_loops=ref_ms / gpu_ms, loss_rel_diff_vs_reference_loops=abs(box["l"].item() - l_ref) / abs(l_ref))
 
     # cfg4: time-dependent Stokes, T = 10
     fx = config_operators("time_dep", 10)
@@ -564,7 +746,10 @@ def run_configs(args):
     except Exception as exc:  # pragma: no cover
         log(f"[configs] large linear case failed: {exc!r}")
     emit({"configs": rows, "linear_large": large, "cores": os.cpu_count(), "cpu_kind": "port (oracle numpy/scipy, fp32)",
-          "reference_own_code": "SURVEY 8a: 5.0 s at N=387, 9.2 s at N=2178 per step (B=1000, 8 threads, torch CPU, reference loops)"})
+          "reference_loops": "oracle.TorchReferenceLoops: the reference's own execution plan (dense fp32 operators, (matrix @ precond).mm per "
+                             "sample, one MSE(sum) per dof in a Python loop, autograd backward; FEONet_steady_Navier-Stokes/train_FEONet.py:301-360, "
+                             "FEONet_Stokes_square/train_FEONet.py:261-296) restated and timed on this host with torch CPU, all cores; "
+                             "bit-equal to the unmodified reference functions in the authoring container (profiles/r02_reference_cpu_container.json)"})
 
 
 def run_e2e(args, torch, feo, ns, fx, dev, world, rank):

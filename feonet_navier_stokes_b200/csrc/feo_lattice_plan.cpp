@@ -56,11 +56,20 @@ int build_lattice_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, i
   if (!A.present()) return not_applicable(L, "no sparse A");
   const int32_t N = A.n;
   // ---- lattice size from the dof counts: n_u = (2n + 1)^2, n_p = (n + 1)^2 ----
-  const int32_t m = (int32_t)std::llround(std::sqrt((double)n_u));
+  // (a linear operator may come without idx_sol: then N = 9 n^2 + 10 n + 3 fixes n, and the pairing is the lattice's own)
+  const bool have_idx = n_u > 0 && idx_i != nullptr && idx_j != nullptr;
+  if (!have_idx && (B1.present() || B2.present())) return not_applicable(L, "convective operator without idx_sol");
+  int32_t m;
+  if (have_idx) {
+    m = (int32_t)std::llround(std::sqrt((double)n_u));
+  } else {
+    const int64_t nn = (int64_t)std::llround((-10.0 + std::sqrt(100.0 - 36.0 * (3.0 - (double)N))) / 18.0);
+    m = (int32_t)(2 * nn + 1);
+    n_u = m * m;
+  }
   if (n_u <= 0 || (int64_t)m * m != n_u || m < 5 || (m & 1) == 0) return not_applicable(L, "n_u is not an odd square");
   const int32_t n = (m - 1) / 2, nc = n + 1;
   if ((int64_t)N != 2 * (int64_t)n_u + (int64_t)nc * nc) return not_applicable(L, "dof count does not match a P2-P1 lattice");
-  if (idx_i == nullptr || idx_j == nullptr) return not_applicable(L, "no idx_sol");
   // ---- the numbering the kernels assume: per lattice row one contiguous run, (u1, u2[, p]) per node ----
   L->n = n;
   L->nc = nc;
@@ -88,7 +97,7 @@ int build_lattice_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, i
         role[(size_t)G.dof(x, y, 1)] = 1;
       }
     std::vector<uint8_t> seen((size_t)N, 0);
-    for (int32_t k = 0; k < n_u; ++k) {
+    for (int32_t k = 0; have_idx && k < n_u; ++k) {
       const int32_t i = idx_i[k], j = idx_j[k];
       if (i < 0 || i >= N || role[(size_t)i] != 0 || j != i + 1 || seen[(size_t)i])
         return not_applicable(L, "idx_sol is not the interleaved lattice numbering");
@@ -183,7 +192,7 @@ int build_lattice_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, i
   int64_t want[3] = {A.nnz(), 0, 0};
   {
     std::vector<uint8_t> is_vel((size_t)N, 0);
-    for (int32_t k = 0; k < n_u; ++k) is_vel[(size_t)idx_i[k]] = is_vel[(size_t)idx_j[k]] = 1;
+    for (int32_t k = 0; have_idx && k < n_u; ++k) is_vel[(size_t)idx_i[k]] = is_vel[(size_t)idx_j[k]] = 1;
     for (int mi = 1; mi < 3; ++mi)
       if (mats[mi]->present())
         for (int32_t r = 0; r < N; ++r)

@@ -180,7 +180,6 @@ class Trainer:
         n_val, ne_val = parse_file_flag(gparams["val_file"])
         if ne != ne_val:
             raise ValueError("train and validation files must use the same mesh")
-        n = mesh_n_from_ne(ne, strict=variant != "hole")  # the hole stand-in mesh is Delaunay: ne only sets its resolution
         do_precond = int(gparams["do_precond"]) > 0
         if gparams.get("npz"):
             # the reference's own file: dense operators -> CSR, the first NUM_DATA samples of each split (:69-85, :218-245)
@@ -196,12 +195,16 @@ class Trainer:
             val = {k: v[:n_val] for k, v in z["validate"].items() if k != "forcing_term"}
             n_train, n_val = len(train["coeff_f"]), len(val["coeff_f"])
         else:
-            # data (seeds 5 / 10: create_data.py:30-33)
+            # data (seeds 5 / 10: create_data.py:30-33); ne fixes the synthetic mesh only here -- a reference npz carries its own
+            n = mesh_n_from_ne(ne, strict=variant != "hole")  # the hole stand-in mesh is Delaunay: ne only sets its resolution
             self.fx, train = synthesize(variant, n, gparams["bc"], n_train, 5, do_precond)
             _, val = synthesize(variant, n, gparams["bc"], n_val, 10, do_precond)
         t = lambda a: torch.tensor(np.asarray(a), dtype=torch.float32)  # noqa: E731
-        lo, hi = parallel.shard_bounds(n_train, self.rank, self.world)
-        self.train = {k: t(v[lo:hi]).to(self.device) for k, v in train.items()}
+        if n_train < self.world:
+            raise ValueError(f"{n_train} training samples cannot be sharded over {self.world} ranks")
+        # every rank keeps the whole (small) training set and takes ITS SHARD OF EACH GLOBAL BATCH (batches()), so that all
+        # ranks run the same number of steps per epoch -- every step issues collectives
+        self.train = {k: t(v).to(self.device) for k, v in train.items()}
         self.val = {k: t(v).to(self.device) for k, v in val.items()}
         self.N, self.n_u = self.fx.N, len(self.fx.idx_u1)
         self.idx = [torch.tensor(np.asarray(i), device=self.device, dtype=torch.long) for i in (self.fx.idx_u1, self.fx.idx_u2, self.fx.idx_p)]
@@ -243,11 +246,20 @@ class Trainer:
                 f.write(f"params: {sum(p.numel() for p in self.model.parameters())}\n{self.model}\n{self.optimizer}\n{gparams}\n")
 
     # -- pieces of the epoch loop ---------------------------------------------------------------------
-    def batches(self, data: Dict[str, torch.Tensor], batch_size: Optional[int]):
+    def batches(self, data: Dict[str, torch.Tensor], batch_size: Optional[int], shard: bool = False):
+        """Global batches of `batch_size` samples (the whole set when unset, as the reference's DataLoader default).  With
+        `shard`, a rank gets its contiguous part of every global batch: the number of batches is the same on every rank; a
+        tail smaller than the world size is merged into the batch before it so that no rank ever holds an empty shard."""
         n = data["coeff_f"].shape[0]
         bs = n if not batch_size else min(batch_size, n)
-        for lo in range(0, n, bs):
-            yield {k: v[lo:lo + bs] for k, v in data.items()}
+        edges = list(range(0, n, bs)) + [n]
+        if shard and len(edges) > 2 and edges[-1] - edges[-2] < self.world:
+            del edges[-2]
+        for lo, hi in zip(edges[:-1], edges[1:]):
+            if shard and self.world > 1:
+                a, b = self.parallel.shard_bounds(hi - lo, self.rank, self.world)
+                lo, hi = lo + a, lo + b
+            yield {k: v[lo:hi] for k, v in data.items()}
 
     def train_step(self, batch) -> Tuple[torch.Tensor, bool]:
         self.optimizer.zero_grad(set_to_none=True)
@@ -314,7 +326,7 @@ class Trainer:
         for epoch in range(1, g["epochs"] + 1):
             self.model.train()
             loss_total = torch.zeros((), device=self.device)
-            for batch in self.batches(self.train, g["batch_size_train"]):
+            for batch in self.batches(self.train, g["batch_size_train"], shard=True):
                 loss, stepped = self.train_step(batch)
                 if stepped:
                     loss_total += loss

@@ -71,16 +71,23 @@ class _Base:
         self._fcache = _TransposeCache()
         self._op: Optional[FEOperator] = None
         self._op_key = None
+        self._op_refs = ()  # the keyed objects themselves: ids / data pointers cannot be recycled while they are held
 
-    @staticmethod
-    def _key(*objs):
-        out = []
-        for o in objs:
-            if isinstance(o, torch.Tensor):
-                out.append((o.data_ptr(), o._version, tuple(o.shape)))
-            else:
-                out.append(id(o))
-        return tuple(out)
+    def _key(self, *objs):
+        """Cache key of the device operator.  Identity (`is`) of the matrix objects plus, for tensors, their in-place version
+        counter; the objects are kept alive in `_op_refs`, so a recycled id() or data_ptr() can never alias a stale operator.
+        (numpy / scipy matrices edited in place are not detected -- build a new `SteadyNavierStokes` / `LinearStokes` then.)"""
+        same = len(objs) == len(self._op_refs) and all(a is b for a, b in zip(objs, self._op_refs))
+        self._op_refs_new = objs
+        versions = tuple(o._version if isinstance(o, torch.Tensor) else 0 for o in objs)
+        return (same, versions)
+
+    def _key_matches(self, key) -> bool:
+        return self._op is not None and key[0] and self._op_key is not None and key[1] == self._op_key[1]
+
+    def _key_commit(self, key):
+        self._op_refs = self._op_refs_new
+        self._op_key = (True, key[1])
 
     def _run_model(self, model, coeff_f, value_f, resol_in):
         """Network forward exactly as the reference's `closure` dispatches it."""
@@ -106,10 +113,12 @@ class LinearStokes(_Base):
             self._operator(matrix, precond)
 
     def _operator(self, matrix, precond) -> FEOperator:
-        key = self._key(matrix, precond) + (self.DO_PRECOND,)
-        if self._op is None or key != self._op_key:
+        key = self._key(matrix, precond)
+        if not self._key_matches(key):
             n = matrix.shape[0]
             if self.DO_PRECOND:
+                if precond is None:
+                    raise ValueError("do_precond is set but no preconditioner was given (precond=None)")
                 P = _dense_host(precond)
                 if _is_identity(P):
                     self._op = FEOperator(n, A=matrix, device=self.device)
@@ -117,7 +126,7 @@ class LinearStokes(_Base):
                     self._op = FEOperator(n, A=matrix, dense_m=_fold_dense(matrix, P), dense_p=P, device=self.device)
             else:
                 self._op = FEOperator(n, A=matrix, device=self.device)
-            self._op_key = key
+            self._key_commit(key)
         return self._op
 
     @property
@@ -171,8 +180,8 @@ class SteadyNavierStokes(_Base):
             self._operator(A, B1, B2, idx_sol)
 
     def _operator(self, A, B1, B2, idx_sol) -> FEOperator:
-        key = self._key(A, B1, B2, self.PRECOND) + (self.DO_PRECOND,)
-        if self._op is None or key != self._op_key:
+        key = self._key(A, B1, B2, self.PRECOND)
+        if not self._key_matches(key):
             n = A.shape[0]
             kw = dict(A=A, B1=B1, B2=B2, idx_sol=idx_sol, ns_precond_branch=self.DO_PRECOND, device=self.device)
             self._identity_precond = True
@@ -182,7 +191,7 @@ class SteadyNavierStokes(_Base):
                     self._identity_precond = False
                     kw.update(dense_m=_fold_dense(A, P), dense_p=P)
             self._op = FEOperator(n, **kw)
-            self._op_key = key
+            self._key_commit(key)
         return self._op
 
     @property
@@ -238,11 +247,15 @@ class TimeDependentStokes(_Base):
             self._operator(S_mat, A_mat, precond, self.DT)
 
     def _operator(self, S_mat, A_mat, precond, dt) -> FEOperator:
-        key = self._key(S_mat, A_mat, precond) + (self.DO_PRECOND, float(dt))
-        if self._op is None or key != self._op_key:
+        key = self._key(S_mat, A_mat, precond)
+        key = (key[0] and getattr(self, "_op_dt", None) == float(dt), key[1])
+        if not self._key_matches(key):
             n = S_mat.shape[0]
             kw = dict(A=A_mat, S=S_mat, idx_sol=self.IDX_SOL, dt=float(dt), device=self.device)
+            self._op_dt = float(dt)
             if self.DO_PRECOND:
+                if precond is None:
+                    raise ValueError("do_precond is set but no preconditioner was given (precond=None)")
                 P = _dense_host(precond)
                 import scipy.sparse as sp
 
@@ -252,7 +265,7 @@ class TimeDependentStokes(_Base):
                 sysm = (S32 + np.float32(dt) * A32).astype(np.float64)
                 kw.update(dense_m=np.asarray(sysm @ P.astype(np.float64), dtype=np.float32), dense_p=P)
             self._op = FEOperator(n, **kw)
-            self._op_key = key
+            self._key_commit(key)
         return self._op
 
     @property

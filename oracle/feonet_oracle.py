@@ -274,3 +274,71 @@ class TorchCpuSteadyNS:
         grad[I] += s * (w1[I] + w1[J])
         grad[J] += s * (w2[I] + w2[J])
         return loss, grad.t()
+
+
+# ----------------------------------------------------------------------------------------------
+# The reference's OWN execution plan on the host cores (bench.py --configs): dense operators, eager torch ops, the
+# per-dof Python loss loop into a CPU tensor, autograd backward -- timed beside the GPU path at cfg1-4.  Restated
+# (not imported: /root/reference does not exist on the GPU box); tests/test_oracle_golden.py pins it to the goldens the
+# reference's unmodified functions produced, tools/time_reference_here.py times both side by side in the authoring container.
+# ----------------------------------------------------------------------------------------------
+class TorchReferenceLoops:
+    """Step = loss forward + `loss.backward()` to d loss / d alpha, exactly as the reference schedules it."""
+
+    def __init__(self, threads: Optional[int] = None):
+        import torch
+
+        if threads:
+            torch.set_num_threads(int(threads))
+        self.torch = torch
+        self.threads = torch.get_num_threads()
+        self.mse_sum = torch.nn.MSELoss(reduction="sum")
+
+    def _per_dof_loss(self, lhs, rhs):
+        """FEONet_steady_Navier-Stokes/train_FEONet.py:354-360 (same block in every variant): one MSE(sum) per dof,
+        written into a CPU tensor by a Python loop, then summed."""
+        torch = self.torch
+        n = lhs.shape[1]
+        per_dof = torch.zeros((n,))
+        for d in range(n):
+            per_dof[d] = self.mse_sum(lhs[:, d], rhs[:, d])
+        return torch.sum(per_dof)
+
+    def steady_ns_step(self, alpha, F, A, B1, B2, I, J, do_precond: bool, precond=None):
+        """FEONet_steady_Navier-Stokes/train_FEONet.py:301-332 + :351-360 + :463; alpha, F [B,N], dense fp32 matrices."""
+        torch = self.torch
+        a = torch.as_tensor(alpha).clone().unsqueeze(1).requires_grad_(True)  # [B,1,N] as the networks emit it
+        Ft, At, B1t, B2t = (torch.as_tensor(x) for x in (F, A, B1, B2))
+        I, J = list(map(int, I)), list(map(int, J))
+        u = a.squeeze(1)
+        s1, s2 = u @ B1t.T, u @ B2t.T
+        conv = torch.zeros_like(u)
+        conv[:, I] += u[:, I] * s1[:, I]
+        conv[:, J] += u[:, I] * s1[:, J]
+        conv[:, I] += u[:, J] * s2[:, I]
+        conv[:, J] += u[:, J] * s2[:, J]
+        if do_precond:
+            Pt = torch.eye(At.shape[0]) if precond is None else torch.as_tensor(precond)
+            lhs, rhs = u @ (At @ Pt).T, Ft - conv  # the N^3 fold runs on every call (:325)
+        else:
+            lhs, rhs = u @ At.T, -Ft + conv
+        loss = self._per_dof_loss(lhs, rhs)
+        loss.backward()
+        return float(loss), a.grad.squeeze(1)
+
+    def linear_stokes_step(self, alpha, F, matrix, precond, do_precond: bool):
+        """FEONet_Stokes_square/train_FEONet.py:261-271 + :290-296 (hole variant :264-274): one (matrix @ precond).mm per
+        SAMPLE inside a list comprehension."""
+        torch = self.torch
+        a = torch.as_tensor(alpha).clone().unsqueeze(1).requires_grad_(True)
+        Ft, Mt = torch.as_tensor(F), torch.as_tensor(matrix)
+        cols = a.transpose(1, 2)  # [B,N,1]
+        if do_precond:
+            Pt = torch.as_tensor(precond)
+            lhs = torch.stack([(Mt @ Pt).mm(c) for c in cols])
+        else:
+            lhs = torch.stack([Mt.mm(c) for c in cols])
+        lhs = torch.sum(lhs, dim=-1)
+        loss = self._per_dof_loss(lhs, Ft)
+        loss.backward()
+        return float(loss), a.grad.squeeze(1)

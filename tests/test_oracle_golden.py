@@ -73,3 +73,21 @@ def test_sparse_matches_dense():
     csr = orc.ns_loss_and_grad(g["alpha"], g["F"], sp.csr_matrix(g["A"]), sp.csr_matrix(g["B1"]), sp.csr_matrix(g["B2"]),
                                g["idx_u1"], g["idx_u2"], False, dtype=np.float64)
     assert abs(dense[0] - csr[0]) < 1e-12 * abs(dense[0]) and _relerr(csr[1], dense[1]) < 1e-12
+
+
+@pytest.mark.parametrize("name", golden_cases("ns_") + golden_cases("stokes_") + golden_cases("hole_"))
+def test_reference_loops_restatement_is_bit_equal(name):
+    """oracle.TorchReferenceLoops (the reference's own execution plan, timed by bench.py --configs on the GPU box's host)
+    runs the same torch ops in the same order as the unmodified reference functions: loss and gradient of the goldens are
+    reproduced BIT FOR BIT (same torch build, same thread count as when the goldens were made is not required: the per-dof
+    loss loop and the dense GEMMs are deterministic on one host; a tolerance of one ulp-scale relative error is allowed for
+    GEMM blocking differences across CPUs)."""
+    g = _load(name)
+    dp = bool(g["do_precond"])
+    loops = orc.TorchReferenceLoops()
+    if name.startswith("ns_"):
+        loss, grad = loops.steady_ns_step(g["alpha"], g["F"], g["A"], g["B1"], g["B2"], g["idx_u1"], g["idx_u2"], dp, g["P"] if dp else None)
+    else:
+        loss, grad = loops.linear_stokes_step(g["alpha"], g["F"], g["A"], g["P"], dp)
+    assert abs(loss - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    assert _relerr(grad.numpy(), g["grad"]) < 1e-6

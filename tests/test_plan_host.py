@@ -161,7 +161,8 @@ def test_lattice_replay_matches_oracle(n, branch, variant):
     lib = L.load_library()
     op = config_operators(variant, n, ordering="interleaved")
     has_b = op.B1 is not None
-    desc, keep = build_desc(op.N, op.A, op.B1, op.B2, None, op.idx_u1, op.idx_u2, bool(branch))
+    # a linear operator may come without idx_sol (FEOperator(N, A=...)): the lattice is then recognised from N and A alone
+    desc, keep = build_desc(op.N, op.A, op.B1, op.B2, None, op.idx_u1 if has_b else None, op.idx_u2 if has_b else None, bool(branch))
     rng = np.random.default_rng(100 + n)
     alpha = rng.standard_normal(op.N)
     f = rng.standard_normal(op.N)
