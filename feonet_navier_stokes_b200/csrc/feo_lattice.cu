@@ -53,6 +53,7 @@ struct LatParams {
   int32_t he, ho;          // lines of an even / odd lattice row run
   uint32_t slot_bytes, bar_off;
   int32_t debug;           // FEO_DEBUG_MODE: 1 = staging only, 2 = compute only (results are garbage)
+  int32_t sync_mask;       // bit 0: release a step's oldest rows early, bit 1: wait for its newest rows late (developer knob FEO_LAT_SYNC)
   int32_t precond;         // forward: 1 -> r = lhs - (f - c), 0 -> r = lhs - (-f + c)
   float esign;             // backward: +1 precond branch, -1 otherwise
   uint8_t cat_cls[25];     // class of a cell by the boundary-layer categories of (cj, ci): lat_cat(cj) * 5 + lat_cat(ci)
@@ -455,8 +456,8 @@ __global__ void __launch_bounds__(NT, 1)
     w.next(p);
     const bool last = w.done() || w.local == 0;  // the step ends a segment: the producer may overwrite the whole ring after it
     const bool active = p.debug != 1 && ci < p.nc;
-    sy.wait_late = p.debug != 2 && !first && active;
-    sy.release_early = !last && active;
+    sy.wait_late = p.debug != 2 && !first && active && (p.sync_mask & 2);
+    sy.release_early = !last && active && (p.sync_mask & 1);
     if (p.debug != 2 && !sy.wait_late) mbar_wait(sy.full_bar, sy.full_ph);
     if (active) {
       uint32_t Bx[5], Ba[5];
@@ -557,6 +558,7 @@ int launch(const feo_operator* op, const DevLatticePlan& L, const float* src0, c
   const uint32_t smem = p.bar_off + 2 * kStagesMax * 8;
   if (smem > kSmemMax) return fail(FEO_ERR_INVALID_ARGUMENT, "lattice kernel: the row ring does not fit shared memory");
   p.debug = env_int("FEO_DEBUG_MODE", 0);
+  p.sync_mask = env_int(BWD ? "FEO_LAT_SYNC_BWD" : "FEO_LAT_SYNC_FWD", 3);
   p.precond = op->ns_branch;
   p.esign = op->ns_branch ? 1.0f : -1.0f;
   if (L.n_classes[dir] > kLatMaxClasses || L.tab[dir].size() != (size_t)L.n_classes[dir] * NCOEF)

@@ -172,6 +172,7 @@ def test_ns_vs_oracle(feo, n, B, branch, ordering, native):
 
 
 def test_ns_is_deterministic_and_tile_size_independent(feo, monkeypatch):
+    monkeypatch.setenv("FEO_PLAN", "tile")  # the tile plan (any CSR); the lattice plan has its own file, tests/test_gpu_lattice.py
     l1, g1, _, _, _ = _ns_case(feo, 10, 96, 1, "interleaved", True)
     l2, g2, _, _, _ = _ns_case(feo, 10, 96, 1, "interleaved", True)
     assert l1 == l2 and torch.equal(g1, g2)  # bit-reproducible: no atomics anywhere
