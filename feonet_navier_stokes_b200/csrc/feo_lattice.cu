@@ -104,25 +104,35 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+  u64 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 // acc += c * x on two packed fp32 lanes, c a scalar (a constant-bank / uniform-register operand of FFMA2)
 __device__ __forceinline__ void fmac(u64& acc, float c, u64 x) { acc = fma2(pk(c, c), x, acc); }
-__device__ __forceinline__ float2 ldg2_stream(const float* p) {
-  float2 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+__device__ __forceinline__ u64 ldg_pair_stream(const float* p) {  // two samples of a load-vector line, read once
+  u64 v;
+  asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v) : "l"(p));
   return v;
 }
+__device__ __forceinline__ void stg_pair(float* p, u64 v) { asm volatile("st.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-// residual from LHS sum, load vector and convection in the reference's operation order:
-// precond branch  r = LHS - (F - c) ; else  r = LHS - (-F + c)   (FEONet_steady_Navier-Stokes/train_FEONet.py:324-330, :356)
-__device__ __forceinline__ float resid1(float lhs, float f, float c, bool precond) {
-  return precond ? __fsub_rn(lhs, __fsub_rn(f, c)) : __fsub_rn(lhs, __fadd_rn(-f, c));
-}
-// c = u_i*Bu1 + u_j*Bu2 as two rounded products and one rounded add (train_FEONet.py:317-322)
-__device__ __forceinline__ float conv1(float d1, float s1, float d2, float s2) { return __fadd_rn(__fmul_rn(d1, s1), __fmul_rn(d2, s2)); }
+// Epilogue arithmetic on sample pairs (FEONet_steady_Navier-Stokes/train_FEONet.py:317-330, :356):
+//   c = u_i Bu1 + u_j Bu2       -> fl(fma(u_i, Bu1, fl(u_j Bu2)))   (ptxas contracts the packed multiply-add: one rounding less
+//                                                                     than the reference's two products and an add)
+//   r = LHS - (F - c)  (precond branch)  /  LHS - (-F + c) = LHS + (F - c)  (else): one rounded F - c, one rounded LHS -/+ it
+__device__ __forceinline__ u64 conv2(u64 d1, u64 s1, u64 d2, u64 s2) { return fma2(d1, s1, mul2(d2, s2)); }
+__device__ __forceinline__ u64 resid2(u64 lhs, u64 f, u64 c, u64 neg_sign) { return fma2(neg_sign, sub2(f, c), lhs); }
 
 // ---- the walk over a CTA's chunk of (column, cj) steps; column = (strip, slab) ---------------------------
 struct Walk {
@@ -258,22 +268,22 @@ struct StepSync {
 // forward: r = A a -/+ (F - c) for the 9 rows of a cell, loss partial
 template <bool FAST, typename P>
 __device__ __forceinline__ void fwd_cell(const P& p, const StepSync& sy, int lane, const uint32_t (&Bx)[5], int cbase, uint32_t ex,
-                                         int32_t dE, int32_t dO, int b0, bool precond, float& lsum) {
-  // element offsets of the cell's rows in the dof-major arrays: V = (dE, dE + 1), P = dE + 2, H = dE + 3, T = dO, D = dO + 2
-  const bool in_ld = b0 < p.ldb, in_b = b0 < p.B;
-  const int64_t oE = (int64_t)dE * p.ldb + b0, oO = (int64_t)dO * p.ldb + b0;
+                                         int64_t oE, int64_t oO, int b0, u64 neg_sign, float& lsum) {
+  // element offsets of the cell's rows in the dof-major arrays (sample b0 included): V = (oE, oE + ldb), P = oE + 2 ldb,
+  // H = oE + 3 ldb, T = oO, D = oO + 2 ldb
+  const bool in_ld = b0 < p.ldb, in_b = b0 < p.B, in_b1 = b0 + 1 < p.B;
   const int64_t offs[kLatTargets] = {oE, oE + 3 * p.ldb, oO, oO + 2 * p.ldb};
-  float2 fv[kLatTargets][2], fp = make_float2(0.f, 0.f);
+  u64 fv[kLatTargets][2], fp = 0ull;
 #pragma unroll
-  for (int t = 0; t < kLatTargets; ++t) fv[t][0] = fv[t][1] = make_float2(0.f, 0.f);
+  for (int t = 0; t < kLatTargets; ++t) fv[t][0] = fv[t][1] = 0ull;
   if (in_ld) {
 #pragma unroll
     for (int t = 0; t < kLatTargets; ++t)
       if (FAST || ((ex >> t) & 1u)) {
-        fv[t][0] = ldg2_stream(p.fT + offs[t]);
-        fv[t][1] = ldg2_stream(p.fT + offs[t] + p.ldb);
+        fv[t][0] = ldg_pair_stream(p.fT + offs[t]);
+        fv[t][1] = ldg_pair_stream(p.fT + offs[t] + p.ldb);
       }
-    fp = ldg2_stream(p.fT + oE + 2 * p.ldb);
+    fp = ldg_pair_stream(p.fT + oE + 2 * p.ldb);
   }
   u64 acc[3][kLatTargets][2], sacc = 0ull;
 #pragma unroll
@@ -297,43 +307,28 @@ __device__ __forceinline__ void fwd_cell(const P& p, const StepSync& sy, int lan
 #undef FSJ
 #undef FP
 #undef FSP
+  auto finish = [&](u64 r, int64_t off) {
+    float r0, r1;
+    unpk(r, r0, r1);
+    if (in_b) lsum = fmaf(r0, r0, lsum);
+    if (in_b1) lsum = fmaf(r1, r1, lsum);
+    if (p.outT != nullptr && in_b) stg_pair(p.outT + off, r);
+  };
 #pragma unroll
   for (int t = 0; t < kLatTargets; ++t) {
     if (!FAST && !((ex >> t) & 1u)) continue;
-    float d1[2], d2[2];
-    unpk(lds64(Bx[tgt_y(t) + 2] + lat_off(tgt_x(t), tgt_y(t), 0)), d1[0], d1[1]);
-    unpk(lds64(Bx[tgt_y(t) + 2] + lat_off(tgt_x(t), tgt_y(t), 1)), d2[0], d2[1]);
+    const u64 d1 = lds64(Bx[tgt_y(t) + 2] + lat_off(tgt_x(t), tgt_y(t), 0)), d2 = lds64(Bx[tgt_y(t) + 2] + lat_off(tgt_x(t), tgt_y(t), 1));
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      float a[2], u[2], v[2];
-      unpk(acc[0][t][c], a[0], a[1]);
-      unpk(acc[1][t][c], u[0], u[1]);
-      unpk(acc[2][t][c], v[0], v[1]);
-      float2 r;
-      r.x = resid1(a[0], fv[t][c].x, conv1(d1[0], u[0], d2[0], v[0]), precond);
-      r.y = resid1(a[1], fv[t][c].y, conv1(d1[1], u[1], d2[1], v[1]), precond);
-      if (in_b) lsum = fmaf(r.x, r.x, lsum);
-      if (b0 + 1 < p.B) lsum = fmaf(r.y, r.y, lsum);
-      if (p.outT != nullptr && in_b) *reinterpret_cast<float2*>(p.outT + offs[t] + (c ? p.ldb : 0)) = r;
-    }
+    for (int c = 0; c < 2; ++c)
+      finish(resid2(acc[0][t][c], fv[t][c], conv2(d1, acc[1][t][c], d2, acc[2][t][c]), neg_sign), offs[t] + (c ? p.ldb : 0));
   }
-  {
-    float a[2];
-    unpk(sacc, a[0], a[1]);
-    float2 r;
-    r.x = resid1(a[0], fp.x, 0.f, precond);
-    r.y = resid1(a[1], fp.y, 0.f, precond);
-    if (in_b) lsum = fmaf(r.x, r.x, lsum);
-    if (b0 + 1 < p.B) lsum = fmaf(r.y, r.y, lsum);
-    if (p.outT != nullptr && in_b) *reinterpret_cast<float2*>(p.outT + oE + 2 * p.ldb) = r;
-  }
+  finish(resid2(sacc, fp, 0ull, neg_sign), oE + 2 * p.ldb);
 }
 
 // backward: grad = 2 g [A^T r + s (B1^T (d1 r) + B2^T (d2 r) + E-term)] for the 9 columns of a cell
 template <bool FAST, typename P>
 __device__ __forceinline__ void bwd_cell(const P& p, const StepSync& sy, int lane, const uint32_t (&Br)[5], const uint32_t (&Ba)[5], int cbase,
-                                         uint32_t ex, int32_t dE, int32_t dO, int b0, float g2) {
-  const int64_t oE = (int64_t)dE * p.ldb + b0, oO = (int64_t)dO * p.ldb + b0;
+                                         uint32_t ex, int64_t oE, int64_t oO, int b0, float g2) {
   const int64_t offs[kLatTargets] = {oE, oE + 3 * p.ldb, oO, oO + 2 * p.ldb};
   u64 g[kLatTargets][2], bu[3][kLatTargets][2], sacc = 0ull;  // bu[1] = Bu1, bu[2] = Bu2 of the own rows ([0] unused)
 #pragma unroll
@@ -376,33 +371,20 @@ __device__ __forceinline__ void bwd_cell(const P& p, const StepSync& sy, int lan
 #undef BP
 #undef BSP
   const bool st = b0 < p.B;
+  const u64 es2 = pk(p.esign, p.esign), g22 = pk(g2, g2);
 #pragma unroll
   for (int t = 0; t < kLatTargets; ++t) {
     if (!FAST && !((ex >> t) & 1u)) continue;
-    float rI[2], rJ[2], gI[2], gJ[2], s1i[2], s1j[2], s2i[2], s2j[2];
-    unpk(lds64(Br[tgt_y(t) + 2] + lat_off(tgt_x(t), tgt_y(t), 0)), rI[0], rI[1]);
-    unpk(lds64(Br[tgt_y(t) + 2] + lat_off(tgt_x(t), tgt_y(t), 1)), rJ[0], rJ[1]);
-    unpk(g[t][0], gI[0], gI[1]);
-    unpk(g[t][1], gJ[0], gJ[1]);
-    unpk(bu[1][t][0], s1i[0], s1i[1]);
-    unpk(bu[1][t][1], s1j[0], s1j[1]);
-    unpk(bu[2][t][0], s2i[0], s2i[1]);
-    unpk(bu[2][t][1], s2j[0], s2j[1]);
-    float2 oI, oJ;
-    oI.x = fmaf(p.esign, fmaf(s1j[0], rJ[0], s1i[0] * rI[0]), gI[0]) * g2;
-    oI.y = fmaf(p.esign, fmaf(s1j[1], rJ[1], s1i[1] * rI[1]), gI[1]) * g2;
-    oJ.x = fmaf(p.esign, fmaf(s2j[0], rJ[0], s2i[0] * rI[0]), gJ[0]) * g2;
-    oJ.y = fmaf(p.esign, fmaf(s2j[1], rJ[1], s2i[1] * rI[1]), gJ[1]) * g2;
+    const u64 rI = lds64(Br[tgt_y(t) + 2] + lat_off(tgt_x(t), tgt_y(t), 0)), rJ = lds64(Br[tgt_y(t) + 2] + lat_off(tgt_x(t), tgt_y(t), 1));
+    // E-term of the own rows: g_I += e (Bu1_I rI + Bu1_J rJ), g_J += e (Bu2_I rI + Bu2_J rJ); scale by 2 g
+    const u64 oI = mul2(fma2(es2, fma2(bu[1][t][1], rJ, mul2(bu[1][t][0], rI)), g[t][0]), g22);
+    const u64 oJ = mul2(fma2(es2, fma2(bu[2][t][1], rJ, mul2(bu[2][t][0], rI)), g[t][1]), g22);
     if (st) {
-      *reinterpret_cast<float2*>(p.outT + offs[t]) = oI;
-      *reinterpret_cast<float2*>(p.outT + offs[t] + p.ldb) = oJ;
+      stg_pair(p.outT + offs[t], oI);
+      stg_pair(p.outT + offs[t] + p.ldb, oJ);
     }
   }
-  if (st) {
-    float a[2];
-    unpk(sacc, a[0], a[1]);
-    *reinterpret_cast<float2*>(p.outT + oE + 2 * p.ldb) = make_float2(a[0] * g2, a[1] * g2);
-  }
+  if (st) stg_pair(p.outT + oE + 2 * p.ldb, mul2(sacc, g22));
 }
 #undef C
 #undef BEGIN
@@ -440,6 +422,9 @@ __global__ void __launch_bounds__(NT, 1)
   Walk w;
   w.start(p);
   uint32_t slot0 = 0;
+  const u64 neg_sign = precond ? pk(-1.f, -1.f) : pk(1.f, 1.f);
+  const int64_t row_pair = (int64_t)(9 * p.n + 5) * p.ldb;  // dofs of an (even, odd) lattice row pair = one cell row further up
+  int64_t oE = 0, oO = 0;
   while (!w.done()) {
     const int32_t ci = w.strip * p.W + warp, cj = w.cj, slab = w.slab;
     const bool first = w.local == 0;
@@ -468,21 +453,27 @@ __global__ void __launch_bounds__(NT, 1)
         Bx[i] = lane_base + slot * p.slot_bytes + cell_off[i & 1];
         Ba[i] = Bx[i] + a_off;
       }
-      const int32_t dE = cj * (9 * p.n + 5) + 5 * ci, dO = cj * (9 * p.n + 5) + (5 * p.n + 3) + 4 * ci;
       const int b0 = slab * kSlab + lane * 2;
+      if (first) {
+        oE = (int64_t)(cj * (9 * p.n + 5) + 5 * ci) * p.ldb + b0;
+        oO = (int64_t)(cj * (9 * p.n + 5) + (5 * p.n + 3) + 4 * ci) * p.ldb + b0;
+      } else {
+        oE += row_pair;
+        oO += row_pair;
+      }
       const uint32_t cls = p.cat_cls[lat_cat(cj, p.nc) * 5 + lat_cat(ci, p.nc)];
       if (!BWD) {
         float lsum = 0.f;
         if (cls == 0)
-          fwd_cell<true>(p, sy, lane, Bx, 0, 15u, dE, dO, b0, precond, lsum);
+          fwd_cell<true>(p, sy, lane, Bx, 0, 15u, oE, oO, b0, neg_sign, lsum);
         else
-          fwd_cell<false>(p, sy, lane, Bx, (int)cls * NCOEF, p.exist[cls], dE, dO, b0, precond, lsum);
+          fwd_cell<false>(p, sy, lane, Bx, (int)cls * NCOEF, p.exist[cls], oE, oO, b0, neg_sign, lsum);
         dsum += (double)lsum;
       } else {
         if (cls == 0)
-          bwd_cell<true>(p, sy, lane, Bx, Ba, 0, 15u, dE, dO, b0, g2);
+          bwd_cell<true>(p, sy, lane, Bx, Ba, 0, 15u, oE, oO, b0, g2);
         else
-          bwd_cell<false>(p, sy, lane, Bx, Ba, (int)cls * NCOEF, p.exist[cls], dE, dO, b0, g2);
+          bwd_cell<false>(p, sy, lane, Bx, Ba, (int)cls * NCOEF, p.exist[cls], oE, oO, b0, g2);
       }
     }
     if (!sy.release_early) {
