@@ -517,7 +517,6 @@ template <bool BWD>
 int launch(const feo_operator* op, const DevLatticePlan& L, const float* src0, const float* src1, const float* fT, float* outT,
            float* partials, size_t partial_cap, const float* grad_loss, int64_t ldb, int32_t B, int* n_partials, cudaStream_t st) {
   constexpr int NCOEF = BWD ? FEO_LAT_BWD_NCOEF : FEO_LAT_FWD_NCOEF;
-  constexpr int NT = BWD ? 384 : 512;
   const int dir = BWD ? 1 : 0;
   LatParams<NCOEF> p;  // 20-30 KB of kernel parameters (the class tables)
   p.fT = fT;
@@ -530,8 +529,9 @@ int launch(const feo_operator* op, const DevLatticePlan& L, const float* src0, c
   p.n = L.n;
   p.nc = L.nc;
   p.N = op->n;
-  const int w_max = BWD ? 11 : 15;
-  p.W = env_int(BWD ? "FEO_LAT_W_BWD" : "FEO_LAT_W_FWD", pick_width(L.nc, w_max));
+  const int w_max = BWD ? 13 : 15;
+  // backward: a 6-row ring of (r, alpha) runs fits 12 cells (13 warps x 128 registers); forward: 15 cells fit a 9-row ring
+  p.W = env_int(BWD ? "FEO_LAT_W_BWD" : "FEO_LAT_W_FWD", pick_width(L.nc, BWD ? 12 : 15));
   if (p.W < 1 || p.W > w_max) return fail(FEO_ERR_INVALID_ARGUMENT, "lattice kernel: strip width out of range");
   p.n_strips = (L.nc + p.W - 1) / p.W;
   const int64_t total = (int64_t)p.n_strips * p.n_slabs * L.nc;
@@ -540,16 +540,17 @@ int launch(const feo_operator* op, const DevLatticePlan& L, const float* src0, c
   p.he = 5 * p.W + 8;
   p.ho = 4 * p.W + 6;
   p.slot_bytes = (uint32_t)p.he * kLineBytes * (BWD ? 2u : 1u);
-  p.R = env_int(BWD ? "FEO_LAT_R_BWD" : "FEO_LAT_R_FWD", BWD ? 7 : 9);
-  if (p.R != 7 && p.R != 9) return fail(FEO_ERR_INVALID_ARGUMENT, "lattice kernel: ring rows must be 7 or 9");
-  while (p.R > 7 && (uint64_t)p.R * p.slot_bytes + 64 > kSmemMax) p.R -= 2;
-  p.D = (p.R - 3) / 2;
+  p.R = env_int(BWD ? "FEO_LAT_R_BWD" : "FEO_LAT_R_FWD", BWD ? 6 : 9);
+  if (p.R < 6 || p.R > 9) return fail(FEO_ERR_INVALID_ARGUMENT, "lattice kernel: ring rows must be 6 .. 9");
+  while (p.R > 6 && (uint64_t)p.R * p.slot_bytes + 64 > kSmemMax) p.R -= 1;
+  p.D = (p.R - 3) / 2;  // rows 2L + 3 - R, 2L + 4 - R belong to the early-released part of steps >= L - D
   p.K = p.D + 1;
   p.bar_off = (uint32_t)p.R * p.slot_bytes;
   const uint32_t smem = p.bar_off + 2 * kStagesMax * 8;
   if (smem > kSmemMax) return fail(FEO_ERR_INVALID_ARGUMENT, "lattice kernel: the row ring does not fit shared memory");
   p.debug = env_int("FEO_DEBUG_MODE", 0);
   p.sync_mask = env_int(BWD ? "FEO_LAT_SYNC_BWD" : "FEO_LAT_SYNC_FWD", 3);
+  if (p.R % 2 == 0) p.sync_mask |= 1;  // an even ring has no spare slot: the slots a fetch needs are free only after the early release
   p.precond = op->ns_branch;
   p.esign = op->ns_branch ? 1.0f : -1.0f;
   if (L.n_classes[dir] > kLatMaxClasses || L.tab[dir].size() != (size_t)L.n_classes[dir] * NCOEF)
@@ -576,9 +577,25 @@ int launch(const feo_operator* op, const DevLatticePlan& L, const float* src0, c
     if (int rc = make_box_map(fT, ldb, op->n, 5 * p.W, &maps.f[0])) return rc;
     if (int rc = make_box_map(fT, ldb, op->n, 4 * p.W, &maps.f[1])) return rc;
   }
-  auto kern = residual_lattice_kernel<BWD, NT>;
-  FEO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)grid, (unsigned)(p.W + 1) * 32, smem, st>>>(maps, p);
+  // the register file (64 K) is split over the launched warps: up to 12 / 13 / 14 / 16 warps -> 168 / 152 / 144 / 128 registers
+  const unsigned nt = (unsigned)(p.W + 1) * 32;
+#define FEO_LAT_LAUNCH(NT)                                                                                          \
+  do {                                                                                                              \
+    auto kern = residual_lattice_kernel<BWD, NT>;                                                                   \
+    FEO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+    kern<<<(unsigned)grid, nt, smem, st>>>(maps, p);                                                                \
+  } while (0)
+  if constexpr (BWD) {
+    if (nt <= 384)
+      FEO_LAT_LAUNCH(384);
+    else if (nt <= 416)
+      FEO_LAT_LAUNCH(416);
+    else
+      FEO_LAT_LAUNCH(448);
+  } else {
+    FEO_LAT_LAUNCH(512);
+  }
+#undef FEO_LAT_LAUNCH
   FEO_CUDA_CHECK(cudaGetLastError());
   return FEO_OK;
 }
