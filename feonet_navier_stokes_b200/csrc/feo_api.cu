@@ -128,7 +128,9 @@ int feo_op_create(const feo_operator_desc* desc, feo_handle_t* out) {
         D.n = lp.n;
         D.nc = lp.nc;
         D.has_conv = lp.has_conv;
-        for (int dir = 0; dir < 2; ++dir) {
+        const char* ew = std::getenv("FEO_LATTICE_ELEMENT");
+        D.element_walk = ew != nullptr && atoi(ew) != 0;
+        for (int dir = 0; dir < kLatTables; ++dir) {
           D.n_classes[dir] = lp.n_classes[dir];
           D.exist[dir] = lp.exist[dir];
           D.tab[dir] = lp.tab[dir];
@@ -401,7 +403,7 @@ int feo_debug_lattice_replay(const feo_operator_desc* desc, int32_t backward, co
   }
   if (!P.applicable) return fail(FEO_ERR_UNSUPPORTED, "lattice plan not applicable: " + P.why_not);
   if (in0 == nullptr || in1 == nullptr || out == nullptr) return FEO_OK;
-  return replay_lattice_plan(P, backward != 0, branch, in0, in1, out);
+  return replay_lattice_plan(P, backward, branch, in0, in1, out);  // backward = table: 0 forward, 1 backward, 2 element-walk forward
 }
 
 }  // extern "C"

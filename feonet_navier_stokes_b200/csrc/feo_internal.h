@@ -189,14 +189,16 @@ struct DevPatchPlan {
   uint32_t* stream = nullptr;  // 32-bit slots, rounds start on 16-byte words
 };
 
+constexpr int kLatTables = 3;  // forward, backward, forward as an element walk (feo_lattice.h)
 // device side of a lattice plan (feo_lattice.h): the third-generation plan for structured P2-P1 lattices
 struct DevLatticePlan {
   bool present = false, has_conv = false;
+  bool element_walk = false;             // developer knob FEO_LATTICE_ELEMENT=1: the forward kernel runs table 2 (A/B measurement)
   int32_t n = 0, nc = 0;
-  uint8_t cat_cls[2][25];                // class of a cell by boundary-layer category (feo_lattice.h), forward / backward
-  int32_t n_classes[2] = {0, 0};
-  std::vector<uint8_t> exist[2];         // host copies: the class tables travel as kernel parameters
-  std::vector<float> tab[2];
+  uint8_t cat_cls[kLatTables][25];       // class of a cell by boundary-layer category (feo_lattice.h)
+  int32_t n_classes[kLatTables] = {0, 0, 0};
+  std::vector<uint8_t> exist[kLatTables];  // host copies: the class tables travel as kernel parameters
+  std::vector<float> tab[kLatTables];
 };
 
 // ---- device-side operator ---------------------------------------------------------------------

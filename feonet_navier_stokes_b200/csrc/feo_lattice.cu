@@ -266,7 +266,7 @@ struct StepSync {
 };
 
 // forward: r = A a -/+ (F - c) for the 9 rows of a cell, loss partial
-template <bool FAST, typename P>
+template <bool FAST, bool ELEM, typename P>
 __device__ __forceinline__ void fwd_cell(const P& p, const StepSync& sy, int lane, const uint32_t (&Bx)[5], int cbase, uint32_t ex,
                                          int64_t oE, int64_t oO, int b0, u64 neg_sign, float& lsum) {
   // element offsets of the cell's rows in the dof-major arrays (sample b0 included): V = (oE, oE + ldb), P = oE + 2 ldb,
@@ -296,11 +296,24 @@ __device__ __forceinline__ void fwd_cell(const P& p, const StepSync& sy, int lan
 #define FSJ(i) fmac(sacc, C(i), xJ);
 #define FP(t, tc, i) fmac(acc[0][t][tc], C(i), xP);
 #define FSP(i) fmac(sacc, C(i), xP);
-  FEO_LAT_FWD_BODY_A
+  // ELEM: the same rows as a matrix-free element walk in gather form (one FMA per element-level entry; A/B variant)
+  if constexpr (ELEM) {
+    FEO_LAT_FWDE_BODY_A
+  } else {
+    FEO_LAT_FWD_BODY_A
+  }
   sy.after_a(lane);
-  FEO_LAT_FWD_BODY_B
+  if constexpr (ELEM) {
+    FEO_LAT_FWDE_BODY_B
+  } else {
+    FEO_LAT_FWD_BODY_B
+  }
   sy.before_c();
-  FEO_LAT_FWD_BODY_C
+  if constexpr (ELEM) {
+    FEO_LAT_FWDE_BODY_C
+  } else {
+    FEO_LAT_FWD_BODY_C
+  }
 #undef LDX
 #undef FV
 #undef FSI
@@ -391,10 +404,12 @@ __device__ __forceinline__ void bwd_cell(const P& p, const StepSync& sy, int lan
 #undef END
 
 // ---- the kernel ---------------------------------------------------------------------------------------------
-template <bool BWD, int NT>
+__host__ __device__ constexpr int lat_ncoef(bool bwd, bool elem) { return bwd ? FEO_LAT_BWD_NCOEF : (elem ? FEO_LAT_FWDE_NCOEF : FEO_LAT_FWD_NCOEF); }
+
+template <bool BWD, int NT, bool ELEM>
 __global__ void __launch_bounds__(NT, 1)
-    residual_lattice_kernel(const __grid_constant__ LatMaps maps, const __grid_constant__ LatParams<BWD ? FEO_LAT_BWD_NCOEF : FEO_LAT_FWD_NCOEF> p) {
-  constexpr int NCOEF = BWD ? FEO_LAT_BWD_NCOEF : FEO_LAT_FWD_NCOEF;
+    residual_lattice_kernel(const __grid_constant__ LatMaps maps, const __grid_constant__ LatParams<lat_ncoef(BWD, ELEM)> p) {
+  constexpr int NCOEF = lat_ncoef(BWD, ELEM);
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sb = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -465,9 +480,9 @@ __global__ void __launch_bounds__(NT, 1)
       if (!BWD) {
         float lsum = 0.f;
         if (cls == 0)
-          fwd_cell<true>(p, sy, lane, Bx, 0, 15u, oE, oO, b0, neg_sign, lsum);
+          fwd_cell<true, ELEM>(p, sy, lane, Bx, 0, 15u, oE, oO, b0, neg_sign, lsum);
         else
-          fwd_cell<false>(p, sy, lane, Bx, (int)cls * NCOEF, p.exist[cls], oE, oO, b0, neg_sign, lsum);
+          fwd_cell<false, ELEM>(p, sy, lane, Bx, (int)cls * NCOEF, p.exist[cls], oE, oO, b0, neg_sign, lsum);
         dsum += (double)lsum;
       } else {
         if (cls == 0)
@@ -513,11 +528,11 @@ int pick_width(int nc, int w_max) {
   return best;
 }
 
-template <bool BWD>
+template <bool BWD, bool ELEM>
 int launch(const feo_operator* op, const DevLatticePlan& L, const float* src0, const float* src1, const float* fT, float* outT,
            float* partials, size_t partial_cap, const float* grad_loss, int64_t ldb, int32_t B, int* n_partials, cudaStream_t st) {
-  constexpr int NCOEF = BWD ? FEO_LAT_BWD_NCOEF : FEO_LAT_FWD_NCOEF;
-  const int dir = BWD ? 1 : 0;
+  constexpr int NCOEF = lat_ncoef(BWD, ELEM);
+  const int dir = BWD ? 1 : (ELEM ? 2 : 0);
   LatParams<NCOEF> p;  // 20-30 KB of kernel parameters (the class tables)
   p.fT = fT;
   p.outT = outT;
@@ -581,7 +596,7 @@ int launch(const feo_operator* op, const DevLatticePlan& L, const float* src0, c
   const unsigned nt = (unsigned)(p.W + 1) * 32;
 #define FEO_LAT_LAUNCH(NT)                                                                                          \
   do {                                                                                                              \
-    auto kern = residual_lattice_kernel<BWD, NT>;                                                                   \
+    auto kern = residual_lattice_kernel<BWD, NT, ELEM>;                                                                   \
     FEO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
     kern<<<(unsigned)grid, nt, smem, st>>>(maps, p);                                                                \
   } while (0)
@@ -614,7 +629,11 @@ int launch_lattice_fwd(const feo_operator* op, const DevLatticePlan& L, const fl
   if (loss_out == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, "loss_out is NULL");
   if (ws == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, "workspace too small");
   int n_partials = 0;
-  if (int rc = launch<false>(op, L, alphaT, alphaT, fT, rT, (float*)ws, ws_bytes / sizeof(float), nullptr, ldb, B, &n_partials, st)) return rc;
+  if (L.element_walk) {
+    if (int rc = launch<false, true>(op, L, alphaT, alphaT, fT, rT, (float*)ws, ws_bytes / sizeof(float), nullptr, ldb, B, &n_partials, st)) return rc;
+  } else {
+    if (int rc = launch<false, false>(op, L, alphaT, alphaT, fT, rT, (float*)ws, ws_bytes / sizeof(float), nullptr, ldb, B, &n_partials, st)) return rc;
+  }
   return finalize_loss((float*)ws, n_partials, 1.0f, loss_out, st);
 }
 
@@ -625,7 +644,7 @@ int launch_lattice_bwd(const feo_operator* op, const DevLatticePlan& L, const fl
   if (int rc = check_layout(gradT, ldb, B, "gradT")) return rc;
   const float* a = L.has_conv ? alphaT : rT;  // linear operators: the alpha tables are all zero, any finite source will do
   if (int rc = check_layout(a, ldb, B, "alphaT")) return rc;
-  return launch<true>(op, L, rT, a, nullptr, gradT, nullptr, 0, grad_loss, ldb, B, nullptr, st);
+  return launch<true, false>(op, L, rT, a, nullptr, gradT, nullptr, 0, grad_loss, ldb, B, nullptr, st);
 }
 
 }  // namespace feo

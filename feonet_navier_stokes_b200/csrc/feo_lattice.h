@@ -32,13 +32,13 @@ struct LatticePlan {
   int32_t nc = 0;   // n + 1
   int32_t N = 0;
   std::vector<int32_t> row_dof0;  // [2n + 5]: dof of u1 at node (0, y) for y = -2 .. 2n + 2 (index y + 2); rows off the lattice: N + 4096
-  // per direction (0 forward, 1 backward)
-  int32_t n_classes[2] = {0, 0};
-  int32_t n_coef[2] = {0, 0};
-  std::vector<uint8_t> cls[2];    // [nc * nc] class of cell (ci, cj) at cj * nc + ci; class 0 = the most frequent complete one
-  uint8_t cat_cls[2][25];         // the same by boundary-layer categories: cls = cat_cls[lat_cat(cj) * 5 + lat_cat(ci)] (verified)
-  std::vector<uint8_t> exist[2];  // [n_classes] bit t: target node t exists (bit 0 is always set, the pressure dof exists with V)
-  std::vector<float> tab[2];      // [n_classes][n_coef]
+  // per table (0 forward, 1 backward, 2 forward as a matrix-free element walk: the A/B variant of DESIGN.md section 3.5)
+  int32_t n_classes[kLatTables] = {0, 0, 0};
+  int32_t n_coef[kLatTables] = {0, 0, 0};
+  std::vector<uint8_t> cls[kLatTables];    // [nc * nc] class of cell (ci, cj) at cj * nc + ci; class 0 = the most frequent complete one
+  uint8_t cat_cls[kLatTables][25];         // the same by boundary-layer categories: cls = cat_cls[lat_cat(cj) * 5 + lat_cat(ci)] (verified)
+  std::vector<uint8_t> exist[kLatTables];  // [n_classes] bit t: target node t exists (bit 0 is always set, the pressure dof exists with V)
+  std::vector<float> tab[kLatTables];      // [n_classes][n_coef]
   int64_t real_entries = 0;
 };
 
@@ -46,8 +46,8 @@ struct LatticePlan {
 int build_lattice_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, int32_t n_u, const int32_t* idx_i, const int32_t* idx_j,
                        int32_t ns_branch, LatticePlan* out);
 // fp64 host replay for one sample: runs the generated cell bodies over the class tables exactly as the kernels do.
-// forward: in0 = alpha, in1 = f -> out = r ;  backward: in0 = r, in1 = alpha -> out = grad / (2 g)
-int replay_lattice_plan(const LatticePlan& L, bool backward, int32_t ns_branch, const double* in0, const double* in1, double* out);
+// table 0 / 2 (forward): in0 = alpha, in1 = f -> out = r ;  table 1 (backward): in0 = r, in1 = alpha -> out = grad / (2 g)
+int replay_lattice_plan(const LatticePlan& L, int table, int32_t ns_branch, const double* in0, const double* in1, double* out);
 
 int launch_lattice_fwd(const feo_operator* op, const DevLatticePlan& L, const float* alphaT, const float* fT, int64_t ldb, int32_t B,
                        float* loss_out, float* rT, void* ws, size_t ws_bytes, cudaStream_t st);

@@ -13,14 +13,18 @@ namespace feo {
 namespace {
 
 struct Desc {
-  int8_t mat, rdx, rdy, rc, cdx, cdy, cc, is_signed, twin;
+  int8_t mat, rdx, rdy, rc, cdx, cdy, cc, is_signed, twin, div, first;
 };
-#define FEO_DESC_ROW(i, mat, rdx, rdy, rc, cdx, cdy, cc, sg, tw) {mat, rdx, rdy, rc, cdx, cdy, cc, sg, tw},
+#define FEO_DESC_ROW(i, mat, rdx, rdy, rc, cdx, cdy, cc, sg, tw, dv, fi) {mat, rdx, rdy, rc, cdx, cdy, cc, sg, tw, dv, fi},
 const Desc kFwdDesc[] = {FEO_LAT_FWD_DESC(FEO_DESC_ROW)};
 const Desc kBwdDesc[] = {FEO_LAT_BWD_DESC(FEO_DESC_ROW)};
+const Desc kFwdElemDesc[] = {FEO_LAT_FWDE_DESC(FEO_DESC_ROW)};
 #undef FEO_DESC_ROW
 static_assert(sizeof(kFwdDesc) / sizeof(Desc) == FEO_LAT_FWD_NCOEF, "forward table layout");
 static_assert(sizeof(kBwdDesc) / sizeof(Desc) == FEO_LAT_BWD_NCOEF, "backward table layout");
+static_assert(sizeof(kFwdElemDesc) / sizeof(Desc) == FEO_LAT_FWDE_NCOEF, "element-walk forward table layout");
+const Desc* const kDesc[kLatTables] = {kFwdDesc, kBwdDesc, kFwdElemDesc};
+constexpr int kNCoef[kLatTables] = {FEO_LAT_FWD_NCOEF, FEO_LAT_BWD_NCOEF, FEO_LAT_FWDE_NCOEF};
 constexpr int kTx[kLatTargets] = {0, 1, 0, 1}, kTy[kLatTargets] = {0, 0, 1, 1};
 
 struct Geometry {
@@ -110,10 +114,10 @@ int build_lattice_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, i
   const HostCsr* mats[3] = {&A, &B1, &B2};
 
   // ---- one table per cell and direction; classes by (existence mask, table) ----
-  int64_t matched[2][3] = {{0, 0, 0}, {0, 0, 0}};
-  for (int dir = 0; dir < 2; ++dir) {
-    const Desc* D = dir ? kBwdDesc : kFwdDesc;
-    const int nd = dir ? FEO_LAT_BWD_NCOEF : FEO_LAT_FWD_NCOEF;
+  int64_t matched[kLatTables][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int dir = 0; dir < kLatTables; ++dir) {
+    const Desc* D = kDesc[dir];
+    const int nd = kNCoef[dir];
     L->n_coef[dir] = nd;
     std::map<std::vector<uint32_t>, int32_t> ids;
     std::vector<std::vector<uint32_t>> keys;
@@ -134,10 +138,11 @@ int build_lattice_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, i
           if (d.twin) {
             const float w = lookup(*mats[d.mat], G.dof(ox + d.rdx, oy + d.rdy, 1), G.dof(ox + d.cdx, oy + d.cdy, 1));
             if (w != v) return not_applicable(L, "the two velocity components of a node pair carry different coefficients");
-            if (v != 0.f) matched[dir][d.mat] += 1;  // the (J, J) entry
+            if (v != 0.f && d.first) matched[dir][d.mat] += 1;  // the (J, J) entry
           }
-          if (v != 0.f) matched[dir][d.mat] += 1;
+          if (v != 0.f && d.first) matched[dir][d.mat] += 1;
           if (d.is_signed) v *= sgn;
+          if (d.div > 1) v /= (float)d.div;  // element walk: `div` statements share the assembled entry
           key[(size_t)i + 1] = f2u(v == 0.f ? 0.f : v);  // -0 and +0 are one class
         }
         auto it = ids.find(key);
@@ -199,7 +204,7 @@ int build_lattice_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, i
           if (is_vel[(size_t)r]) want[mi] += mats[mi]->rowptr[r + 1] - mats[mi]->rowptr[r];
   }
   for (int mi = 0; mi < 3; ++mi) {
-    if (matched[0][mi] != want[mi]) return not_applicable(L, "matrix entries outside the lattice stencil (forward)");
+    if (matched[0][mi] != want[mi] || matched[2][mi] != want[mi]) return not_applicable(L, "matrix entries outside the lattice stencil (forward)");
     if (matched[1][mi] != (mi == 0 ? want[mi] : 2 * want[mi])) return not_applicable(L, "matrix entries outside the lattice stencil (backward)");
   }
   L->real_entries = want[0] + want[1] + want[2];
@@ -208,14 +213,16 @@ int build_lattice_plan(const HostCsr& A, const HostCsr& B1, const HostCsr& B2, i
 }
 
 // ---- fp64 replay: the generated bodies over doubles --------------------------------------------------
-int replay_lattice_plan(const LatticePlan& L, bool backward, int32_t ns_branch, const double* in0, const double* in1, double* out) {
+int replay_lattice_plan(const LatticePlan& L, int table, int32_t ns_branch, const double* in0, const double* in1, double* out) {
+  if (table < 0 || table >= kLatTables) return fail(FEO_ERR_INVALID_ARGUMENT, "lattice replay: unknown table");
+  const bool backward = table == 1;
   if (!L.applicable) return fail(FEO_ERR_UNSUPPORTED, "lattice plan not applicable: " + L.why_not);
   Geometry G;
   G.n = L.n;
   G.m = 2 * L.n + 1;
   G.N = L.N;
   G.row0 = L.row_dof0.data() + 2;
-  const int dir = backward ? 1 : 0;
+  const int dir = table;
   const int nd = L.n_coef[dir];
   const bool precond = ns_branch != 0;
   const double esign = precond ? 1.0 : -1.0;
@@ -241,7 +248,11 @@ int replay_lattice_plan(const LatticePlan& L, bool backward, int32_t ns_branch, 
 #define FSJ(i) sacc += C(i) * xJ;
 #define FP(t, tc, i) acc[0][t][tc] += C(i) * xP;
 #define FSP(i) sacc += C(i) * xP;
-        FEO_LAT_FWD_BODY_A FEO_LAT_FWD_BODY_B FEO_LAT_FWD_BODY_C
+        if (table == 2) {
+          FEO_LAT_FWDE_BODY_A FEO_LAT_FWDE_BODY_B FEO_LAT_FWDE_BODY_C
+        } else {
+          FEO_LAT_FWD_BODY_A FEO_LAT_FWD_BODY_B FEO_LAT_FWD_BODY_C
+        }
 #undef LDX
 #undef FV
 #undef FSI

@@ -117,3 +117,20 @@ def test_lattice_linear_stokes_without_idx_sol(feo, monkeypatch):
     assert abs(loss.item() - lo) <= LOSS_RTOL * lo
     assert _rel(rT[:, :B].t().cpu().numpy(), r) < 1e-5
     assert _rel(gT[:, :B].t().cpu().numpy(), go) < GRAD_RTOL
+
+
+def test_element_walk_variant_matches(feo, monkeypatch):
+    """FEO_LATTICE_ELEMENT=1: the forward kernel evaluates the rows as a matrix-free element walk in gather form (one FMA per
+    element-level entry, DESIGN.md section 3.5: the measured alternative to the assembled stencil).  Same loss / residual."""
+    from feonet_navier_stokes_b200.fixtures import config_operators
+
+    fx = config_operators("steady_ns", 14, ordering="interleaved")
+    rng = np.random.default_rng(77)
+    alpha = (0.3 * rng.standard_normal((70, fx.N))).astype(np.float32)
+    F = rng.standard_normal((70, fx.N)).astype(np.float32)
+    lo, go, _ = orc.ns_loss_and_grad(alpha, F, fx.A, fx.B1, fx.B2, fx.idx_u1, fx.idx_u2, True, dtype=np.float64)
+    monkeypatch.setenv("FEO_PLAN", "lattice")
+    monkeypatch.setenv("FEO_LATTICE_ELEMENT", "1")
+    l1, g1, _ = _run(feo, fx, alpha, F, 1)
+    assert abs(l1 - lo) <= LOSS_RTOL * abs(lo)
+    assert _rel(g1, go) < GRAD_RTOL

@@ -181,6 +181,11 @@ def test_lattice_replay_matches_oracle(n, branch, variant):
     rc, g, _ = _lattice_replay(lib, desc, True, ro, alpha, op.N)
     assert rc == 0
     assert np.allclose(2.0 * g, go, rtol=1e-10, atol=1e-11)
+    # table 2: the forward rows as a matrix-free element walk (every assembled entry split over the elements that sum to it;
+    # the A/B variant of DESIGN.md section 3.5) -- same residual up to the fp32 rounding of the split coefficients
+    rc, r2, _ = _lattice_replay(lib, desc, 2, alpha, f, op.N)
+    assert rc == 0
+    assert np.allclose(r2, ro, rtol=2e-6, atol=2e-6)
 
 
 def test_lattice_plan_rejects_what_it_does_not_model():

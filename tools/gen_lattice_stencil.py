@@ -112,8 +112,8 @@ class Table:
     def __init__(self):
         self.desc = []
 
-    def add(self, mat, row, col, signed=False, twin=False):
-        self.desc.append((mat, row, col, signed, twin))
+    def add(self, mat, row, col, signed=False, twin=False, div=1, first=True):
+        self.desc.append((mat, row, col, signed, twin, div, first))
         return len(self.desc) - 1
 
 
@@ -162,6 +162,105 @@ def gen_forward(keys):
             stmts.append(f"FSP({i})")
         if stmts:
             body.append(f"  BEGIN LDX(xP, {dx}, {dy}, 2) " + " ".join(stmts) + " END")
+    return T, parts
+
+
+def element_multiplicity():
+    """{(mat, row(tx,ty,comp), col(dx,dy,comp)): number of ELEMENTS that contribute a non-zero local entry} for the rows of one
+    interior cell: what a matrix-free element walk (north_star: gather by dofmap, contract with the element tensor) evaluates
+    separately and the assembled stencil has already summed.  From the fixture's own element integrals."""
+    from feonet_navier_stokes_b200.fixtures.taylor_hood import _element_integrals
+
+    n = 4
+    mesh = structured_mesh(n)
+    m = 2 * n + 1
+    ox, oy = 4, 4  # an interior cell
+    mult = {}
+    tol = 1e-12
+
+    def off(node):
+        return (int(node % m) - ox, int(node // m) - oy)
+
+    for sl, Kdd, D, Q, _ in _element_integrals(mesh):
+        lap = Kdd[:, 0, 0] + Kdd[:, 1, 1]
+        for e in range(lap.shape[0]):
+            nodes = [off(v) for v in mesh.tri_p2[sl][e]]
+            verts = [off(mesh.p1_to_p2[v]) for v in mesh.tri_p1[sl][e]]
+            for a, ta in enumerate(nodes):
+                if ta in TARGETS:
+                    for b, mb in enumerate(nodes):
+                        for name, val in (("A", lap[e, a, b]), ("B1", D[e, 0, a, b]), ("B2", D[e, 1, a, b])):
+                            if abs(val) > tol:
+                                for c in (0, 1):
+                                    k = (name, (ta[0], ta[1], c), (mb[0], mb[1], c))
+                                    mult[k] = mult.get(k, 0) + 1
+                    for j, vq in enumerate(verts):
+                        for c in (0, 1):
+                            if abs(Q[e, c, a, j]) > tol:
+                                k = ("A", (ta[0], ta[1], c), (vq[0], vq[1], 2))
+                                mult[k] = mult.get(k, 0) + 1
+            for j, vq in enumerate(verts):
+                if vq == (0, 0):
+                    for b, mb in enumerate(nodes):
+                        for c in (0, 1):
+                            if abs(Q[e, c, b, j]) > tol:
+                                k = ("A", (0, 0, 2), (mb[0], mb[1], c))
+                                mult[k] = mult.get(k, 0) + 1
+    return mult
+
+
+def gen_forward_element(keys):
+    """The forward body of a matrix-free ELEMENT walk in gather form (row-owned, no scatter): every element incident to a target
+    node contributes its own local row, i.e. one FMA per (element, local row, local column, matrix) instead of one per assembled
+    entry.  Each assembled coefficient is split evenly over the element statements that sum to it (the planner only has the
+    assembled CSR), so the results are the assembled ones up to round-off while the arithmetic COST is the element walk's.
+    Used for the A/B measurement of DESIGN.md section 3.5 (FEO_LATTICE_ELEMENT=1), never by default."""
+    mult = element_multiplicity()
+    T = Table()
+    parts = {}
+
+    for part, rows in PARTS:
+        body = parts.setdefault(part, [])
+        for (dx, dy) in window_nodes(rows):
+            stmts, use = [], [False, False]
+            for ti, (tx, ty) in enumerate(TARGETS):
+                for mi, name in enumerate(MATS):
+                    present = (name, (tx, ty, 0), (dx, dy, 0)) in keys or (name, (tx, ty, 1), (dx, dy, 1)) in keys
+                    k = mult.get((name, (tx, ty, 0), (dx, dy, 0)), 0)
+                    if present or k:
+                        k = max(k, 1)
+                        for r in range(k):
+                            i = T.add(name, (tx, ty, 0), (dx, dy, 0), twin=True, div=k, first=r == 0)
+                            stmts.append(f"FV({mi}, {ti}, {i})")
+                        use = [True, True]
+            for cc in (0, 1):
+                k = mult.get(("A", (0, 0, 2), (dx, dy, cc)), 0)
+                if ("A", (0, 0, 2), (dx, dy, cc)) in keys or k:
+                    k = max(k, 1)
+                    for r in range(k):
+                        i = T.add("A", (0, 0, 2), (dx, dy, cc), div=k, first=r == 0)
+                        stmts.append(f"FS{'IJ'[cc]}({i})")
+                    use[cc] = True
+            if stmts:
+                loads = [f"LDX(x{'IJ'[c]}, {dx}, {dy}, {c})" for c in (0, 1) if use[c]]
+                body.append("  BEGIN " + " ".join(loads + stmts) + " END")
+        for (dx, dy) in window_nodes(rows):
+            if dx % 2 or dy % 2:
+                continue
+            stmts = []
+            for ti, (tx, ty) in enumerate(TARGETS):
+                for tc in (0, 1):
+                    k = mult.get(("A", (tx, ty, tc), (dx, dy, 2)), 0)
+                    if ("A", (tx, ty, tc), (dx, dy, 2)) in keys or k:
+                        k = max(k, 1)
+                        for r in range(k):
+                            i = T.add("A", (tx, ty, tc), (dx, dy, 2), div=k, first=r == 0)
+                            stmts.append(f"FP({ti}, {tc}, {i})")
+            if ("A", (0, 0, 2), (dx, dy, 2)) in keys:
+                i = T.add("A", (0, 0, 2), (dx, dy, 2))
+                stmts.append(f"FSP({i})")
+            if stmts:
+                body.append(f"  BEGIN LDX(xP, {dx}, {dy}, 2) " + " ".join(stmts) + " END")
     return T, parts
 
 
@@ -227,9 +326,10 @@ def emit(keys):
     lines = [
         "// GENERATED by tools/gen_lattice_stencil.py -- do not edit.  Macro-stencil of the lattice plan (feo_lattice.h):",
         "// coefficient-table layouts and the straight-line cell bodies for the right-diagonal structured P2-P1 lattice.",
-        "// DESC(index, matrix (0 A, 1 B1, 2 B2), row dx, dy, comp, col dx, dy, comp, signed, twin): table[index] = M[row, col]",
-        "//   (times the branch sign when signed); comp 0 = u1 (I), 1 = u2 (J), 2 = pressure; node offsets are relative to the",
-        "//   cell origin (2 ci, 2 cj); twin = the (J, J) entry of the same node pair must carry the same value.",
+        "// DESC(index, matrix (0 A, 1 B1, 2 B2), row dx, dy, comp, col dx, dy, comp, signed, twin, div, first):",
+        "//   table[index] = M[row, col] / div (times the branch sign when signed); comp 0 = u1 (I), 1 = u2 (J), 2 = pressure; node",
+        "//   offsets are relative to the cell origin (2 ci, 2 cj); twin = the (J, J) entry of the same node pair must carry the same",
+        "//   value; div > 1 only in the element-walk table FWDE, where `div` statements share one assembled entry (first marks one).",
         "// Bodies: one BEGIN ... END group per source node: LDX / LDR / LDA(var, dx, dy, comp) gather a line of alpha (forward),",
         "//   r and alpha (backward), then",
         "//   forward:  FV(matrix, target, i) FSI(i) FSJ(i) FP(target, comp, i) FSP(i)",
@@ -239,13 +339,13 @@ def emit(keys):
         "// Each body comes in three parts by window row: A = rows -2, -1 (the rows a step releases first), B = row 0,",
         "//   C = rows 1, 2 (the rows a step receives last) -- the kernels release / wait for staged rows between the parts.",
     ]
-    for tag, gen in (("FWD", gen_forward), ("BWD", gen_backward)):
+    for tag, gen in (("FWD", gen_forward), ("BWD", gen_backward), ("FWDE", gen_forward_element)):
         T, body = gen(keys)
         lines.append(f"#define FEO_LAT_{tag}_NCOEF {len(T.desc)}")
         lines.append(f"#define FEO_LAT_{tag}_DESC(DESC) \\")
-        for i, (mat, row, col, signed, twin) in enumerate(T.desc):
+        for i, (mat, row, col, signed, twin, div, first) in enumerate(T.desc):
             lines.append(
-                f"  DESC({i}, {mat_id[mat]}, {row[0]}, {row[1]}, {row[2]}, {col[0]}, {col[1]}, {col[2]}, {int(signed)}, {int(twin)}) \\"
+                f"  DESC({i}, {mat_id[mat]}, {row[0]}, {row[1]}, {row[2]}, {col[0]}, {col[1]}, {col[2]}, {int(signed)}, {int(twin)}, {div}, {int(first)}) \\"
             )
         lines.append("")
         for part, _ in PARTS:
@@ -263,5 +363,6 @@ if __name__ == "__main__":
     emit(keys)
     tf, bf = gen_forward(keys)
     tb, bb = gen_backward(keys)
+    te, be = gen_forward_element(keys)
     print(f"union pattern: {len(keys)} matrix entries per cell; forward table {len(tf.desc)} coefficients, "
-          f"backward table {len(tb.desc)} coefficients -> {OUT}")
+          f"backward table {len(tb.desc)} coefficients, element-walk forward table {len(te.desc)} coefficients -> {OUT}")
