@@ -25,7 +25,8 @@ int canonicalize(const feo_csr& in, int32_t n, const char* name, HostCsr* out) {
   out->col.clear();
   out->val.clear();
   if (in.rowptr == nullptr) return FEO_OK;
-  if (in.col == nullptr || in.val == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, std::string(name) + ": col/val NULL");
+  if ((in.col == nullptr || in.val == nullptr) && in.rowptr[n] != 0)  // an all-zero matrix may come with empty arrays
+    return fail(FEO_ERR_INVALID_ARGUMENT, std::string(name) + ": col/val NULL");
   if (in.rowptr[0] != 0) return fail(FEO_ERR_INVALID_ARGUMENT, std::string(name) + ": rowptr[0] != 0");
   out->rowptr.assign(n + 1, 0);
   std::vector<std::pair<int32_t, float>> row;

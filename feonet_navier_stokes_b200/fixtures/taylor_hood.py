@@ -432,12 +432,19 @@ def assemble_operators(
     )
 
 
-def spai(A: np.ndarray, m: int) -> np.ndarray:
+def spai(A: np.ndarray, m: int, start: str = "onenormest") -> np.ndarray:
     """Minimal-residual sparse-approximate-inverse iteration, dense restatement of the reference's
-    `spai` (`FEONet_Stokes_square/train_FEONet.py:104-121`): M <- M + a (I - A M)."""
+    `spai` (`FEONet_Stokes_square/train_FEONet.py:104-121`): M <- M + a (I - A M), started from 2 / ||A A^T||_1 * A with the
+    reference's 1-norm estimate (scipy `onenormest`) or, start="exact", the exact norm."""
     A = np.asarray(A, dtype=np.float64)
     n = A.shape[0]
-    M = (2.0 / np.linalg.norm(A @ A.T, 1)) * A
+    if start == "onenormest":
+        from scipy.sparse.linalg import onenormest
+
+        norm1 = float(onenormest(A @ A.T))
+    else:
+        norm1 = float(np.linalg.norm(A @ A.T, 1))
+    M = (2.0 / norm1) * A
     eye = np.eye(n)
     for _ in range(m):
         G = eye - A @ M

@@ -182,6 +182,79 @@ class SeqResidualLossFn(torch.autograd.Function):
         return grad, None, None, None
 
 
+class NsDenseResidualLossFn(torch.autograd.Function):
+    """Steady Navier-Stokes with a genuinely dense preconditioner (FEONet_steady_Navier-Stokes/train_FEONet.py:324-326 with
+    PRECOND != I): r = alpha (A P)^T - (F - c), c from the raw alpha.  The convective part comes from the fused sparse kernels of
+    an operator that holds B1, B2 and an EMPTY A (its residual is c - F), the linear part from one tensor-core apply that
+    subtracts F - c and reduces the squares; backward = M^T r (dense) + the sparse kernels' convective terms.  No eager index
+    arithmetic, no materialised LHS / RHS."""
+
+    @staticmethod
+    def forward(ctx, alpha, F, op: FEOperator, op_conv: FEOperator, fcache):
+        B, N = alpha.shape
+        native = is_dof_major(alpha)
+        aT = _prep(op, alpha.detach())
+        ldb = aT.shape[1]
+        fT = fcache.get(op, F, ldb) if fcache is not None else _prep(op, F.detach(), ldb)
+        _, cT = op_conv.residual_fwd(aT, fT, B)  # 0 - (F - c)
+        rT, loss = op.dense_apply(L.FEO_DENSE_M, aT, B, sub=cT.neg_(), want_loss=True)
+        ctx.op, ctx.op_conv, ctx.B, ctx.native = op, op_conv, B, native
+        ctx.save_for_backward(aT, rT)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        aT, rT = ctx.saved_tensors
+        op: FEOperator = ctx.op
+        g = grad_out.detach().to(torch.float32).contiguous()
+        gT = op.dense_apply(L.FEO_DENSE_MT, rT, ctx.B, scale=2.0, scale_dev=g)
+        gT.add_(ctx.op_conv.residual_bwd(aT, rT, ctx.B, grad_loss=g))
+        return op.from_dof_major(gT, ctx.B, contiguous=not ctx.native), None, None, None, None
+
+
+class SeqDenseResidualLossFn(torch.autograd.Function):
+    """loss = (1/T) sum_t |M x_t - S prev_t - dt F|^2 with the dense preconditioned system matrix M = (S + dt A) P
+    (FEONet_time_dep_Stokes/train_FEONet.py:343-362 with do_precond, :398-400).  The right-hand side S prev + dt F is formed
+    once (sparse apply), then ONE tensor-core apply evaluates M x, subtracts it and reduces the squares (feo_dense_apply with
+    `sub` and `loss_out`): no materialised LHS, no eager reduction.  Backward: g_t = (2/T) [M^T r_t - S^T r_{t+1}], r_T = 0."""
+
+    @staticmethod
+    def forward(ctx, pred_seq, u_init, F, op: FEOperator, dt: float):
+        B, T, N = pred_seq.shape
+        BT = B * T
+        pT = _prep(op, pred_seq.detach().reshape(BT, N))  # pseudo-samples j = b * T + t
+        ld = pT.shape[1]
+        u0T = _prep(op, u_init.detach())
+        fT = _prep(op, F.detach(), u0T.shape[1])
+        prevT = op.new(ld)
+        pv, xv = prevT[:, :BT].view(N, B, T), pT[:, :BT].view(N, B, T)
+        pv[:, :, 1:] = xv[:, :, :-1]
+        pv[:, :, 0] = u0T[:, :B]
+        if ld > BT:
+            prevT[:, BT:] = 0.0
+        rhsT = op.spmm(L.FEO_MAT_S, False, prevT, BT)
+        rhsT[:, :BT].view(N, B, T).add_(fT[:, :B].unsqueeze(2), alpha=float(dt))
+        rT, loss = op.dense_apply(L.FEO_DENSE_M, pT, BT, sub=rhsT, want_loss=True)
+        ctx.op, ctx.B, ctx.T = op, B, T
+        ctx.save_for_backward(rT)
+        return loss / T
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (rT,) = ctx.saved_tensors
+        op: FEOperator = ctx.op
+        B, T = ctx.B, ctx.T
+        BT, N = B * T, rT.shape[0]
+        g = grad_out.detach().to(torch.float32).contiguous()
+        gT = op.dense_apply(L.FEO_DENSE_MT, rT, BT, scale=2.0 / T, scale_dev=g)
+        nextT = torch.zeros_like(rT)
+        nextT[:, :BT].view(N, B, T)[:, :, :-1] = rT[:, :BT].view(N, B, T)[:, :, 1:]
+        sT = op.spmm(L.FEO_MAT_S, True, nextT, BT)
+        gT.add_(sT * (g * (-2.0 / T)))
+        grad = op.from_dof_major(gT, BT, contiguous=True).reshape(B, T, -1)
+        return grad, None, None, None, None
+
+
 def precond_output(op: FEOperator, pred: torch.Tensor) -> torch.Tensor:
     """u = (P @ pred^T)^T, the second output of `closure`.  Only ever used detached in the reference
     (FEONet_Stokes_square/train_FEONet.py:401, steady NS :478 -- quirk 9), so no graph is kept."""

@@ -18,7 +18,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 __all__ = ["NetA", "Net2D", "Net3D", "FCNN", "ConvBNAct", "DoubleConv", "UNetFeatureExtractor", "UNetHead",
-           "UNetWithHead", "LinearT", "conv1d", "conv2d", "conv3d"]
+           "UNetWithHead", "VectorToSequenceRNN", "LinearT", "conv1d", "conv2d", "conv3d"]
 
 
 class LinearT(nn.Linear):
@@ -191,3 +191,34 @@ class UNetWithHead(nn.Module):
 
     def forward(self, x):
         return self.head(self.feature(x))
+
+
+class VectorToSequenceRNN(nn.Module):
+    """Autoregressive GRU / LSTM decoder of the time-dependent variant (`FEONet_time_dep_Stokes/network.py:342-399`; same
+    constructor arguments and state_dict keys `fc_init`, `rnn`, `fc_out`): the initial coefficient vector [B, input_dim] seeds
+    the first layer's hidden state, a zero start token goes in, every output [B, 1, output_dim] is fed back as the next input;
+    returns [B, seq_len, output_dim]."""
+
+    def __init__(self, input_dim=1003, hidden_dim=512, output_dim=1003, rnn_type="gru", num_layers=1):
+        super().__init__()
+        self.input_dim, self.hidden_dim, self.output_dim, self.num_layers = input_dim, hidden_dim, output_dim, num_layers
+        self.fc_init = nn.Linear(input_dim, hidden_dim)
+        kinds = {"gru": nn.GRU, "lstm": nn.LSTM}
+        if rnn_type.lower() not in kinds:
+            raise ValueError("rnn_type must be 'gru' or 'lstm'")
+        self.rnn = kinds[rnn_type.lower()](output_dim, hidden_dim, num_layers=num_layers, batch_first=True)
+        self.fc_out = nn.Linear(hidden_dim, output_dim)
+
+    def forward(self, x, seq_len):
+        B = x.size(0)
+        state = torch.cat([torch.tanh(self.fc_init(x)).unsqueeze(0),
+                           torch.zeros(self.num_layers - 1, B, self.hidden_dim, device=x.device)], dim=0)
+        if isinstance(self.rnn, nn.LSTM):
+            state = (state, torch.zeros(self.num_layers, B, self.hidden_dim, device=x.device))
+        token = torch.zeros(B, 1, self.output_dim, device=x.device)
+        steps = []
+        for _ in range(seq_len):
+            out, state = self.rnn(token, state)
+            token = self.fc_out(out)
+            steps.append(token)
+        return torch.cat(steps, dim=1)

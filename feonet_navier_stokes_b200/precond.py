@@ -12,16 +12,29 @@ import numpy as np
 import torch
 
 
-def spai_device(A, m: int, device=None, dtype=torch.float64) -> torch.Tensor:
-    """m SPAI steps on `device`; returns the dense preconditioner [N, N] (same dtype) on that device."""
+def spai_device(A, m: int, device=None, dtype=torch.float64, start: str = "onenormest") -> torch.Tensor:
+    """m SPAI steps on `device`; returns the dense preconditioner [N, N] (same dtype) on that device.
+
+    start="onenormest" (default) scales the initial guess exactly as the reference does, with scipy's 1-norm ESTIMATE of
+    A A^T (one scalar, evaluated on the host from the device product; the reference's own dependency); start="exact" uses the
+    exact 1-norm.  The two coincide unless the estimator misses the maximal column (it is exact for every operator in
+    tests/)."""
     dev = torch.device(device if device is not None else "cuda")
     if hasattr(A, "todense"):
         A = np.asarray(A.todense())
     A = torch.as_tensor(np.asarray(A) if not isinstance(A, torch.Tensor) else A, dtype=dtype, device=dev)
     n = A.shape[0]
     eye = torch.eye(n, dtype=dtype, device=dev)
-    # the reference uses scipy's onenormest(A A^T), an estimate of the 1-norm; the exact norm is cheap here
-    M = (2.0 / torch.linalg.matrix_norm(A @ A.T, ord=1)) * A
+    AAt = A @ A.T
+    if start == "onenormest":
+        from scipy.sparse.linalg import onenormest
+
+        norm1 = float(onenormest(AAt.cpu().numpy()))
+    elif start == "exact":
+        norm1 = float(torch.linalg.matrix_norm(AAt, ord=1))
+    else:
+        raise ValueError("start must be 'onenormest' or 'exact'")
+    M = (2.0 / norm1) * A
     for _ in range(int(m)):
         G = eye - A @ M
         AG = A @ G

@@ -12,7 +12,12 @@ loss path:
   come from a sparse direct solve (linear Stokes) or a Newton iteration on the algebraic system (steady NS,
   `compare_ordering_nonlinear.ipynb#c25`);
 * the loss and its backward are `feonet_navier_stokes_b200` kernels (there is no CPU path);
-* the guards read ONE device flag per step instead of one `.item()` per dof and per check;
+* the guards read ONE device flag per step instead of one `.item()` per dof and per check; a step whose loss, prediction or
+  any parameter gradient is not finite is SKIPPED (no optimizer step) -- the reference's `continue` in its gradient scan
+  (:465-469) only leaves the inner loop over parameters and still steps with the bad gradient;
+* `--variant time_dep` drives the time-dependent closure (`FEONet_time_dep_Stokes/train_FEONet.py:364-406`, loop :491-506) with the
+  RNN model (`VectorToSequenceRNN`; flags `--seq_len --rnn_type --hidden_dim --num_layers --dt` as there); initial velocities and
+  the implicit-Euler reference trajectories (`create_data.py:75-91`) are synthesised;
 * `torchrun` launches shard the sample batch over ranks (parallel.py), gradients are summed with NCCL.
 
     python -m feonet_navier_stokes_b200.train_FEONet --variant steady_ns --bc channel_flow --forcing_term sincos \
@@ -30,7 +35,7 @@ from typing import Dict, Optional, Tuple
 import numpy as np
 import torch
 
-VARIANTS = ("stokes_square", "hole", "steady_ns")
+VARIANTS = ("stokes_square", "hole", "steady_ns", "time_dep")
 
 
 def build_parser() -> argparse.ArgumentParser:
@@ -45,7 +50,14 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--domain", type=str, default="dolfin", choices=["dolfin", "square"])
     # train parameters (reference names)
     p.add_argument("--pretrained", type=str, default=None)
-    p.add_argument("--model", type=str, default="FCNN", choices=["Net2D", "FCNN", "UNetWithHead"])
+    p.add_argument("--model", type=str, default="FCNN", choices=["Net2D", "FCNN", "UNetWithHead", "RNN"],
+                   help="RNN = VectorToSequenceRNN, the time-dependent variant's default (FEONet_time_dep_Stokes/train_FEONet.py:45-46)")
+    # time-dependent variant (FEONet_time_dep_Stokes/train_FEONet.py:37-58)
+    p.add_argument("--dt", type=float, default=0.1)
+    p.add_argument("--seq_len", type=int, default=10)
+    p.add_argument("--rnn_type", type=str, default="gru", choices=["gru", "lstm"])
+    p.add_argument("--hidden_dim", type=int, default=512)
+    p.add_argument("--num_layers", type=int, default=1)
     p.add_argument("--optimizer", type=str, default="Adam", choices=["LBFGS", "Adam", "SGD", "AdamW", "Adagrad"])
     p.add_argument("--do_precond", type=int, default=0)
     p.add_argument("--batch_size_train", type=int, default=None)
@@ -140,10 +152,43 @@ def synthesize(variant: str, n: int, bc: str, num: int, seed: int, precond_branc
     return fx, data
 
 
-def make_model(name: str, resol_in: int, d_out: int, filters: int, ks: int, blocks: int, dof_major_head: bool):
+def synthesize_time_dep(n: int, num: int, seed: int, dt: float, seq_len: int):
+    """(fixture, dict of numpy arrays) for the time-dependent variant: initial velocities init_x, init_y [num, n_u] (zero on the
+    walls, amplitudes ~ U(0,1) as `coeffs_init`), the constant-force load vector replicated [num, N]
+    (`FEONet_time_dep_Stokes/train_FEONet.py:235,244`) and the implicit-Euler trajectories (S + dt A) u+ = S u + dt f
+    [num, seq_len + 1, N] that `create_data.py:75-91` stores as `coeffs_u` (here by a sparse LU in fp64)."""
+    import scipy.sparse.linalg as spla
+
+    from .fixtures import config_operators
+
+    fx = config_operators("time_dep", n, ordering="interleaved")
+    rng = np.random.default_rng(seed)
+    amp = rng.uniform(0.0, 1.0, size=(num, 2))
+    x, y = fx.mesh.p2_xy[:, 0], fx.mesh.p2_xy[:, 1]
+    bump = np.sin(np.pi * x) * y * (1.0 - y)
+    init_x, init_y = amp[:, :1] * bump[None, :], 0.5 * amp[:, 1:] * bump[None, :] * np.cos(np.pi * x)[None, :]
+    load = fx.load_vector_sincos(np.array([[1.0, 0.0, 0.0, 0.0, 0.0, 0.0]]))[0] * 0.0  # f = 0 in the interior ...
+    load[fx.bc_dofs] = fx.bc_vals  # ... and the boundary values on the Dirichlet rows (constant in time)
+    M = (fx.S + dt * fx.A).tocsc()
+    lu = spla.splu(M)
+    U = np.zeros((num, seq_len + 1, fx.N))
+    U[:, 0, fx.idx_u1], U[:, 0, fx.idx_u2] = init_x, init_y
+    for t in range(seq_len):
+        U[:, t + 1] = lu.solve((fx.S @ U[:, t].T + dt * load[:, None])).T
+    data = {"coeff_f": amp, "init_x": init_x, "init_y": init_y, "load_vec_f": np.repeat(load[None], num, axis=0),
+            "coeffs_u": U, "fenics_u1": U[:, 1:, fx.idx_u1].reshape(num, -1), "fenics_u2": U[:, 1:, fx.idx_u2].reshape(num, -1),
+            "fenics_p": U[:, 1:, fx.idx_p].reshape(num, -1)}
+    return fx, data
+
+
+def make_model(name: str, resol_in: int, d_out: int, filters: int, ks: int, blocks: int, dof_major_head: bool, gparams=None):
     from . import network as net
 
     pad = (ks - 1) // 2
+    if name == "RNN":
+        g = gparams or {}
+        return net.VectorToSequenceRNN(input_dim=d_out, hidden_dim=g.get("hidden_dim", 512), output_dim=d_out,
+                                       rnn_type=g.get("rnn_type", "gru"), num_layers=g.get("num_layers", 1))
     if name == "Net2D":
         return net.Net2D(resol_in, 2, filters, d_out, kernel_size=ks, padding=pad, blocks=blocks, dof_major_head=dof_major_head)
     if name == "FCNN":
@@ -197,8 +242,12 @@ class Trainer:
         else:
             # data (seeds 5 / 10: create_data.py:30-33); ne fixes the synthetic mesh only here -- a reference npz carries its own
             n = mesh_n_from_ne(ne, strict=variant != "hole")  # the hole stand-in mesh is Delaunay: ne only sets its resolution
-            self.fx, train = synthesize(variant, n, gparams["bc"], n_train, 5, do_precond)
-            _, val = synthesize(variant, n, gparams["bc"], n_val, 10, do_precond)
+            if variant == "time_dep":
+                self.fx, train = synthesize_time_dep(n, n_train, 5, gparams["dt"], gparams["seq_len"])
+                _, val = synthesize_time_dep(n, n_val, 10, gparams["dt"], gparams["seq_len"])
+            else:
+                self.fx, train = synthesize(variant, n, gparams["bc"], n_train, 5, do_precond)
+                _, val = synthesize(variant, n, gparams["bc"], n_val, 10, do_precond)
         t = lambda a: torch.tensor(np.asarray(a), dtype=torch.float32)  # noqa: E731
         if n_train < self.world:
             raise ValueError(f"{n_train} training samples cannot be sharded over {self.world} ranks")
@@ -211,7 +260,18 @@ class Trainer:
         # operator state (the reference's module globals)
         A = self.fx.A
         self.P = None
-        if variant == "steady_ns":
+        if variant == "time_dep":
+            # FEONet_time_dep_Stokes/train_FEONet.py:364-406, loop :491-506; the sequence model sees the assembled u_init
+            if gparams["model"] != "RNN":
+                raise ValueError("the time-dependent shell drives the RNN model (VectorToSequenceRNN); UNet1D / UNet2D / UNetTemporal "
+                                 "are image models of the reference that this repo does not mirror")
+            if do_precond:
+                self.P = feo.spai_device(self.fx.S + gparams["dt"] * A, gparams["spai_steps"], self.device).to(torch.float32).cpu()
+            self.problem = feo.TimeDependentStokes(self.fx.S, A, self.fx.idx_sol, dt=gparams["dt"], do_precond=do_precond, precond=self.P,
+                                                   model_name="RNN", device=self.device)
+            S_, T_ = self.fx.S, gparams["seq_len"]
+            self.closure_args = lambda b: (None, b["init_x"], b["init_y"], b["load_vec_f"], S_, A, None, self.P, gparams["dt"], T_)  # noqa: E731
+        elif variant == "steady_ns":
             # PRECOND = np.eye(N) whenever --do_precond > 0 (steady NS :142): the identity is detected, never stored densely
             self.problem = feo.SteadyNavierStokes(A, self.fx.B1, self.fx.B2, self.fx.idx_sol, do_precond=do_precond, precond=None,
                                                   model_name=gparams["model"], force=gparams["forcing_term"], device=self.device)
@@ -227,7 +287,7 @@ class Trainer:
             else:
                 self.closure_args = lambda b: (b["coeff_f"], b["load_vec_f"], A, self.P, gparams["resol_in"])  # noqa: E731
         self.model = make_model(gparams["model"], gparams["resol_in"], self.N, gparams["filters"], gparams["ks"], gparams["blocks"],
-                                bool(gparams["dof_major_head"])).to(self.device)
+                                bool(gparams["dof_major_head"]), gparams).to(self.device)
         if gparams["pretrained"]:
             self.model.load_state_dict(torch.load(gparams["pretrained"], map_location=self.device))
         if self.world > 1:
@@ -252,6 +312,8 @@ class Trainer:
         tail smaller than the world size is merged into the batch before it so that no rank ever holds an empty shard."""
         n = data["coeff_f"].shape[0]
         bs = n if not batch_size else min(batch_size, n)
+        if shard:
+            bs = max(bs, self.world)  # a global batch has at least one sample per rank
         edges = list(range(0, n, bs)) + [n]
         if shard and len(edges) > 2 and edges[-1] - edges[-2] < self.world:
             del edges[-2]
@@ -296,8 +358,13 @@ class Trainer:
         n = 0
         for b in self.batches(data, batch_size):
             _, u_pred = self.problem.closure(self.model, *self.closure_args(b))
-            u = u_pred.reshape(b["coeff_f"].shape[0], self.N)
-            parts = [u[:, self.idx[0]], u[:, self.idx[1]], u[:, self.idx[2]]]
+            nb = b["coeff_f"].shape[0]
+            if u_pred.dim() == 3 and u_pred.shape[1] != 1:  # time-dependent: [B, T, N] against the T later slices of the trajectory
+                parts = [u_pred[:, :, i].reshape(nb, -1) for i in self.idx]
+                u = u_pred
+            else:
+                u = u_pred.reshape(nb, self.N)
+                parts = [u[:, self.idx[0]], u[:, self.idx[1]], u[:, self.idx[2]]]
             true = [b["fenics_u1"], b["fenics_u2"], b["fenics_p"]]
             for key, pr, tr in zip(("u1", "u2", "p"), parts, true):
                 err[key] += float(self.feo.rel_L2_error(pr, tr).sum().item())

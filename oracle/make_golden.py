@@ -146,6 +146,80 @@ def golden_time_dep(tag, n, B, T, dt, do_precond, seed):
     )
 
 
+def _reference_network(variant_dir):
+    """The reference's own network.py, imported from /root/reference (plain module: no side effects at import)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location(f"refnet_{abs(hash(variant_dir))}", os.path.join(REFERENCE_ROOT, variant_dir, "network.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _state_arrays(model, prefix):
+    return {f"{prefix}{k.replace('.', '__')}": v.detach().numpy() for k, v in model.state_dict().items()}
+
+
+def _grad_arrays(model, prefix):
+    return {f"{prefix}{k.replace('.', '__')}": p.grad.detach().numpy() for k, p in model.named_parameters()}
+
+
+def golden_trainstep_ns(tag, n, B, do_precond, seed):
+    """One training-step evaluation of the reference: its closure (FEONet_steady_Navier-Stokes/train_FEONet.py:334-365) on ITS
+    FCNN (network.py:120-138, eval mode: dropout off so that the step is reproducible) and `loss.backward()` (:463): loss and the
+    gradient of every network parameter."""
+    rng = np.random.default_rng(seed)
+    torch.manual_seed(seed)
+    op = config_operators("steady_ns", n, ordering="interleaved")
+    N = op.N
+    A, B1, B2 = _dense32(op.A), _dense32(op.B1), _dense32(op.B2)
+    coeff_f = rng.uniform(0.0, 1.0, size=(B, 6)).astype(np.float32)
+    F = rng.standard_normal((B, N)).astype(np.float32)
+    idx_sol = make_idx_sol(op.idx_u1, op.idx_u2, op.idx_p)
+    t = lambda a: torch.tensor(a).float()  # noqa: E731
+    ns = load_reference_functions("steady_ns", dict(DO_PRECOND=bool(do_precond), PRECOND=torch.eye(N), IDX_SOL=idx_sol, NUM_PTS=N,
+                                                    FORCE="sincos", gparams={"model": "FCNN"}))
+    model = _reference_network("FEONet_steady_Navier-Stokes").FCNN(6, N, [16, 32, 64]).eval()
+    state = _state_arrays(model, "state__")
+    loss, u_pred = ns["closure"](model, t(coeff_f), None, t(F), t(A), t(B1), t(B2), 8)
+    loss.backward()
+    _save(tag, variant="steady_ns", do_precond=bool(do_precond), A=A.astype(np.float32), B1=B1.astype(np.float32), B2=B2.astype(np.float32),
+          idx_u1=op.idx_u1, idx_u2=op.idx_u2, idx_p=op.idx_p, coeff_f=coeff_f, F=F, loss=np.float32(loss.item()),
+          u_pred=u_pred.detach().numpy(), hidden=np.array([16, 32, 64]), **state, **_grad_arrays(model, "grad__"))
+
+
+def golden_trainstep_time_dep(tag, n, B, T, dt, seed):
+    """The same for the time-dependent variant: closure (FEONet_time_dep_Stokes/train_FEONet.py:364-406) on the reference's
+    VectorToSequenceRNN (network.py:342-399), loss.backward() (:507)."""
+    rng = np.random.default_rng(seed)
+    torch.manual_seed(seed)
+    op = config_operators("time_dep", n, ordering="interleaved")
+    N = op.N
+    A, S = _dense32(op.A), _dense32(op.S)
+    init = (0.5 * rng.standard_normal((B, 2, op.mesh.n_u))).astype(np.float32)
+    F = np.repeat(rng.standard_normal((1, N)).astype(np.float32), B, axis=0)
+    idx_sol = make_idx_sol(op.idx_u1, op.idx_u2, op.idx_p)
+    t = lambda a: torch.tensor(a).float()  # noqa: E731
+    ns = load_reference_functions("time_dep", dict(DO_PRECOND=False, IDX_SOL=idx_sol, NUM_PTS=N, DT=dt, BC="lower",
+                                                   gparams={"model": "RNN"}, P=t(np.zeros((2, 2)))))
+    model = _reference_network("FEONet_time_dep_Stokes").VectorToSequenceRNN(input_dim=N, hidden_dim=24, output_dim=N, rnn_type="gru", num_layers=1)
+    state = _state_arrays(model, "state__")
+    loss, out = ns["closure"](model, None, t(init[:, 0:1, :]), t(init[:, 1:2, :]), t(F), t(S), t(A), None, t(np.zeros_like(A)), dt, T)
+    loss.backward()
+    _save(tag, variant="time_dep", do_precond=False, A=A.astype(np.float32), S=S.astype(np.float32), dt=np.float64(dt), T=np.int64(T),
+          idx_u1=op.idx_u1, idx_u2=op.idx_u2, idx_p=op.idx_p, init_x=init[:, 0], init_y=init[:, 1], F=F, loss=np.float32(loss.item()),
+          u_pred=out.detach().numpy(), hidden=np.array([24]), **state, **_grad_arrays(model, "grad__"))
+
+
+def golden_spai(tag, variant, n, m):
+    """The reference's own `spai(A, m)` (FEONet_Stokes_square/train_FEONet.py:104-121: onenormest start, dense numpy / scipy)."""
+    op = config_operators(variant, n)
+    A = _dense32(op.A)
+    ns = load_reference_functions("stokes_square", dict(tqdm=lambda it: it))
+    M = np.asarray(ns["spai"](A, m))
+    _save(tag, A=A, m=np.int64(m), M=M, residual=np.float64(np.linalg.norm(np.eye(A.shape[0]) - A @ M)))
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
@@ -166,6 +240,12 @@ def main():
     # A.3 time-dependent Stokes
     golden_time_dep("timedep_noprecond_n3", 3, 5, 4, 0.1, False, 30)
     golden_time_dep("timedep_precond_n3", 3, 4, 3, 0.01, True, 31)
+    golden_spai("spai_stokes_n3_m40", "stokes_square", 3, 40)
+    golden_spai("spai_hole_n4_m25", "hole", 4, 25)
+    # one training-step evaluation with the reference's own networks (loss + parameter gradients)
+    golden_trainstep_ns("trainstep_ns_precond_n4", 4, 6, True, 40)
+    golden_trainstep_ns("trainstep_ns_noprecond_n4", 4, 5, False, 41)
+    golden_trainstep_time_dep("trainstep_timedep_n4", 4, 5, 4, 0.1, 42)
 
 
 if __name__ == "__main__":

@@ -133,6 +133,66 @@ def test_golden_time_dep(feo, name):
 
 
 # ------------------------------------------------------------------------------------------------
+# one training-step evaluation against the reference's own closure + network + autograd (goldens made by oracle/make_golden.py
+# from the unmodified reference functions and the reference's network.py): loss and EVERY parameter gradient
+# ------------------------------------------------------------------------------------------------
+def _load_state(model, g):
+    sd = {k[len("state__"):].replace("__", "."): torch.tensor(g[k]) for k in g.files if k.startswith("state__")}
+    model.load_state_dict(sd)
+    return model
+
+
+def _check_param_grads(model, g):
+    worst = 0.0
+    for k, p in model.named_parameters():
+        ref = g["grad__" + k.replace(".", "__")]
+        worst = max(worst, _rel(p.grad.cpu().numpy(), ref))
+    return worst
+
+
+@pytest.mark.parametrize("name", golden_cases("trainstep_ns_"))
+@pytest.mark.parametrize("dof_major_head", [False, True])
+def test_golden_trainstep_steady_ns(feo, name, dof_major_head):
+    """closure (FEONet_steady_Navier-Stokes/train_FEONet.py:334-365) + loss.backward() (:463) with the FCNN of :178-179."""
+    from feonet_navier_stokes_b200 import network
+
+    g = _load(name)
+    dev = torch.device("cuda")
+    t = lambda a: torch.tensor(a, device=dev)  # noqa: E731
+    N = g["A"].shape[0]
+    model = _load_state(network.FCNN(6, N, [int(h) for h in g["hidden"]], dof_major_head=dof_major_head), g).to(dev).eval()
+    ns = feo.SteadyNavierStokes(g["A"], g["B1"], g["B2"], _idx_sol(g), do_precond=bool(g["do_precond"]), precond=None, model_name="FCNN", device=dev)
+    loss, u_pred = ns.closure(model, t(g["coeff_f"]), None, t(g["F"]), g["A"], g["B1"], g["B2"], 8)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= LOSS_RTOL * abs(float(g["loss"]))
+    assert _rel(u_pred.detach().cpu().numpy().reshape(g["u_pred"].shape), g["u_pred"]) < 1e-5
+    assert _check_param_grads(model, g) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("name", golden_cases("trainstep_timedep_"))
+def test_golden_trainstep_time_dep(feo, name):
+    """closure (FEONet_time_dep_Stokes/train_FEONet.py:364-406) + loss.backward() with VectorToSequenceRNN (network.py:342-399)."""
+    from feonet_navier_stokes_b200 import network
+
+    g = _load(name)
+    dev = torch.device("cuda")
+    t = lambda a: torch.tensor(a, device=dev)  # noqa: E731
+    N, dt, T = g["A"].shape[0], float(g["dt"]), int(g["T"])
+    model = _load_state(network.VectorToSequenceRNN(input_dim=N, hidden_dim=int(g["hidden"][0]), output_dim=N), g).to(dev).train()  # no dropout inside; cuDNN's RNN backward wants train mode
+    td = feo.TimeDependentStokes(g["S"], g["A"], _idx_sol(g), dt=dt, do_precond=False, model_name="RNN", device=dev)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False  # the golden is torch CPU fp32; cuDNN's GRU would otherwise run its GEMMs in TF32 (1e-4)
+    try:
+        loss, out = td.closure(model, None, t(g["init_x"]).unsqueeze(1), t(g["init_y"]).unsqueeze(1), t(g["F"]), g["S"], g["A"], None, None, dt, T)
+        loss.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert abs(loss.item() - float(g["loss"])) <= LOSS_RTOL * abs(float(g["loss"]))
+    assert _rel(out.detach().cpu().numpy(), g["u_pred"]) < 1e-5
+    assert _check_param_grads(model, g) < GRAD_RTOL
+
+
+# ------------------------------------------------------------------------------------------------
 # oracle on seeded inputs at the reference's config sizes (cfg3 N=2178, cfg4 N=1003, cfg1 N=387)
 # ------------------------------------------------------------------------------------------------
 def _ns_case(feo, n, B, branch, ordering, native, seed=0):
@@ -510,6 +570,16 @@ def test_sincos_forcing_grid_kernel(feo, resol):
     assert out.shape == ref.shape == (33, 2, resol, resol)
     assert torch.allclose(out.cpu(), ref, rtol=0, atol=2e-6)
     assert np.allclose(ref.numpy(), orc.sincos_forcing_grid(coeff.numpy(), resol), atol=2e-6)
+
+
+@pytest.mark.parametrize("name", golden_cases("spai_"))
+def test_spai_on_device_matches_the_reference(feo, name):
+    """feo.spai_device against the reference's own `spai` output (FEONet_Stokes_square/train_FEONet.py:104-121, onenormest start;
+    golden made by oracle/make_golden.py from the unmodified function)."""
+    g = _load(name)
+    P = feo.spai_device(g["A"], int(g["m"])).cpu().numpy()
+    assert _rel(P, g["M"]) < 1e-10
+    assert abs(np.linalg.norm(np.eye(P.shape[0]) - g["A"] @ P) - float(g["residual"])) < 1e-9
 
 
 def test_spai_on_device_matches_the_host_iteration(feo):

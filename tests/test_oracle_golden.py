@@ -91,3 +91,15 @@ def test_reference_loops_restatement_is_bit_equal(name):
         loss, grad = loops.linear_stokes_step(g["alpha"], g["F"], g["A"], g["P"], dp)
     assert abs(loss - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
     assert _relerr(grad.numpy(), g["grad"]) < 1e-6
+
+
+@pytest.mark.parametrize("name", golden_cases("spai_"))
+def test_spai_restatement_matches_the_reference(name):
+    """fixtures.spai (host restatement, onenormest start) against the output of the reference's own `spai`
+    (FEONet_Stokes_square/train_FEONet.py:104-121), AST-extracted and run by oracle/make_golden.py."""
+    from feonet_navier_stokes_b200.fixtures import spai
+
+    g = _load(name)
+    M = spai(g["A"], int(g["m"]))
+    assert _relerr(M, g["M"]) < 1e-12
+    assert abs(np.linalg.norm(np.eye(M.shape[0]) - g["A"] @ M) - float(g["residual"])) < 1e-10

@@ -37,12 +37,48 @@ def test_synthetic_stokes_solutions():
     assert np.abs(U @ fx.A.T.toarray() - data["load_vec_f"]).max() < 1e-10
 
 
+def test_synthetic_time_dep_trajectories_zero_the_reference_residual():
+    """The implicit-Euler trajectories the time-dependent shell validates against (create_data.py:75-91) make the reference's
+    sequence residual vanish (FEONet_time_dep_Stokes/train_FEONet.py:343-362, :398-400)."""
+    fx, data = T.synthesize_time_dep(4, 3, 5, 0.1, 5)
+    U = data["coeffs_u"]
+    assert U.shape == (3, 6, fx.N)
+    u0 = orc.assemble_u_init(data["init_x"], data["init_y"], fx.idx_u1, fx.idx_u2, fx.N, dtype=np.float64)
+    assert np.array_equal(u0, U[:, 0])
+    loss, _, _ = orc.seq_loss_and_grad(U[:, 1:], data["load_vec_f"], fx.S, fx.A, None, 0.1, u0, False, dtype=np.float64)
+    assert loss < 1e-20 * float((U ** 2).sum())
+    args = T.build_parser().parse_args("--variant time_dep --model RNN --seq_len 10 --rnn_type gru --dt 0.01 --train_file 8N32 --val_file 4N32".split())
+    assert args.model == "RNN" and args.seq_len == 10 and args.dt == 0.01
+
+
+def test_batches_are_the_same_on_every_rank():
+    """Each rank takes its shard of every GLOBAL batch: the same number of steps everywhere (every step issues collectives), no
+    empty shard (a tail smaller than the world size joins the batch before it)."""
+    import torch
+
+    class Stub:
+        batches = T.Trainer.batches
+
+    from feonet_navier_stokes_b200 import parallel
+
+    data = {"coeff_f": torch.arange(10).float().unsqueeze(1)}
+    seen = []
+    for rank in range(4):
+        st = Stub()
+        st.world, st.rank, st.parallel = 4, rank, parallel
+        seen.append([b["coeff_f"].flatten().tolist() for b in st.batches(data, 3, shard=True)])
+    assert len({len(x) for x in seen}) == 1 and all(len(b) > 0 for x in seen for b in x)
+    flat = sorted(v for x in seen for b in x for v in b)
+    assert flat == list(map(float, range(10)))  # every sample exactly once per epoch
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant,do_precond", [("steady_ns", 1), ("stokes_square", 0), ("stokes_square", 1)])
+@pytest.mark.parametrize("variant,do_precond", [("steady_ns", 1), ("stokes_square", 0), ("stokes_square", 1), ("time_dep", 0)])
 def test_training_run_reduces_the_loss(tmp_path, variant, do_precond):
     import torch
 
-    argv = ["--variant", variant, "--train_file", "32N32", "--val_file", "8N32", "--model", "FCNN", "--optimizer", "Adam",
+    argv = ["--variant", variant, "--train_file", "32N32", "--val_file", "8N32", "--model", "RNN" if variant == "time_dep" else "FCNN",
+            "--optimizer", "Adam", "--hidden_dim", "64", "--seq_len", "4",
             "--do_precond", str(do_precond), "--epochs", "60", "--log_every", "20", "--lr", "3e-3", "--out", str(tmp_path),
             "--spai_steps", "50"]
     tr = T.Trainer(dict(T.build_parser().parse_args(argv).__dict__), device=torch.device("cuda"))
