@@ -643,12 +643,19 @@ def run_configs(args):
     # the reference's own execution plan (dense operators, per-sample / per-dof Python loops, autograd) on this host's cores
     loops = orc.TorchReferenceLoops(os.cpu_count())
 
-    def report(name, N, gpu_ms, cpu_ms, loss_gpu, loss_cpu, grad_gpu, grad_cpu, note):
+    peak_gbs, _ = measured_peak_gbs()
+
+    def report(name, N, gpu_ms, cpu_ms, loss_gpu, loss_cpu, grad_gpu, grad_cpu, note, alg_bytes=None, alg_flops=None):
         g, c = np.asarray(grad_gpu, dtype=np.float64), np.asarray(grad_cpu, dtype=np.float64)
         rows.append({"config": name, "N": N, "batch": B, "gpu_ms_fwd_bwd": gpu_ms, "gpu_samples_per_s": B / (gpu_ms * 1e-3),
                      "cpu_port_ms_fwd_bwd": cpu_ms, "cpu_port_samples_per_s": B / (cpu_ms * 1e-3), "speedup": cpu_ms / gpu_ms,
                      "loss_rel_diff_vs_fp64": abs(loss_gpu - loss_cpu) / abs(loss_cpu),
                      "grad_rel_diff_vs_fp64": float(np.linalg.norm(g - c) / np.linalg.norm(c)), "note": note})
+        if alg_bytes is not None:  # SURVEY 8d algorithmic bytes of the step (reference-facing row-major API: layout passes included in the time)
+            rows[-1].update(algorithmic_bytes=alg_bytes, algorithmic_GBs=alg_bytes / (gpu_ms * 1e-3) / 1e9,
+                            hbm_roofline_frac=alg_bytes / (gpu_ms * 1e-3) / 1e9 / peak_gbs)
+        if alg_flops is not None:
+            rows[-1].update(algorithmic_flops=alg_flops, fp32_equivalent_TFLOPs=alg_flops / (gpu_ms * 1e-3) / 1e12)
         log(f"[configs] {rows[-1]}")
 
     # cfg1 / cfg2: linear Stokes, preconditioned (dense apply on the tensor cores)
@@ -674,7 +681,8 @@ def run_configs(args):
         cpu_ms, _ = time_cpu(lambda: orc.stokes_loss_and_grad(alpha, F, A, P, True, dtype=np.float32))
         lo, go, _ = orc.stokes_loss_and_grad(alpha, F, A, P, True, dtype=np.float64)  # yardstick for the differences
         report(name + (f" N={fx.N}" if "N=" not in name else ""), fx.N, gpu_ms, cpu_ms,
-               box["l"].item(), float(lo), box["g"].cpu().numpy(), go, "dense A.P folded at set-up, tcgen05 3xTF32 apply")
+               box["l"].item(), float(lo), box["g"].cpu().numpy(), go, "dense A.P folded at set-up, tcgen05 3xTF32 apply",
+               alg_flops=4.0 * fx.N * fx.N * B)  # one GEMM forward, one backward
         ref_ms, (l_ref, g_ref) = time_cpu(lambda: loops.linear_stokes_step(alpha, F, A, P, True), reps=1)
         rows[-1].update(reference_loops_ms_fwd_bwd=ref_ms, reference_loops_samples_per_s=B / (ref_ms * 1e-3),
                         speedup_vs_reference_loops=ref_ms / gpu_ms, loss_rel_diff_vs_reference_loops=abs(box["l"].item() - l_ref) / abs(l_ref))
@@ -698,7 +706,8 @@ def run_configs(args):
         cpu_ms, _ = time_cpu(lambda: orc.ns_loss_and_grad(alpha, F, fx.A, fx.B1, fx.B2, fx.idx_u1, fx.idx_u2, precond, dtype=np.float32))
         lo, go, _ = orc.ns_loss_and_grad(alpha, F, fx.A, fx.B1, fx.B2, fx.idx_u1, fx.idx_u2, precond, dtype=np.float64)
         report(f"cfg3 steady NS N={fx.N} ({'precond=I' if precond else 'no precond'} sign branch)", fx.N, gpu_ms, cpu_ms,
-               box["l"].item(), float(lo), box["g"].cpu().numpy(), go, "fused residual kernels incl. row-major <-> dof-major transposes")
+               box["l"].item(), float(lo), box["g"].cpu().numpy(), go, "fused residual kernels incl. row-major <-> dof-major transposes",
+               alg_bytes=24.0 * fx.N * B)
         dense = [np.asarray(K.todense(), dtype=np.float32) for K in (fx.A, fx.B1, fx.B2)]
         ref_ms, (l_ref, g_ref) = time_cpu(lambda: loops.steady_ns_step(alpha, F, *dense, fx.idx_u1, fx.idx_u2, precond), reps=1)
         rows[-1].update(reference_loops_ms_fwd_bwd=ref_ms, reference_loops_samples_per_s=B / (ref_ms * 1e-3),
@@ -723,7 +732,8 @@ def run_configs(args):
     cpu_ms, _ = time_cpu(lambda: orc.seq_loss_and_grad(pred, F, fx.S, fx.A, None, dt, u0, False, dtype=np.float32))
     lo, go, _ = orc.seq_loss_and_grad(pred, F, fx.S, fx.A, None, dt, u0, False, dtype=np.float64)
     report(f"cfg4 time-dependent Stokes N={fx.N} T={T}", fx.N, gpu_ms, cpu_ms, box["l"].item(), float(lo),
-           box["g"].cpu().numpy(), go, "seq_kernel fwd/bwd, one sample = T rows")
+           box["g"].cpu().numpy(), go, "seq_kernel fwd/bwd, one sample = T rows; launch- and L2-latency-bound at this size (41 MB per tensor)",
+           alg_bytes=float(B) * (T * 20.0 * fx.N + 4.0 * fx.N))
     # the linear Stokes operator (no convective term: A-quads forward, 20 N B algorithmic bytes) at the cfg5 mesh size
     large = None
     try:
