@@ -2,6 +2,15 @@
 import csv, json, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+
+
+def short_name(k):
+    m = re.search(r"residual_lattice_kernel<\(?(?:bool\))?\s*(\w+)", k)
+    if m:
+        return "residual_lattice_kernel<" + ("bwd" if m.group(1) in ("1", "true") else "fwd") + ">"
+    m = re.search(r"(residual_\w+|\w+_kernel)", k)
+    return m.group(1) if m else k.split("(")[0].replace("void ", "")[:70]
+
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
@@ -14,15 +23,14 @@ ki, vi, ui = H.index("Kernel Name"), H.index("Metric Value"), H.index("Metric Un
 launches = [(r[ki], float(r[vi].replace(",", "")) * (1e-3 if r[ui] == "ns" else 1.0)) for r in rows[h + 1:] if len(r) == len(H) and r[0].isdigit()]
 tot = {}
 for k, us in launches:
-    m = re.search(r"(residual_\w+|\w+_kernel)", k)
-    name = m.group(1) if m else k.split("(")[0].replace("void ", "")[:70]
+    name = short_name(k)
     t = tot.setdefault(name, [0, 0.0])
     t[0] += 1
     t[1] += us
 total_us = sum(v[1] for v in tot.values())
 with open(os.path.join(P, f"{tag}_launches.md"), "w") as f:
     f.write(f"# ncu launch list ({tag})\n\n`ncu --metrics gpu__time_duration.sum --clock-control none -c 60` on "
-            "`python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e` (cfg5, N=1 001 334, B=1024, one B200).\n"
+            "`python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-train-step --no-parity --no-precond-gemm` (cfg5, N=1 001 334, B=1024, one B200).\n"
             "Per-launch times are serialised and cold-cache: compare shares, not absolutes.\n\n"
             "| kernel | launches | total us | avg us | share |\n|---|---|---|---|---|\n")
     for name, (n, us) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
@@ -49,8 +57,7 @@ with open(os.path.join(P, f"{tag}_ncu_summary.md"), "w") as f:
             "command; one launch of each fused kernel.  Times under ncu are not bench values.\n\n")
     for r in rr[2:]:
         d = dict(zip(hdr, r))
-        m = re.search(r"(residual_\w+|\w+_kernel)", d["Kernel Name"])
-        name = m.group(1) if m else d["Kernel Name"][:60]
+        name = short_name(d["Kernel Name"])
         f.write(f"## {name}\n\n| metric | value | unit |\n|---|---|---|\n")
         for w in want[1:]:
             if w in d:
@@ -64,6 +71,9 @@ with open(os.path.join(P, f"{tag}_ncu_summary.md"), "w") as f:
     open("/tmp/_src.csv", "w").write(src)
     hot = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_hot.py"), "/tmp/_src.csv", "12"], capture_output=True, text=True).stdout
     f.write("## Stall samples by SASS instruction (top 12 per kernel)\n\n```\n" + hot + "```\n")
-json.dump(traffic, open(os.path.join(P, f"traffic_{tag}.json"), "w"), indent=1)
+traffic_named = dict(traffic)
+traffic_named["source"] = f"ncu --set full --clock-control none, one launch each (tools/profile_bench.sh {tag}): dram__bytes_read.sum + dram__bytes_write.sum"
+traffic_named["algorithmic_bytes_per_launch"] = 12304392192
+json.dump(traffic_named, open(os.path.join(P, f"traffic_{tag}.json"), "w"), indent=1)
 print(open(os.path.join(P, f"{tag}_launches.md")).read()[:1500])
 print(json.dumps(traffic))
