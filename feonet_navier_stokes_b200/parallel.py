@@ -97,13 +97,17 @@ def allreduce_gradients(module: torch.nn.Module, bucket_mb: float = 64.0, async_
 class GradientReducer:
     """Asynchronous SUM all-reduce of gradient pieces as they become available during backward.
 
-    `launch(t)` enqueues an NCCL all-reduce of `t` (in place) behind the work already queued on the current stream and
-    returns at once; the collective runs on the process group's own stream, so the GEMMs the caller queues next overlap
-    it.  `finish()` makes the current stream wait for every launched piece (call it before the optimizer step)."""
+    `launch(t)` enqueues an all-reduce of `t` (in place) behind the work already queued on the current stream and returns at
+    once; the collective runs on the process group's own stream, so the GEMMs the caller queues next overlap it.
+    `deposit(param, grad)` registers the tensor the pieces belong to: it is handed to `param.grad` only in `finish()`, AFTER
+    every piece has been reduced -- a tensor returned to autograd while its reduction is still in flight would be cloned or
+    read by AccumulateGrad before the sum has landed.  `finish()` makes the current stream wait for every launched piece and
+    assigns the deposited gradients (call it after `backward()`, before the optimizer step; required at any world size)."""
 
     def __init__(self, enabled: bool = True):
         self.enabled = bool(enabled) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.work = []
+        self.deposits = []
         self.bytes = 0
 
     def launch(self, t: torch.Tensor) -> None:
@@ -112,17 +116,23 @@ class GradientReducer:
         self.bytes += t.numel() * t.element_size()
         self.work.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True))
 
+    def deposit(self, param: torch.nn.Parameter, grad: torch.Tensor) -> None:
+        self.deposits.append((param, grad))
+
     def finish(self) -> int:
         for h in self.work:
             h.wait()  # stream-level wait for NCCL work: the host does not block
-        n, self.work, self.bytes = self.bytes, [], 0
+        for param, grad in self.deposits:
+            param.grad = grad if param.grad is None else param.grad + grad
+        n, self.work, self.deposits, self.bytes = self.bytes, [], [], 0
         return n
 
 
 class _OverlappedLinearTFn(torch.autograd.Function):
     """y = x W^T + b with a dof-major result (as network.LinearT); the backward forms dW in `chunks` row blocks (dof
     ranges) and hands each block to the reducer as soon as its GEMM is queued, so the all-reduce of block k runs while the
-    GEMMs of the blocks after it (and dx) execute."""
+    GEMMs of the blocks after it (and dx) execute.  dW and db reach `.grad` through the reducer (`finish()`), not through
+    autograd."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, chunks: int, reducer: GradientReducer):
@@ -131,7 +141,7 @@ class _OverlappedLinearTFn(torch.autograd.Function):
         xt = (torch.nn.functional.pad(x, (0, 0, 0, pad)) if pad else x).t()  # [in, ceil4(B)]
         yt = torch.addmm(bias.unsqueeze(1), weight, xt) if bias is not None else weight @ xt
         ctx.save_for_backward(x, weight)
-        ctx.has_bias, ctx.chunks, ctx.reducer = bias is not None, int(chunks), reducer
+        ctx.bias, ctx.chunks, ctx.reducer, ctx.weight = bias, int(chunks), reducer, weight
         return yt[:, :B].t()
 
     @staticmethod
@@ -145,17 +155,19 @@ class _OverlappedLinearTFn(torch.autograd.Function):
             r1 = min(out_f, r0 + step)
             torch.mm(gT[r0:r1], x, out=dW[r0:r1])
             ctx.reducer.launch(dW[r0:r1])
-        db = None
-        if ctx.has_bias:
+        ctx.reducer.deposit(ctx.weight, dW)
+        if ctx.bias is not None:
             db = gT.sum(dim=1)
             ctx.reducer.launch(db)
+            ctx.reducer.deposit(ctx.bias, db)
         dx = g @ weight if ctx.needs_input_grad[0] else None
-        return dx, dW, db, None, None
+        return dx, None, None, None, None
 
 
 class OverlappedLinearT(torch.nn.Linear):
     """Drop-in for the final `nn.Linear` / `network.LinearT` of a FEONet model under data parallelism (same parameters
-    and state_dict keys): dof-major output, gradient all-reduce overlapped with its own backward GEMMs."""
+    and state_dict keys): dof-major output, gradient all-reduce overlapped with its own backward GEMMs.  Its parameter
+    gradients appear in `.grad` when `reducer.finish()` is called (after `backward()`)."""
 
     def __init__(self, in_features, out_features, bias=True, chunks: int = 8, reducer: Optional[GradientReducer] = None):
         super().__init__(in_features, out_features, bias=bias)

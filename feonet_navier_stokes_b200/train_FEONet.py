@@ -290,8 +290,14 @@ class Trainer:
                                 bool(gparams["dof_major_head"]), gparams).to(self.device)
         if gparams["pretrained"]:
             self.model.load_state_dict(torch.load(gparams["pretrained"], map_location=self.device))
+        self.reducer, self.head_params = None, []
         if self.world > 1:
             parallel.broadcast_parameters(self.model)
+            if gparams["model"] == "FCNN" and gparams["optimizer"] != "LBFGS":
+                # the head holds almost all parameters (256 x N): its gradient all-reduce overlaps its own backward GEMMs
+                self.reducer = parallel.GradientReducer()
+                self.model.model[-1] = parallel.OverlappedLinearT.from_linear(self.model.model[-1], chunks=8, reducer=self.reducer)
+                self.head_params = list(self.model.model[-1].parameters())
             if any(isinstance(m, torch.nn.modules.batchnorm._BatchNorm) for m in self.model.modules()):
                 self.model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(self.model)  # full-batch statistics as on one GPU
         self.optimizer = make_optimizer(gparams["optimizer"], self.model, gparams["lr"])
@@ -327,6 +333,9 @@ class Trainer:
         self.optimizer.zero_grad(set_to_none=True)
         loss, u_pred = self.problem.closure(self.model, *self.closure_args(batch))
         loss.backward()
+        if self.reducer is not None:  # head gradients were reduced during backward; the small layers follow in one bucket
+            self.parallel.allreduce_remaining(self.model, self.head_params, self.reducer)
+            self.reducer.finish()
         # bad-value guards of the reference (:434-469) folded into one device flag, read once
         ok = torch.isfinite(loss) & torch.isfinite(u_pred).all()
         for p in self.model.parameters():
@@ -338,7 +347,8 @@ class Trainer:
             ok = flag > 0
         if not bool(ok.item()):
             return loss.detach(), False  # skip this batch
-        self.parallel.allreduce_gradients(self.model)
+        if self.reducer is None:
+            self.parallel.allreduce_gradients(self.model)
         if isinstance(self.optimizer, torch.optim.LBFGS):
             def reeval():
                 self.optimizer.zero_grad(set_to_none=True)

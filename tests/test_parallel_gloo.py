@@ -69,3 +69,37 @@ def test_shard_bounds_cover_batch():
             spans = [par.shard_bounds(n, r, world) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def _worker_overlapped(rank, world, port, out_dir):
+    """The bench's DP training step (parallel.OverlappedLinearT + GradientReducer + allreduce_remaining): the head's weight
+    gradient is all-reduced chunk by chunk DURING backward, the other layers afterwards."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    par.init_distributed("gloo")
+    model, A0, x0, F0 = _make(seed=0)
+    reducer = par.GradientReducer()
+    assert reducer.enabled
+    model[-1] = par.OverlappedLinearT.from_linear(model[-1], chunks=3, reducer=reducer)
+    head = list(model[-1].parameters())
+    xs, Fs = par.shard_batch(x0, rank, world), par.shard_batch(F0, rank, world)
+    loss, _ = _loss(model, A0, xs, Fs)
+    loss.backward()
+    par.allreduce_remaining(model, head, reducer)
+    nbytes = reducer.finish()
+    assert nbytes == 4 * (head[0].numel() + head[1].numel())
+    torch.save({"grads": [p.grad.detach().clone() for p in model.parameters()], "loss": par.allreduce_loss(loss)}, os.path.join(out_dir, f"o{rank}.pt"))
+    torch.distributed.destroy_process_group()
+
+
+def test_overlapped_head_allreduce_matches_single_process():
+    world, port = 2, _free_port()
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_worker_overlapped, args=(world, port, d), nprocs=world, join=True)
+        outs = [torch.load(os.path.join(d, f"o{r}.pt")) for r in range(world)]
+    model, A, x, F = _make(seed=0)
+    loss, _ = _loss(model, A, x, F)
+    loss.backward()
+    for o in outs:
+        assert torch.allclose(o["loss"], loss.detach(), rtol=1e-5)
+        for g, p in zip(o["grads"], model.parameters()):
+            assert torch.allclose(g, p.grad, rtol=1e-4, atol=1e-5)  # SUM over ranks = the full-batch gradient
