@@ -79,7 +79,7 @@ def parse_args():
     ap.add_argument("--no-precond-gemm", action="store_true")
     ap.add_argument("--no-train-step", action="store_true", help="skip the DP training-step arm (FCNN head + gradient all-reduce)")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity check against the fp64 oracle")
-    ap.add_argument("--train-steps", type=int, default=6)
+    ap.add_argument("--train-steps", type=int, default=8)
     ap.add_argument("--configs", action="store_true", help="time cfg1-4 (parity-test cases) on cuda:0 beside the CPU port; not the bench line")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-chunk", type=int, default=256, help="samples per host->device chunk of the end-to-end leg")
@@ -474,13 +474,21 @@ def run_train_step(args, torch, feo, ns, fx, dev, world, rank):
         F.normal_(0.0, 1.0, generator=gen)
         head = list(model.model[-1].parameters())
 
-        def step():
+        waits = []
+
+        def step(timed=False):
             optim.zero_grad(set_to_none=True)
             loss, _ = ns.closure(model, coeff, None, F, fx.A, fx.B1, fx.B2, 64)
             loss.backward()
-            if reduce_grads and world > 1:
-                parallel.allreduce_remaining(model, head, reducer)
-                reducer.finish()
+            if world > 1:
+                if timed:  # how long the compute stream sits between the end of backward and the last reduced gradient
+                    waits.append((ev(), ev()))
+                    waits[-1][0].record()
+                if reduce_grads:
+                    parallel.allreduce_remaining(model, head, reducer)
+                reducer.finish()  # hands the head's gradients to .grad (after their reduction, when one was launched)
+                if timed:
+                    waits[-1][1].record()
             optim.step()
             return loss
 
@@ -492,16 +500,17 @@ def run_train_step(args, torch, feo, ns, fx, dev, world, rank):
         e0, e1 = ev(), ev()
         e0.record()
         for _ in range(K):
-            loss = step()
+            loss = step(timed=True)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / K
+        wait_ms = sum(a.elapsed_time(b) for a, b in waits) / max(1, len(waits))
         if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            t = torch.tensor([ms, wait_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            ms, wait_ms = float(t[0].item()), float(t[1].item())
         del coeff, F
-        return ms, float(loss.item())
+        return ms, float(loss.item()), wait_ms
 
     B = args.batch
     out = {"model": "FCNN(6,[16,32,64,128,256],N) tanh MLP, dropout 0.2, fp32 (TF32 off, torch default), fused Adam",
@@ -509,11 +518,11 @@ def run_train_step(args, torch, feo, ns, fx, dev, world, rank):
     model, reducer, optim = build(True, world > 1)
     out["params"] = sum(p.numel() for p in model.parameters())
     out["grad_bytes"] = 4 * out["params"]
-    ms_full, loss = time_steps(model, reducer, optim, B, True)
+    ms_full, loss, wait_full = time_steps(model, reducer, optim, B, True)
     out["weak"] = {"batch_per_gpu": B, "ms_per_step": ms_full, "samples_per_s": world * B / (ms_full * 1e-3), "loss": loss}
     if world > 1:
         reducer.enabled = False
-        ms_noar, _ = time_steps(model, reducer, optim, B, False)
+        ms_noar, _, wait_noar = time_steps(model, reducer, optim, B, False)
         reducer.enabled = True
         # the collective alone: the same chunks, nothing to overlap with
         w = model.model[-1].weight
@@ -538,17 +547,20 @@ def run_train_step(args, torch, feo, ns, fx, dev, world, rank):
         del bufs, rest
         out["weak"].update({"ms_per_step_without_allreduce": ms_noar, "allreduce_alone_ms": ar_ms,
                             "allreduce_busbw_GBs": 2.0 * (world - 1) / world * out["grad_bytes"] / (ar_ms * 1e-3) / 1e9,
-                            "allreduce_exposed_ms": max(0.0, ms_full - ms_noar),
-                            "allreduce_exposed_frac": max(0.0, ms_full - ms_noar) / ar_ms,
+                            # exposed = what the compute stream waits between the end of backward and the last reduced gradient
+                            # (CUDA events inside the step), minus the same interval of the run without the collective
+                            "allreduce_exposed_ms": max(0.0, wait_full - wait_noar),
+                            "allreduce_exposed_frac": max(0.0, wait_full - wait_noar) / ar_ms,
+                            "step_difference_ms": ms_full - ms_noar,
                             "limiting_collective": "NCCL all-reduce(SUM) of the head weight gradient (256 x N fp32), 8 dof-range chunks"})
         Bs = max(1, B // world)
-        ms_strong, _ = time_steps(model, reducer, optim, Bs, True)
+        ms_strong, _, _ = time_steps(model, reducer, optim, Bs, True)
         out["strong"] = {"batch_per_gpu": Bs, "global_batch": Bs * world, "ms_per_step": ms_strong,
                          "samples_per_s": world * Bs / (ms_strong * 1e-3)}
     del model, optim
     if world == 1:  # the drop-in question: what does closure() cost with the reference's row-major nn.Linear head?
         model, reducer, optim = build(False, False)
-        ms_rm, _ = time_steps(model, reducer, optim, B, False)
+        ms_rm, _, _ = time_steps(model, reducer, optim, B, False)
         out["closure_row_major_head"] = {"ms_per_step": ms_rm, "samples_per_s": B / (ms_rm * 1e-3),
                                          "note": "network.FCNN with the reference's nn.Linear head ([B,1,N] row-major): the loss op transposes in and out"}
         del model, optim
