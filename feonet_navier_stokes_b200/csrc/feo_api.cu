@@ -245,8 +245,15 @@ int feo_op_get_info(feo_handle_t h, feo_op_info* info) {
 size_t feo_workspace_bytes(feo_handle_t h, int32_t B, int32_t T) {
   if (h == nullptr || B <= 0) return 0;
   if (T < 1) T = 1;
-  return loss_partials_needed(h->n, std::max(std::max(h->tiles_f.warps, h->patch_f.warps), h->lattice.present ? lattice_fwd_warps() : 0),
-                              (int64_t)B * T);
+  size_t need = loss_partials_needed(h->n, std::max(std::max(h->tiles_f.warps, h->patch_f.warps), h->lattice.present ? lattice_fwd_warps() : 0),
+                                     (int64_t)B * T);
+  if (h->dMs != nullptr || h->dPs != nullptr) {
+    // dense applies: loss partials of the tile grid (1 KB aligned), then the pre-split activations (feo_dense_tc.cu)
+    const int64_t cols = ((int64_t)B * T + 3) / 4 * 4;
+    const size_t tc_count = (size_t)((cols + 63) / 64 + 1) * (size_t)((h->n + 127) / 128);
+    need = std::max(need, (tc_count * sizeof(float) + 1023) / 1024 * 1024 + dense_xsplit_bytes(h->n, (int64_t)B * T));
+  }
+  return need;
 }
 
 int feo_transpose(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int32_t rows, int32_t cols,

@@ -39,6 +39,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
@@ -385,6 +386,205 @@ __global__ void __launch_bounds__(kTcBlock, BN == 128 ? 2 : 3) dense_apply_tc_ke
   if (CL > 1) cluster_sync();  // no CTA leaves while its peer may still signal it
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Second generation (round 2): the activations are pre-split too.
+//
+// The first kernel is paced by its XT operand pipeline (global -> registers -> cvt.rna -> STS by eight warps: a run without
+// any MMA takes 0.144 of its 0.162 ms at N = 2549, B = 1024).  Here a bandwidth-bound PRE-PASS (dense_split_x_kernel: XT is
+// 10 MB, its split 20 MB) writes, per (column tile, k-block), one block [hi | lo] already in the K-major core-matrix layout,
+// so that BOTH operands of a stage arrive by bulk copies (UBLKCP) on one transaction barrier and no warp touches operand
+// data.  The accumulator ping-pongs between two TMEM regions: while the eight epilogue warps drain chunk c (tcgen05.ld,
+// round-to-nearest adds in registers: the truncation drain) the issuer already accumulates chunk c + 1 into the other one.
+//   barriers: full[S]       stage landed (24 KB of transactions: D block 16 KB + X block 8 KB at BN = 64)
+//             mma_done[2]   per k-block parity: MMAs of k-block kb completed -> its stage may be refilled (issuer only)
+//             chunk_done[2] per accumulator: every MMA of the chunk completed -> drain it (epilogue warps)
+//             drained[2]    per accumulator: read back by all 256 epilogue threads -> the issuer may overwrite it
+// ---------------------------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(256) dense_split_x_kernel(const float* __restrict__ XT, int32_t n, int64_t ldb, float* __restrict__ Xs,
+                                                            int32_t nkb) {
+  // block (column tile ct, k-block kb) -> Xs + (ct * nkb + kb) * [hi BN x 16 | lo BN x 16], element (c, k) at
+  // (k / 4) * BN * 16 + c * 16 + (k % 4) * 4 bytes of its half
+  const int ct = blockIdx.x, kb = blockIdx.y;
+  uint8_t* blk = reinterpret_cast<uint8_t*>(Xs) + ((size_t)ct * nkb + kb) * b_stage_bytes(BN);
+  constexpr uint32_t kHalf = (uint32_t)BN * TBK * 4;
+  for (int it = threadIdx.x; it < BN * (TBK / 4); it += 256) {
+    const int c = it % BN, q = it / BN;  // consecutive threads read consecutive samples of one row of XT
+    const int64_t col = (int64_t)ct * BN + c;
+    float t[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = kb * TBK + q * 4 + i;
+      t[i] = (k < n && col < ldb) ? __ldg(XT + (int64_t)k * ldb + col) : 0.f;
+    }
+    store_split(blk, blk + kHalf, (uint32_t)q * (BN * 16) + (uint32_t)c * 16, make_float4(t[0], t[1], t[2], t[3]));
+  }
+}
+
+template <int BN, int S, int CL>
+__global__ void __launch_bounds__(kTcBlock, (BN <= 64 || (BN == 128 && S == 3)) ? 2 : 1) dense_apply_tc2_kernel(const float* __restrict__ Dsplit, const float* __restrict__ Xsplit, int32_t n,
+                                                                     float* __restrict__ CT, int64_t ldb, int32_t B, float scale,
+                                                                     const float* __restrict__ scale_dev, const float* __restrict__ sub,
+                                                                     float* __restrict__ partials, int32_t flush, int32_t debug) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t s_full[S];
+  __shared__ __align__(8) uint64_t s_mma[2];
+  __shared__ __align__(8) uint64_t s_chunk[2];
+  __shared__ __align__(8) uint64_t s_drained[2];
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_part[kTcThreads / 32];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool is_issuer = __shfl_sync(0xffffffffu, warp, 0) == kTcThreads / 32;
+  const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * BN;
+  constexpr uint32_t kTmemCols = BN <= 64 ? 128 : (BN <= 128 ? 256 : 512);  // two accumulators of BN columns (allocations are powers of two)
+  constexpr uint32_t kBBytes = (uint32_t)BN * TBK * 4;
+  constexpr uint32_t kAStage = 2 * kABytes, kBStage = b_stage_bytes(BN), kStage = kAStage + kBStage;
+  constexpr int kAhead = S - 2;
+  constexpr uint32_t kLboB = BN * 16;
+  constexpr uint32_t kIdesc = instr_desc(BN);
+  constexpr int WC = BN / 2;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (int s = 0; s < S; ++s) mbar_init(smem_u32(&s_full[s]), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&s_mma[s]), CL);
+      mbar_init(smem_u32(&s_chunk[s]), 1);
+      mbar_init(smem_u32(&s_drained[s]), kTcThreads);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (CL > 1) cluster_sync();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+  const int nkb = (n + TBK - 1) / TBK;
+  const int n_chunks = (nkb + flush - 1) / flush;
+  const float* a_src = Dsplit + (size_t)blockIdx.y * nkb * (kAStage / 4);
+  const float* x_src = Xsplit + (size_t)blockIdx.x * nkb * (kBStage / 4);
+
+  const uint32_t t_own = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * WC);
+  float acc[WC];
+#pragma unroll
+  for (int i = 0; i < WC; ++i) acc[i] = 0.f;
+
+  if (is_issuer) {
+    const uint32_t half = CL == 1 ? 0u : cluster_ctarank() * kABytes;
+    auto copy_stage = [&](int stage, int kb) {
+      const uint32_t bar = smem_u32(&s_full[0]) + (uint32_t)stage * 8;
+      mbar_expect_tx(bar, kStage);
+      const uint32_t dst = smem_u32(smem) + (uint32_t)stage * kStage;
+      const float* srca = a_src + (size_t)kb * (kAStage / 4) + half / 4;
+      if (CL == 1) bulk_copy(dst, srca, kAStage, bar);
+      else bulk_copy_multicast(dst + half, srca, kABytes, bar, (uint16_t)3);
+      bulk_copy(dst + kAStage, x_src + (size_t)kb * (kBStage / 4), kBStage, bar);
+    };
+    if (elect_one())
+      for (int kb = 0; kb < kAhead && kb < nkb; ++kb) copy_stage(kb, kb);
+    int c_stage = kAhead % S;
+    constexpr uint32_t kDescHi = (kSbo >> 4) | (1u << 14);
+    const uint32_t a_lo0 = ((smem_u32(smem) & 0x3ffffu) >> 4) | ((kLboA >> 4) << 16);
+    const uint32_t b_lo0 = (((smem_u32(smem) + kAStage) & 0x3ffffu) >> 4) | ((kLboB >> 4) << 16);
+    auto desc = [&](uint32_t lo) { return ((uint64_t)kDescHi << 32) | (uint64_t)lo; };
+    int stage = 0, phase = 0, chunk_pos = 0, chunk = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb & 1;
+      const uint32_t bar_s = smem_u32(&s_mma[0]) + (uint32_t)s * 8;
+      if (kb >= 2) mbar_wait(bar_s, ((kb >> 1) - 1) & 1);  // MMAs of kb - 2 done: stage (kb + kAhead) % S is free
+      if (kb + kAhead < nkb) {
+        if (elect_one()) copy_stage(c_stage, kb + kAhead);
+        if (++c_stage == S) c_stage = 0;
+      }
+      mbar_wait(smem_u32(&s_full[0]) + (uint32_t)stage * 8, phase);
+      const bool first = chunk_pos == 0;
+      const int buf = chunk & 1;
+      if (first && chunk >= 2) mbar_wait(smem_u32(&s_drained[0]) + (uint32_t)buf * 8, ((chunk >> 1) - 1) & 1);  // accumulator free again
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const bool last_of_chunk = chunk_pos == flush - 1 || kb == nkb - 1;
+      if (elect_one()) {
+        const uint32_t la = a_lo0 + (uint32_t)stage * (kStage >> 4), lb = b_lo0 + (uint32_t)stage * (kStage >> 4);
+        const uint32_t td = tmem + (uint32_t)buf * BN;
+#pragma unroll
+        for (int ks = 0; ks < TBK / 8; ++ks) {
+          const uint64_t a_hi = desc(la + ks * (2 * kLboA >> 4)), a_lo = desc(la + (kABytes >> 4) + ks * (2 * kLboA >> 4));
+          const uint64_t b_hi = desc(lb + ks * (2 * kLboB >> 4)), b_lo = desc(lb + (kBBytes >> 4) + ks * (2 * kLboB >> 4));
+          if (debug < 2) umma_tf32(td, a_lo, b_hi, kIdesc, !(first && ks == 0));
+          if (debug < 1) umma_tf32(td, a_hi, b_lo, kIdesc, 1);
+          if (debug < 1) umma_tf32(td, a_hi, b_hi, kIdesc, 1);
+        }
+        if (CL == 1) umma_commit(bar_s);
+        else umma_commit_multicast(bar_s, (uint16_t)3);
+        if (last_of_chunk) umma_commit(smem_u32(&s_chunk[0]) + (uint32_t)buf * 8);
+      }
+      __syncwarp();
+      if (++stage == S) stage = 0, phase ^= 1;
+      if (last_of_chunk) chunk_pos = 0, ++chunk;
+      else ++chunk_pos;
+    }
+  } else {
+    for (int c = 0; c < n_chunks; ++c) {
+      const int buf = c & 1;
+      mbar_wait(smem_u32(&s_chunk[0]) + (uint32_t)buf * 8, (c >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < WC / 16; ++j) {
+        uint32_t v[16];
+        tmem_ld16(t_own + (uint32_t)(buf * BN + j * 16), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[j * 16 + i] += __uint_as_float(v[i]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(smem_u32(&s_drained[0]) + (uint32_t)buf * 8);
+    }
+  }
+
+  // epilogue (as in the first kernel)
+  const float sc = scale * (scale_dev != nullptr ? __ldg(scale_dev) : 1.0f);
+  const int m = m0 + (warp & 3) * 32 + lane;
+  const int cbase = (warp >> 2) * WC;
+  float lsum = 0.f;
+#pragma unroll
+  for (int q = 0; q < WC / 4; ++q) {
+    const int c = n0 + cbase + q * 4;
+    if (!is_issuer && m < n && c < ldb) {
+      float4 o = make_float4(sc * acc[q * 4 + 0], sc * acc[q * 4 + 1], sc * acc[q * 4 + 2], sc * acc[q * 4 + 3]);
+      if (sub != nullptr) {
+        const float4 sv = __ldg(reinterpret_cast<const float4*>(sub + (int64_t)m * ldb + c));
+        o.x -= sv.x;
+        o.y -= sv.y;
+        o.z -= sv.z;
+        o.w -= sv.w;
+      }
+      if (c + 0 < B) lsum = fmaf(o.x, o.x, lsum);
+      if (c + 1 < B) lsum = fmaf(o.y, o.y, lsum);
+      if (c + 2 < B) lsum = fmaf(o.z, o.z, lsum);
+      if (c + 3 < B) lsum = fmaf(o.w, o.w, lsum);
+      *reinterpret_cast<float4*>(CT + (int64_t)m * ldb + c) = o;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+  if (lane == 0 && !is_issuer) s_part[warp] = lsum;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tid == 0 && partials != nullptr) {
+    float t = 0.f;
+    for (int w = 0; w < kTcThreads / 32; ++w) t += s_part[w];
+    partials[blockIdx.y * gridDim.x + blockIdx.x] = t;
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+  }
+  if (CL > 1) cluster_sync();
+}
+
 int env_int(const char* name, int dflt) {
   const char* e = std::getenv(name);
   const int v = e != nullptr ? atoi(e) : dflt;
@@ -416,6 +616,35 @@ int launch_tc(dim3 grid, const float* Dsplit, int32_t n, const float* XT, float*
                                     (int32_t)flush, (int32_t)debug));
   return FEO_OK;
 }
+template <int BN, int S, int CL>
+int launch_tc2(dim3 grid, const float* Dsplit, float* Xsplit, int32_t n, const float* XT, float* CT, int64_t ldb, int32_t B, float scale,
+               const float* scale_dev, const float* sub, float* partials, int flush, cudaStream_t st) {
+  static bool configured = false;
+  static const int debug = env_int("FEO_DENSE_DEBUG", 0);
+  const int smem_bytes = S * (int)(2 * kABytes + b_stage_bytes(BN));
+  if (!configured) {
+    FEO_CUDA_CHECK(cudaFuncSetAttribute(dense_apply_tc2_kernel<BN, S, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured = true;
+  }
+  const int nkb = (n + TBK - 1) / TBK;
+  dense_split_x_kernel<BN><<<dim3(grid.x, (unsigned)nkb), 256, 0, st>>>(XT, n, ldb, Xsplit, nkb);
+  FEO_CUDA_CHECK(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kTcBlock);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  FEO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dense_apply_tc2_kernel<BN, S, CL>, Dsplit, (const float*)Xsplit, n, CT, ldb, B, scale, scale_dev, sub,
+                                    partials, (int32_t)flush, (int32_t)debug));
+  return FEO_OK;
+}
 // cvt.rna.tf32.f32 on the host: round to nearest, ties away from zero, to 10 mantissa bits
 float rna_tf32(float x) {
   uint32_t u = f2u(x);
@@ -443,28 +672,84 @@ std::vector<float> dense_split_tiles(const float* src, int32_t n, bool transpose
   return out;
 }
 
+// bytes of the pre-split activations of the second-generation kernel: one [hi | lo] block per (column tile, k-block), column
+// tiles padded to the cluster size; the largest over the tile widths the launcher may pick (a multiple of 1 KB)
+size_t dense_xsplit_bytes(int32_t n, int64_t cols) {
+  const int64_t c4 = (cols + 3) / 4 * 4, nkb = (n + TBK - 1) / TBK;
+  size_t need = 0;
+  for (int bn : {64, 128, 160}) need = std::max(need, (size_t)((c4 + bn - 1) / bn + 1) * (size_t)nkb * b_stage_bytes(bn));
+  return need;
+}
+
+int sm_count(int* out);  // feo_tiled.cu
+
 int launch_dense_tc(const float* Dsplit, int32_t n, const float* XT, float* CT, int64_t ldb, int32_t B,
                     float scale, const float* scale_dev, const float* sub, float* partials, int* count_out,
-                    cudaStream_t st) {
+                    float* xsplit, size_t xsplit_bytes, cudaStream_t st) {
   static const int flush = env_int("FEO_DENSE_FLUSH", kFlushDefault);
   static const int bn_env = env_int("FEO_DENSE_BN", 0);
   if (Dsplit == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, "dense operator not present in this handle");
   const int64_t cols = (B + 3) / 4 * 4;
   const int64_t row_tiles = (n + TBM - 1) / TBM;
-  // 64-column tiles put three CTAs on every SM and were the fastest at every measured size (N = 387 .. 2549,
-  // B = 1024 .. 8192); 128-column tiles (half the operator re-reads, 128 registers) stay selectable for experiments
-  int bn = 64;
-  if (bn_env == 64 || bn_env == 128) bn = bn_env;
   // FEO_DENSE_CLUSTER=2: pairs of column tiles share every operator stage through cluster multicast (each CTA fetches one
   // half).  Measured equal to the plain launch (0.164 vs 0.162 ms at N = 2549, B = 1024; 0.90 vs 0.89 ms at B = 8192):
   // the crossbar traffic it halves is not what paces the kernel, so the plain launch stays the default.
   static const int cl_env = env_int("FEO_DENSE_CLUSTER", 0);
   const int cl = cl_env == 2 ? 2 : 1;
+  static const int sa_env = env_int("FEO_DENSE_ASTAGES", 0);
+  // second generation (pre-split activations, ping-pong accumulators): the default whenever the caller's workspace holds
+  // the split (feo_workspace_bytes accounts for it); FEO_DENSE_GEN=1 keeps the first kernel
+  static const int gen_env = env_int("FEO_DENSE_GEN", 2);
+  if (gen_env != 1 && xsplit != nullptr && xsplit_bytes >= dense_xsplit_bytes(n, cols)) {
+    // Tile width: an M = 128 MMA takes the same time at N = 64 as at N = 128 (tools/micro9.cu) and proportionally longer
+    // above, and the tiles of one SM share its tensor pipe, so the run time goes as
+    //   ceil(tiles / SMs) * max(BN, 128):
+    // at N = 2549, B = 1024 that is 3 x 128 for 64-column tiles (320 tiles), 2 x 128 for 128 (160) and 1 x 160 for 160-column
+    // tiles (140 tiles: one per SM).  Ties go to the narrower tile (more SMs share the operand traffic).
+    int sms = 148;
+    if (int rc = sm_count(&sms)) return rc;
+    int bn = 64;
+    int64_t best = -1;
+    for (int cand : {64, 128, 160}) {
+      const int64_t tiles = row_tiles * ((cols + cand - 1) / cand);
+      const int64_t cost = (tiles + sms - 1) / sms * std::max(cand, 128);
+      if (best < 0 || cost < best) best = cost, bn = cand;
+    }
+    if (bn_env == 64 || bn_env == 128 || bn_env == 160) bn = bn_env;
+    const unsigned col_tiles = (unsigned)((cols + bn - 1) / bn);
+    dim3 grid((col_tiles + cl - 1) / cl * cl, (unsigned)row_tiles);
+    *count_out = (int)(grid.x * grid.y);
+    // stages: 24 / 32 / 36 KB each; two CTAs per SM up to 128 columns (four stages at 64, three at 128), one at 160 (six)
+    const int s_dflt = bn == 64 ? 4 : (bn == 128 ? 3 : 6);
+    const int s2 = sa_env >= 3 && sa_env <= 6 ? sa_env : s_dflt;
+#define FEO_TC2_CASE(BN_, S_, CL_) \
+  if (bn == BN_ && s2 == S_ && cl == CL_) \
+  return launch_tc2<BN_, S_, CL_>(grid, Dsplit, xsplit, n, XT, CT, ldb, B, scale, scale_dev, sub, partials, flush, st)
+    FEO_TC2_CASE(64, 3, 1);
+    FEO_TC2_CASE(64, 4, 1);
+    FEO_TC2_CASE(64, 5, 1);
+    FEO_TC2_CASE(64, 6, 1);
+    FEO_TC2_CASE(64, 4, 2);
+    FEO_TC2_CASE(128, 3, 1);
+    FEO_TC2_CASE(128, 4, 1);
+    FEO_TC2_CASE(128, 5, 1);
+    FEO_TC2_CASE(128, 6, 1);
+    FEO_TC2_CASE(128, 3, 2);
+    FEO_TC2_CASE(160, 4, 1);
+    FEO_TC2_CASE(160, 5, 1);
+    FEO_TC2_CASE(160, 6, 1);
+    FEO_TC2_CASE(160, 6, 2);
+#undef FEO_TC2_CASE
+    return fail(FEO_ERR_INVALID_ARGUMENT, "dense_apply: no second-generation kernel for this tile configuration");
+  }
+  // first generation: 64-column tiles put three CTAs on every SM and were the fastest at every measured size (N = 387 .. 2549,
+  // B = 1024 .. 8192); 128-column tiles (half the operator re-reads, 128 registers) stay selectable for experiments
+  int bn = 64;
+  if (bn_env == 64 || bn_env == 128) bn = bn_env;
   // cluster launches need a grid that is a multiple of the cluster: a padding column tile runs the protocol and stores nothing
   const unsigned col_tiles = (unsigned)((cols + bn - 1) / bn);
   dim3 grid((col_tiles + cl - 1) / cl * cl, (unsigned)row_tiles);
   *count_out = (int)(grid.x * grid.y);
-  static const int sa_env = env_int("FEO_DENSE_ASTAGES", 0);
   const int sa = sa_env >= 3 && sa_env <= 5 ? sa_env : 3;
 #define FEO_TC_CASE(BN_, SA_, CL_) \
   if (bn == BN_ && sa == SA_ && cl == CL_) \

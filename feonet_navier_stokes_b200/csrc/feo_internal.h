@@ -253,7 +253,8 @@ int launch_dense(const float* D, const float* Dsplit, int32_t n, const float* XT
 std::vector<float> dense_split_tiles(const float* src, int32_t n, bool transposed);
 int launch_dense_tc(const float* Dsplit, int32_t n, const float* XT, float* CT, int64_t ldb, int32_t B,
                     float scale, const float* scale_dev, const float* sub, float* partials, int* count_out,
-                    cudaStream_t st);
+                    float* xsplit, size_t xsplit_bytes, cudaStream_t st);
+size_t dense_xsplit_bytes(int32_t n, int64_t cols);  // scratch of the pre-split activations (second-generation dense kernel)
 int launch_sincos_grid(const float* coeff, int32_t B, int32_t resol, float* out, cudaStream_t st);
 size_t loss_partials_needed(int32_t n, int32_t fused_warps, int64_t cols);
 size_t fused_partials_needed(int32_t warps);  // floats: one loss partial per (persistent CTA, consumer warp)

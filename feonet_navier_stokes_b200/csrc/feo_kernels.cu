@@ -448,7 +448,15 @@ int launch_dense(const float* D, const float* Dsplit, int32_t n, const float* XT
     // the tensor-core kernel writes one partial per 128 x 64 tile, the column tiles padded to the cluster size
     const size_t tc_count = (size_t)(((B + 3) / 4 * 4 + 63) / 64 + 1) * (size_t)((n + 127) / 128);
     if (loss_out != nullptr && ws_bytes < tc_count * sizeof(float)) return fail(FEO_ERR_INVALID_ARGUMENT, "workspace too small");
-    if (int rc = launch_dense_tc(Dsplit, n, XT, CT, ldb, B, scale, scale_dev, sub, partials, &count, st)) return rc;
+    // the workspace: loss partials first, then (1 KB aligned) the pre-split activations of the second-generation kernel
+    const size_t part_bytes = (tc_count * sizeof(float) + 1023) / 1024 * 1024;
+    float* xsplit = nullptr;
+    size_t xsplit_bytes = 0;
+    if (ws != nullptr && ws_bytes > part_bytes) {
+      xsplit = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + part_bytes);
+      xsplit_bytes = ws_bytes - part_bytes;
+    }
+    if (int rc = launch_dense_tc(Dsplit, n, XT, CT, ldb, B, scale, scale_dev, sub, partials, &count, xsplit, xsplit_bytes, st)) return rc;
   } else {
     dense_apply_kernel<<<grid, 256, 0, st>>>(D, n, ldd, XT, CT, ldb, B, scale, scale_dev, sub, partials);
     FEO_CUDA_CHECK(cudaGetLastError());
