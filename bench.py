@@ -641,6 +641,17 @@ def run_configs(args):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / iters
 
+    def graph_ms(loss_fn, inp, eager_loss):
+        """The same loss + gradient as ONE CUDA-graph replay (feo.GraphedLossGrad): what the step costs without launch latency."""
+        try:
+            gl = feo.GraphedLossGrad(loss_fn, [inp])
+            ms = time_gpu(lambda: gl(), 50)
+            l, _ = gl()
+            return {"gpu_ms_fwd_bwd_graph": ms, "graph_loss_rel_diff_vs_eager": abs(l.item() - eager_loss) / abs(eager_loss)}
+        except Exception as exc:  # pragma: no cover
+            log(f"[configs] graph capture failed: {exc!r}")
+            return {}
+
     def time_cpu(fn, reps=3):
         fn()
         t0 = time.perf_counter()
@@ -695,6 +706,7 @@ def run_configs(args):
         report(name + (f" N={fx.N}" if "N=" not in name else ""), fx.N, gpu_ms, cpu_ms,
                box["l"].item(), float(lo), box["g"].cpu().numpy(), go, "dense A.P folded at set-up, tcgen05 3xTF32 apply",
                alg_flops=4.0 * fx.N * fx.N * B)  # one GEMM forward, one backward
+        rows[-1].update(graph_ms(lambda a_: st.residual_loss(a_, Ft, At, Pt), a, box["l"].item()))
         ref_ms, (l_ref, g_ref) = time_cpu(lambda: loops.linear_stokes_step(alpha, F, A, P, True), reps=1)
         rows[-1].update(reference_loops_ms_fwd_bwd=ref_ms, reference_loops_samples_per_s=B / (ref_ms * 1e-3),
                         speedup_vs_reference_loops=ref_ms / gpu_ms, loss_rel_diff_vs_reference_loops=abs(box["l"].item() - l_ref) / abs(l_ref))
@@ -720,6 +732,7 @@ def run_configs(args):
         report(f"cfg3 steady NS N={fx.N} ({'precond=I' if precond else 'no precond'} sign branch)", fx.N, gpu_ms, cpu_ms,
                box["l"].item(), float(lo), box["g"].cpu().numpy(), go, "fused residual kernels incl. row-major <-> dof-major transposes",
                alg_bytes=24.0 * fx.N * B)
+        rows[-1].update(graph_ms(lambda a_: nsm.residual_loss(a_, Ft, fx.A, fx.B1, fx.B2, fx.idx_sol), a, box["l"].item()))
         dense = [np.asarray(K.todense(), dtype=np.float32) for K in (fx.A, fx.B1, fx.B2)]
         ref_ms, (l_ref, g_ref) = time_cpu(lambda: loops.steady_ns_step(alpha, F, *dense, fx.idx_u1, fx.idx_u2, precond), reps=1)
         rows[-1].update(reference_loops_ms_fwd_bwd=ref_ms, reference_loops_samples_per_s=B / (ref_ms * 1e-3),
@@ -746,6 +759,7 @@ def run_configs(args):
     report(f"cfg4 time-dependent Stokes N={fx.N} T={T}", fx.N, gpu_ms, cpu_ms, box["l"].item(), float(lo),
            box["g"].cpu().numpy(), go, "seq_kernel fwd/bwd, one sample = T rows; launch- and L2-latency-bound at this size (41 MB per tensor)",
            alg_bytes=float(B) * (T * 20.0 * fx.N + 4.0 * fx.N))
+    rows[-1].update(graph_ms(lambda p_: td.residual_loss(p_, Ft, fx.S, fx.A, None, dt, u0t), pt, box["l"].item()))
     # the linear Stokes operator (no convective term: A-quads forward, 20 N B algorithmic bytes) at the cfg5 mesh size
     large = None
     try:
@@ -767,11 +781,55 @@ def run_configs(args):
         log(f"[configs] {large}")
     except Exception as exc:  # pragma: no cover
         log(f"[configs] large linear case failed: {exc!r}")
-    emit({"configs": rows, "linear_large": large, "cores": os.cpu_count(), "cpu_kind": "port (oracle numpy/scipy, fp32)",
+    for r in rows:
+        if "algorithmic_bytes" in r and "gpu_ms_fwd_bwd_graph" in r:
+            r["hbm_roofline_frac_graph"] = r["algorithmic_bytes"] / (r["gpu_ms_fwd_bwd_graph"] * 1e-3) / 1e9 / peak_gbs
+    shell = None
+    try:
+        shell = run_train_shell_timing(torch, dev)
+    except Exception as exc:  # pragma: no cover
+        log(f"[configs] train-shell timing failed: {exc!r}")
+    emit({"configs": rows, "linear_large": large, "train_shell": shell, "cores": os.cpu_count(), "cpu_kind": "port (oracle numpy/scipy, fp32)",
           "reference_loops": "oracle.TorchReferenceLoops: the reference's own execution plan (dense fp32 operators, (matrix @ precond).mm per "
                              "sample, one MSE(sum) per dof in a Python loop, autograd backward; FEONet_steady_Navier-Stokes/train_FEONet.py:301-360, "
                              "FEONet_Stokes_square/train_FEONet.py:261-296) restated and timed on this host with torch CPU, all cores; "
                              "bit-equal to the unmodified reference functions in the authoring container (profiles/r02_reference_cpu_container.json)"})
+
+
+def run_train_shell_timing(torch, dev, steps=100):
+    """One optimiser step of the training shell (network forward, residual loss, backward, bad-value guard, Adam) at the
+    reference's sizes, eager against ONE CUDA-graph replay (`--cuda_graph 1`, graphs.GraphedTrainStep): the body of the
+    reference's epoch loop, FEONet_steady_Navier-Stokes/train_FEONet.py:453-473.  Full-batch, data resident on the device."""
+    import tempfile
+
+    from feonet_navier_stokes_b200 import train_FEONet as T
+
+    out = []
+    cases = (("stokes_square FCNN preconditioned (tensor-core apply)", ["--variant", "stokes_square", "--train_file", "1000N72", "--val_file", "8N72",
+                                                                         "--model", "FCNN", "--do_precond", "1", "--spai_steps", "50"]),
+             ("stokes_square Net2D", ["--variant", "stokes_square", "--train_file", "1000N72", "--val_file", "8N72", "--model", "Net2D", "--do_precond", "0"]),
+             ("time_dep RNN T=10", ["--variant", "time_dep", "--train_file", "256N200", "--val_file", "8N200", "--model", "RNN", "--seq_len", "10"]))
+    for name, argv in cases:
+        row = {"case": name}
+        for graph in (0, 1):
+            with tempfile.TemporaryDirectory() as tmp:
+                g = dict(T.build_parser().parse_args(argv + ["--optimizer", "Adam", "--out", tmp, "--cuda_graph", str(graph)]).__dict__)
+                tr = T.Trainer(g, device=dev)
+                batch = next(tr.batches(tr.train, None, shard=True))
+                for _ in range(5):
+                    tr.train_step(batch)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(steps):
+                    loss, _ = tr.train_step(batch)
+                torch.cuda.synchronize()
+                ms = 1e3 * (time.perf_counter() - t0) / steps
+                row.update({"N": tr.N, "batch": int(next(iter(batch.values())).shape[0]), ("graph_ms_per_step" if graph else "eager_ms_per_step"): ms,
+                            ("graph_loss" if graph else "eager_loss"): float(loss.item())})
+        row["speedup"] = row["eager_ms_per_step"] / row["graph_ms_per_step"]
+        log(f"[configs] train shell {row}")
+        out.append(row)
+    return out
 
 
 def run_e2e(args, torch, feo, ns, fx, dev, world, rank):

@@ -59,6 +59,10 @@ class _TransposeCache:
         self.val = None
 
     def get(self, op: FEOperator, f: torch.Tensor, ldb: int) -> torch.Tensor:
+        if f.is_cuda and torch.cuda.is_current_stream_capturing():
+            # CUDA-graph capture (graphs.py): the layout pass must be IN the graph -- a replay sees whatever the caller has
+            # copied into the static load-vector buffer since, which a copy cached at capture time would not
+            return _prep(op, f.detach(), ldb)
         if self.src is not f or self.version != f._version or self.ldb != ldb:
             self.val = _prep(op, f.detach(), ldb)
             self.src, self.version, self.ldb = f, f._version, ldb

@@ -76,6 +76,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--spai_steps", type=int, default=200, help="minimal-residual iterations of the SPAI preconditioner")
     p.add_argument("--dof_major_head", type=int, default=1, help="let the last layer write the coefficients dof-major")
+    p.add_argument("--cuda_graph", type=int, default=0,
+                   help="capture the whole optimiser step (network, loss, backward, guard, update) in a CUDA graph: one GPU, Adam / AdamW / SGD")
     p.add_argument("--npz", type=str, default=None,
                    help="an assemble_fenics.py npz (data_ordered/P2x1_ne..._BC[_force].npz) to train on instead of synthesised data")
     return p
@@ -300,7 +302,16 @@ class Trainer:
                 self.head_params = list(self.model.model[-1].parameters())
             if any(isinstance(m, torch.nn.modules.batchnorm._BatchNorm) for m in self.model.modules()):
                 self.model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(self.model)  # full-batch statistics as on one GPU
-        self.optimizer = make_optimizer(gparams["optimizer"], self.model, gparams["lr"])
+        self.graphed = bool(gparams.get("cuda_graph", 0))
+        self._graphs: Dict[int, object] = {}
+        if self.graphed:
+            from .graphs import make_capturable_optimizer
+
+            if self.world > 1:
+                raise ValueError("--cuda_graph captures a single-GPU step (the overlapped gradient all-reduce runs on a second stream)")
+            self.optimizer = make_capturable_optimizer(gparams["optimizer"], self.model.parameters(), gparams["lr"])
+        else:
+            self.optimizer = make_optimizer(gparams["optimizer"], self.model, gparams["lr"])
         self.losses, self.train_err, self.test_err = [], [], []
         stamp = str(datetime.datetime.now()).replace(" ", "T").replace(":", "").split(".")[0].replace("-", "")
         self.folder = os.path.join(gparams["out"], str(ne), gparams["bc"], gparams["forcing_term"], f"{gparams['model']}_epochs{gparams['epochs']}_{stamp}")
@@ -329,7 +340,34 @@ class Trainer:
                 lo, hi = lo + a, lo + b
             yield {k: v[lo:hi] for k, v in data.items()}
 
+    def train_step_graphed(self, batch) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The same step as one CUDA-graph replay (graphs.GraphedTrainStep): no host read, the guard skips the update on the
+        device.  One graph per batch size; full-batch training (the reference's default) replays on the resident tensors
+        themselves, mini-batches are copied into the graph's static buffers."""
+        from .graphs import GraphedTrainStep
+
+        nb = next(iter(batch.values())).shape[0]
+        step = self._graphs.get(nb)
+        if step is None:
+            full = nb == next(iter(self.train.values())).shape[0]
+
+            class _Seen(dict):  # which tensors of a batch the closure reads (targets such as fenics_u1 stay out of the graph)
+                used = set()
+
+                def __getitem__(self, k):
+                    self.used.add(k)
+                    return dict.__getitem__(self, k)
+
+            probe = _Seen(batch)
+            self.closure_args(probe)
+            static = {k: (batch[k] if full else batch[k].clone()) for k in sorted(probe.used)}
+            body = lambda b: self.problem.closure(self.model, *self.closure_args(b))  # noqa: E731
+            step = self._graphs[nb] = GraphedTrainStep(self.model, self.optimizer, body, static)
+        return step(batch)
+
     def train_step(self, batch) -> Tuple[torch.Tensor, bool]:
+        if self.graphed:
+            return self.train_step_graphed(batch)
         self.optimizer.zero_grad(set_to_none=True)
         loss, u_pred = self.problem.closure(self.model, *self.closure_args(batch))
         loss.backward()
@@ -403,13 +441,18 @@ class Trainer:
         for epoch in range(1, g["epochs"] + 1):
             self.model.train()
             loss_total = torch.zeros((), device=self.device)
+            skipped_dev = torch.zeros((), device=self.device)
             for batch in self.batches(self.train, g["batch_size_train"], shard=True):
                 loss, stepped = self.train_step(batch)
-                if stepped:
+                if torch.is_tensor(stepped):  # graphed step: the flag stays on the device until the next log line
+                    loss_total += torch.where(stepped, loss, torch.zeros_like(loss))
+                    skipped_dev += (~stepped).to(skipped_dev.dtype)
+                elif stepped:
                     loss_total += loss
                 else:
                     skipped += 1
             if epoch % g["log_every"] == 0 or epoch == g["epochs"]:
+                skipped += int(skipped_dev.item())
                 lt = float(loss_total.item())
                 self.losses.append(lt)
                 tr = self.evaluate(self.train, g["batch_size_val"])
