@@ -99,6 +99,9 @@ int feo_op_create(const feo_operator_desc* desc, feo_handle_t* out) {
     if ((rc = upload_csr(op, M, &op->csr[FEO_MAT_M]))) return bail(rc);
     if ((rc = upload_csr(op, transpose(M), &op->csrT[FEO_MAT_M]))) return bail(rc);
     op->nnz[FEO_MAT_M] = M.nnz();
+    const SeqPlan pf = build_seq_plan(M, S), pb = build_seq_plan(transpose(M), transpose(S));
+    if ((rc = upload(op, pf.rowptr, &op->seq_f.rowptr)) || (rc = upload(op, pf.ent, &op->seq_f.ent))) return bail(rc);
+    if ((rc = upload(op, pb.rowptr, &op->seq_b.rowptr)) || (rc = upload(op, pb.ent, &op->seq_b.ent))) return bail(rc);
     op->has_seq = true;
   }
   if (desc->n_u > 0) {
@@ -297,14 +300,14 @@ int feo_dense_apply(feo_handle_t h, int32_t which, const float* XT, float* CT, i
 int feo_seq_fwd(feo_handle_t h, const float* predT, const float* u0T, const float* fT, int64_t ldj, int64_t ldb,
                 int32_t B, int32_t T, float* loss_out, float* rT, void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = check_handle(h)) return rc;
-  return launch_seq(h->csr[FEO_MAT_M], h->csr[FEO_MAT_S], h->n, false, predT, u0T, fT, h->dt, ldj, ldb, B, T, nullptr, rT,
+  return launch_seq(h->seq_f, h->n, false, predT, u0T, fT, h->dt, ldj, ldb, B, T, nullptr, rT,
                     loss_out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int feo_seq_bwd(feo_handle_t h, const float* rT, const float* grad_loss, float* gradT, int64_t ldj, int32_t B, int32_t T,
                 void* stream) {
   if (int rc = check_handle(h)) return rc;
-  return launch_seq(h->csrT[FEO_MAT_M], h->csrT[FEO_MAT_S], h->n, true, rT, nullptr, nullptr, h->dt, ldj, 0, B, T,
+  return launch_seq(h->seq_b, h->n, true, rT, nullptr, nullptr, h->dt, ldj, 0, B, T,
                     grad_loss, gradT, nullptr, nullptr, 0, (cudaStream_t)stream);
 }
 

@@ -96,4 +96,23 @@ HostCsr axpy(const HostCsr& s, float dt, const HostCsr& a) {
   return m;
 }
 
+SeqPlan build_seq_plan(const HostCsr& m, const HostCsr& s) {
+  // One word per column of the union pattern, ascending: the kernel adds the M terms and the S terms of a row in the order
+  // of their own CSR rows (an absent coefficient is an exact fma with 0), as two separate spmm passes would.
+  SeqPlan p;
+  p.rowptr.assign(m.n + 1, 0);
+  for (int32_t r = 0; r < m.n; ++r) {
+    int32_t i = m.rowptr[r], ie = m.rowptr[r + 1], j = s.rowptr[r], je = s.rowptr[r + 1];
+    while (i < ie || j < je) {
+      const int32_t cm = i < ie ? m.col[i] : INT32_MAX, cs = j < je ? s.col[j] : INT32_MAX;
+      SeqEnt e{std::min(cm, cs), 0.f, 0.f, 0};
+      if (cm == e.col) e.m = m.val[i++];
+      if (cs == e.col) e.s = s.val[j++];
+      p.ent.push_back(e);
+    }
+    p.rowptr[r + 1] = (int32_t)p.ent.size();
+  }
+  return p;
+}
+
 }  // namespace feo

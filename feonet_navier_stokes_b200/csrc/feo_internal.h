@@ -33,6 +33,18 @@ int canonicalize(const feo_csr& in, int32_t n, const char* name, HostCsr* out);
 HostCsr transpose(const HostCsr& a);
 HostCsr axpy(const HostCsr& s, float dt, const HostCsr& a);  // S + dt*A
 
+// ---- time-dependent path: union pattern of M = S + dt A and S, one 16-byte word per entry (feo_kernels.cu: seq_kernel) ----
+struct alignas(16) SeqEnt {
+  int32_t col;
+  float m, s;  // coefficient of M (applied to x[j]) and of S (applied to the neighbouring time level x[j -/+ 1])
+  int32_t pad;
+};
+struct SeqPlan {
+  std::vector<int32_t> rowptr;
+  std::vector<SeqEnt> ent;
+};
+SeqPlan build_seq_plan(const HostCsr& m, const HostCsr& s);  // rows merged by ascending column
+
 // ---- union pattern of A, B1, B2 with the pair structure of idx_sol (feo_tiles.cpp), shared by the tile and patch planners ----
 struct UEnt {
   int32_t col;
@@ -202,6 +214,12 @@ struct DevLatticePlan {
 };
 
 // ---- device-side operator ---------------------------------------------------------------------
+struct DevSeqPlan {
+  int32_t* rowptr = nullptr;
+  SeqEnt* ent = nullptr;
+  bool present() const { return rowptr != nullptr; }
+};
+
 struct DevCsr {
   int32_t* rowptr = nullptr;
   int32_t* col = nullptr;
@@ -218,6 +236,7 @@ struct feo_operator {
   int32_t ns_branch = 0;
   float dt = 0.f;
   feo::DevCsr csr[5], csrT[5];
+  feo::DevSeqPlan seq_f, seq_b;  // union (M, S) rows / union (M^T, S^T) rows of the time-dependent residual
   int32_t *idx_i = nullptr, *idx_j = nullptr;
   feo::DevTilePlan tiles_f, tiles_b;
   feo::DevPatchPlan patch_f, patch_b;  // used instead of the tile plans when both are present
@@ -239,7 +258,7 @@ int launch_transpose(const float* src, int64_t src_ld, float* dst, int64_t dst_l
                      const int32_t* dst_row_map, cudaStream_t st);
 int launch_spmm(const DevCsr& K, int32_t n, const float* XT, float* YT, int64_t ldb, int32_t B, float scale,
                 int32_t accumulate, cudaStream_t st);
-int launch_seq(const DevCsr& M, const DevCsr& S, int32_t n, bool backward, const float* XT, const float* u0T,
+int launch_seq(const DevSeqPlan& P, int32_t n, bool backward, const float* XT, const float* u0T,
                const float* fT, float dt, int64_t ldj, int64_t ldb, int32_t B, int32_t T, const float* grad_loss,
                float* outT, float* loss_out, void* ws, size_t ws_bytes, cudaStream_t st);
 int launch_sq_diff_sum(const float* xT, const float* yT, int32_t n, int64_t ldb, int32_t B, float scale,

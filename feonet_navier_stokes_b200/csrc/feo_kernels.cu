@@ -108,80 +108,155 @@ __global__ void __launch_bounds__(kThreads) spmm_kernel(const int32_t* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// time-dependent Stokes: two-operand sparse apply with a shift along the pseudo-sample axis
-//   forward : out[r][j] = sum M[r,c] X[c][j] - sum S[r,c] prev(c,j) - dt F[r][b]
-//   backward: out[c][j] = g * ( sum M^T[c,r] R[r][j] - [t<T-1] sum S^T[c,r] R[r][j+1] )
-// j = b*T + t; lanes own consecutive j (coalesced scalar accesses).
+// time-dependent Stokes residual (FEONet_time_dep_Stokes/train_FEONet.py:343-362, :398-400), pseudo-samples j = b*T + t
+// contiguous in memory (dof-major [n, ldj]):
+//   forward   r[i, j] = sum_c M[i,c] x[c, j]  -  ( sum_c S[i,c] prev[c, j] + dt F[i, b] ),   prev[c, j] = t > 0 ? x[c, j-1] : u0[c, b]
+//   backward  g[c, j] = 2/T gl ( sum_i M[i,c] r[i, j]  -  [t < T-1] sum_i S[i,c] r[i, j+1] )
+// One warp = one row x 256 pseudo-samples (two tiles of 128), a lane owns FOUR CONSECUTIVE j per tile: per column of the
+// union pattern (M, S share it; one 16-byte word {col, m, s}) ONE 128-bit gather per tile feeds both sums -- the neighbouring
+// time level of three of the four elements is already in the lane's registers, the fourth comes from the neighbouring lane
+// by shuffle (lane 0 / 31 load it), and the t = 0 elements (one in T) read u0.  The row's words are fetched by the lanes in
+// one coalesced load and handed round by shuffle, and every load of two columns (gathers, lane-edge elements, initial
+// conditions) is issued before the first use: the first version (two passes of scalar gathers, a dependent word load per
+// entry) was bound by exposed L2 latency.
+// The order of every row sum is that of the separate CSR rows (absent coefficients are exact zero terms).
 // ---------------------------------------------------------------------------------------------
+constexpr int kSeqTiles = 1;   // tiles of 128 pseudo-samples per warp
+#ifndef FEO_SEQ_BATCH
+#define FEO_SEQ_BATCH 2         // columns whose loads are in flight together
+#endif
+#ifndef FEO_SEQ_MINB
+#define FEO_SEQ_MINB 4          // resident blocks the register allocation aims at
+#endif
 template <bool BACKWARD>
-__global__ void __launch_bounds__(kThreads) seq_kernel(const int32_t* __restrict__ m_rowptr,
-                                                       const int32_t* __restrict__ m_col,
-                                                       const float* __restrict__ m_val,
-                                                       const int32_t* __restrict__ s_rowptr,
-                                                       const int32_t* __restrict__ s_col,
-                                                       const float* __restrict__ s_val, int32_t n,
+__global__ void __launch_bounds__(kThreads, FEO_SEQ_MINB) seq_kernel(const int32_t* __restrict__ rowptr, const SeqEnt* __restrict__ ent, int32_t n,
                                                        const float* __restrict__ XT, const float* __restrict__ u0T,
                                                        const float* __restrict__ fT, float dt, int64_t ldj,
                                                        int64_t ldb, int32_t B, int32_t T,
                                                        const float* __restrict__ grad_loss, float* __restrict__ outT,
                                                        float* __restrict__ partials) {
+  constexpr int NT = kSeqTiles;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int r = blockIdx.x * nwarps + warp;
-  const int J = B * T;
+  const int J = B * T;  // the launcher checks that B * T + 256 fits 32 bits: one 32-bit division per lane and tile below
   float lsum = 0.f;
-  if (r < n) {
-    int j[4], t[4], bs[4];
-    bool ok[4];
+  if (r < n) {  // warp-uniform
+    int j0[NT];
+    bool valid[NT], ok[NT][4], edge[NT][4];
+    int bs[NT][4], e1[NT], eb[NT];  // forward, T >= 4: the lane's only t = 0 element of the tile (if any) and its sample
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      j[i] = blockIdx.y * kWarpSamples + i * 32 + lane;
-      ok[i] = j[i] < J;
-      const int jj = ok[i] ? j[i] : 0;
-      bs[i] = jj / T;
-      t[i] = jj - bs[i] * T;
-      j[i] = jj;
-    }
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    {
-      const int kb = __ldg(m_rowptr + r), ke = __ldg(m_rowptr + r + 1);
-      for (int k = kb; k < ke; ++k) {
-        const int64_t base = (int64_t)__ldg(m_col + k) * ldj;
-        const float v = __ldg(m_val + k);
+    for (int q = 0; q < NT; ++q) {
+      j0[q] = (blockIdx.y * NT + q) * kWarpSamples + lane * 4;
+      valid[q] = j0[q] < ldj;  // ldj % 4 == 0: the four elements exist in memory (columns >= J are padding)
+      e1[q] = -1, eb[q] = 0;
+      const int jc = j0[q] < J ? j0[q] : 0;
+      int b = jc / T, t = jc - b * T;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i] = fmaf(v, __ldg(XT + base + j[i]), acc[i]);
+      for (int i = 0; i < 4; ++i) {
+        ok[q][i] = j0[q] + i < J;
+        bs[q][i] = ok[q][i] ? b : 0;
+        // forward: the previous level of t = 0 is the initial condition; backward: the last level has no successor
+        edge[q][i] = BACKWARD ? (!ok[q][i] || t == T - 1) : (ok[q][i] && t == 0);
+        if (!BACKWARD && edge[q][i]) e1[q] = i, eb[q] = b;
+        if (++t == T) t = 0, ++b;
       }
     }
-    float acc2[4] = {0.f, 0.f, 0.f, 0.f};
-    {
-      const int kb = __ldg(s_rowptr + r), ke = __ldg(s_rowptr + r + 1);
-      for (int k = kb; k < ke; ++k) {
-        const int c = __ldg(s_col + k);
-        const float v = __ldg(s_val + k);
+    const bool one_edge = T >= 4;  // warp-uniform
+    float fv[NT][4];              // forward: the load vector of the row, fetched before the sums
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float x;
-          if (!BACKWARD)
-            x = t[i] > 0 ? __ldg(XT + (int64_t)c * ldj + j[i] - 1) : __ldg(u0T + (int64_t)c * ldb + bs[i]);
-          else
-            x = t[i] < T - 1 ? __ldg(XT + (int64_t)c * ldj + j[i] + 1) : 0.f;
-          acc2[i] = fmaf(v, x, acc2[i]);
+    for (int q = 0; q < NT; ++q)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) fv[q][i] = (!BACKWARD && ok[q][i]) ? __ldg(fT + (int64_t)r * ldb + bs[q][i]) : 0.f;
+    float acc[NT][4], acc2[NT][4];
+#pragma unroll
+    for (int q = 0; q < NT; ++q)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[q][i] = 0.f, acc2[q][i] = 0.f;
+    const int kb = __ldg(rowptr + r), ke = __ldg(rowptr + r + 1);
+    const int4* words = reinterpret_cast<const int4*>(ent);
+
+    struct Col {
+      int c;
+      float m, s;
+      float4 x[NT];
+      float nb[NT], u[NT];
+    };
+    auto fetch = [&](const int4& mine, int src, Col& k) {
+      k.c = __shfl_sync(0xffffffffu, mine.x, src);
+      k.m = __int_as_float(__shfl_sync(0xffffffffu, mine.y, src));
+      k.s = __int_as_float(__shfl_sync(0xffffffffu, mine.z, src));
+#pragma unroll
+      for (int q = 0; q < NT; ++q) {
+        const float* row = XT + (int64_t)k.c * ldj + j0[q];
+        k.x[q] = valid[q] ? __ldg(reinterpret_cast<const float4*>(row)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        // the element beyond the lane's four that the shuffle cannot deliver
+        if (!BACKWARD) k.nb[q] = (lane == 0 && valid[q] && j0[q] > 0) ? __ldg(row - 1) : 0.f;
+        else k.nb[q] = (lane == 31 && j0[q] + 4 < J) ? __ldg(row + 4) : 0.f;
+        k.u[q] = (!BACKWARD && one_edge && e1[q] >= 0 && k.s != 0.f) ? __ldg(u0T + (int64_t)k.c * ldb + eb[q]) : 0.f;
+      }
+    };
+    auto apply = [&](const Col& k) {
+#pragma unroll
+      for (int q = 0; q < NT; ++q) {
+        const float4 x = k.x[q];
+        float y[4];  // the neighbouring time level
+        if (!BACKWARD) {
+          const float up = __shfl_up_sync(0xffffffffu, x.w, 1);
+          y[0] = lane == 0 ? k.nb[q] : up, y[1] = x.x, y[2] = x.y, y[3] = x.z;
+          if (one_edge) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) y[i] = e1[q] == i ? k.u[q] : y[i];
+          } else if (k.s != 0.f) {  // warp-uniform: columns outside S need no initial condition
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (edge[q][i]) y[i] = __ldg(u0T + (int64_t)k.c * ldb + bs[q][i]);
+          }
+        } else {
+          const float dn = __shfl_down_sync(0xffffffffu, x.x, 1);
+          y[0] = x.y, y[1] = x.z, y[2] = x.w, y[3] = lane == 31 ? k.nb[q] : dn;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (edge[q][i]) y[i] = 0.f;
         }
+        acc[q][0] = fmaf(k.m, x.x, acc[q][0]), acc[q][1] = fmaf(k.m, x.y, acc[q][1]);
+        acc[q][2] = fmaf(k.m, x.z, acc[q][2]), acc[q][3] = fmaf(k.m, x.w, acc[q][3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc2[q][i] = fmaf(k.s, y[i], acc2[q][i]);
+      }
+    };
+    for (int k0 = kb; k0 < ke; k0 += 32) {  // 32 words per coalesced fetch
+      const int cnt = min(32, ke - k0);
+      const int4 mine = lane < cnt ? __ldg(words + k0 + lane) : make_int4(0, 0, 0, 0);
+      int k = 0;
+      for (; k + FEO_SEQ_BATCH <= cnt; k += FEO_SEQ_BATCH) {  // the loads of FEO_SEQ_BATCH columns in flight
+        Col c[FEO_SEQ_BATCH];
+#pragma unroll
+        for (int u = 0; u < FEO_SEQ_BATCH; ++u) fetch(mine, k + u, c[u]);
+#pragma unroll
+        for (int u = 0; u < FEO_SEQ_BATCH; ++u) apply(c[u]);
+      }
+      for (; k < cnt; ++k) {
+        Col c0;
+        fetch(mine, k, c0);
+        apply(c0);
       }
     }
     const float g = BACKWARD ? (2.0f / (float)T) * (grad_loss != nullptr ? __ldg(grad_loss) : 1.0f) : 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (!ok[i]) continue;
-      float o;
-      if (!BACKWARD) {
-        // RHS_t = prev S^T + dt F ; r = LHS - RHS (FEONet_time_dep_Stokes/train_FEONet.py:357, :398)
-        const float rhs = fmaf(dt, __ldg(fT + (int64_t)r * ldb + bs[i]), acc2[i]);
-        o = acc[i] - rhs;
-        lsum = fmaf(o, o, lsum);
-      } else {
-        o = g * (acc[i] - acc2[i]);
+    for (int q = 0; q < NT; ++q) {
+      float o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (!BACKWARD) {
+          // RHS_t = prev S^T + dt F ; r = LHS - RHS (FEONet_time_dep_Stokes/train_FEONet.py:357, :398)
+          const float rhs = fmaf(dt, fv[q][i], acc2[q][i]);
+          o[i] = ok[q][i] ? acc[q][i] - rhs : 0.f;
+          lsum = fmaf(o[i], o[i], lsum);
+        } else {
+          o[i] = ok[q][i] ? g * (acc[q][i] - acc2[q][i]) : 0.f;
+        }
       }
-      outT[(int64_t)r * ldj + j[i]] = o;
+      if (valid[q]) *reinterpret_cast<float4*>(outT + (int64_t)r * ldj + j0[q]) = make_float4(o[0], o[1], o[2], o[3]);
     }
   }
   if (!BACKWARD) block_partial(lsum, partials, blockIdx.y * gridDim.x + blockIdx.x);
@@ -276,27 +351,28 @@ int launch_spmm(const DevCsr& K, int32_t n, const float* XT, float* YT, int64_t 
   return FEO_OK;
 }
 
-int launch_seq(const DevCsr& M, const DevCsr& S, int32_t n, bool backward, const float* XT, const float* u0T,
+int launch_seq(const DevSeqPlan& P, int32_t n, bool backward, const float* XT, const float* u0T,
                const float* fT, float dt, int64_t ldj, int64_t ldb, int32_t B, int32_t T, const float* grad_loss,
                float* outT, float* loss_out, void* ws, size_t ws_bytes, cudaStream_t st) {
-  if (!M.present() || !S.present()) return fail(FEO_ERR_INVALID_ARGUMENT, "sequence path needs S and A");
+  if (!P.present()) return fail(FEO_ERR_INVALID_ARGUMENT, "sequence path needs S and A");
   if (B <= 0 || T <= 0) return fail(FEO_ERR_INVALID_ARGUMENT, "B and T must be positive");
   const int64_t J = (int64_t)B * T;
-  if (XT == nullptr || outT == nullptr || ldj < J) return fail(FEO_ERR_INVALID_ARGUMENT, "seq: bad XT/outT/ldj");
-  const int by = (int)((J + kWarpSamples - 1) / kWarpSamples);
+  if (XT == nullptr || outT == nullptr || ldj < J || ldj % 4 != 0) return fail(FEO_ERR_INVALID_ARGUMENT, "seq: bad XT/outT/ldj");
+  if (ldj > (int64_t)INT32_MAX - 2 * kSeqTiles * kWarpSamples) return fail(FEO_ERR_UNSUPPORTED, "seq: B * T too large for one launch");
+  if ((reinterpret_cast<uintptr_t>(XT) | reinterpret_cast<uintptr_t>(outT)) % 16 != 0)
+    return fail(FEO_ERR_INVALID_ARGUMENT, "seq: XT/outT must be 16-byte aligned");
+  const int by = (int)((J + kSeqTiles * kWarpSamples - 1) / (kSeqTiles * kWarpSamples));
   dim3 grid((n + 7) / 8, by);
   if (!backward) {
     if (u0T == nullptr || fT == nullptr || ldb < B || loss_out == nullptr)
       return fail(FEO_ERR_INVALID_ARGUMENT, "seq fwd: bad u0T/fT/ldb/loss_out");
     const int count = grid.x * grid.y;
     if (ws == nullptr || ws_bytes < (size_t)count * sizeof(float)) return fail(FEO_ERR_INVALID_ARGUMENT, "workspace too small");
-    seq_kernel<false><<<grid, kThreads, 0, st>>>(M.rowptr, M.col, M.val, S.rowptr, S.col, S.val, n, XT, u0T, fT, dt,
-                                                 ldj, ldb, B, T, nullptr, outT, (float*)ws);
+    seq_kernel<false><<<grid, kThreads, 0, st>>>(P.rowptr, P.ent, n, XT, u0T, fT, dt, ldj, ldb, B, T, nullptr, outT, (float*)ws);
     FEO_CUDA_CHECK(cudaGetLastError());
     return finalize((float*)ws, count, 1.0f / (float)T, loss_out, st);
   }
-  seq_kernel<true><<<grid, kThreads, 0, st>>>(M.rowptr, M.col, M.val, S.rowptr, S.col, S.val, n, XT, nullptr, nullptr,
-                                              dt, ldj, ldb, B, T, grad_loss, outT, nullptr);
+  seq_kernel<true><<<grid, kThreads, 0, st>>>(P.rowptr, P.ent, n, XT, nullptr, nullptr, dt, ldj, ldb, B, T, grad_loss, outT, nullptr);
   FEO_CUDA_CHECK(cudaGetLastError());
   return FEO_OK;
 }

@@ -492,6 +492,30 @@ def test_time_dep_cfg4_vs_oracle(feo):
     assert _rel(grad.cpu().numpy(), go) < GRAD_RTOL
 
 
+@pytest.mark.parametrize("B,T", [(1, 1), (5, 1), (7, 2), (3, 3), (37, 7), (130, 1), (65, 4), (26, 10), (1, 300)])
+def test_time_dep_sequence_shapes_vs_oracle(feo, B, T):
+    """The vectorised sequence kernel (four consecutive pseudo-samples per lane, neighbouring time level by shuffle): sequence
+    lengths below the vector width, pseudo-sample counts that are not multiples of 4 or 128, time levels that straddle lane
+    and warp-tile boundaries (FEONet_time_dep_Stokes/train_FEONet.py:343-362, :398-400)."""
+    from feonet_navier_stokes_b200.fixtures import config_operators
+
+    fx = config_operators("time_dep", 4)
+    dev = torch.device("cuda")
+    dt = 0.05
+    rng = np.random.default_rng(100 * B + T)
+    pred = (0.3 * rng.standard_normal((B, T, fx.N))).astype(np.float32)
+    u0 = rng.standard_normal((B, fx.N)).astype(np.float32)
+    F = rng.standard_normal((B, fx.N)).astype(np.float32)
+    td = feo.TimeDependentStokes(fx.S, fx.A, fx.idx_sol, dt=dt, do_precond=False, device=dev)
+    p = torch.tensor(pred, device=dev, requires_grad=True)
+    loss = td.residual_loss(p, torch.tensor(F, device=dev), fx.S, fx.A, None, dt, torch.tensor(u0, device=dev))
+    (grad,) = torch.autograd.grad(loss, p)
+    lo, go, _ = orc.seq_loss_and_grad(pred, F, fx.S, fx.A, None, dt, u0, False, dtype=np.float64)
+    assert abs(loss.item() - lo) <= LOSS_RTOL * abs(lo)
+    assert _rel(grad.cpu().numpy(), go) < GRAD_RTOL
+    assert np.abs(grad.cpu().numpy() - go).max() <= 1e-4 * np.abs(go).max()
+
+
 def test_errors_are_loud(feo):
     from feonet_navier_stokes_b200 import _lib as L
     from feonet_navier_stokes_b200.fixtures import config_operators
