@@ -55,6 +55,8 @@ SIGNATURES = {
     "feo_op_get_info": (C.c_int, [_vp, C.POINTER(FeoOpInfo)]),
     "feo_workspace_bytes": (_sz, [_vp, _i32, _i32]),
     "feo_transpose": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "feo_transpose_gather": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "feo_op_plan": (C.c_int, [_vp]),
     "feo_residual_fwd": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "feo_residual_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "feo_spmm": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i64, _i32, _f32, _i32, _vp]),

@@ -261,7 +261,17 @@ size_t feo_workspace_bytes(feo_handle_t h, int32_t B, int32_t T) {
 
 int feo_transpose(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int32_t rows, int32_t cols,
                   const int32_t* dst_row_map, void* stream) {
-  return launch_transpose(src, src_ld, dst, dst_ld, rows, cols, dst_row_map, (cudaStream_t)stream);
+  return launch_transpose(src, src_ld, dst, dst_ld, rows, cols, dst_row_map, nullptr, (cudaStream_t)stream);
+}
+
+int feo_transpose_gather(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int32_t rows, int32_t cols,
+                         const int32_t* src_row_map, void* stream) {
+  return launch_transpose(src, src_ld, dst, dst_ld, rows, cols, nullptr, src_row_map, (cudaStream_t)stream);
+}
+
+int feo_op_plan(feo_handle_t h) {
+  if (h == nullptr || !h->has_sparse) return FEO_PLAN_NONE;
+  return h->lattice.present ? FEO_PLAN_LATTICE : h->patch_f.present ? FEO_PLAN_PATCH : FEO_PLAN_TILE;
 }
 
 int feo_residual_fwd(feo_handle_t h, const float* alphaT, const float* fT, int64_t ldb, int32_t B, float* loss_out,
@@ -319,8 +329,8 @@ int feo_assemble_u_init(feo_handle_t h, const float* init_x, const float* init_y
     return fail(FEO_ERR_INVALID_ARGUMENT, "assemble_u_init: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   FEO_CUDA_CHECK(cudaMemsetAsync(u0T, 0, (size_t)h->n * ldb * sizeof(float), st));
-  if (int rc = launch_transpose(init_x, h->n_u, u0T, ldb, B, h->n_u, h->idx_i, st)) return rc;
-  return launch_transpose(init_y, h->n_u, u0T, ldb, B, h->n_u, h->idx_j, st);
+  if (int rc = launch_transpose(init_x, h->n_u, u0T, ldb, B, h->n_u, h->idx_i, nullptr, st)) return rc;
+  return launch_transpose(init_y, h->n_u, u0T, ldb, B, h->n_u, h->idx_j, nullptr, st);
 }
 
 int feo_sincos_forcing_grid(const float* coeff_f, int32_t B, int32_t resol_in, float* value_f, void* stream) {

@@ -255,7 +255,7 @@ struct feo_operator {
 namespace feo {
 // kernel launchers (feo_kernels.cu / feo_tiled.cu)
 int launch_transpose(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int32_t rows, int32_t cols,
-                     const int32_t* dst_row_map, cudaStream_t st);
+                     const int32_t* dst_row_map, const int32_t* src_row_map, cudaStream_t st);
 int launch_spmm(const DevCsr& K, int32_t n, const float* XT, float* YT, int64_t ldb, int32_t B, float scale,
                 int32_t accumulate, cudaStream_t st);
 int launch_seq(const DevSeqPlan& P, int32_t n, bool backward, const float* XT, const float* u0T,

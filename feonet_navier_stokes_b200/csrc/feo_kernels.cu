@@ -279,25 +279,39 @@ __global__ void __launch_bounds__(kThreads) sq_diff_kernel(const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
-// tiled transpose (optionally scattering destination rows through a map)
+// tiled transpose; optionally the destination rows are scattered through a map (assemble_u_init, dof permutation on the way
+// in) or the source rows gathered through one (dof permutation on the way out): either way whole 256-byte runs move
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ src, int64_t src_ld,
                                                         float* __restrict__ dst, int64_t dst_ld, int32_t rows,
-                                                        int32_t cols, const int32_t* __restrict__ dst_row_map) {
+                                                        int32_t cols, const int32_t* __restrict__ dst_row_map,
+                                                        const int32_t* __restrict__ src_row_map) {
   __shared__ float tile[64][65];
+  __shared__ int32_t s_map[64];  // the tile's 64 mapped rows, looked up once
   const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
+  if (src_row_map != nullptr) {
+    if (threadIdx.x < 64) s_map[threadIdx.x] = r0 + threadIdx.x < rows ? __ldg(src_row_map + r0 + threadIdx.x) : 0;
+    __syncthreads();
+  }
 #pragma unroll 4
   for (int i = ty; i < 64; i += 4) {
     const int r = r0 + i, c = c0 + tx;
-    tile[i][tx] = (r < rows && c < cols) ? __ldg(src + (int64_t)r * src_ld + c) : 0.f;
+    if (r < rows && c < cols) {
+      const int64_t srow = src_row_map != nullptr ? (int64_t)s_map[i] : (int64_t)r;
+      tile[i][tx] = __ldg(src + srow * src_ld + c);
+    } else {
+      tile[i][tx] = 0.f;
+    }
   }
+  if (dst_row_map != nullptr && src_row_map != nullptr) __syncthreads();  // the gather above has finished with s_map
+  if (dst_row_map != nullptr && threadIdx.x < 64) s_map[threadIdx.x] = c0 + threadIdx.x < cols ? __ldg(dst_row_map + c0 + threadIdx.x) : 0;
   __syncthreads();
 #pragma unroll 4
   for (int i = ty; i < 64; i += 4) {
     const int c = c0 + i, r = r0 + tx;
     if (c < cols && r < rows) {
-      const int64_t drow = dst_row_map != nullptr ? (int64_t)__ldg(dst_row_map + c) : (int64_t)c;
+      const int64_t drow = dst_row_map != nullptr ? (int64_t)s_map[i] : (int64_t)c;
       dst[drow * dst_ld + r] = tile[tx][i];
     }
   }
@@ -330,11 +344,11 @@ static int finalize(float* partials, int count, float scale, float* loss_out, cu
 }
 
 int launch_transpose(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int32_t rows, int32_t cols,
-                     const int32_t* dst_row_map, cudaStream_t st) {
+                     const int32_t* dst_row_map, const int32_t* src_row_map, cudaStream_t st) {
   if (rows <= 0 || cols <= 0) return FEO_OK;
   if (src == nullptr || dst == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, "transpose: NULL pointer");
   dim3 grid((cols + 63) / 64, (rows + 63) / 64);
-  transpose_kernel<<<grid, 256, 0, st>>>(src, src_ld, dst, dst_ld, rows, cols, dst_row_map);
+  transpose_kernel<<<grid, 256, 0, st>>>(src, src_ld, dst, dst_ld, rows, cols, dst_row_map, src_row_map);
   FEO_CUDA_CHECK(cudaGetLastError());
   return FEO_OK;
 }

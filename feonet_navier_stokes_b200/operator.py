@@ -113,7 +113,11 @@ class FEOperator:
 
     def __init__(self, n: int, A=None, B1=None, B2=None, S=None, idx_sol: Optional[Sequence] = None,
                  ns_precond_branch: bool = False, dt: float = 0.0, dense_m=None, dense_p=None,
-                 device: Optional[torch.device] = None):
+                 device: Optional[torch.device] = None, dof_perm=None):
+        """dof_perm (optional, reorder.py): new_of_old[d] = internal position of the caller's dof d.  Every matrix and idx_sol
+        are renumbered at set-up; tensors cross `to_dof_major` / `from_dof_major` in the CALLER's numbering and the layout
+        passes apply the permutation (row-major tensors: inside the transpose they need anyway; dof-major tensors: one row
+        gather).  Everything between those two calls -- every kernel -- works in the internal numbering."""
         if not torch.cuda.is_available():
             raise L.FeoError("FEOperator needs a CUDA device: the FEM residual path has no CPU fallback")
         self.lib = L.load_library()
@@ -122,6 +126,20 @@ class FEOperator:
         idx_i = idx_j = None
         if idx_sol is not None:
             idx_i, idx_j = idx_sol[0], idx_sol[1]
+        self.perm_new_of_old = self.perm_old_of_new = None
+        if dof_perm is not None:
+            from . import reorder as R
+
+            pn = np.asarray(dof_perm, dtype=np.int64)
+            if pn.shape != (self.n,) or not np.array_equal(np.sort(pn), np.arange(self.n)):
+                raise ValueError("dof_perm must be a permutation of range(n)")
+            if not R.is_identity(pn):
+                A, B1, B2, S = (None if K is None else R.permute_csr(K, pn) for K in (A, B1, B2, S))
+                dense_m, dense_p = (None if M is None else R.permute_dense(M, pn) for M in (dense_m, dense_p))
+                if idx_i is not None:
+                    idx_i, idx_j = pn[np.asarray(idx_i, dtype=np.int64)], pn[np.asarray(idx_j, dtype=np.int64)]
+                self.perm_new_of_old = torch.tensor(pn, dtype=torch.int32, device=self.device)
+                self.perm_old_of_new = torch.tensor(np.argsort(pn), dtype=torch.int32, device=self.device)
         desc, keep = build_desc(n, A, B1, B2, S, idx_i, idx_j, ns_precond_branch, dt, dense_m, dense_p)
         self._handle = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -136,6 +154,7 @@ class FEOperator:
         self.has_dense_p = bool(info.has_dense_p)
         self.has_sparse = info.n_tiles_fwd > 0
         self.ns_precond_branch = bool(ns_precond_branch)
+        self.plan = {0: "none", 1: "tile", 2: "patch", 3: "lattice"}[int(self.lib.feo_op_plan(self._handle))]
         self._ws = None
         self.launches = 0  # kernels launched through this handle (bench.py's gpu_launches)
 
@@ -180,27 +199,37 @@ class FEOperator:
     # -- layout -------------------------------------------------------------------------------
     def to_dof_major(self, x: torch.Tensor, ldb: Optional[int] = None) -> torch.Tensor:
         """row-major [B,N] (any strides) -> dof-major storage [N, ldb]; zero-copy when x already is
-        a dof-major view (stride(0)==1, stride(1)%4==0, 16-B aligned)."""
+        a dof-major view (stride(0)==1, stride(1)%4==0, 16-B aligned).  With a dof permutation the rows of the result are in
+        the INTERNAL numbering: scattered by the transpose itself, or gathered row by row from a dof-major input."""
         assert x.dim() == 2 and x.dtype == torch.float32 and x.is_cuda
         B, N = x.shape
         want = ceil4(B) if ldb is None else ldb
         if (x.stride(0) == 1 or B == 1) and x.stride(1) % 4 == 0 and x.stride(1) >= ceil4(B) and x.data_ptr() % 16 == 0 \
                 and (ldb is None or x.stride(1) == ldb) and x.untyped_storage().nbytes() - x.storage_offset() * 4 >= N * x.stride(1) * 4:
-            return torch.as_strided(x, (N, x.stride(1)), (x.stride(1), 1))
+            xT = torch.as_strided(x, (N, x.stride(1)), (x.stride(1), 1))
+            if self.perm_old_of_new is None:
+                return xT
+            return xT.index_select(0, self.perm_old_of_new)  # whole 4*ldb-byte rows move: a coalesced gather pass
         if x.stride(1) != 1:
             x = x.contiguous()
         out = torch.empty((N, want), dtype=torch.float32, device=x.device)
-        self._call(self.lib.feo_transpose, self._p(x), x.stride(0), self._p(out), want, B, N, None, self._stream())
+        self._call(self.lib.feo_transpose, self._p(x), x.stride(0), self._p(out), want, B, N, self._p(self.perm_new_of_old), self._stream())
         self.launches += 1
         return out
 
     def from_dof_major(self, xT: torch.Tensor, B: int, contiguous: bool = False) -> torch.Tensor:
-        """dof-major storage [N, ldb] -> [B,N] tensor; a strided view unless `contiguous`."""
+        """dof-major storage [N, ldb] (internal numbering) -> [B,N] tensor in the caller's numbering; a strided view unless
+        `contiguous`."""
         if not contiguous:
+            if self.perm_new_of_old is not None:
+                xT = xT.index_select(0, self.perm_new_of_old)
             return xT[:, :B].t()
         N, ldb = xT.shape
         out = torch.empty((B, N), dtype=torch.float32, device=xT.device)
-        self._call(self.lib.feo_transpose, self._p(xT), ldb, self._p(out), N, N, B, None, self._stream())
+        if self.perm_new_of_old is None:
+            self._call(self.lib.feo_transpose, self._p(xT), ldb, self._p(out), N, N, B, None, self._stream())
+        else:  # out[b, d] = xT[new_of_old[d], b]
+            self._call(self.lib.feo_transpose_gather, self._p(xT), ldb, self._p(out), N, N, B, self._p(self.perm_new_of_old), self._stream())
         self.launches += 1
         return out
 

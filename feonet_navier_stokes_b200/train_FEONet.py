@@ -237,7 +237,7 @@ class Trainer:
             z = load_reference_npz(gparams["npz"])
             i_, j_, k_ = z["idx_sol"]
             self.fx = SimpleNamespace(N=z["N"], A=z["A"] if "A" in z else z["matrix"], B1=z.get("B1"), B2=z.get("B2"),
-                                      idx_u1=np.asarray(i_), idx_u2=np.asarray(j_), idx_p=np.asarray(k_), idx_sol=z["idx_sol"])
+                                      idx_u1=np.asarray(i_), idx_u2=np.asarray(j_), idx_p=np.asarray(k_), idx_sol=z["idx_sol"], pos=z.get("p"))
             train = {k: v[:n_train] for k, v in z["train"].items() if k != "forcing_term"}
             val = {k: v[:n_val] for k, v in z["validate"].items() if k != "forcing_term"}
             n_train, n_val = len(train["coeff_f"]), len(val["coeff_f"])
@@ -276,7 +276,8 @@ class Trainer:
         elif variant == "steady_ns":
             # PRECOND = np.eye(N) whenever --do_precond > 0 (steady NS :142): the identity is detected, never stored densely
             self.problem = feo.SteadyNavierStokes(A, self.fx.B1, self.fx.B2, self.fx.idx_sol, do_precond=do_precond, precond=None,
-                                                  model_name=gparams["model"], force=gparams["forcing_term"], device=self.device)
+                                                  model_name=gparams["model"], force=gparams["forcing_term"], device=self.device,
+                                                  dof_positions=getattr(self.fx, "pos", None))
             self.closure_args = lambda b: (b["coeff_f"], None, b["load_vec_f"], A, self.fx.B1, self.fx.B2, gparams["resol_in"])  # noqa: E731
         else:
             if do_precond:

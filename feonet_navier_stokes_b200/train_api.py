@@ -169,8 +169,13 @@ class SteadyNavierStokes(_Base):
     gparams['model']."""
 
     def __init__(self, A=None, B1=None, B2=None, idx_sol=None, do_precond: bool = False, precond=None,
-                 model_name: str = "FCNN", force: str = "sincos", device=None):
+                 model_name: str = "FCNN", force: str = "sincos", device=None, dof_positions=None):
+        """dof_positions (optional): the [N, 2] coordinates of every global dof -- the `p` array of the reference's npz
+        (`W.tabulate_dof_coordinates()`, assemble_fenics.py:125, :138).  With them an operator assembled on a structured mesh
+        in FEniCS' own dof order is renumbered internally so that the lattice kernels apply (reorder.py); tensors keep the
+        caller's numbering."""
         super().__init__(device)
+        self.dof_positions = dof_positions
         self.DO_PRECOND = bool(do_precond)
         self.PRECOND = precond
         self.IDX_SOL = idx_sol
@@ -196,7 +201,16 @@ class SteadyNavierStokes(_Base):
 
                     self._op_conv = FEOperator(n, A=sp.csr_matrix((n, n), dtype=np.float32), B1=B1, B2=B2, idx_sol=idx_sol,
                                                ns_precond_branch=True, device=self.device)
-            self._op = FEOperator(n, **kw)
+            perm = None
+            if self.dof_positions is not None and self._identity_precond and idx_sol is not None:
+                from .reorder import is_identity, lattice_permutation
+
+                perm = lattice_permutation(idx_sol, np.asarray(self.dof_positions))
+                if is_identity(perm):
+                    perm = None
+            self._op = FEOperator(n, dof_perm=perm, **kw)
+            if perm is not None and self._op.plan != "lattice":  # the renumbering bought nothing: keep the caller's order
+                self._op = FEOperator(n, **kw)
             self._key_commit(key)
         return self._op
 

@@ -41,6 +41,7 @@ extern "C" {
 
 /* Which stored matrix a generic apply uses. */
 enum feo_matrix_id { FEO_MAT_A = 0, FEO_MAT_B1 = 1, FEO_MAT_B2 = 2, FEO_MAT_S = 3, FEO_MAT_M = 4 /* S + dt*A */ };
+enum feo_plan_id { FEO_PLAN_NONE = 0, FEO_PLAN_TILE = 1, FEO_PLAN_PATCH = 2, FEO_PLAN_LATTICE = 3 };
 
 /* Dense operators kept by a handle. */
 enum feo_dense_id { FEO_DENSE_M = 0 /* LHS operator, e.g. A@P */, FEO_DENSE_MT = 1, FEO_DENSE_P = 2 /* preconditioner */ };
@@ -104,6 +105,13 @@ size_t feo_workspace_bytes(feo_handle_t h, int32_t B, int32_t T);
  * destination row is dst_row_map[c] (used by feo_assemble_u_init). */
 int feo_transpose(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int32_t rows, int32_t cols,
                   const int32_t* dst_row_map, void* stream);
+/* The same with the SOURCE row gathered through a map: dst[c * dst_ld + r] = src[src_row_map[r] * src_ld + c].
+ * feo_transpose's dst_row_map (way in) and this (way out) fold a dof permutation into the layout pass the row-major
+ * boundary runs anyway -- how an operator in FEniCS' dof order reaches the lattice kernels (reorder.py). */
+int feo_transpose_gather(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int32_t rows, int32_t cols,
+                         const int32_t* src_row_map, void* stream);
+/* Which plan the fused residual kernels of this handle run: FEO_PLAN_* (none when the handle has no sparse A). */
+int feo_op_plan(feo_handle_t h);
 
 /* Fused sparse residual loss -----------------------------------------------------------------
  * Replaces weak_form + the per-dof loss loop of closure:

@@ -134,3 +134,52 @@ def test_element_walk_variant_matches(feo, monkeypatch):
     l1, g1, _ = _run(feo, fx, alpha, F, 1)
     assert abs(l1 - lo) <= LOSS_RTOL * abs(lo)
     assert _rel(g1, go) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("n,B,branch", [(6, 9, 1), (13, 70, 0)])
+def test_any_dof_order_reaches_the_lattice_kernels(feo, n, B, branch):
+    """An operator in another dof numbering (blocked [u1 | u2 | p], and a random relabelling of it -- FEniCS' mixed-space order
+    is neither) with the dof coordinates the reference stores (`p`, assemble_fenics.py:125, :138): renumbered at set-up
+    (reorder.py), permutation folded into the layout passes.  Results in the CALLER's numbering: equal to the oracle on the
+    caller's operator and, bit for bit, to the interleaved operator's results on the permuted inputs."""
+    from feonet_navier_stokes_b200.fixtures import config_operators
+    from feonet_navier_stokes_b200.reorder import lattice_permutation, permute_csr
+
+    dev = torch.device("cuda")
+    rng = np.random.default_rng(7 * n + B)
+    fb = config_operators("steady_ns", n, ordering="blocked")
+    fi = config_operators("steady_ns", n, ordering="interleaved")
+    N = fb.N
+    shuffle = rng.permutation(N)  # new label of blocked dof d
+    cases = [(fb.A, fb.B1, fb.B2, fb.idx_sol, fb.pos)]
+    inv = np.argsort(shuffle)
+    cases.append((permute_csr(fb.A, shuffle), permute_csr(fb.B1, shuffle), permute_csr(fb.B2, shuffle),
+                  [shuffle[np.asarray(ix)] for ix in fb.idx_sol], fb.pos[inv]))
+    for A, B1, B2, idx_sol, pos in cases:
+        perm = lattice_permutation(idx_sol, pos)
+        assert perm is not None
+        alpha = (0.3 * rng.standard_normal((B, N))).astype(np.float32)
+        F = rng.standard_normal((B, N)).astype(np.float32)
+        lo, go, _ = orc.ns_loss_and_grad(alpha, F, A, B1, B2, np.asarray(idx_sol[0]), np.asarray(idx_sol[1]), bool(branch), dtype=np.float64)
+        ns = feo.SteadyNavierStokes(A, B1, B2, idx_sol, do_precond=bool(branch), device=dev, dof_positions=pos)
+        assert ns.operator.plan == "lattice"
+        plain = feo.SteadyNavierStokes(A, B1, B2, idx_sol, do_precond=bool(branch), device=dev)
+        assert plain.operator.plan == "tile"
+        # the interleaved operator on the permuted inputs: the same kernels on the same numbers
+        old_of_new = np.argsort(perm)
+        li, gi, _ = _run(feo, fi, alpha[:, old_of_new], F[:, old_of_new], branch)
+        for native in (False, True):
+            a = torch.tensor(alpha, device=dev)
+            a = feo.to_dof_major_tensor(a) if native else a.unsqueeze(1)
+            a.requires_grad_(True)
+            loss = ns.residual_loss(a, torch.tensor(F, device=dev), A, B1, B2, idx_sol)
+            (g,) = torch.autograd.grad(loss, a)
+            g = g.reshape(B, N).cpu().numpy()
+            assert abs(loss.item() - lo) <= LOSS_RTOL * abs(lo)
+            assert _rel(g, go) < GRAD_RTOL and _relmax(g, go) < GRAD_RTOL
+            assert loss.item() == li and np.array_equal(g[:, old_of_new], gi)
+        # the materialised weak_form outputs go through the same layout passes
+        a = torch.tensor(alpha, device=dev).unsqueeze(1)
+        lhs, rhs = ns.weak_form(a, torch.tensor(F, device=dev), A, B1, B2, idx_sol)
+        lhs0, rhs0 = plain.weak_form(a, torch.tensor(F, device=dev), A, B1, B2, idx_sol)
+        assert torch.allclose(lhs, lhs0, rtol=1e-5, atol=1e-5) and torch.allclose(rhs, rhs0, rtol=1e-5, atol=1e-5)

@@ -214,3 +214,36 @@ def test_lattice_plan_rejects_what_it_does_not_model():
     k = len(good.idx_u1) // 2
     A[int(good.idx_u1[k]), int(good.idx_u2[k])] = 0.25  # cross-component entry
     assert not applicable(good, A=A.tocsr())
+
+
+def test_lattice_permutation_from_dof_coordinates():
+    """reorder.lattice_permutation: from idx_sol and the dof coordinates the reference stores (`p`), the renumbering that
+    turns a blocked (or arbitrarily relabelled) structured operator into exactly the interleaved one the lattice plan models;
+    anything that is not a full structured lattice is refused."""
+    import scipy.sparse as sp
+
+    from feonet_navier_stokes_b200.fixtures import config_operators
+    from feonet_navier_stokes_b200.reorder import is_identity, lattice_permutation, permute_csr, permute_dense
+
+    fb = config_operators("steady_ns", 5, ordering="blocked")
+    fi = config_operators("steady_ns", 5, ordering="interleaved")
+    perm = lattice_permutation(fb.idx_sol, fb.pos)
+    assert perm is not None and not is_identity(perm)
+    for Kb, Ki in ((fb.A, fi.A), (fb.B1, fi.B1), (fb.B2, fi.B2)):
+        P, Q = permute_csr(Kb, perm), sp.csr_matrix(Ki).astype(np.float32)
+        Q.eliminate_zeros()
+        Q.sort_indices()
+        assert np.array_equal(P.indptr, Q.indptr) and np.array_equal(P.indices, Q.indices) and np.array_equal(P.data, Q.data)
+    assert np.array_equal(perm[np.asarray(fb.idx_u1)], np.asarray(fi.idx_u1)) and np.array_equal(perm[np.asarray(fb.idx_p)], np.asarray(fi.idx_p))
+    assert is_identity(lattice_permutation(fi.idx_sol, fi.pos))
+    D = np.arange(fb.N * fb.N, dtype=np.float32).reshape(fb.N, fb.N)
+    assert np.array_equal(permute_dense(D, perm)[perm[3], perm[7]], D[3, 7])
+    # refusals: an unstructured mesh, a non-colocated pairing, coordinates off the lattice
+    fh = config_operators("hole", 6)
+    assert lattice_permutation(fh.idx_sol, fh.pos) is None
+    J = np.asarray(fb.idx_u2).copy()
+    J[[0, 1]] = J[[1, 0]]
+    assert lattice_permutation([fb.idx_u1, J, fb.idx_p], fb.pos) is None
+    pos = fb.pos.copy()
+    pos[3, 0] += 0.01
+    assert lattice_permutation(fb.idx_sol, pos) is None
