@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(kThreads) sq_diff_kernel(const float* __restri
 // tiled transpose; optionally the destination rows are scattered through a map (assemble_u_init, dof permutation on the way
 // in) or the source rows gathered through one (dof permutation on the way out): either way whole 256-byte runs move
 // ---------------------------------------------------------------------------------------------
+template <bool SMAP, bool DMAP>
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ src, int64_t src_ld,
                                                         float* __restrict__ dst, int64_t dst_ld, int32_t rows,
                                                         int32_t cols, const int32_t* __restrict__ dst_row_map,
@@ -290,28 +291,27 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
   __shared__ int32_t s_map[64];  // the tile's 64 mapped rows, looked up once
   const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
-  if (src_row_map != nullptr) {
+  if (SMAP) {
     if (threadIdx.x < 64) s_map[threadIdx.x] = r0 + threadIdx.x < rows ? __ldg(src_row_map + r0 + threadIdx.x) : 0;
     __syncthreads();
   }
-#pragma unroll 4
-  for (int i = ty; i < 64; i += 4) {
-    const int r = r0 + i, c = c0 + tx;
-    if (r < rows && c < cols) {
-      const int64_t srow = src_row_map != nullptr ? (int64_t)s_map[i] : (int64_t)r;
-      tile[i][tx] = __ldg(src + srow * src_ld + c);
-    } else {
-      tile[i][tx] = 0.f;
-    }
+  float v[16];  // all sixteen loads of a thread in flight before the first shared-memory store
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int i = ty + 4 * k, r = r0 + i, c = c0 + tx;
+    const int64_t srow = SMAP ? (int64_t)s_map[i] : (int64_t)r;
+    v[k] = (r < rows && c < cols) ? __ldg(src + srow * src_ld + c) : 0.f;
   }
-  if (dst_row_map != nullptr && src_row_map != nullptr) __syncthreads();  // the gather above has finished with s_map
-  if (dst_row_map != nullptr && threadIdx.x < 64) s_map[threadIdx.x] = c0 + threadIdx.x < cols ? __ldg(dst_row_map + c0 + threadIdx.x) : 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) tile[ty + 4 * k][tx] = v[k];
+  if (SMAP && DMAP) __syncthreads();  // the gather above has finished with s_map
+  if (DMAP && threadIdx.x < 64) s_map[threadIdx.x] = c0 + threadIdx.x < cols ? __ldg(dst_row_map + c0 + threadIdx.x) : 0;
   __syncthreads();
-#pragma unroll 4
-  for (int i = ty; i < 64; i += 4) {
-    const int c = c0 + i, r = r0 + tx;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int i = ty + 4 * k, c = c0 + i, r = r0 + tx;
     if (c < cols && r < rows) {
-      const int64_t drow = dst_row_map != nullptr ? (int64_t)s_map[i] : (int64_t)c;
+      const int64_t drow = DMAP ? (int64_t)s_map[i] : (int64_t)c;
       dst[drow * dst_ld + r] = tile[tx][i];
     }
   }
@@ -348,7 +348,14 @@ int launch_transpose(const float* src, int64_t src_ld, float* dst, int64_t dst_l
   if (rows <= 0 || cols <= 0) return FEO_OK;
   if (src == nullptr || dst == nullptr) return fail(FEO_ERR_INVALID_ARGUMENT, "transpose: NULL pointer");
   dim3 grid((cols + 63) / 64, (rows + 63) / 64);
-  transpose_kernel<<<grid, 256, 0, st>>>(src, src_ld, dst, dst_ld, rows, cols, dst_row_map, src_row_map);
+  if (src_row_map != nullptr && dst_row_map != nullptr)
+    transpose_kernel<true, true><<<grid, 256, 0, st>>>(src, src_ld, dst, dst_ld, rows, cols, dst_row_map, src_row_map);
+  else if (src_row_map != nullptr)
+    transpose_kernel<true, false><<<grid, 256, 0, st>>>(src, src_ld, dst, dst_ld, rows, cols, dst_row_map, src_row_map);
+  else if (dst_row_map != nullptr)
+    transpose_kernel<false, true><<<grid, 256, 0, st>>>(src, src_ld, dst, dst_ld, rows, cols, dst_row_map, src_row_map);
+  else
+    transpose_kernel<false, false><<<grid, 256, 0, st>>>(src, src_ld, dst, dst_ld, rows, cols, dst_row_map, src_row_map);
   FEO_CUDA_CHECK(cudaGetLastError());
   return FEO_OK;
 }

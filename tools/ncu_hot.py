@@ -3,6 +3,7 @@ import csv, sys
 path = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 rows = list(csv.reader(open(path)))
+seen = set()  # the source page lists a kernel once per view: print each (kernel, sample count) once
 i = 0
 while i < len(rows):
     if rows[i] and rows[i][0] == "Kernel Name":
@@ -15,6 +16,10 @@ while i < len(rows):
                 body.append(dict(zip(hdr, rows[j])))
             j += 1
         tot = sum(int(r["# Samples"] or 0) for r in body)
+        if (name, tot) in seen:
+            i = j
+            continue
+        seen.add((name, tot))
         print(f"== {name[:90]}  total samples {tot}, {len(body)} instrs")
         stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
         agg = {c: sum(int(r[c] or 0) for r in body) for c in stall_cols}
