@@ -144,6 +144,45 @@ __device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mas
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
 }
+// ---- CTA-pair (cta_group::2) helpers --------------------------------------------------------------------------------
+// the address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquires what a peer CTA released
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAITC_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONEC_%=;\n\t"
+      "bra WAITC_%=;\n\t"
+      "DONEC_%=:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// one M = 256 MMA over the pair: each CTA contributes its own 128 rows of A and its half (N / 2 rows) of the B tile from the
+// same shared-memory offsets, and receives its 128 accumulator rows in its own tensor memory; issued by the leader CTA only
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // one arrival on the same mbarrier of both CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -400,14 +439,16 @@ __global__ void __launch_bounds__(kTcBlock, BN == 128 ? 2 : 3) dense_apply_tc_ke
 //             chunk_done[2] per accumulator: every MMA of the chunk completed -> drain it (epilogue warps)
 //             drained[2]    per accumulator: read back by all 256 epilogue threads -> the issuer may overwrite it
 // ---------------------------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, int HALVES>
 __global__ void __launch_bounds__(256) dense_split_x_kernel(const float* __restrict__ XT, int32_t n, int64_t ldb, float* __restrict__ Xs,
                                                             int32_t nkb) {
   // block (column tile ct, k-block kb) -> Xs + (ct * nkb + kb) * [hi BN x 16 | lo BN x 16], element (c, k) at
-  // (k / 4) * BN * 16 + c * 16 + (k % 4) * 4 bytes of its half
+  // (k / 4) * BN * 16 + c * 16 + (k % 4) * 4 bytes of its half; HALVES = 2 (CTA pairs): the block is two such [hi | lo] blocks
+  // of BN / 2 columns each, one per CTA of the pair
+  constexpr int W = BN / HALVES;  // columns of one [hi | lo] sub-block
   const int ct = blockIdx.x, kb = blockIdx.y;
   uint8_t* blk = reinterpret_cast<uint8_t*>(Xs) + ((size_t)ct * nkb + kb) * b_stage_bytes(BN);
-  constexpr uint32_t kHalf = (uint32_t)BN * TBK * 4;
+  constexpr uint32_t kHalf = (uint32_t)W * TBK * 4;
   for (int it = threadIdx.x; it < BN * (TBK / 4); it += 256) {
     const int c = it % BN, q = it / BN;  // consecutive threads read consecutive samples of one row of XT
     const int64_t col = (int64_t)ct * BN + c;
@@ -417,7 +458,8 @@ __global__ void __launch_bounds__(256) dense_split_x_kernel(const float* __restr
       const int k = kb * TBK + q * 4 + i;
       t[i] = (k < n && col < ldb) ? __ldg(XT + (int64_t)k * ldb + col) : 0.f;
     }
-    store_split(blk, blk + kHalf, (uint32_t)q * (BN * 16) + (uint32_t)c * 16, make_float4(t[0], t[1], t[2], t[3]));
+    uint8_t* sub = blk + (size_t)(c / W) * 2 * kHalf;
+    store_split(sub, sub + kHalf, (uint32_t)q * (W * 16) + (uint32_t)(c % W) * 16, make_float4(t[0], t[1], t[2], t[3]));
   }
 }
 
@@ -585,6 +627,198 @@ __global__ void __launch_bounds__(kTcBlock, (BN <= 64 || (BN == 128 && S == 3)) 
   if (CL > 1) cluster_sync();
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Third generation: CTA pairs (tcgen05 cta_group::2).
+//
+// The second kernel is paced by what each SM has to take in: its 128-row operator panel AND its whole activation tile, both as
+// [hi | lo] -- 36 KB per k-block at 160 columns, ~59 B/clk for the whole run (a run without MMAs is barely faster).  Here two
+// CTAs on the SMs of one TPC (cluster 1 x 2: two row tiles of the same column tile) run ONE M = 256 MMA per product: each
+// holds its own 128 operator rows and only HALF of the activation tile (the tensor cores of the pair read both halves), so an
+// SM takes in 16 + 10 instead of 16 + 20 KB per k-block and reads 39 instead of 54 KB of operands per k-block from its shared
+// memory.  The leader CTA (rank 0) issues the MMAs and commits to the mbarriers of both CTAs; the peer relays "my stage has
+// landed" to the leader (remote mbarrier arrive), both fill their own stages and drain their own 128 accumulator rows.
+//   barriers: full[S]      own stage landed (transaction bytes)          peer[S]     (leader) the peer's stage landed
+//             mma_done[2]  MMAs of a k-block done, in both CTAs (multicast commit) -> stage free
+//             chunk_done[2] accumulator complete, in both CTAs            drained[2]  (leader) read back by all 512 epilogue threads
+// ---------------------------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr uint32_t instr_desc_pair(int BN) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24); }
+
+template <int BN, int S>
+__global__ void __launch_bounds__(kTcBlock, 1) dense_apply_tc3_kernel(const float* __restrict__ Dsplit, const float* __restrict__ Xsplit, int32_t n,
+                                                                     int32_t row_tiles, float* __restrict__ CT, int64_t ldb, int32_t B, float scale,
+                                                                     const float* __restrict__ scale_dev, const float* __restrict__ sub,
+                                                                     float* __restrict__ partials, int32_t flush, int32_t debug) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t s_full[S];
+  __shared__ __align__(8) uint64_t s_peer[S];
+  __shared__ __align__(8) uint64_t s_mma[2];
+  __shared__ __align__(8) uint64_t s_chunk[2];
+  __shared__ __align__(8) uint64_t s_drained[2];
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_part[kTcThreads / 32];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool is_issuer = __shfl_sync(0xffffffffu, warp, 0) == kTcThreads / 32;
+  const uint32_t rank = cluster_ctarank();  // cluster (1, 2, 1): the two row tiles 2p, 2p + 1 of one column tile
+  const bool leader = rank == 0;
+  const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * BN;
+  constexpr int HB = BN / 2;                                                   // activation columns held by one CTA
+  constexpr uint32_t kTmemCols = BN <= 64 ? 128 : (BN <= 128 ? 256 : 512);    // two accumulators of BN columns
+  constexpr uint32_t kXHalf = 2u * HB * TBK * 4;                              // this CTA's [hi | lo] activation sub-block
+  constexpr uint32_t kXBytes = (uint32_t)HB * TBK * 4;                        // hi or lo of it
+  constexpr uint32_t kAStage = 2 * kABytes, kStage = kAStage + kXHalf;
+  constexpr int kAhead = S - 2;
+  constexpr uint32_t kLboB = HB * 16;
+  constexpr uint32_t kIdesc = instr_desc_pair(BN);
+  constexpr int WC = BN / 2;
+
+  if (warp == 0) {  // the same warp of both CTAs: a pair allocation
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(smem_u32(&s_full[s]), 1);
+      mbar_init(smem_u32(&s_peer[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&s_mma[s]), 1);
+      mbar_init(smem_u32(&s_chunk[s]), 1);
+      mbar_init(smem_u32(&s_drained[s]), 2 * kTcThreads);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync();  // both CTAs' mbarriers and the pair's tensor memory exist
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+  const int nkb = (n + TBK - 1) / TBK;
+  const int n_chunks = (nkb + flush - 1) / flush;
+  const int a_tile = min((int)blockIdx.y, row_tiles - 1);  // an odd count of row tiles: the padding CTA re-reads the last one, stores nothing
+  const float* a_src = Dsplit + (size_t)a_tile * nkb * (kAStage / 4);
+  const float* x_src = Xsplit + (size_t)blockIdx.x * nkb * (b_stage_bytes(BN) / 4) + (size_t)rank * (kXHalf / 4);
+
+  const uint32_t t_own = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * WC);
+  float acc[WC];
+#pragma unroll
+  for (int i = 0; i < WC; ++i) acc[i] = 0.f;
+
+  if (is_issuer) {
+    auto copy_stage = [&](int stage, int kb) {
+      const uint32_t bar = smem_u32(&s_full[0]) + (uint32_t)stage * 8;
+      mbar_expect_tx(bar, kStage);
+      const uint32_t dst = smem_u32(smem) + (uint32_t)stage * kStage;
+      bulk_copy(dst, a_src + (size_t)kb * (kAStage / 4), kAStage, bar);
+      bulk_copy(dst + kAStage, x_src + (size_t)kb * (b_stage_bytes(BN) / 4), kXHalf, bar);
+    };
+    if (elect_one())
+      for (int kb = 0; kb < kAhead && kb < nkb; ++kb) copy_stage(kb, kb);
+    int c_stage = kAhead % S;
+    constexpr uint32_t kDescHi = (kSbo >> 4) | (1u << 14);
+    const uint32_t a_lo0 = ((smem_u32(smem) & 0x3ffffu) >> 4) | ((kLboA >> 4) << 16);
+    const uint32_t b_lo0 = (((smem_u32(smem) + kAStage) & 0x3ffffu) >> 4) | ((kLboB >> 4) << 16);
+    auto desc = [&](uint32_t lo) { return ((uint64_t)kDescHi << 32) | (uint64_t)lo; };
+    const uint32_t peer_bar_of_leader = mapa(smem_u32(&s_peer[0]), 0);
+    int stage = 0, phase = 0, chunk_pos = 0, chunk = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb & 1;
+      const uint32_t bar_s = smem_u32(&s_mma[0]) + (uint32_t)s * 8;
+      if (kb >= 2) mbar_wait(bar_s, ((kb >> 1) - 1) & 1);  // MMAs of kb - 2 done (pair-wide): stage (kb + kAhead) % S is free
+      if (kb + kAhead < nkb) {
+        if (elect_one()) copy_stage(c_stage, kb + kAhead);
+        if (++c_stage == S) c_stage = 0;
+      }
+      mbar_wait(smem_u32(&s_full[0]) + (uint32_t)stage * 8, phase);
+      const bool first = chunk_pos == 0;
+      const int buf = chunk & 1;
+      const bool last_of_chunk = chunk_pos == flush - 1 || kb == nkb - 1;
+      if (!leader) {
+        if (elect_one()) mbar_arrive_cluster(peer_bar_of_leader + (uint32_t)stage * 8);  // relay: this CTA's stage has landed
+      } else {
+        mbar_wait_cluster(smem_u32(&s_peer[0]) + (uint32_t)stage * 8, phase);
+        if (first && chunk >= 2) mbar_wait_cluster(smem_u32(&s_drained[0]) + (uint32_t)buf * 8, ((chunk >> 1) - 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t la = a_lo0 + (uint32_t)stage * (kStage >> 4), lb = b_lo0 + (uint32_t)stage * (kStage >> 4);
+          const uint32_t td = tmem + (uint32_t)buf * BN;
+#pragma unroll
+          for (int ks = 0; ks < TBK / 8; ++ks) {
+            const uint64_t a_hi = desc(la + ks * (2 * kLboA >> 4)), a_lo = desc(la + (kABytes >> 4) + ks * (2 * kLboA >> 4));
+            const uint64_t b_hi = desc(lb + ks * (2 * kLboB >> 4)), b_lo = desc(lb + (kXBytes >> 4) + ks * (2 * kLboB >> 4));
+            if (debug < 2) umma_tf32_pair(td, a_lo, b_hi, kIdesc, !(first && ks == 0));
+            if (debug < 1) umma_tf32_pair(td, a_hi, b_lo, kIdesc, 1);
+            if (debug < 1) umma_tf32_pair(td, a_hi, b_hi, kIdesc, 1);
+          }
+          umma_commit_pair(bar_s);
+          if (last_of_chunk) umma_commit_pair(smem_u32(&s_chunk[0]) + (uint32_t)buf * 8);
+        }
+      }
+      __syncwarp();
+      if (++stage == S) stage = 0, phase ^= 1;
+      if (last_of_chunk) chunk_pos = 0, ++chunk;
+      else ++chunk_pos;
+    }
+  } else {
+    const uint32_t drained_of_leader = mapa(smem_u32(&s_drained[0]), 0);
+    for (int c = 0; c < n_chunks; ++c) {
+      const int buf = c & 1;
+      mbar_wait(smem_u32(&s_chunk[0]) + (uint32_t)buf * 8, (c >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < WC / 16; ++j) {
+        uint32_t v[16];
+        tmem_ld16(t_own + (uint32_t)(buf * BN + j * 16), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[j * 16 + i] += __uint_as_float(v[i]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive_cluster(drained_of_leader + (uint32_t)buf * 8);
+    }
+  }
+
+  // epilogue (as in the first kernel)
+  const float sc = scale * (scale_dev != nullptr ? __ldg(scale_dev) : 1.0f);
+  const int m = m0 + (warp & 3) * 32 + lane;
+  const int cbase = (warp >> 2) * WC;
+  float lsum = 0.f;
+#pragma unroll
+  for (int q = 0; q < WC / 4; ++q) {
+    const int c = n0 + cbase + q * 4;
+    if (!is_issuer && m < n && c < ldb) {
+      float4 o = make_float4(sc * acc[q * 4 + 0], sc * acc[q * 4 + 1], sc * acc[q * 4 + 2], sc * acc[q * 4 + 3]);
+      if (sub != nullptr) {
+        const float4 sv = __ldg(reinterpret_cast<const float4*>(sub + (int64_t)m * ldb + c));
+        o.x -= sv.x;
+        o.y -= sv.y;
+        o.z -= sv.z;
+        o.w -= sv.w;
+      }
+      if (c + 0 < B) lsum = fmaf(o.x, o.x, lsum);
+      if (c + 1 < B) lsum = fmaf(o.y, o.y, lsum);
+      if (c + 2 < B) lsum = fmaf(o.z, o.z, lsum);
+      if (c + 3 < B) lsum = fmaf(o.w, o.w, lsum);
+      *reinterpret_cast<float4*>(CT + (int64_t)m * ldb + c) = o;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+  if (lane == 0 && !is_issuer) s_part[warp] = lsum;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tid == 0 && partials != nullptr) {
+    float t = 0.f;
+    for (int w = 0; w < kTcThreads / 32; ++w) t += s_part[w];
+    partials[blockIdx.y * gridDim.x + blockIdx.x] = t;
+  }
+  cluster_sync();  // neither CTA frees the pair's tensor memory or leaves while the other may still use or signal it
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+  }
+}
+
 int env_int(const char* name, int dflt) {
   const char* e = std::getenv(name);
   const int v = e != nullptr ? atoi(e) : dflt;
@@ -627,7 +861,7 @@ int launch_tc2(dim3 grid, const float* Dsplit, float* Xsplit, int32_t n, const f
     configured = true;
   }
   const int nkb = (n + TBK - 1) / TBK;
-  dense_split_x_kernel<BN><<<dim3(grid.x, (unsigned)nkb), 256, 0, st>>>(XT, n, ldb, Xsplit, nkb);
+  dense_split_x_kernel<BN, 1><<<dim3(grid.x, (unsigned)nkb), 256, 0, st>>>(XT, n, ldb, Xsplit, nkb);
   FEO_CUDA_CHECK(cudaGetLastError());
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -642,6 +876,35 @@ int launch_tc2(dim3 grid, const float* Dsplit, float* Xsplit, int32_t n, const f
   cfg.attrs = attr;
   cfg.numAttrs = CL > 1 ? 1 : 0;
   FEO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dense_apply_tc2_kernel<BN, S, CL>, Dsplit, (const float*)Xsplit, n, CT, ldb, B, scale, scale_dev, sub,
+                                    partials, (int32_t)flush, (int32_t)debug));
+  return FEO_OK;
+}
+template <int BN, int S>
+int launch_tc3(dim3 grid, const float* Dsplit, float* Xsplit, int32_t n, int32_t row_tiles, const float* XT, float* CT, int64_t ldb, int32_t B,
+               float scale, const float* scale_dev, const float* sub, float* partials, int flush, cudaStream_t st) {
+  static bool configured = false;
+  static const int debug = env_int("FEO_DENSE_DEBUG", 0);
+  const int smem_bytes = S * (int)(2 * kABytes + b_stage_bytes(BN) / 2);
+  if (!configured) {
+    FEO_CUDA_CHECK(cudaFuncSetAttribute(dense_apply_tc3_kernel<BN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured = true;
+  }
+  const int nkb = (n + TBK - 1) / TBK;
+  dense_split_x_kernel<BN, 2><<<dim3(grid.x, (unsigned)nkb), 256, 0, st>>>(XT, n, ldb, Xsplit, nkb);
+  FEO_CUDA_CHECK(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kTcBlock);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 2;  // the two row tiles of a pair
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FEO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dense_apply_tc3_kernel<BN, S>, Dsplit, (const float*)Xsplit, n, row_tiles, CT, ldb, B, scale, scale_dev, sub,
                                     partials, (int32_t)flush, (int32_t)debug));
   return FEO_OK;
 }
@@ -719,6 +982,24 @@ int launch_dense_tc(const float* Dsplit, int32_t n, const float* XT, float* CT, 
     const unsigned col_tiles = (unsigned)((cols + bn - 1) / bn);
     dim3 grid((col_tiles + cl - 1) / cl * cl, (unsigned)row_tiles);
     *count_out = (int)(grid.x * grid.y);
+    if (gen_env == 3 && bn >= 128 && cl == 1) {
+      // CTA pairs: the row tiles are paired (an odd count gets a padding CTA), eight stages of 24 / 26 KB
+      const int64_t rt2 = (row_tiles + 1) / 2 * 2;
+      dim3 grid3(col_tiles, (unsigned)rt2);
+      *count_out = (int)(grid3.x * grid3.y);
+      const int s3 = sa_env >= 3 && sa_env <= 8 ? sa_env : 8;
+#define FEO_TC3_CASE(BN_, S_) \
+  if (bn == BN_ && s3 == S_)  \
+  return launch_tc3<BN_, S_>(grid3, Dsplit, xsplit, n, (int32_t)row_tiles, XT, CT, ldb, B, scale, scale_dev, sub, partials, flush, st)
+      FEO_TC3_CASE(128, 4);
+      FEO_TC3_CASE(128, 6);
+      FEO_TC3_CASE(128, 8);
+      FEO_TC3_CASE(160, 4);
+      FEO_TC3_CASE(160, 6);
+      FEO_TC3_CASE(160, 8);
+#undef FEO_TC3_CASE
+      return fail(FEO_ERR_INVALID_ARGUMENT, "dense_apply: no third-generation kernel for this tile configuration");
+    }
     // stages: 24 / 32 / 36 KB each; two CTAs per SM up to 128 columns (four stages at 64, three at 128), one at 160 (six)
     const int s_dflt = bn == 64 ? 4 : (bn == 128 ? 3 : 6);
     const int s2 = sa_env >= 3 && sa_env <= 6 ? sa_env : s_dflt;
