@@ -36,6 +36,7 @@
 // Shared-memory operand layout (canonical K-major, SWIZZLE_NONE): element (r, k) of a [128 x 16] tile lives at
 //   (k / 4) * 2048 + r * 16 + (k % 4) * 4   bytes,
 // i.e. 8 x 16-byte core matrices, 128 B each, SBO (next 8 rows) = 128 B, LBO (next 4 k) = 2048 B.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -46,6 +47,7 @@
 #include "feo_internal.h"
 
 namespace feo {
+int make_row_map(const float* base, int32_t row_floats, int64_t rows, int32_t box_rows, CUtensorMap* out);  // feo_tiled.cu
 namespace {
 
 constexpr int TBM = 128, TBK = 16;                      // CT tile rows, k-block; tile columns BN = 128 or 64 (template)
@@ -154,6 +156,19 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {  // non-blocking: has the phase completed?
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquires what a peer CTA released
   asm volatile(
       "{\n\t"
@@ -166,6 +181,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
       "}" ::"r"(bar),
       "r"(parity)
       : "memory");
+}
+// 2-D tensor-map load of a CTA pair: the bytes land in THIS CTA's shared memory, the transaction is counted on the mbarrier at
+// `leader_bar` (a shared::cluster address: the leader's barrier) -- the hardware hand-over that needs no software relay
+__device__ __forceinline__ void tma_box_pair(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint32_t leader_bar) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(leader_bar)
+               : "memory");
 }
 // one M = 256 MMA over the pair: each CTA contributes its own 128 rows of A and its half (N / 2 rows) of the B tile from the
 // same shared-memory offsets, and receives its 128 accumulator rows in its own tensor memory; issued by the leader CTA only
@@ -467,10 +489,10 @@ template <int BN, int S, int CL>
 __global__ void __launch_bounds__(kTcBlock, (BN <= 64 || (BN == 128 && S == 3)) ? 2 : 1) dense_apply_tc2_kernel(const float* __restrict__ Dsplit, const float* __restrict__ Xsplit, int32_t n,
                                                                      float* __restrict__ CT, int64_t ldb, int32_t B, float scale,
                                                                      const float* __restrict__ scale_dev, const float* __restrict__ sub,
-                                                                     float* __restrict__ partials, int32_t flush, int32_t debug) {
+                                                                     float* __restrict__ partials, int32_t flush, int32_t debug, int32_t gap) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t s_full[S];
-  __shared__ __align__(8) uint64_t s_mma[2];
+  __shared__ __align__(8) uint64_t s_empty[S];  // per stage: the MMAs that read it have completed
   __shared__ __align__(8) uint64_t s_chunk[2];
   __shared__ __align__(8) uint64_t s_drained[2];
   __shared__ uint32_t s_tmem;
@@ -482,7 +504,9 @@ __global__ void __launch_bounds__(kTcBlock, (BN <= 64 || (BN == 128 && S == 3)) 
   constexpr uint32_t kTmemCols = BN <= 64 ? 128 : (BN <= 128 ? 256 : 512);  // two accumulators of BN columns (allocations are powers of two)
   constexpr uint32_t kBBytes = (uint32_t)BN * TBK * 4;
   constexpr uint32_t kAStage = 2 * kABytes, kBStage = b_stage_bytes(BN), kStage = kAStage + kBStage;
-  constexpr int kAhead = S - 2;
+  // copies run kAhead = S - gap k-blocks ahead; a stage is refilled once the commit of the k-block `gap` back has arrived: the
+  // arrival of a tcgen05.commit takes long enough that a gap of 2 (round 2's first version) paced the whole pipeline
+  const int kAhead = S - gap;
   constexpr uint32_t kLboB = BN * 16;
   constexpr uint32_t kIdesc = instr_desc(BN);
   constexpr int WC = BN / 2;
@@ -492,9 +516,11 @@ __global__ void __launch_bounds__(kTcBlock, (BN <= 64 || (BN == 128 && S == 3)) 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 32) {
-    for (int s = 0; s < S; ++s) mbar_init(smem_u32(&s_full[s]), 1);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(smem_u32(&s_full[s]), 1);
+      mbar_init(smem_u32(&s_empty[s]), CL);
+    }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&s_mma[s]), CL);
       mbar_init(smem_u32(&s_chunk[s]), 1);
       mbar_init(smem_u32(&s_drained[s]), kTcThreads);
     }
@@ -534,10 +560,12 @@ __global__ void __launch_bounds__(kTcBlock, (BN <= 64 || (BN == 128 && S == 3)) 
     const uint32_t b_lo0 = (((smem_u32(smem) + kAStage) & 0x3ffffu) >> 4) | ((kLboB >> 4) << 16);
     auto desc = [&](uint32_t lo) { return ((uint64_t)kDescHi << 32) | (uint64_t)lo; };
     int stage = 0, phase = 0, chunk_pos = 0, chunk = 0;
+    int e_stage = 0, e_phase = 0;  // the stage this iteration refills: last read by k-block kb - gap
     for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb & 1;
-      const uint32_t bar_s = smem_u32(&s_mma[0]) + (uint32_t)s * 8;
-      if (kb >= 2) mbar_wait(bar_s, ((kb >> 1) - 1) & 1);  // MMAs of kb - 2 done: stage (kb + kAhead) % S is free
+      if (kb >= gap) {
+        mbar_wait(smem_u32(&s_empty[0]) + (uint32_t)e_stage * 8, e_phase);
+        if (++e_stage == S) e_stage = 0, e_phase ^= 1;
+      }
       if (kb + kAhead < nkb) {
         if (elect_one()) copy_stage(c_stage, kb + kAhead);
         if (++c_stage == S) c_stage = 0;
@@ -559,8 +587,9 @@ __global__ void __launch_bounds__(kTcBlock, (BN <= 64 || (BN == 128 && S == 3)) 
           if (debug < 1) umma_tf32(td, a_hi, b_lo, kIdesc, 1);
           if (debug < 1) umma_tf32(td, a_hi, b_hi, kIdesc, 1);
         }
-        if (CL == 1) umma_commit(bar_s);
-        else umma_commit_multicast(bar_s, (uint16_t)3);
+        const uint32_t bar_e = smem_u32(&s_empty[0]) + (uint32_t)stage * 8;
+        if (CL == 1) umma_commit(bar_e);
+        else umma_commit_multicast(bar_e, (uint16_t)3);
         if (last_of_chunk) umma_commit(smem_u32(&s_chunk[0]) + (uint32_t)buf * 8);
       }
       __syncwarp();
@@ -632,42 +661,50 @@ __global__ void __launch_bounds__(kTcBlock, (BN <= 64 || (BN == 128 && S == 3)) 
 //
 // The second kernel is paced by what each SM has to take in: its 128-row operator panel AND its whole activation tile, both as
 // [hi | lo] -- 36 KB per k-block at 160 columns, ~59 B/clk for the whole run (a run without MMAs is barely faster).  Here two
-// CTAs on the SMs of one TPC (cluster 1 x 2: two row tiles of the same column tile) run ONE M = 256 MMA per product: each
+// CTAs on the SMs of one TPC (cluster 2 x 1: two row tiles of the same column tile) run ONE M = 256 MMA per product: each
 // holds its own 128 operator rows and only HALF of the activation tile (the tensor cores of the pair read both halves), so an
 // SM takes in 16 + 10 instead of 16 + 20 KB per k-block and reads 39 instead of 54 KB of operands per k-block from its shared
-// memory.  The leader CTA (rank 0) issues the MMAs and commits to the mbarriers of both CTAs; the peer relays "my stage has
-// landed" to the leader (remote mbarrier arrive), both fill their own stages and drain their own 128 accumulator rows.
-//   barriers: full[S]      own stage landed (transaction bytes)          peer[S]     (leader) the peer's stage landed
-//             mma_done[2]  MMAs of a k-block done, in both CTAs (multicast commit) -> stage free
+// memory.  The leader CTA (rank 0) issues the MMAs and commits to the mbarriers of both CTAs; both fill their own stages with
+// tensor-map loads (cp.async.bulk.tensor .cta_group::2) whose transactions are counted on the LEADER's full barrier -- a first
+// version relayed "my stage has landed" by a remote mbarrier arrive per k-block and lost 60 % to the cluster-scope handshakes.
+//   barriers: full[S]      (leader) both stages landed (transaction bytes of both CTAs)
+//             empty[S]     MMAs of the k-block that read a stage done, in both CTAs (multicast commit) -> stage free
 //             chunk_done[2] accumulator complete, in both CTAs            drained[2]  (leader) read back by all 512 epilogue threads
 // ---------------------------------------------------------------------------------------------------------------------
 __host__ __device__ constexpr uint32_t instr_desc_pair(int BN) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24); }
 
+constexpr uint32_t kRowBytes = 1024;  // the pre-split arrays as rows of 256 floats for the tensor-map loads of the pair kernel
+struct PairMaps {
+  CUtensorMap a;  // the pre-split operator: a box of 16 rows = one 16 KB [hi | lo] stage of a row tile
+  CUtensorMap x;  // the pre-split activations: a box of BN / 16 rows = one CTA's [hi | lo] half of a stage
+};
+
 template <int BN, int S>
-__global__ void __launch_bounds__(kTcBlock, 1) dense_apply_tc3_kernel(const float* __restrict__ Dsplit, const float* __restrict__ Xsplit, int32_t n,
+__global__ void __launch_bounds__(kTcBlock, 1) dense_apply_tc3_kernel(const __grid_constant__ PairMaps maps, int32_t n,
                                                                      int32_t row_tiles, float* __restrict__ CT, int64_t ldb, int32_t B, float scale,
                                                                      const float* __restrict__ scale_dev, const float* __restrict__ sub,
-                                                                     float* __restrict__ partials, int32_t flush, int32_t debug) {
+                                                                     float* __restrict__ partials, int32_t flush, int32_t debug, int32_t gap) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t s_full[S];
-  __shared__ __align__(8) uint64_t s_peer[S];
-  __shared__ __align__(8) uint64_t s_mma[2];
+  __shared__ __align__(8) uint64_t s_empty[S];
   __shared__ __align__(8) uint64_t s_chunk[2];
-  __shared__ __align__(8) uint64_t s_drained[2];
+  __shared__ __align__(8) uint64_t s_drained[2];   // (leader) both CTAs have read the accumulator back: one arrival per CTA
+  __shared__ __align__(8) uint64_t s_drained_local[2];  // this CTA's 256 epilogue threads have
   __shared__ uint32_t s_tmem;
   __shared__ float s_part[kTcThreads / 32];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool is_issuer = __shfl_sync(0xffffffffu, warp, 0) == kTcThreads / 32;
-  const uint32_t rank = cluster_ctarank();  // cluster (1, 2, 1): the two row tiles 2p, 2p + 1 of one column tile
+  const uint32_t rank = cluster_ctarank();  // cluster (2, 1, 1): the two row tiles 2p, 2p + 1 of one column tile
+  const int row_tile = blockIdx.x, col_tile = blockIdx.y;  // pairs are formed along x (a 2-CTA kernel needs an even cluster x)
   const bool leader = rank == 0;
-  const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * BN;
+  const int m0 = row_tile * TBM, n0 = col_tile * BN;
   constexpr int HB = BN / 2;                                                   // activation columns held by one CTA
   constexpr uint32_t kTmemCols = BN <= 64 ? 128 : (BN <= 128 ? 256 : 512);    // two accumulators of BN columns
   constexpr uint32_t kXHalf = 2u * HB * TBK * 4;                              // this CTA's [hi | lo] activation sub-block
   constexpr uint32_t kXBytes = (uint32_t)HB * TBK * 4;                        // hi or lo of it
   constexpr uint32_t kAStage = 2 * kABytes, kStage = kAStage + kXHalf;
-  constexpr int kAhead = S - 2;
+  const int kAhead = S - gap;  // copies run S - gap k-blocks ahead, a stage is refilled after the commit of k-block kb - gap
   constexpr uint32_t kLboB = HB * 16;
   constexpr uint32_t kIdesc = instr_desc_pair(BN);
   constexpr int WC = BN / 2;
@@ -679,12 +716,12 @@ __global__ void __launch_bounds__(kTcBlock, 1) dense_apply_tc3_kernel(const floa
   if (tid == 32) {
     for (int s = 0; s < S; ++s) {
       mbar_init(smem_u32(&s_full[s]), 1);
-      mbar_init(smem_u32(&s_peer[s]), 1);
+      mbar_init(smem_u32(&s_empty[s]), 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&s_mma[s]), 1);
       mbar_init(smem_u32(&s_chunk[s]), 1);
-      mbar_init(smem_u32(&s_drained[s]), 2 * kTcThreads);
+      mbar_init(smem_u32(&s_drained[s]), 2);
+      mbar_init(smem_u32(&s_drained_local[s]), kTcThreads);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -695,9 +732,10 @@ __global__ void __launch_bounds__(kTcBlock, 1) dense_apply_tc3_kernel(const floa
   const uint32_t tmem = s_tmem;
   const int nkb = (n + TBK - 1) / TBK;
   const int n_chunks = (nkb + flush - 1) / flush;
-  const int a_tile = min((int)blockIdx.y, row_tiles - 1);  // an odd count of row tiles: the padding CTA re-reads the last one, stores nothing
-  const float* a_src = Dsplit + (size_t)a_tile * nkb * (kAStage / 4);
-  const float* x_src = Xsplit + (size_t)blockIdx.x * nkb * (b_stage_bytes(BN) / 4) + (size_t)rank * (kXHalf / 4);
+  const int a_tile = min(row_tile, row_tiles - 1);  // an odd count of row tiles: the padding CTA re-reads the last one, stores nothing
+  // row coordinates (rows of 256 bytes) of this CTA's first operator stage and first activation half-stage
+  const int32_t a_row0 = a_tile * nkb * (int32_t)(kAStage / kRowBytes);
+  const int32_t x_row0 = col_tile * nkb * (int32_t)(b_stage_bytes(BN) / kRowBytes) + (int32_t)rank * (int32_t)(kXHalf / kRowBytes);
 
   const uint32_t t_own = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * WC);
   float acc[WC];
@@ -705,12 +743,14 @@ __global__ void __launch_bounds__(kTcBlock, 1) dense_apply_tc3_kernel(const floa
   for (int i = 0; i < WC; ++i) acc[i] = 0.f;
 
   if (is_issuer) {
+    // both CTAs' loads count on the LEADER's full barrier, which expects the bytes of both stages
+    const uint32_t full_of_leader = mapa(smem_u32(&s_full[0]), 0);
     auto copy_stage = [&](int stage, int kb) {
-      const uint32_t bar = smem_u32(&s_full[0]) + (uint32_t)stage * 8;
-      mbar_expect_tx(bar, kStage);
+      const uint32_t bar = full_of_leader + (uint32_t)stage * 8;
+      if (leader) mbar_expect_tx(smem_u32(&s_full[0]) + (uint32_t)stage * 8, 2 * kStage);
       const uint32_t dst = smem_u32(smem) + (uint32_t)stage * kStage;
-      bulk_copy(dst, a_src + (size_t)kb * (kAStage / 4), kAStage, bar);
-      bulk_copy(dst + kAStage, x_src + (size_t)kb * (b_stage_bytes(BN) / 4), kXHalf, bar);
+      tma_box_pair(dst, &maps.a, 0, a_row0 + kb * (int32_t)(kAStage / kRowBytes), bar);
+      tma_box_pair(dst + kAStage, &maps.x, 0, x_row0 + kb * (int32_t)(b_stage_bytes(BN) / kRowBytes), bar);
     };
     if (elect_one())
       for (int kb = 0; kb < kAhead && kb < nkb; ++kb) copy_stage(kb, kb);
@@ -719,24 +759,25 @@ __global__ void __launch_bounds__(kTcBlock, 1) dense_apply_tc3_kernel(const floa
     const uint32_t a_lo0 = ((smem_u32(smem) & 0x3ffffu) >> 4) | ((kLboA >> 4) << 16);
     const uint32_t b_lo0 = (((smem_u32(smem) + kAStage) & 0x3ffffu) >> 4) | ((kLboB >> 4) << 16);
     auto desc = [&](uint32_t lo) { return ((uint64_t)kDescHi << 32) | (uint64_t)lo; };
-    const uint32_t peer_bar_of_leader = mapa(smem_u32(&s_peer[0]), 0);
     int stage = 0, phase = 0, chunk_pos = 0, chunk = 0;
+    int e_stage = 0, e_phase = 0;            // the stage the copy of this iteration refills, last read by k-block kb - gap
     for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb & 1;
-      const uint32_t bar_s = smem_u32(&s_mma[0]) + (uint32_t)s * 8;
-      if (kb >= 2) mbar_wait(bar_s, ((kb >> 1) - 1) & 1);  // MMAs of kb - 2 done (pair-wide): stage (kb + kAhead) % S is free
+      // One "empty" mbarrier PER STAGE (the commit of k-block kb arrives on empty[kb % S] of both CTAs): the leader may run
+      // several k-blocks ahead of the peer's loop, and a barrier shared by alternating k-blocks could then complete two
+      // phases between two looks of the peer.
+      if (kb >= gap) {
+        mbar_wait(smem_u32(&s_empty[0]) + (uint32_t)e_stage * 8, e_phase);  // MMAs of kb - gap done, pair-wide
+        if (++e_stage == S) e_stage = 0, e_phase ^= 1;
+      }
       if (kb + kAhead < nkb) {
         if (elect_one()) copy_stage(c_stage, kb + kAhead);
         if (++c_stage == S) c_stage = 0;
       }
-      mbar_wait(smem_u32(&s_full[0]) + (uint32_t)stage * 8, phase);
       const bool first = chunk_pos == 0;
       const int buf = chunk & 1;
       const bool last_of_chunk = chunk_pos == flush - 1 || kb == nkb - 1;
-      if (!leader) {
-        if (elect_one()) mbar_arrive_cluster(peer_bar_of_leader + (uint32_t)stage * 8);  // relay: this CTA's stage has landed
-      } else {
-        mbar_wait_cluster(smem_u32(&s_peer[0]) + (uint32_t)stage * 8, phase);
+      if (leader) {
+        mbar_wait(smem_u32(&s_full[0]) + (uint32_t)stage * 8, phase);  // both CTAs' stages have landed
         if (first && chunk >= 2) mbar_wait_cluster(smem_u32(&s_drained[0]) + (uint32_t)buf * 8, ((chunk >> 1) - 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
@@ -750,7 +791,7 @@ __global__ void __launch_bounds__(kTcBlock, 1) dense_apply_tc3_kernel(const floa
             if (debug < 1) umma_tf32_pair(td, a_hi, b_lo, kIdesc, 1);
             if (debug < 1) umma_tf32_pair(td, a_hi, b_hi, kIdesc, 1);
           }
-          umma_commit_pair(bar_s);
+          umma_commit_pair(smem_u32(&s_empty[0]) + (uint32_t)stage * 8);
           if (last_of_chunk) umma_commit_pair(smem_u32(&s_chunk[0]) + (uint32_t)buf * 8);
         }
       }
@@ -774,7 +815,12 @@ __global__ void __launch_bounds__(kTcBlock, 1) dense_apply_tc3_kernel(const floa
         for (int i = 0; i < 16; ++i) acc[j * 16 + i] += __uint_as_float(v[i]);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive_cluster(drained_of_leader + (uint32_t)buf * 8);
+      // 256 local arrivals, then ONE remote arrival per CTA on the leader's barrier (512 cluster-scope releases per chunk cost more)
+      mbar_arrive(smem_u32(&s_drained_local[0]) + (uint32_t)buf * 8);
+      if (tid == 0) {
+        mbar_wait(smem_u32(&s_drained_local[0]) + (uint32_t)buf * 8, (c >> 1) & 1);
+        mbar_arrive_cluster(drained_of_leader + (uint32_t)buf * 8);
+      }
     }
   }
 
@@ -875,8 +921,10 @@ int launch_tc2(dim3 grid, const float* Dsplit, float* Xsplit, int32_t n, const f
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CL > 1 ? 1 : 0;
+  static const int gap_env = env_int("FEO_DENSE_GAP", 0);
+  const int gap = gap_env >= 2 && gap_env < S ? gap_env : std::max(2, S / 2);
   FEO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dense_apply_tc2_kernel<BN, S, CL>, Dsplit, (const float*)Xsplit, n, CT, ldb, B, scale, scale_dev, sub,
-                                    partials, (int32_t)flush, (int32_t)debug));
+                                    partials, (int32_t)flush, (int32_t)debug, (int32_t)gap));
   return FEO_OK;
 }
 template <int BN, int S>
@@ -890,8 +938,14 @@ int launch_tc3(dim3 grid, const float* Dsplit, float* Xsplit, int32_t n, int32_t
     configured = true;
   }
   const int nkb = (n + TBK - 1) / TBK;
-  dense_split_x_kernel<BN, 2><<<dim3(grid.x, (unsigned)nkb), 256, 0, st>>>(XT, n, ldb, Xsplit, nkb);
+  dense_split_x_kernel<BN, 2><<<dim3(grid.y, (unsigned)nkb), 256, 0, st>>>(XT, n, ldb, Xsplit, nkb);
   FEO_CUDA_CHECK(cudaGetLastError());
+  // the pre-split arrays as rows of 256 floats (1 KB): stages are boxes of whole rows
+  PairMaps maps;
+  const int64_t a_rows = (int64_t)row_tiles * nkb * (2 * kABytes / kRowBytes), x_rows = (int64_t)grid.y * nkb * (b_stage_bytes(BN) / kRowBytes);
+  if (a_rows > INT32_MAX || x_rows > INT32_MAX) return fail(FEO_ERR_UNSUPPORTED, "dense_apply: operand too large for the pair kernel");
+  if (int rc = make_row_map(Dsplit, kRowBytes / 4, a_rows, (int32_t)(2 * kABytes / kRowBytes), &maps.a)) return rc;
+  if (int rc = make_row_map(Xsplit, kRowBytes / 4, x_rows, (int32_t)(b_stage_bytes(BN) / 2 / kRowBytes), &maps.x)) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(kTcBlock);
@@ -899,13 +953,15 @@ int launch_tc3(dim3 grid, const float* Dsplit, float* Xsplit, int32_t n, int32_t
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = 2;  // the two row tiles of a pair
+  attr[0].val.clusterDim.x = 2;  // the two row tiles of a pair
+  attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  FEO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dense_apply_tc3_kernel<BN, S>, Dsplit, (const float*)Xsplit, n, row_tiles, CT, ldb, B, scale, scale_dev, sub,
-                                    partials, (int32_t)flush, (int32_t)debug));
+  static const int gap_env = env_int("FEO_DENSE_GAP", 0);
+  const int gap = gap_env >= 2 && gap_env < S ? gap_env : std::max(2, S / 2);
+  FEO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dense_apply_tc3_kernel<BN, S>, maps, n, row_tiles, CT, ldb, B, scale, scale_dev, sub, partials, (int32_t)flush,
+                                    (int32_t)debug, (int32_t)gap));
   return FEO_OK;
 }
 // cvt.rna.tf32.f32 on the host: round to nearest, ties away from zero, to 10 mantissa bits
@@ -982,10 +1038,15 @@ int launch_dense_tc(const float* Dsplit, int32_t n, const float* XT, float* CT, 
     const unsigned col_tiles = (unsigned)((cols + bn - 1) / bn);
     dim3 grid((col_tiles + cl - 1) / cl * cl, (unsigned)row_tiles);
     *count_out = (int)(grid.x * grid.y);
-    if (gen_env == 3 && bn >= 128 && cl == 1) {
+    // Third generation (CTA pairs) where it measured faster: wide tiles that fit ONE wave of the GPU (every pair resident at
+    // once; N = 2549, B = 1024: 0.091 vs 0.101 ms).  Over several waves a pair needs both SMs of a TPC free at the same
+    // time and the second generation wins (B = 8192: 0.62 vs 0.68 ms).  FEO_DENSE_GEN=2 / 3 force one.
+    const int64_t rt2 = (row_tiles + 1) / 2 * 2;
+    const bool pairs_fit = bn >= 128 && cl == 1 && (int64_t)col_tiles * rt2 <= sms;
+    static const bool gen_forced = std::getenv("FEO_DENSE_GEN") != nullptr;
+    if (bn >= 128 && cl == 1 && (gen_env == 3 || (!gen_forced && pairs_fit))) {
       // CTA pairs: the row tiles are paired (an odd count gets a padding CTA), eight stages of 24 / 26 KB
-      const int64_t rt2 = (row_tiles + 1) / 2 * 2;
-      dim3 grid3(col_tiles, (unsigned)rt2);
+      dim3 grid3((unsigned)rt2, col_tiles);  // x: row tiles (paired), y: column tiles
       *count_out = (int)(grid3.x * grid3.y);
       const int s3 = sa_env >= 3 && sa_env <= 8 ? sa_env : 8;
 #define FEO_TC3_CASE(BN_, S_) \

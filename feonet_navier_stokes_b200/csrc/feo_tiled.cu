@@ -1039,6 +1039,22 @@ int make_box_map(const float* base, int64_t ldb, int32_t n, int32_t box_rows, CU
   if (r != CUDA_SUCCESS) return fail(FEO_ERR_CUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
   return FEO_OK;
 }
+// a contiguous fp32 array seen as rows of `row_floats` (<= 256) floats, box = box_rows whole rows: bulk movement of pre-tiled
+// blocks through the tensor-map path (the CTA-pair loads of feo_dense_tc.cu need a tensor map to count on the peer's mbarrier)
+int make_row_map(const float* base, int32_t row_floats, int64_t rows, int32_t box_rows, CUtensorMap* out) {
+  EncodeTiledFn enc;
+  if (int rc = get_encode(&enc)) return rc;
+  if (row_floats < 4 || row_floats > 256 || box_rows < 1 || box_rows > 256 || rows < 1) return fail(FEO_ERR_INVALID_ARGUMENT, "TMA row map out of range");
+  const cuuint64_t dims[2] = {(cuuint64_t)row_floats, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)row_floats * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)row_floats, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FEO_ERR_CUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+  return FEO_OK;
+}
 namespace {
 
 // persistent launch: one CTA per SM (or per unit when there are fewer units), `warps` consumer warps + 1 producer warp

@@ -440,10 +440,14 @@ def test_dense_apply_tensor_core_vs_fp64(feo, n, B):
     assert abs(loss.item() - (r64 ** 2).sum()) <= LOSS_RTOL * (r64 ** 2).sum()
 
 
-@pytest.mark.parametrize("env", [{"FEO_DENSE_CLUSTER": "2"}, {"FEO_DENSE_BN": "128"}, {"FEO_DENSE_SIMT": "1"}])
+@pytest.mark.parametrize("env", [{"FEO_DENSE_CLUSTER": "2"}, {"FEO_DENSE_BN": "128"}, {"FEO_DENSE_SIMT": "1"}, {"FEO_DENSE_GEN": "1"},
+                                 {"FEO_DENSE_GEN": "2", "FEO_DENSE_BN": "160"}, {"FEO_DENSE_GEN": "3", "FEO_DENSE_BN": "128"},
+                                 {"FEO_DENSE_GEN": "3", "FEO_DENSE_BN": "160", "FEO_DENSE_ASTAGES": "4", "FEO_DENSE_GAP": "2"}])
 def test_dense_apply_optional_paths_subprocess(feo, env):
     """The dense apply reads its tuning knobs once per process: the optional paths (cluster multicast of the operator stages,
-    128-column tiles, the fp32 FMA comparison kernel) are exercised in a child process, ragged sizes, against fp64."""
+    128- / 160-column tiles, the three kernel generations -- activations split in registers, pre-split, CTA pairs with
+    cta_group::2 incl. odd row-tile counts that get a padding CTA --, the fp32 FMA comparison kernel) are exercised in a child
+    process, ragged sizes, against fp64."""
     import subprocess
     import sys
 
