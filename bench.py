@@ -604,7 +604,7 @@ def run_precond_gemm(torch, feo, dev, n=2549, B=1024, iters=30):
         pass
     tensor_tf = 6.0 * n * n * B / (ms * 1e-3) / 1e12
     out = {
-        "kernel": "dense_split_x_kernel + dense_apply_tc2_kernel (tcgen05 kind::tf32, 3xTF32 split, both operands by bulk copies, two TMEM accumulators, tile width per problem) + finalize_loss_kernel", "n": n, "batch": B,
+        "kernel": "dense_split_x_kernel + dense_apply_tc3_kernel (tcgen05 kind::tf32 cta_group::2 CTA pairs, 3xTF32 split, both operands pre-split and fetched by tensor-map loads, two TMEM accumulators, tile width per problem; dense_apply_tc2_kernel when the pairs do not fit one wave) + finalize_loss_kernel", "n": n, "batch": B,
         "ms_per_apply": ms, "fp32_equivalent_tflops": 2.0 * n * n * B / (ms * 1e-3) / 1e12, "tensor_pipe_tflops": tensor_tf,
         "loss_rel_err_vs_fp64": abs(loss.item() - loss_ref) / loss_ref,
         "max_abs_err_vs_fp64": float((rT[:, :B].double() - ref).abs().max()),
