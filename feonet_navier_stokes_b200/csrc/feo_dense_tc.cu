@@ -182,6 +182,18 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
       "r"(parity)
       : "memory");
 }
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // a shared::cta address with this bit cleared names the same offset in the pair's leader
+// the same load delivered to the same offset of every CTA in `mask` (cluster ranks), counted on the full barrier of each
+// destination's pair leader
+__device__ __forceinline__ void tma_box_pair_multicast(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar & kPeerBitMask), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_mask(uint32_t bar, uint16_t mask) {  // one arrival on the same mbarrier of every CTA in `mask`
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
 // 2-D tensor-map load of a CTA pair: the bytes land in THIS CTA's shared memory, the transaction is counted on the mbarrier at
 // `leader_bar` (a shared::cluster address: the leader's barrier) -- the hardware hand-over that needs no software relay
 __device__ __forceinline__ void tma_box_pair(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint32_t leader_bar) {
@@ -677,9 +689,11 @@ constexpr uint32_t kRowBytes = 1024;  // the pre-split arrays as rows of 256 flo
 struct PairMaps {
   CUtensorMap a;  // the pre-split operator: a box of 16 rows = one 16 KB [hi | lo] stage of a row tile
   CUtensorMap x;  // the pre-split activations: a box of BN / 16 rows = one CTA's [hi | lo] half of a stage
+  CUtensorMap ah; // the operator again with a box of 8 rows: the hi or the lo half of a stage (clusters of two pairs)
 };
 
-template <int BN, int S>
+template <int BN, int S, int CM, int G>  // CM = 2: clusters of two pairs (two column tiles) that share every operator stage by multicast;
+                                         // G: k-blocks per stage (one full / empty hand-over, one commit per G k-blocks)
 __global__ void __launch_bounds__(kTcBlock, 1) dense_apply_tc3_kernel(const __grid_constant__ PairMaps maps, int32_t n,
                                                                      int32_t row_tiles, float* __restrict__ CT, int64_t ldb, int32_t B, float scale,
                                                                      const float* __restrict__ scale_dev, const float* __restrict__ sub,
@@ -687,23 +701,29 @@ __global__ void __launch_bounds__(kTcBlock, 1) dense_apply_tc3_kernel(const __gr
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t s_full[S];
   __shared__ __align__(8) uint64_t s_empty[S];
-  __shared__ __align__(8) uint64_t s_chunk[2];
-  __shared__ __align__(8) uint64_t s_drained[2];   // (leader) both CTAs have read the accumulator back: one arrival per CTA
-  __shared__ __align__(8) uint64_t s_drained_local[2];  // this CTA's 256 epilogue threads have
+  // accumulators in tensor memory: three where 3 BN <= 512 columns -- a drain (commit multicast, tcgen05.ld, local barrier, remote
+  // arrival at the leader) takes about as long as the MMAs of one chunk, so with two the leader waited for it at every chunk
+  constexpr int NACC = 3 * BN <= 512 ? 3 : 2;
+  __shared__ __align__(8) uint64_t s_chunk[NACC];
+  __shared__ __align__(8) uint64_t s_drained[NACC];        // (leader) both CTAs have read the accumulator back: one arrival per CTA
+  __shared__ __align__(8) uint64_t s_drained_local[NACC];  // this CTA's 256 epilogue threads have
   __shared__ uint32_t s_tmem;
   __shared__ float s_part[kTcThreads / 32];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool is_issuer = __shfl_sync(0xffffffffu, warp, 0) == kTcThreads / 32;
-  const uint32_t rank = cluster_ctarank();  // cluster (2, 1, 1): the two row tiles 2p, 2p + 1 of one column tile
+  const uint32_t crank = cluster_ctarank();  // cluster (2, CM, 1), x fastest: pairs are the ranks (2 cy, 2 cy + 1)
+  const uint32_t rank = crank & 1u, cy = crank >> 1;  // rank in the pair: the two row tiles 2p, 2p + 1 of one column tile
+  const uint32_t pair_leader = crank & ~1u;
   const int row_tile = blockIdx.x, col_tile = blockIdx.y;  // pairs are formed along x (a 2-CTA kernel needs an even cluster x)
   const bool leader = rank == 0;
   const int m0 = row_tile * TBM, n0 = col_tile * BN;
   constexpr int HB = BN / 2;                                                   // activation columns held by one CTA
-  constexpr uint32_t kTmemCols = BN <= 64 ? 128 : (BN <= 128 ? 256 : 512);    // two accumulators of BN columns
+  constexpr uint32_t kTmemCols = NACC * BN <= 128 ? 128 : (NACC * BN <= 256 ? 256 : 512);  // NACC accumulators of BN columns
   constexpr uint32_t kXHalf = 2u * HB * TBK * 4;                              // this CTA's [hi | lo] activation sub-block
   constexpr uint32_t kXBytes = (uint32_t)HB * TBK * 4;                        // hi or lo of it
-  constexpr uint32_t kAStage = 2 * kABytes, kStage = kAStage + kXHalf;
+  constexpr uint32_t kAStage = 2 * kABytes, kStage = G * (kAStage + kXHalf);  // a stage: G operator blocks, then G activation half-blocks
+  static_assert(G == 1 || CM == 1, "multi-k-block stages are built for single pairs");
   const int kAhead = S - gap;  // copies run S - gap k-blocks ahead, a stage is refilled after the commit of k-block kb - gap
   constexpr uint32_t kLboB = HB * 16;
   constexpr uint32_t kIdesc = instr_desc_pair(BN);
@@ -716,9 +736,9 @@ __global__ void __launch_bounds__(kTcBlock, 1) dense_apply_tc3_kernel(const __gr
   if (tid == 32) {
     for (int s = 0; s < S; ++s) {
       mbar_init(smem_u32(&s_full[s]), 1);
-      mbar_init(smem_u32(&s_empty[s]), 1);
+      mbar_init(smem_u32(&s_empty[s]), CM);  // one commit per pair of the cluster
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NACC; ++s) {
       mbar_init(smem_u32(&s_chunk[s]), 1);
       mbar_init(smem_u32(&s_drained[s]), 2);
       mbar_init(smem_u32(&s_drained_local[s]), kTcThreads);
@@ -731,7 +751,9 @@ __global__ void __launch_bounds__(kTcBlock, 1) dense_apply_tc3_kernel(const __gr
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = s_tmem;
   const int nkb = (n + TBK - 1) / TBK;
-  const int n_chunks = (nkb + flush - 1) / flush;
+  const int nsb = (nkb + G - 1) / G;                 // stages' worth of k-blocks ("super-blocks"); the loops below count these
+  const int flush_sb = max(1, flush / G);
+  const int n_chunks = (nsb + flush_sb - 1) / flush_sb;
   const int a_tile = min(row_tile, row_tiles - 1);  // an odd count of row tiles: the padding CTA re-reads the last one, stores nothing
   // row coordinates (rows of 256 bytes) of this CTA's first operator stage and first activation half-stage
   const int32_t a_row0 = a_tile * nkb * (int32_t)(kAStage / kRowBytes);
@@ -743,25 +765,36 @@ __global__ void __launch_bounds__(kTcBlock, 1) dense_apply_tc3_kernel(const __gr
   for (int i = 0; i < WC; ++i) acc[i] = 0.f;
 
   if (is_issuer) {
-    // both CTAs' loads count on the LEADER's full barrier, which expects the bytes of both stages
-    const uint32_t full_of_leader = mapa(smem_u32(&s_full[0]), 0);
-    auto copy_stage = [&](int stage, int kb) {
-      const uint32_t bar = full_of_leader + (uint32_t)stage * 8;
-      if (leader) mbar_expect_tx(smem_u32(&s_full[0]) + (uint32_t)stage * 8, 2 * kStage);
+    // both CTAs' loads count on the full barrier of the pair's LEADER, which expects the bytes of both stages.  CM = 2: the two
+    // column tiles of the cluster read the same operator rows -- the cy = 0 CTA fetches the hi half of its row tile's stage, the
+    // cy = 1 CTA the lo half, each multicast to both (half the operator reads from L2)
+    const uint16_t col_mask = (uint16_t)((1u << rank) | (1u << (rank + 2)));  // this row tile's CTAs in both column tiles
+    auto copy_stage = [&](int stage, int sb) {
+      const uint32_t bar = smem_u32(&s_full[0]) + (uint32_t)stage * 8;
+      if (leader) mbar_expect_tx(bar, 2 * kStage);
       const uint32_t dst = smem_u32(smem) + (uint32_t)stage * kStage;
-      tma_box_pair(dst, &maps.a, 0, a_row0 + kb * (int32_t)(kAStage / kRowBytes), bar);
-      tma_box_pair(dst + kAStage, &maps.x, 0, x_row0 + kb * (int32_t)(b_stage_bytes(BN) / kRowBytes), bar);
+      const int32_t a_row = a_row0 + sb * G * (int32_t)(kAStage / kRowBytes);
+      if (CM == 1) {  // G consecutive operator blocks of the row tile: one box (rows past the array are zero-filled and counted)
+        tma_box_pair_multicast(dst, &maps.a, 0, a_row, bar, (uint16_t)(1u << crank));
+      } else {
+        const uint32_t half = cy * kABytes;
+        tma_box_pair_multicast(dst + half, &maps.ah, 0, a_row + (int32_t)(half / kRowBytes), bar, col_mask);
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        tma_box_pair_multicast(dst + G * kAStage + g * kXHalf, &maps.x, 0, x_row0 + (sb * G + g) * (int32_t)(b_stage_bytes(BN) / kRowBytes), bar,
+                               (uint16_t)(1u << crank));
     };
     if (elect_one())
-      for (int kb = 0; kb < kAhead && kb < nkb; ++kb) copy_stage(kb, kb);
+      for (int sb = 0; sb < kAhead && sb < nsb; ++sb) copy_stage(sb, sb);
     int c_stage = kAhead % S;
     constexpr uint32_t kDescHi = (kSbo >> 4) | (1u << 14);
     const uint32_t a_lo0 = ((smem_u32(smem) & 0x3ffffu) >> 4) | ((kLboA >> 4) << 16);
-    const uint32_t b_lo0 = (((smem_u32(smem) + kAStage) & 0x3ffffu) >> 4) | ((kLboB >> 4) << 16);
+    const uint32_t b_lo0 = (((smem_u32(smem) + G * kAStage) & 0x3ffffu) >> 4) | ((kLboB >> 4) << 16);
     auto desc = [&](uint32_t lo) { return ((uint64_t)kDescHi << 32) | (uint64_t)lo; };
     int stage = 0, phase = 0, chunk_pos = 0, chunk = 0;
     int e_stage = 0, e_phase = 0;            // the stage the copy of this iteration refills, last read by k-block kb - gap
-    for (int kb = 0; kb < nkb; ++kb) {
+    for (int kb = 0; kb < nsb; ++kb) {  // kb counts super-blocks of G k-blocks here
       // One "empty" mbarrier PER STAGE (the commit of k-block kb arrives on empty[kb % S] of both CTAs): the leader may run
       // several k-blocks ahead of the peer's loop, and a barrier shared by alternating k-blocks could then complete two
       // phases between two looks of the peer.
@@ -769,30 +802,36 @@ __global__ void __launch_bounds__(kTcBlock, 1) dense_apply_tc3_kernel(const __gr
         mbar_wait(smem_u32(&s_empty[0]) + (uint32_t)e_stage * 8, e_phase);  // MMAs of kb - gap done, pair-wide
         if (++e_stage == S) e_stage = 0, e_phase ^= 1;
       }
-      if (kb + kAhead < nkb) {
+      if (kb + kAhead < nsb) {
         if (elect_one()) copy_stage(c_stage, kb + kAhead);
         if (++c_stage == S) c_stage = 0;
       }
       const bool first = chunk_pos == 0;
-      const int buf = chunk & 1;
-      const bool last_of_chunk = chunk_pos == flush - 1 || kb == nkb - 1;
+      const int buf = chunk % NACC;
+      const bool last_of_chunk = chunk_pos == flush_sb - 1 || kb == nsb - 1;
       if (leader) {
         mbar_wait(smem_u32(&s_full[0]) + (uint32_t)stage * 8, phase);  // both CTAs' stages have landed
-        if (first && chunk >= 2) mbar_wait_cluster(smem_u32(&s_drained[0]) + (uint32_t)buf * 8, ((chunk >> 1) - 1) & 1);
+        if (first && chunk >= NACC) mbar_wait_cluster(smem_u32(&s_drained[0]) + (uint32_t)buf * 8, ((chunk / NACC) - 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
           const uint32_t la = a_lo0 + (uint32_t)stage * (kStage >> 4), lb = b_lo0 + (uint32_t)stage * (kStage >> 4);
           const uint32_t td = tmem + (uint32_t)buf * BN;
 #pragma unroll
-          for (int ks = 0; ks < TBK / 8; ++ks) {
-            const uint64_t a_hi = desc(la + ks * (2 * kLboA >> 4)), a_lo = desc(la + (kABytes >> 4) + ks * (2 * kLboA >> 4));
-            const uint64_t b_hi = desc(lb + ks * (2 * kLboB >> 4)), b_lo = desc(lb + (kXBytes >> 4) + ks * (2 * kLboB >> 4));
-            if (debug < 2) umma_tf32_pair(td, a_lo, b_hi, kIdesc, !(first && ks == 0));
-            if (debug < 1) umma_tf32_pair(td, a_hi, b_lo, kIdesc, 1);
-            if (debug < 1) umma_tf32_pair(td, a_hi, b_hi, kIdesc, 1);
+          for (int g = 0; g < G; ++g) {
+            if (kb * G + g < nkb) {  // the last stage may hold fewer k-blocks
+#pragma unroll
+              for (int ks = 0; ks < TBK / 8; ++ks) {
+                const uint32_t lag = la + g * (kAStage >> 4) + ks * (2 * kLboA >> 4), lbg = lb + g * (kXHalf >> 4) + ks * (2 * kLboB >> 4);
+                const uint64_t a_hi = desc(lag), a_lo = desc(lag + (kABytes >> 4));
+                const uint64_t b_hi = desc(lbg), b_lo = desc(lbg + (kXBytes >> 4));
+                if (debug < 2) umma_tf32_pair(td, a_lo, b_hi, kIdesc, !(first && g == 0 && ks == 0));
+                if (debug < 1) umma_tf32_pair(td, a_hi, b_lo, kIdesc, 1);
+                if (debug < 1) umma_tf32_pair(td, a_hi, b_hi, kIdesc, 1);
+              }
+            }
           }
-          umma_commit_pair(smem_u32(&s_empty[0]) + (uint32_t)stage * 8);
-          if (last_of_chunk) umma_commit_pair(smem_u32(&s_chunk[0]) + (uint32_t)buf * 8);
+          umma_commit_pair_mask(smem_u32(&s_empty[0]) + (uint32_t)stage * 8, (uint16_t)((1u << (2 * CM)) - 1));  // every CTA of the cluster
+          if (last_of_chunk) umma_commit_pair_mask(smem_u32(&s_chunk[0]) + (uint32_t)buf * 8, (uint16_t)(3u << pair_leader));  // this pair
         }
       }
       __syncwarp();
@@ -801,10 +840,10 @@ __global__ void __launch_bounds__(kTcBlock, 1) dense_apply_tc3_kernel(const __gr
       else ++chunk_pos;
     }
   } else {
-    const uint32_t drained_of_leader = mapa(smem_u32(&s_drained[0]), 0);
+    const uint32_t drained_of_leader = mapa(smem_u32(&s_drained[0]), pair_leader);
     for (int c = 0; c < n_chunks; ++c) {
-      const int buf = c & 1;
-      mbar_wait(smem_u32(&s_chunk[0]) + (uint32_t)buf * 8, (c >> 1) & 1);
+      const int buf = c % NACC;
+      mbar_wait(smem_u32(&s_chunk[0]) + (uint32_t)buf * 8, (c / NACC) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int j = 0; j < WC / 16; ++j) {
@@ -818,7 +857,7 @@ __global__ void __launch_bounds__(kTcBlock, 1) dense_apply_tc3_kernel(const __gr
       // 256 local arrivals, then ONE remote arrival per CTA on the leader's barrier (512 cluster-scope releases per chunk cost more)
       mbar_arrive(smem_u32(&s_drained_local[0]) + (uint32_t)buf * 8);
       if (tid == 0) {
-        mbar_wait(smem_u32(&s_drained_local[0]) + (uint32_t)buf * 8, (c >> 1) & 1);
+        mbar_wait(smem_u32(&s_drained_local[0]) + (uint32_t)buf * 8, (c / NACC) & 1);
         mbar_arrive_cluster(drained_of_leader + (uint32_t)buf * 8);
       }
     }
@@ -927,14 +966,14 @@ int launch_tc2(dim3 grid, const float* Dsplit, float* Xsplit, int32_t n, const f
                                     partials, (int32_t)flush, (int32_t)debug, (int32_t)gap));
   return FEO_OK;
 }
-template <int BN, int S>
+template <int BN, int S, int CM, int G>
 int launch_tc3(dim3 grid, const float* Dsplit, float* Xsplit, int32_t n, int32_t row_tiles, const float* XT, float* CT, int64_t ldb, int32_t B,
                float scale, const float* scale_dev, const float* sub, float* partials, int flush, cudaStream_t st) {
   static bool configured = false;
   static const int debug = env_int("FEO_DENSE_DEBUG", 0);
-  const int smem_bytes = S * (int)(2 * kABytes + b_stage_bytes(BN) / 2);
+  const int smem_bytes = S * G * (int)(2 * kABytes + b_stage_bytes(BN) / 2);
   if (!configured) {
-    FEO_CUDA_CHECK(cudaFuncSetAttribute(dense_apply_tc3_kernel<BN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    FEO_CUDA_CHECK(cudaFuncSetAttribute(dense_apply_tc3_kernel<BN, S, CM, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = true;
   }
   const int nkb = (n + TBK - 1) / TBK;
@@ -944,7 +983,8 @@ int launch_tc3(dim3 grid, const float* Dsplit, float* Xsplit, int32_t n, int32_t
   PairMaps maps;
   const int64_t a_rows = (int64_t)row_tiles * nkb * (2 * kABytes / kRowBytes), x_rows = (int64_t)grid.y * nkb * (b_stage_bytes(BN) / kRowBytes);
   if (a_rows > INT32_MAX || x_rows > INT32_MAX) return fail(FEO_ERR_UNSUPPORTED, "dense_apply: operand too large for the pair kernel");
-  if (int rc = make_row_map(Dsplit, kRowBytes / 4, a_rows, (int32_t)(2 * kABytes / kRowBytes), &maps.a)) return rc;
+  if (int rc = make_row_map(Dsplit, kRowBytes / 4, a_rows, (int32_t)(G * 2 * kABytes / kRowBytes), &maps.a)) return rc;
+  if (int rc = make_row_map(Dsplit, kRowBytes / 4, a_rows, (int32_t)(kABytes / kRowBytes), &maps.ah)) return rc;
   if (int rc = make_row_map(Xsplit, kRowBytes / 4, x_rows, (int32_t)(b_stage_bytes(BN) / 2 / kRowBytes), &maps.x)) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -953,14 +993,14 @@ int launch_tc3(dim3 grid, const float* Dsplit, float* Xsplit, int32_t n, int32_t
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;  // the two row tiles of a pair
-  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.x = 2;   // the two row tiles of a pair
+  attr[0].val.clusterDim.y = CM;  // column tiles that share the operator stages
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   static const int gap_env = env_int("FEO_DENSE_GAP", 0);
-  const int gap = gap_env >= 2 && gap_env < S ? gap_env : std::max(2, S / 2);
-  FEO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dense_apply_tc3_kernel<BN, S>, maps, n, row_tiles, CT, ldb, B, scale, scale_dev, sub, partials, (int32_t)flush,
+  const int gap = gap_env >= 1 && gap_env < S ? gap_env : std::max(1, S / 2);
+  FEO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dense_apply_tc3_kernel<BN, S, CM, G>, maps, n, row_tiles, CT, ldb, B, scale, scale_dev, sub, partials, (int32_t)flush,
                                     (int32_t)debug, (int32_t)gap));
   return FEO_OK;
 }
@@ -996,7 +1036,7 @@ std::vector<float> dense_split_tiles(const float* src, int32_t n, bool transpose
 size_t dense_xsplit_bytes(int32_t n, int64_t cols) {
   const int64_t c4 = (cols + 3) / 4 * 4, nkb = (n + TBK - 1) / TBK;
   size_t need = 0;
-  for (int bn : {64, 128, 160}) need = std::max(need, (size_t)((c4 + bn - 1) / bn + 1) * (size_t)nkb * b_stage_bytes(bn));
+  for (int bn : {64, 128, 160, 192}) need = std::max(need, (size_t)((c4 + bn - 1) / bn + 1) * (size_t)nkb * b_stage_bytes(bn));
   return need;
 }
 
@@ -1034,7 +1074,7 @@ int launch_dense_tc(const float* Dsplit, int32_t n, const float* XT, float* CT, 
       const int64_t cost = (tiles + sms - 1) / sms * std::max(cand, 128);
       if (best < 0 || cost < best) best = cost, bn = cand;
     }
-    if (bn_env == 64 || bn_env == 128 || bn_env == 160) bn = bn_env;
+    if (bn_env == 64 || bn_env == 128 || bn_env == 160 || bn_env == 192) bn = bn_env;
     const unsigned col_tiles = (unsigned)((cols + bn - 1) / bn);
     dim3 grid((col_tiles + cl - 1) / cl * cl, (unsigned)row_tiles);
     *count_out = (int)(grid.x * grid.y);
@@ -1044,20 +1084,38 @@ int launch_dense_tc(const float* Dsplit, int32_t n, const float* XT, float* CT, 
     const int64_t rt2 = (row_tiles + 1) / 2 * 2;
     const bool pairs_fit = bn >= 128 && cl == 1 && (int64_t)col_tiles * rt2 <= sms;
     static const bool gen_forced = std::getenv("FEO_DENSE_GEN") != nullptr;
+    static const int cm_env = env_int("FEO_DENSE_CM", 0);
     if (bn >= 128 && cl == 1 && (gen_env == 3 || (!gen_forced && pairs_fit))) {
-      // CTA pairs: the row tiles are paired (an odd count gets a padding CTA), eight stages of 24 / 26 KB
-      dim3 grid3((unsigned)rt2, col_tiles);  // x: row tiles (paired), y: column tiles
+      // CTA pairs: the row tiles are paired (an odd count gets a padding CTA); FEO_DENSE_CM=2: two column tiles per cluster
+      // share the operator stages by multicast (an odd count of column tiles gets a padding column)
+      const int cm = cm_env == 2 ? 2 : 1;
+      const unsigned ct3 = (col_tiles + cm - 1) / cm * cm;
+      dim3 grid3((unsigned)rt2, ct3);  // x: row tiles (paired), y: column tiles
       *count_out = (int)(grid3.x * grid3.y);
-      const int s3 = sa_env >= 3 && sa_env <= 8 ? sa_env : 8;
-#define FEO_TC3_CASE(BN_, S_) \
-  if (bn == BN_ && s3 == S_)  \
-  return launch_tc3<BN_, S_>(grid3, Dsplit, xsplit, n, (int32_t)row_tiles, XT, CT, ldb, B, scale, scale_dev, sub, partials, flush, st)
-      FEO_TC3_CASE(128, 4);
-      FEO_TC3_CASE(128, 6);
-      FEO_TC3_CASE(128, 8);
-      FEO_TC3_CASE(160, 4);
-      FEO_TC3_CASE(160, 6);
-      FEO_TC3_CASE(160, 8);
+      // FEO_DENSE_KG: k-blocks per stage (1 / 2 / 4); the stage count shrinks accordingly (S * G stages' worth of k-blocks <= 8)
+      static const int kg_env = env_int("FEO_DENSE_KG", 0);
+      const int kg = (kg_env == 1 || kg_env == 2 || kg_env == 4) && cm == 1 ? kg_env : (cm == 1 ? 2 : 1);
+      const int s_max = (bn == 192 ? 7 : 8) / kg;
+      const int s3 = sa_env >= 2 && sa_env <= s_max ? sa_env : s_max;
+#define FEO_TC3_CASE(BN_, S_, CM_, G_)                    \
+  if (bn == BN_ && s3 == S_ && cm == CM_ && kg == G_)     \
+  return launch_tc3<BN_, S_, CM_, G_>(grid3, Dsplit, xsplit, n, (int32_t)row_tiles, XT, CT, ldb, B, scale, scale_dev, sub, partials, flush, st)
+      FEO_TC3_CASE(128, 4, 1, 1);
+      FEO_TC3_CASE(128, 8, 1, 1);
+      FEO_TC3_CASE(160, 4, 1, 1);
+      FEO_TC3_CASE(160, 6, 1, 1);
+      FEO_TC3_CASE(160, 8, 1, 1);
+      FEO_TC3_CASE(192, 7, 1, 1);
+      FEO_TC3_CASE(128, 4, 1, 2);
+      FEO_TC3_CASE(160, 4, 1, 2);
+      FEO_TC3_CASE(160, 3, 1, 2);
+      FEO_TC3_CASE(192, 3, 1, 2);
+      FEO_TC3_CASE(128, 2, 1, 4);
+      FEO_TC3_CASE(160, 2, 1, 4);
+      FEO_TC3_CASE(128, 8, 2, 1);
+      FEO_TC3_CASE(160, 8, 2, 1);
+      FEO_TC3_CASE(192, 7, 2, 1);
+      FEO_TC3_CASE(192, 5, 2, 1);
 #undef FEO_TC3_CASE
       return fail(FEO_ERR_INVALID_ARGUMENT, "dense_apply: no third-generation kernel for this tile configuration");
     }
