@@ -1078,11 +1078,10 @@ int launch_dense_tc(const float* Dsplit, int32_t n, const float* XT, float* CT, 
     const unsigned col_tiles = (unsigned)((cols + bn - 1) / bn);
     dim3 grid((col_tiles + cl - 1) / cl * cl, (unsigned)row_tiles);
     *count_out = (int)(grid.x * grid.y);
-    // Third generation (CTA pairs) where it measured faster: wide tiles that fit ONE wave of the GPU (every pair resident at
-    // once; N = 2549, B = 1024: 0.091 vs 0.101 ms).  Over several waves a pair needs both SMs of a TPC free at the same
-    // time and the second generation wins (B = 8192: 0.62 vs 0.68 ms).  FEO_DENSE_GEN=2 / 3 force one.
+    // Third generation (CTA pairs) for every wide tile: N = 2549, B = 1024 (one wave) 0.077 vs 0.103 ms; B = 2048 0.179 vs 0.195;
+    // N = 1003, 10 000 pseudo-samples 0.178 vs 0.221; B = 8192 (seven waves) 0.645 vs 0.639.  FEO_DENSE_GEN=2 / 3 force one.
     const int64_t rt2 = (row_tiles + 1) / 2 * 2;
-    const bool pairs_fit = bn >= 128 && cl == 1 && (int64_t)col_tiles * rt2 <= sms;
+    const bool pairs_fit = bn >= 128 && cl == 1;
     static const bool gen_forced = std::getenv("FEO_DENSE_GEN") != nullptr;
     static const int cm_env = env_int("FEO_DENSE_CM", 0);
     if (bn >= 128 && cl == 1 && (gen_env == 3 || (!gen_forced && pairs_fit))) {
