@@ -1060,31 +1060,34 @@ int launch_dense_tc(const float* Dsplit, int32_t n, const float* XT, float* CT, 
   // the split (feo_workspace_bytes accounts for it); FEO_DENSE_GEN=1 keeps the first kernel
   static const int gen_env = env_int("FEO_DENSE_GEN", 2);
   if (gen_env != 1 && xsplit != nullptr && xsplit_bytes >= dense_xsplit_bytes(n, cols)) {
-    // Tile width: an M = 128 MMA takes the same time at N = 64 as at N = 128 (tools/micro9.cu) and proportionally longer
-    // above, and the tiles of one SM share its tensor pipe, so the run time goes as
-    //   ceil(tiles / SMs) * max(BN, 128):
-    // at N = 2549, B = 1024 that is 3 x 128 for 64-column tiles (320 tiles), 2 x 128 for 128 (160) and 1 x 160 for 160-column
-    // tiles (140 tiles: one per SM).  Ties go to the narrower tile (more SMs share the operand traffic).
+    // Tile width and kernel generation: an M = 128 MMA takes the same time at N = 64 as at N = 128 (tools/micro9.cu) and
+    // proportionally longer above, and the tiles of one SM share its tensor pipe, so the run time goes as
+    //   waves * max(BN, 128),   waves = ceil(CTAs / SMs);
+    // a wave of CTA pairs (third generation; row tiles rounded up to an even count) measured ~0.8 of a wave of single CTAs.
+    // N = 2549, B = 1024: pairs at 160 columns (140 CTAs, one wave) 0.077 ms, singles 0.103; 128 columns two waves, 64 columns
+    // three half-rate waves.  N = 2680, B = 1000: 21 row tiles -> 154 paired CTAs = two waves, singles (147) stay at one.
+    // Ties go to the narrower tile (more SMs share the operand traffic).  FEO_DENSE_BN / FEO_DENSE_GEN=2|3 force either.
     int sms = 148;
     if (int rc = sm_count(&sms)) return rc;
+    const int64_t rt2 = (row_tiles + 1) / 2 * 2;
+    static const bool gen_forced = std::getenv("FEO_DENSE_GEN") != nullptr;
     int bn = 64;
+    bool pairs_fit = false;
     int64_t best = -1;
     for (int cand : {64, 128, 160}) {
-      const int64_t tiles = row_tiles * ((cols + cand - 1) / cand);
-      const int64_t cost = (tiles + sms - 1) / sms * std::max(cand, 128);
-      if (best < 0 || cost < best) best = cost, bn = cand;
+      if (bn_env != 0 && cand != bn_env) continue;
+      const int64_t ct = (cols + cand - 1) / cand;
+      const int64_t c2 = (row_tiles * ct + sms - 1) / sms * std::max(cand, 128) * 10;
+      const int64_t c3 = (rt2 * ct + sms - 1) / sms * std::max(cand, 128) * 8;
+      if ((!gen_forced || gen_env == 2) && (best < 0 || c2 < best)) best = c2, bn = cand, pairs_fit = false;
+      if (cand >= 128 && cl == 1 && (!gen_forced || gen_env == 3) && (best < 0 || c3 < best)) best = c3, bn = cand, pairs_fit = true;
     }
-    if (bn_env == 64 || bn_env == 128 || bn_env == 160 || bn_env == 192) bn = bn_env;
+    if (bn_env == 192) bn = 192, pairs_fit = cl == 1;  // 192-column tiles exist for the pair kernel only
     const unsigned col_tiles = (unsigned)((cols + bn - 1) / bn);
     dim3 grid((col_tiles + cl - 1) / cl * cl, (unsigned)row_tiles);
     *count_out = (int)(grid.x * grid.y);
-    // Third generation (CTA pairs) for every wide tile: N = 2549, B = 1024 (one wave) 0.077 vs 0.103 ms; B = 2048 0.179 vs 0.195;
-    // N = 1003, 10 000 pseudo-samples 0.178 vs 0.221; B = 8192 (seven waves) 0.645 vs 0.639.  FEO_DENSE_GEN=2 / 3 force one.
-    const int64_t rt2 = (row_tiles + 1) / 2 * 2;
-    const bool pairs_fit = bn >= 128 && cl == 1;
-    static const bool gen_forced = std::getenv("FEO_DENSE_GEN") != nullptr;
     static const int cm_env = env_int("FEO_DENSE_CM", 0);
-    if (bn >= 128 && cl == 1 && (gen_env == 3 || (!gen_forced && pairs_fit))) {
+    if (bn >= 128 && cl == 1 && pairs_fit) {
       // CTA pairs: the row tiles are paired (an odd count gets a padding CTA); FEO_DENSE_CM=2: two column tiles per cluster
       // share the operator stages by multicast (an odd count of column tiles gets a padding column)
       const int cm = cm_env == 2 ? 2 : 1;
