@@ -842,6 +842,9 @@ def run_e2e(args, torch, feo, ns, fx, dev, world, rank):
     import torch.distributed as dist
 
     N, B = fx.N, args.batch
+    from feonet_navier_stokes_b200.parallel import bind_to_gpu_numa_node
+
+    numa = bind_to_gpu_numa_node(dev) if world > 1 else None  # the pinned batches below land on the GPU's own NUMA node
     a_host = torch.empty(B, N, pin_memory=True)
     f_host = torch.empty(B, N, pin_memory=True)
     chunk = min(B, args.e2e_chunk)
@@ -875,7 +878,8 @@ def run_e2e(args, torch, feo, ns, fx, dev, world, rank):
     return {"value": world * B * k / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * 4 * N * B,
             "d2h_bytes_per_step": 4, "steps": k, "ms_per_step": ms / k, "loss": loss_host,
             "note": f"feo.HostBatchPipeline: pinned host row-major alpha,F -> H2D in chunks of {chunk} samples on a copy stream, "
-                    "overlapped with layout transposes + fused fwd+bwd of the previous chunk -> gradients on the device, loss D2H"}
+                    "overlapped with layout transposes + fused fwd+bwd of the previous chunk -> gradients on the device, loss D2H",
+            "numa_node_rank0": numa}
 
 
 def main():

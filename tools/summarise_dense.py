@@ -30,11 +30,13 @@ for r in lr[1:4]:
 out += ["```", "", "Plain timing of the same command (CUDA events, no profiler; second generation, first generation `FEO_DENSE_GEN=1`, fp32 FMA kernel `FEO_DENSE_SIMT=1`):", "", "```"]
 out += [l.rstrip() for l in open(os.path.join(G, f"dense_plain_{tag}.log")) if l.strip()]
 out += ["```"]
-for name, title in (("dense_sweep.log", "Tile width / stage sweep (`tools/dense_sweep.sh`; FEO_DENSE_BN, FEO_DENSE_ASTAGES, FEO_DENSE_CLUSTER) and other sizes with the automatic choice"),
-                    ("dense_sweep_small.log", "Small sizes (`tools/dense_sweep_small.sh`): launch-bound, all variants within the noise of a three-kernel Python loop")):
-    p = os.path.join(G, name)
+for mode, title in (("gens", "Kernel generations (default = launcher's choice, pairs, pre-split single CTAs, first generation, fp32 FMA) and other sizes, pairs vs single CTAs"),
+                    ("tiles", "Second generation: tile widths, stages, cluster multicast, refill gap, drains, developer timing modes"),
+                    ("pairs", "Third generation (CTA pairs): k-blocks per stage, stages, drains, clusters of two pairs, 192-column tiles, no-MMA floor"),
+                    ("small", "Small sizes: launch-bound, all variants within the noise of a three-kernel Python loop")):
+    p = os.path.join(G, f"dense_sweeps_{mode}.log")
     if os.path.exists(p):
-        out += ["", title + ":", "", "```"] + [l.rstrip()[:175] for l in open(p) if l.strip()] + ["```"]
+        out += ["", f"{title} (`tools/dense_sweeps.sh {mode}`):", "", "```"] + [l.rstrip()[:175] for l in open(p) if l.strip()] + ["```"]
 extra = os.path.join(P, f"{tag}_dense_notes.md")
 if os.path.exists(extra):
     out += ["", open(extra).read().rstrip()]
