@@ -19,7 +19,7 @@ default); outputs are views of graph-owned memory, valid until the next replay.
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Callable, Dict, Optional, Sequence, Tuple
 
 import torch
 

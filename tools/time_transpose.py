@@ -14,7 +14,6 @@ dev = torch.device("cuda:0")
 x = torch.randn(B, N, device=dev)
 xT = torch.empty(N, B, device=dev)
 y = torch.empty(B, N, device=dev)
-n_u = (N - 3) // 3
 perm = torch.tensor(np.random.default_rng(0).permutation(N).astype(np.int32), device=dev)
 # blocked -> interleaved-like map: locally regular (stride 2-3), as reorder.lattice_permutation produces
 reg = torch.tensor((np.arange(N, dtype=np.int64) * 3 % N if N % 3 else np.arange(N)).astype(np.int32), device=dev)
