@@ -775,15 +775,14 @@ __global__ void __launch_bounds__(kTcBlock, 1) dense_apply_tc3_kernel(const __gr
       const uint32_t dst = smem_u32(smem) + (uint32_t)stage * kStage;
       const int32_t a_row = a_row0 + sb * G * (int32_t)(kAStage / kRowBytes);
       if (CM == 1) {  // G consecutive operator blocks of the row tile: one box (rows past the array are zero-filled and counted)
-        tma_box_pair_multicast(dst, &maps.a, 0, a_row, bar, (uint16_t)(1u << crank));
+        tma_box_pair(dst, &maps.a, 0, a_row, bar & kPeerBitMask);
       } else {
         const uint32_t half = cy * kABytes;
         tma_box_pair_multicast(dst + half, &maps.ah, 0, a_row + (int32_t)(half / kRowBytes), bar, col_mask);
       }
 #pragma unroll
       for (int g = 0; g < G; ++g)
-        tma_box_pair_multicast(dst + G * kAStage + g * kXHalf, &maps.x, 0, x_row0 + (sb * G + g) * (int32_t)(b_stage_bytes(BN) / kRowBytes), bar,
-                               (uint16_t)(1u << crank));
+        tma_box_pair(dst + G * kAStage + g * kXHalf, &maps.x, 0, x_row0 + (sb * G + g) * (int32_t)(b_stage_bytes(BN) / kRowBytes), bar & kPeerBitMask);
     };
     if (elect_one())
       for (int sb = 0; sb < kAhead && sb < nsb; ++sb) copy_stage(sb, sb);
