@@ -284,7 +284,8 @@ class Trainer:
                 self.P = feo.spai_device(A, gparams["spai_steps"], self.device).to(torch.float32).cpu()
             hole = variant == "hole"
             self.problem = feo.LinearStokes(A, self.P, do_precond=do_precond, model_name=gparams["model"], force=gparams["forcing_term"],
-                                            hole_signature=hole, device=self.device)
+                                            hole_signature=hole, device=self.device, idx_sol=self.fx.idx_sol,
+                                            dof_positions=getattr(self.fx, "pos", None))
             if hole:
                 self.closure_args = lambda b: (b["coeff_f"], None, b["load_vec_f"], A, self.P, gparams["resol_in"])  # noqa: E731
             else:

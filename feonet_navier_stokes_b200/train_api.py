@@ -105,8 +105,12 @@ class LinearStokes(_Base):
     State mirrored from the reference's globals: DO_PRECOND, NUM_PTS, gparams['model'], FORCE."""
 
     def __init__(self, matrix=None, precond=None, do_precond: bool = False, model_name: str = "FCNN",
-                 force: str = "sincos", hole_signature: bool = False, device=None):
+                 force: str = "sincos", hole_signature: bool = False, device=None, idx_sol=None, dof_positions=None):
+        """idx_sol, dof_positions (optional; the reference's npz carries both, its Stokes `weak_form` uses neither): with them a
+        structured-mesh operator in FEniCS' dof order is renumbered internally so that the un-preconditioned residual runs in the
+        lattice kernels (reorder.py); tensors keep the caller's numbering."""
         super().__init__(device)
+        self.idx_sol, self.dof_positions = idx_sol, dof_positions
         self.DO_PRECOND = bool(do_precond)
         self.model_name, self.force, self.hole_signature = model_name, force, hole_signature
         if matrix is not None:
@@ -125,7 +129,17 @@ class LinearStokes(_Base):
                 else:
                     self._op = FEOperator(n, A=matrix, dense_m=_fold_dense(matrix, P), dense_p=P, device=self.device)
             else:
-                self._op = FEOperator(n, A=matrix, device=self.device)
+                perm = None
+                if self.dof_positions is not None and self.idx_sol is not None:
+                    from .reorder import is_identity, lattice_permutation
+
+                    perm = lattice_permutation(self.idx_sol, np.asarray(self.dof_positions))
+                    if is_identity(perm):
+                        perm = None
+                # the renumbered operator carries idx_sol so that the planner can pair the velocity dofs
+                self._op = FEOperator(n, A=matrix, idx_sol=self.idx_sol if perm is not None else None, dof_perm=perm, device=self.device)
+                if perm is not None and self._op.plan != "lattice":
+                    self._op = FEOperator(n, A=matrix, device=self.device)
             self._key_commit(key)
         return self._op
 

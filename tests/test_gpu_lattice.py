@@ -183,3 +183,25 @@ def test_any_dof_order_reaches_the_lattice_kernels(feo, n, B, branch):
         lhs, rhs = ns.weak_form(a, torch.tensor(F, device=dev), A, B1, B2, idx_sol)
         lhs0, rhs0 = plain.weak_form(a, torch.tensor(F, device=dev), A, B1, B2, idx_sol)
         assert torch.allclose(lhs, lhs0, rtol=1e-5, atol=1e-5) and torch.allclose(rhs, rhs0, rtol=1e-5, atol=1e-5)
+
+
+def test_linear_stokes_in_another_dof_order_reaches_the_lattice_kernels(feo):
+    """The linear Stokes operator (FEONet_Stokes_square/train_FEONet.py:261-271) in blocked order with idx_sol and the dof
+    coordinates: renumbered into the lattice plan, results in the caller's numbering against the oracle."""
+    from feonet_navier_stokes_b200.fixtures import config_operators
+
+    dev = torch.device("cuda")
+    fb = config_operators("stokes_square", 9, ordering="blocked")
+    rng = np.random.default_rng(5)
+    B = 45
+    alpha = (0.3 * rng.standard_normal((B, fb.N))).astype(np.float32)
+    F = rng.standard_normal((B, fb.N)).astype(np.float32)
+    lo, go, _ = orc.stokes_loss_and_grad(alpha, F, fb.A, None, False, dtype=np.float64)
+    st = feo.LinearStokes(fb.A, None, do_precond=False, device=dev, idx_sol=fb.idx_sol, dof_positions=fb.pos)
+    assert st.operator.plan == "lattice"
+    assert feo.LinearStokes(fb.A, None, do_precond=False, device=dev).operator.plan == "tile"
+    a = torch.tensor(alpha, device=dev).unsqueeze(1).requires_grad_(True)
+    loss = st.residual_loss(a, torch.tensor(F, device=dev), fb.A, None)
+    (g,) = torch.autograd.grad(loss, a)
+    assert abs(loss.item() - lo) <= LOSS_RTOL * abs(lo)
+    assert _rel(g.squeeze(1).cpu().numpy(), go) < GRAD_RTOL
