@@ -567,6 +567,18 @@ def run_train_step(args, torch, feo, ns, fx, dev, world, rank):
         out["closure_row_major_head"] = {"ms_per_step": ms_rm, "samples_per_s": B / (ms_rm * 1e-3),
                                          "note": "network.FCNN with the reference's nn.Linear head ([B,1,N] row-major): the loss op transposes in and out"}
         del model, optim
+        # where the step's time goes: the same step with PyTorch's own TF32 switch for the network's GEMMs (NOT the reference's
+        # numerics, not part of `weak`; the loss path is unchanged fp32) -- the head's three 0.54-TFLOP fp32 GEMMs are PyTorch's part
+        prev = torch.backends.cuda.matmul.allow_tf32
+        try:
+            torch.backends.cuda.matmul.allow_tf32 = True
+            model, reducer, optim = build(True, False)
+            ms_tf32, _, _ = time_steps(model, reducer, optim, B, False)
+            out["weak_network_tf32"] = {"ms_per_step": ms_tf32, "samples_per_s": B / (ms_tf32 * 1e-3),
+                                        "note": "torch.backends.cuda.matmul.allow_tf32 = True for the network layers only; informational"}
+            del model, optim
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
     torch.cuda.empty_cache()
     log(f"[bench] train_step {out}")
     return out
