@@ -247,3 +247,17 @@ def test_lattice_permutation_from_dof_coordinates():
     pos = fb.pos.copy()
     pos[3, 0] += 0.01
     assert lattice_permutation(fb.idx_sol, pos) is None
+
+
+def test_numa_binding_is_a_no_op_without_a_visible_topology():
+    """parallel.bind_to_gpu_numa_node leaves the affinity alone when there is no GPU / no sysfs topology to read."""
+    import os
+
+    from feonet_navier_stokes_b200.parallel import bind_to_gpu_numa_node
+
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa_node("cuda:0") is None or isinstance(bind_to_gpu_numa_node("cuda:0"), int)
+    import torch
+
+    if not torch.cuda.is_available():
+        assert os.sched_getaffinity(0) == before
